@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the MCPC hot path (BASELINE.json: "Langevin latent-updates/sec (chains x layers x T)
+and train images/sec").
+
+Workload at N=1 (BASELINE.json configs[1]): the `mcpc_ml` net d=[20,128,128]->784, relu,
+Bernoulli top, batch 1024 per GPU; one *step* = one MCPC learning call = T=150 Langevin inference steps
+(mixing 50 + sampling 100, SGD lr 0.03, noise var 2) + the local weight update accumulated over the 100
+sampling steps + optimizer_p (Adam lr 0.01) step  (utils/training_evaluation.py:43-56, table_1.py:195-212,
+figure_5.py:54-55 of the reference).  N>1: the batch is sharded (1024 chains per GPU, weak scaling), no
+communication during inference, one NCCL all-reduce of the weight gradients per step.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # the CPU restatement of the reference on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CFG = dict(input_size=20, hidden_size=128, hidden2_size=128, output_size=784, activation_fn="relu")
+DIMS = (20, 128, 128)
+D_OUT = 784
+MIXING, SAMPLING = 50, 100
+T_MCPC = MIXING + SAMPLING
+T_MAP = 250
+LR_X_MCPC, LR_X_MAP, LR_P = 0.03, 0.1, 0.01
+MAC = 20 * 128 + 128 * 128 + 128 * 784          # weight MACs per chain-step (Linear_0 sees zero inputs)
+FLOPS_INFER_STEP = 4 * MAC                        # fwd + back-projection
+FLOPS_DW_STEP = 2 * MAC
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="chains per GPU")
+    ap.add_argument("--precision", default=os.environ.get("MCPC_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--cpu-sample-steps", type=int, default=int(os.environ.get("MCPC_CPU_SAMPLE_STEPS", "30")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+#  CPU arm: the oracle port of the reference's algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(B, n_steps, repeats=1):
+    """Time `n_steps` Langevin steps (with the per-step dW contractions autograd performs in the
+    reference, pc_trainer.py:862) of the C2 workload with the numpy restatement.  Returns seconds/step."""
+    from oracle import mcpc_oracle as orc
+    rng = np.random.default_rng(0)
+
+    def lin(o, i):
+        k = 1.0 / np.sqrt(i)
+        return rng.uniform(-k, k, (o, i)).astype(np.float32), rng.uniform(-k, k, (o,)).astype(np.float32)
+    Ws, bs = zip(*[lin(20, 20), lin(128, 20), lin(128, 128), lin(784, 128)])
+    net = orc.OracleNet(W=list(Ws), b=list(bs), n_layers=3, act=[orc.ACT_RELU] * 3, energy_scale=[1.0] * 3,
+                        top=orc.TOP_BERNOULLI)
+    x0 = [rng.standard_normal((B, d)).astype(np.float32) for d in DIMS]
+    y = (rng.random((B, D_OUT)) < 0.5).astype(np.float32)
+    std = np.sqrt(2.0 / LR_X_MCPC)
+    best = None
+    for _ in range(repeats):
+        noise = [[(rng.standard_normal((B, d)) * std).astype(np.float32) for d in DIMS] for _ in range(n_steps)]
+        t0 = time.perf_counter()
+        orc.infer(net, x0, np.zeros((B, 20), np.float32), y, n_steps, optimizer="sgd", lr=LR_X_MCPC, noise=noise,
+                  acc_begin=0, acc_end=n_steps, always_param_grads=True)
+        dt = (time.perf_counter() - t0) / n_steps
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B = args.batch
+    n = max(2, args.cpu_sample_steps)
+    cpu_port_run(B, 2)                                  # warm-up (BLAS thread pools, page faults)
+    times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        times.append(cpu_port_run(B, n))
+    sec_per_langevin_step = float(np.median(times))
+    step_s = sec_per_langevin_step * T_MCPC            # steps are homogeneous: scale the sample to T=150
+    value = B * len(DIMS) * T_MCPC / step_s
+    line = {
+        "impl": "reference", "metric": "langevin_latent_updates_per_s", "value": value, "unit": "latent-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(B, 1, "fp32"),
+        "cpu_baseline": {"value": value, "unit": "latent-updates/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} of the {T_MCPC} Langevin steps of one MCPC call at B={B} (incl. the per-step dW "
+                                   f"contractions autograd performs), median of {len(times)} runs, scaled linearly to T={T_MCPC}; "
+                                   "numpy/OpenBLAS restatement (oracle/mcpc_oracle.py) -- the Python reference itself cannot "
+                                   "travel to the GPU box"},
+        "e2e": {"value": value, "unit": "latent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "train_images_per_s": B / step_s,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(B, n_gpus, precision):
+    return {"workload": "C2 mcpc_ml MNIST-shape MCPC learning call (SURVEY §8d)", "net": "20-128-128->784 relu, Bernoulli top",
+            "batch_per_gpu": B, "global_batch": B * n_gpus, "T": T_MCPC, "mixing": MIXING, "sampling": SAMPLING,
+            "x_optimizer": "SGD lr 0.03 + Langevin noise var 2 (in-kernel Philox)", "p_optimizer": "Adam lr 0.01",
+            "precision": precision, "l2": "flushed with a 256 MiB write between timed iterations",
+            "parallelism": f"dp{n_gpus} (chains sharded, one all-reduce of dW per step)" if n_gpus > 1 else "single GPU"}
+
+
+# ------------------------------------------------------------------------------------------------
+#  clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, burst)"
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+#  our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torch.optim as optim
+
+    from montecarlopredictivecoding_b200 import _native
+    from montecarlopredictivecoding_b200 import mcpc_utils as mu
+    from montecarlopredictivecoding_b200 import predictive_coding as pc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.load()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(0)                                   # identical random-init weights on every rank
+    model = mu.get_model(CFG, use_cuda=False).to(dev)
+    config = {"T_pc": T_MAP, "optimizer_x_fn_pc": optim.Adam, "optimizer_x_kwargs_pc": {"lr": LR_X_MAP},
+              "mixing": MIXING, "sampling": SAMPLING, "optimizer_x_kwargs_mcpc": {"lr": LR_X_MCPC},
+              "optimizer_p_fn_mcpc": optim.Adam, "optimizer_p_kwargs_mcpc": {"lr": LR_P}}
+    map_trainer = mu.get_pc_trainer(model, config, is_mcpc=True)
+    mcpc_trainer = mu.get_mcpc_trainer(model, config, training=True)
+    for tr in (map_trainer, mcpc_trainer):
+        tr.set_precision(args.precision)
+        if world > 1:
+            tr.set_data_parallel()
+    pseudo_input = torch.zeros(B, CFG["input_size"], device=dev)
+    gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    n_pool = 8
+    host_targets = [(torch.rand(B, D_OUT, generator=gen) < 0.5).float().pin_memory() for _ in range(n_pool)]
+    dev_targets = [t.to(dev) for t in host_targets]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def map_call(y):
+        map_trainer.train_on_batch(inputs=pseudo_input, loss_fn=mu.bernoulli_fn, loss_fn_kwargs={"_target": y, "_var": 1.0},
+                                   is_log_progress=False, is_return_results_every_t=False,
+                                   is_checking_after_callback_after_t=False)
+
+    def mcpc_call(y):
+        return mcpc_trainer.train_on_batch(
+            inputs=pseudo_input, loss_fn=mu.bernoulli_fn, loss_fn_kwargs={"_target": y, "_var": 1.0},
+            callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": mcpc_trainer},
+            is_sample_x_at_batch_start=False, is_log_progress=False, is_return_results_every_t=True,
+            is_checking_after_callback_after_t=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    import warnings
+    warnings.simplefilter("ignore")
+    for i in range(W):
+        map_call(dev_targets[i % n_pool])
+        mcpc_call(dev_targets[i % n_pool])
+
+    # ---- timed: K MCPC learning calls, inputs resident in HBM --------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.mcpc_launch_count()
+    barrier()
+    evs = []
+    for i in range(K):
+        y = dev_targets[i % n_pool]
+        flush.fill_(i & 0xFF)                               # evict L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mcpc_call(y)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = lib.mcpc_launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    total_s = max_over_ranks(dev_ms * 1e-3)
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- e2e: targets start in pinned HOST memory, result lists are read back every step ----------
+    barrier()
+    evs = []
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = host_targets[i % n_pool].to(dev, non_blocking=True)
+        res = mcpc_call(y)                                  # returns Python lists => D2H of the [2,T] scalars inside
+        e1.record()
+        evs.append((e0, e1))
+        assert len(res["energy"]) == T_MCPC
+    barrier()
+    e2e_s = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) * 1e-3)
+
+    # ---- the reference's full training pattern: MAP warm-up (Adam, T=250) + MCPC call --
+    barrier()
+    kk = max(2, min(K, 5))
+    t_ev = []
+    for i in range(kk):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        map_call(dev_targets[i % n_pool])
+        mcpc_call(dev_targets[i % n_pool])
+        e1.record()
+        t_ev.append((e0, e1))
+    barrier()
+    full_s = max_over_ranks(sum(a.elapsed_time(b) for a, b in t_ev) * 1e-3) / kk
+
+    # ---- dominant kernel alone (roofline): events around the mcpc_infer launch of an MCPC call ----
+    eng = mcpc_trainer._get_engine()
+    orig_infer = eng.infer
+    k_ev = []
+
+    def timed_infer(call):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_infer(call)
+        e1.record()
+        k_ev.append((e0, e1))
+    eng.infer = timed_infer
+    for i in range(5):
+        flush.fill_(i)
+        mcpc_call(dev_targets[i % n_pool])
+    torch.cuda.synchronize(dev)
+    eng.infer = orig_infer
+    infer_ms = float(np.median([a.elapsed_time(b) for a, b in k_ev]))
+
+    if rank == 0:
+        peak_tf, peak_hbm, peak_src = measured_peaks()
+        step_s = total_s / K
+        L = len(DIMS)
+        value = world * B * L * T_MCPC / step_s
+        flops_infer_launch = B * T_MCPC * FLOPS_INFER_STEP
+        achieved_tf = flops_infer_launch / (infer_ms * 1e-3) / 1e12
+        line = {
+            "metric": "langevin_latent_updates_per_s", "value": value, "unit": "latent-updates/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": workload_config(B, world, args.precision),
+            "train_images_per_s": world * B / step_s,
+            "train_images_per_s_with_map_warmup": world * B / full_s,
+            "e2e": {"value": world * B * L * T_MCPC / (e2e_s / K), "unit": "latent-updates/s",
+                    "h2d_bytes_per_step": B * D_OUT * 4, "d2h_bytes_per_step": 2 * T_MCPC * 8,
+                    "ms_per_step": e2e_s / K * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "mcpc_infer (all T steps, one launch)",
+                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": infer_ms,
+                         "algorithmic_flops_per_launch": flops_infer_launch,
+                         "note": "4*MAC flops per chain-step x B x T (SURVEY §8d); latents stay on chip, HBM traffic is the "
+                                 "saved dW operands only"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n = max(2, args.cpu_sample_steps)
+            cpu_port_run(B, 2)
+            sec = cpu_port_run(B, n)
+            cpu_step = sec * T_MCPC
+            line["cpu_baseline"] = {
+                "value": B * L * T_MCPC / cpu_step, "unit": "latent-updates/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": f"{n} of the {T_MCPC} Langevin steps of the same call at B={B} (incl. per-step dW like autograd in the "
+                          f"reference), scaled linearly to T={T_MCPC}; numpy restatement oracle/mcpc_oracle.py"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

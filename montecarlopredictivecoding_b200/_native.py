@@ -1,0 +1,143 @@
+"""ctypes binding of libmcpc_b200.so (include/mcpc_b200.h).
+
+There is no CPU fallback: if the library cannot be loaded (or built with nvcc) every call
+raises.  The structures below mirror the C header field by field.
+"""
+import ctypes as C
+import os
+import threading
+
+MAX_LAYERS = 8
+ACT_IDENTITY, ACT_RELU, ACT_TANH = 0, 1, 2
+TOP_NONE, TOP_ZERO, TOP_GAUSS, TOP_BERNOULLI = 0, 1, 2, 3
+OPT_SGD, OPT_ADAM = 0, 1
+NOISE_NONE, NOISE_SUPPLIED, NOISE_PHILOX = 0, 1, 2
+PREC_FP32, PREC_BF16 = 0, 1
+ABI_VERSION = 1
+
+_FP = C.c_void_p   # device pointers travel as integers
+
+
+class McpcNet(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32),
+        ("d_in", C.c_int32),
+        ("dims", C.c_int32 * MAX_LAYERS),
+        ("d_out", C.c_int32),
+        ("act", C.c_int32 * MAX_LAYERS),
+        ("energy_scale", C.c_float * MAX_LAYERS),
+        ("energy_coefficient", C.c_float),
+        ("top", C.c_int32),
+        ("top_inv_var", C.c_float),
+        ("mask_start_col", C.c_int32),
+    ]
+
+
+class McpcIO(C.Structure):
+    _fields_ = [
+        ("W", _FP * (MAX_LAYERS + 1)),
+        ("b", _FP * (MAX_LAYERS + 1)),
+        ("x", _FP * MAX_LAYERS),
+        ("inputs", _FP),
+        ("target", _FP),
+        ("noise", _FP),
+        ("adam_m", _FP * MAX_LAYERS),
+        ("adam_v", _FP * MAX_LAYERS),
+        ("x_grad", _FP * MAX_LAYERS),
+        ("energy", _FP),
+        ("loss", _FP),
+        ("traj_x", _FP * MAX_LAYERS),
+        ("traj_out", _FP),
+        ("save_g", _FP),
+        ("save_f", _FP),
+    ]
+
+
+class McpcOpts(C.Structure):
+    _fields_ = [
+        ("lr", C.c_double),
+        ("adam_beta1", C.c_double),
+        ("adam_beta2", C.c_double),
+        ("adam_eps", C.c_double),
+        ("noise_scale", C.c_double),
+        ("seed", C.c_uint64),
+        ("chain_offset", C.c_uint64),
+        ("n_steps", C.c_int32),
+        ("t_begin", C.c_int32),
+        ("optimizer", C.c_int32),
+        ("update_x", C.c_int32),
+        ("adam_step0", C.c_int32),
+        ("noise_mode", C.c_int32),
+        ("traj_every", C.c_int32),
+        ("save_begin", C.c_int32),
+        ("save_end", C.c_int32),
+        ("precision", C.c_int32),
+    ]
+
+
+class McpcGradIO(C.Structure):
+    _fields_ = [
+        ("save_g", _FP),
+        ("save_f", _FP),
+        ("inputs", _FP),
+        ("gW", _FP * (MAX_LAYERS + 1)),
+        ("gb", _FP * (MAX_LAYERS + 1)),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+LIB_NAME = "libmcpc_b200.so"
+EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_infer", "mcpc_weight_grad",
+           "mcpc_fill_noise")
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+
+def load():
+    """Load (building in-tree with nvcc when the .so is missing) and type the entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(path)
+        lib.mcpc_version.restype = C.c_int
+        lib.mcpc_last_error.restype = C.c_char_p
+        lib.mcpc_launch_count.restype = C.c_uint64
+        lib.mcpc_workspace_bytes.restype = C.c_int
+        lib.mcpc_workspace_bytes.argtypes = [C.POINTER(McpcNet), C.c_int32, C.c_int32, C.c_int32,
+                                             C.POINTER(C.c_size_t)]
+        lib.mcpc_infer.restype = C.c_int
+        lib.mcpc_infer.argtypes = [C.POINTER(McpcNet), C.POINTER(McpcIO), C.POINTER(McpcOpts), C.c_int32,
+                                   C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.mcpc_weight_grad.restype = C.c_int
+        lib.mcpc_weight_grad.argtypes = [C.POINTER(McpcNet), C.POINTER(McpcGradIO), C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p]
+        lib.mcpc_fill_noise.restype = C.c_int
+        lib.mcpc_fill_noise.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
+                                        C.c_float, C.c_void_p, C.c_void_p]
+        got = lib.mcpc_version()
+        if got != ABI_VERSION:
+            raise NativeError(f"{LIB_NAME} ABI version {got}, python binding expects {ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mcpc_last_error().decode(errors="replace")
+        if rc == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise NativeError(f"{what} failed (code {rc}): {msg}")

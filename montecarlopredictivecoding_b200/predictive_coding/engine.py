@@ -1,0 +1,173 @@
+"""Tensor-level front of the C ABI: packs torch tensors into McpcNet/McpcIO/McpcOpts and calls
+libmcpc_b200.so on torch's current CUDA stream.  This is the only engine the product ships;
+it refuses anything that is not a contiguous fp32 CUDA tensor (no CPU fallback).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from .. import _native as N
+from .plan import NetPlan, TopPlan
+
+
+@dataclass
+class InferCall:
+    plan: NetPlan
+    top: TopPlan
+    energy_coefficient: float
+    B: int
+    W: List[torch.Tensor]
+    b: List[Optional[torch.Tensor]]
+    x: List[torch.Tensor]
+    inputs: Optional[torch.Tensor]
+    target: Optional[torch.Tensor]
+    energy: Optional[torch.Tensor]          # float64 [n_steps]
+    loss: Optional[torch.Tensor]            # float64 [n_steps]
+    n_steps: int
+    t_begin: int = 0
+    optimizer: int = N.OPT_SGD
+    update_x: bool = True
+    lr: float = 0.1
+    betas: tuple = (0.9, 0.999)
+    adam_eps: float = 1e-8
+    adam_step0: int = 0
+    adam_m: Optional[List[torch.Tensor]] = None
+    adam_v: Optional[List[torch.Tensor]] = None
+    noise_mode: int = N.NOISE_NONE
+    noise: Optional[torch.Tensor] = None    # [n_steps, B, SD] raw gradient noise
+    noise_scale: float = 0.0
+    seed: int = 0
+    chain_offset: int = 0
+    x_grad: Optional[List[torch.Tensor]] = None
+    traj_x: List[Optional[torch.Tensor]] = field(default_factory=list)
+    traj_out: Optional[torch.Tensor] = None
+    traj_every: int = 1
+    save_g: Optional[torch.Tensor] = None
+    save_f: Optional[torch.Tensor] = None
+    save_begin: int = 0
+    save_end: int = 0
+    precision: int = N.PREC_FP32
+
+
+def net_struct(plan: NetPlan, top: TopPlan, energy_coefficient: float) -> N.McpcNet:
+    net = N.McpcNet()
+    net.n_layers = plan.L
+    net.d_in = plan.d_in
+    net.d_out = plan.d_out
+    for l in range(plan.L):
+        net.dims[l] = plan.dims[l]
+        net.act[l] = plan.act[l]
+        net.energy_scale[l] = plan.energy_scale[l]
+    net.energy_coefficient = energy_coefficient
+    net.top = top.kind
+    net.top_inv_var = top.inv_var
+    net.mask_start_col = top.mask_start
+    return net
+
+
+def _ptr(t: Optional[torch.Tensor], what: str, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA device: the B200 build has no CPU path")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError(f"{what} must be a contiguous {dtype} tensor (got {t.dtype}, contiguous={t.is_contiguous()})")
+    return t.data_ptr()
+
+
+class NativeEngine:
+    """Calls the sm_100a kernels through the C ABI."""
+
+    name = "native"
+
+    def __init__(self):
+        self._lib = N.load()
+        self._ws = {}
+
+    def _workspace(self, net, B, n_steps, precision, device):
+        need = C.c_size_t(0)
+        N.check(self._lib.mcpc_workspace_bytes(C.byref(net), B, n_steps, precision, C.byref(need)),
+                "mcpc_workspace_bytes")
+        key = (device.index, )
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < need.value:
+            buf = torch.empty(max(need.value, 1 << 20), dtype=torch.uint8, device=device)
+            self._ws[key] = buf
+        return buf
+
+    def infer(self, c: InferCall) -> None:
+        plan = c.plan
+        dev = c.x[0].device
+        net = net_struct(plan, c.top, c.energy_coefficient)
+        io = N.McpcIO()
+        for i, (W, b) in enumerate(zip(c.W, c.b)):
+            io.W[i] = _ptr(W, f"weight of Linear {i}")
+            io.b[i] = _ptr(b, f"bias of Linear {i}")
+        for l in range(plan.L):
+            io.x[l] = _ptr(c.x[l], f"latent x[{l}]")
+            if c.adam_m is not None:
+                io.adam_m[l] = _ptr(c.adam_m[l], "adam_m")
+                io.adam_v[l] = _ptr(c.adam_v[l], "adam_v")
+            if c.x_grad is not None:
+                io.x_grad[l] = _ptr(c.x_grad[l], "x_grad")
+            if c.traj_x and c.traj_x[l] is not None:
+                io.traj_x[l] = _ptr(c.traj_x[l], "traj_x")
+        io.inputs = _ptr(c.inputs, "inputs")
+        io.target = _ptr(c.target, "target")
+        io.noise = _ptr(c.noise, "noise")
+        io.energy = _ptr(c.energy, "energy", torch.float64)
+        io.loss = _ptr(c.loss, "loss", torch.float64)
+        io.traj_out = _ptr(c.traj_out, "traj_out")
+        io.save_g = _ptr(c.save_g, "save_g")
+        io.save_f = _ptr(c.save_f, "save_f")
+        o = N.McpcOpts()
+        o.lr = float(c.lr)
+        o.adam_beta1, o.adam_beta2 = float(c.betas[0]), float(c.betas[1])
+        o.adam_eps = float(c.adam_eps)
+        o.noise_scale = float(c.noise_scale)
+        o.seed = int(c.seed) & 0xFFFFFFFFFFFFFFFF
+        o.chain_offset = int(c.chain_offset)
+        o.n_steps = int(c.n_steps)
+        o.t_begin = int(c.t_begin)
+        o.optimizer = int(c.optimizer)
+        o.update_x = 1 if c.update_x else 0
+        o.adam_step0 = int(c.adam_step0)
+        o.noise_mode = int(c.noise_mode)
+        o.traj_every = int(c.traj_every)
+        o.save_begin = int(c.save_begin)
+        o.save_end = int(c.save_end)
+        o.precision = int(c.precision)
+        ws = self._workspace(net, c.B, c.n_steps, c.precision, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            N.check(self._lib.mcpc_infer(C.byref(net), C.byref(io), C.byref(o), c.B, ws.data_ptr(), ws.numel(),
+                                         C.c_void_p(stream)), "mcpc_infer")
+
+    def weight_grad(self, plan: NetPlan, top: TopPlan, energy_coefficient: float, B: int, n_save: int,
+                    save_g: torch.Tensor, save_f: torch.Tensor, inputs: Optional[torch.Tensor],
+                    gW: List[Optional[torch.Tensor]], gb: List[Optional[torch.Tensor]], precision: int) -> None:
+        dev = save_g.device
+        net = net_struct(plan, top, energy_coefficient)
+        io = N.McpcGradIO()
+        io.save_g = _ptr(save_g, "save_g")
+        io.save_f = _ptr(save_f, "save_f")
+        io.inputs = _ptr(inputs, "inputs")
+        for i in range(len(gW)):
+            io.gW[i] = _ptr(gW[i], "gW")
+            io.gb[i] = _ptr(gb[i], "gb")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            N.check(self._lib.mcpc_weight_grad(C.byref(net), C.byref(io), B, n_save, precision, C.c_void_p(stream)),
+                    "mcpc_weight_grad")
+
+    def fill_noise(self, seed: int, t_begin: int, n_steps: int, chain_offset: int, B: int, n_units: int,
+                   noise_scale: float, device) -> torch.Tensor:
+        out = torch.empty(n_steps, B, n_units, dtype=torch.float32, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            N.check(self._lib.mcpc_fill_noise(seed & 0xFFFFFFFFFFFFFFFF, t_begin, n_steps, chain_offset, B, n_units,
+                                              float(noise_scale), out.data_ptr(), C.c_void_p(stream)),
+                    "mcpc_fill_noise")
+        return out

@@ -1,0 +1,245 @@
+"""Plan compiler: turn a user ``nn.Module`` + ``loss_fn`` + callback into the flat description
+the fused kernels take (``McpcNet``), or say precisely why that is impossible.
+
+The reference executes arbitrary Python per step (autograd over any module graph).  The B200
+path recognises the one graph family every script of the reference builds --
+``[Linear, PCLayer, act?]* [Linear]?`` (utils/model.py:54-65, figure_2.py:40-44,
+figure_3.py:50-55, figure_4.py:104-108, figure_6.py:45-49,85) -- and classifies the Python
+callables numerically instead of by name, so user-written equivalents work too:
+
+  * ``energy_fn``   must equal c * 0.5 * (mu - x)^2 elementwise   (pc_layer.py:17-18, figure_3.py:47-48)
+  * ``loss_fn``     must be one of: constant (zero_fn), Gaussian (1/var)*0.5*sum(o-y)^2,
+                    Bernoulli sum BCEWithLogits(o, y); each optionally restricted to the last
+                    columns (the *_mask variants)                  (utils/model.py:17-33)
+  * ``callback_after_t`` is folded into the kernel when it is ``random_step`` (utils/model.py:35-44)
+"""
+import inspect
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from .layer import PCLayer
+
+_ACT_OF = {nn.ReLU: N.ACT_RELU, nn.Tanh: N.ACT_TANH, nn.Identity: N.ACT_IDENTITY}
+
+
+class UnsupportedModel(NotImplementedError):
+    """The model / callable is outside what the fused sm_100a kernels implement."""
+
+
+@dataclass
+class NetPlan:
+    linears: List[nn.Linear]            # L (+1 when an output Linear exists)
+    pc_layers: List[PCLayer]
+    act: List[int]
+    energy_scale: List[float]
+    d_in: int
+    dims: List[int]
+    d_out: int
+    signature: tuple = field(default=())
+
+    @property
+    def L(self):
+        return len(self.pc_layers)
+
+    @property
+    def SD(self):
+        return sum(self.dims)
+
+
+@dataclass
+class TopPlan:
+    kind: int                 # N.TOP_*
+    inv_var: float = 1.0
+    mask_start: int = 0
+    target_key: Optional[str] = None
+
+
+_energy_cache = {}
+
+
+def classify_energy_fn(fn) -> float:
+    """Return c such that fn({'mu','x'}) == c*0.5*(mu-x)^2, or raise UnsupportedModel."""
+    key = id(fn)
+    hit = _energy_cache.get(key)
+    if hit is not None and hit[0] is fn:
+        return hit[1]
+    mu = torch.tensor([[0.0, 1.0, -2.0, 0.5, 3.0]], dtype=torch.float64)
+    x = torch.tensor([[0.25, -1.0, 1.5, 0.5, -0.75]], dtype=torch.float64)
+    try:
+        e = fn({"mu": mu, "x": x})
+    except Exception as exc:  # noqa: BLE001
+        raise UnsupportedModel(f"energy_fn could not be probed ({exc!r}); the fused kernel needs c*0.5*(mu-x)^2") from exc
+    base = 0.5 * (mu - x) ** 2
+    if not isinstance(e, torch.Tensor) or e.shape != base.shape:
+        raise UnsupportedModel("energy_fn must be elementwise c*0.5*(mu-x)^2 for the fused kernel")
+    nz = base > 0
+    ratio = (e[nz] / base[nz])
+    c = float(ratio[0])
+    if not torch.allclose(ratio, torch.full_like(ratio, c), rtol=1e-6, atol=0) or \
+            not torch.allclose(e[~nz], torch.zeros_like(e[~nz]), atol=1e-12) or not (c > 0):
+        raise UnsupportedModel("energy_fn is not a positive multiple of 0.5*(mu-x)^2; only (scaled) quadratic "
+                               "energies are implemented in the fused kernel")
+    _energy_cache[key] = (fn, c)
+    return c
+
+
+def compile_net(model: nn.Module) -> NetPlan:
+    """Walk the module list and recognise ``[Linear, PCLayer, act?]* [Linear]?``."""
+    mods = list(model.children()) if not isinstance(model, (nn.Linear, PCLayer)) else [model]
+    if any(len(list(m.children())) > 0 for m in mods):
+        raise UnsupportedModel("nested containers are not supported by the fused kernel; use a flat nn.Sequential of "
+                               "Linear / PCLayer / activation modules")
+    linears, pcs, acts = [], [], []
+    i, n = 0, len(mods)
+    pending_linear = None
+    while i < n:
+        m = mods[i]
+        if isinstance(m, nn.Linear):
+            if pending_linear is not None:
+                raise UnsupportedModel("two Linear layers without a PCLayer between them")
+            pending_linear = m
+            i += 1
+        elif isinstance(m, PCLayer):
+            if pending_linear is None:
+                raise UnsupportedModel("every PCLayer must directly follow its own nn.Linear")
+            if m._S is not None or m._M is not None or m.is_keep_energy_per_datapoint or m.is_holding_error:
+                raise UnsupportedModel("PCLayer S/M masks, per-datapoint energies and held errors are not implemented "
+                                       "in the fused kernel")
+            linears.append(pending_linear)
+            pending_linear = None
+            pcs.append(m)
+            act = N.ACT_IDENTITY
+            if i + 1 < n and type(mods[i + 1]) in _ACT_OF:
+                act = _ACT_OF[type(mods[i + 1])]
+                i += 1
+            acts.append(act)
+            i += 1
+        else:
+            raise UnsupportedModel(f"module {type(m).__name__} at position {i} is not part of the supported pattern "
+                                   "[Linear, PCLayer, ReLU|Tanh|Identity]* [Linear]")
+    if not pcs:
+        raise UnsupportedModel("the model has no PCLayer")
+    if len(pcs) > N.MAX_LAYERS:
+        raise UnsupportedModel(f"more than {N.MAX_LAYERS} PCLayers")
+    d_out = 0
+    if pending_linear is not None:
+        linears.append(pending_linear)
+        d_out = pending_linear.out_features
+    dims = [lin.out_features for lin in linears[:len(pcs)]]
+    prev = linears[0].in_features
+    for lin in linears:
+        if lin.in_features != prev:
+            raise UnsupportedModel("Linear in/out features do not chain")
+        prev = lin.out_features
+    scales = [classify_energy_fn(p._energy_fn) for p in pcs]
+    sig = tuple(id(m) for m in mods)
+    return NetPlan(linears=linears, pc_layers=pcs, act=acts, energy_scale=scales, d_in=linears[0].in_features,
+                   dims=dims, d_out=d_out, signature=sig)
+
+
+_loss_cache = {}
+
+
+def classify_loss(loss_fn, loss_fn_kwargs: dict, B: int, d_out: int, device) -> TopPlan:
+    """Probe ``loss_fn`` with a 2-row batch and match value + gradient against the closed forms."""
+    if loss_fn is None:
+        return TopPlan(kind=N.TOP_NONE)
+    if d_out == 0:
+        raise UnsupportedModel("loss_fn on a free output PCLayer is not supported")
+    tkeys = [k for k, v in loss_fn_kwargs.items() if isinstance(v, torch.Tensor) and v.dim() == 2
+             and tuple(v.shape) == (B, d_out)]
+    scalars = tuple(sorted((k, repr(v)) for k, v in loss_fn_kwargs.items() if not isinstance(v, torch.Tensor)))
+    key = (id(loss_fn), d_out, scalars, tuple(tkeys))
+    hit = _loss_cache.get(key)
+    if hit is not None and hit[0] is loss_fn:
+        return hit[1]
+    if len(tkeys) > 1:
+        raise UnsupportedModel("loss_fn takes more than one [B, d_out] tensor; cannot tell which is the target")
+    other_tensors = [k for k, v in loss_fn_kwargs.items() if isinstance(v, torch.Tensor) and k not in tkeys]
+    if other_tensors:
+        raise UnsupportedModel(f"loss_fn tensor kwargs {other_tensors} are not understood by the fused kernel")
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    o = (torch.randn(2, d_out, generator=g, dtype=torch.float64) * 1.5).requires_grad_(True)
+    kw = dict(loss_fn_kwargs)
+    y = None
+    if tkeys:
+        y = (torch.rand(2, d_out, generator=g, dtype=torch.float64) < 0.5).double() * 0.75 + 0.125
+        kw[tkeys[0]] = y
+    try:
+        val = loss_fn(o, **kw)
+    except Exception as exc:  # noqa: BLE001
+        raise UnsupportedModel(f"loss_fn could not be probed on a 2-row batch ({exc!r})") from exc
+    plan = None
+    if not isinstance(val, torch.Tensor) or not val.requires_grad:
+        if float(val) == 0.0:
+            plan = TopPlan(kind=N.TOP_ZERO)
+        else:
+            raise UnsupportedModel("loss_fn does not depend on the outputs but is not zero")
+    else:
+        if val.dim() != 0:
+            raise UnsupportedModel("loss_fn must return a scalar")
+        (grad,) = torch.autograd.grad(val, o)
+        col_used = (grad != 0).any(dim=0)
+        if not bool(col_used.any()):
+            raise UnsupportedModel("loss_fn has zero gradient everywhere")
+        ms = int(torch.nonzero(col_used)[0])
+        if not bool(col_used[ms:].all()) or y is None:
+            raise UnsupportedModel("loss_fn must act on a contiguous block of trailing output columns of a target")
+        om, ym, gm = o.detach()[:, ms:], y[:, ms:], grad[:, ms:]
+        # Bernoulli: grad = sigmoid(o) - y, value = sum BCE-with-logits
+        bern_g = torch.sigmoid(om) - ym
+        bern_v = (torch.clamp(om, min=0) - om * ym + torch.log1p(torch.exp(-om.abs()))).sum()
+        ratio = gm / (om - ym)
+        iv = float(ratio.flatten()[0])
+        gauss_v = iv * 0.5 * ((om - ym) ** 2).sum()
+        if torch.allclose(gm, bern_g, rtol=1e-9, atol=1e-12) and torch.allclose(val.detach(), bern_v, rtol=1e-9):
+            plan = TopPlan(kind=N.TOP_BERNOULLI, mask_start=ms, target_key=tkeys[0])
+        elif iv > 0 and torch.allclose(ratio, torch.full_like(ratio, iv), rtol=1e-9) and \
+                torch.allclose(val.detach(), gauss_v, rtol=1e-9):
+            plan = TopPlan(kind=N.TOP_GAUSS, inv_var=iv, mask_start=ms, target_key=tkeys[0])
+        else:
+            raise UnsupportedModel("loss_fn is neither Gaussian (1/var)*0.5*sum(o-y)^2 nor Bernoulli "
+                                   "sum BCEWithLogits(o,y) (optionally on trailing columns); only those are fused")
+    _loss_cache[key] = (loss_fn, plan)
+    return plan
+
+
+@dataclass
+class LangevinPlan:
+    var: float
+
+
+def classify_callback_after_t(cb, kwargs: dict, trainer) -> Optional[LangevinPlan]:
+    """Recognise the Langevin ``random_step`` callback (utils/model.py:35-44).
+
+    Returns the noise variance when the callback can be folded into the kernel, ``None`` when
+    it must be executed as opaque Python (step-by-step mode).
+    """
+    if cb is None:
+        return None
+    tagged = getattr(cb, "__mcpc_langevin__", False)
+    named = getattr(cb, "__name__", "") == "random_step" and \
+        (getattr(cb, "__module__", "") or "").split(".")[-1] == "model"
+    if not (tagged or named):
+        return None
+    if kwargs.get("_pc_trainer", None) is not trainer:
+        return None
+    if set(kwargs) - {"_pc_trainer", "var"}:
+        return None
+    var = kwargs.get("var", None)
+    if var is None:
+        try:
+            var = inspect.signature(cb).parameters["var"].default
+        except (KeyError, TypeError, ValueError):
+            return None
+    try:
+        var = float(var)
+    except (TypeError, ValueError):
+        return None
+    if not (var >= 0.0):
+        return None
+    return LangevinPlan(var=var)
