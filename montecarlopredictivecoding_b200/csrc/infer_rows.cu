@@ -14,6 +14,8 @@
 //            x <- x - lr * noise                              utils/model.py:42-44 (random_step)
 // fp32 FMA on CUDA cores throughout, accurate expf/log1pf/tanhf: this is the mode the 1e-5
 // per-step parity tests run in.  The tensor-core path lives in infer_tc.cu.
+#include <cstdlib>
+
 #include "mcpc_common.cuh"
 #include "philox.cuh"
 
@@ -59,6 +61,42 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// acc[r] += sum_{k in [k0,K)} a[r*astride + k] * w[k*wstride]   (k0 a multiple of 4).
+// The weight column is strided in memory (one element per k, coalesced ACROSS the warp), so its loads are
+// software-pipelined 8 deep: the next 8 weights are in flight while the current 8 feed R*8 FMAs.
+template <int R>
+__device__ __forceinline__ void dot_strided(const float* __restrict__ w, size_t wstride, int k0, int K,
+                                            const float* a, int astride, float (&acc)[R]) {
+  int k = k0;
+  if (k + 8 <= K) {
+    float wc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wc[i] = __ldg(w + (size_t)(k + i) * wstride);
+    for (; k + 8 <= K; k += 8) {
+      float wn[8];
+      const bool more = (k + 16 <= K);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wn[i] = more ? __ldg(w + (size_t)(k + 8 + i) * wstride) : 0.0f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a + r * astride + k);
+        const float4 a1 = *reinterpret_cast<const float4*>(a + r * astride + k + 4);
+        float s = acc[r];
+        s = fmaf(a0.x, wc[0], s); s = fmaf(a0.y, wc[1], s); s = fmaf(a0.z, wc[2], s); s = fmaf(a0.w, wc[3], s);
+        s = fmaf(a1.x, wc[4], s); s = fmaf(a1.y, wc[5], s); s = fmaf(a1.z, wc[6], s); s = fmaf(a1.w, wc[7], s);
+        acc[r] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wc[i] = wn[i];
+    }
+  }
+  for (; k < K; ++k) {
+    const float w0 = __ldg(w + (size_t)k * wstride);
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = fmaf(a[r * astride + k], w0, acc[r]);
+  }
 }
 
 template <int R>
@@ -126,24 +164,7 @@ __global__ void __launch_bounds__(kThreads) infer_rows_kernel(const __grid_const
       if (l > 0 || p.inputs != nullptr) {
         const float* __restrict__ wt = p.WT[l] + j;                       // [K][N]
         const float* a = as + ((l == 0) ? 0 : p.d_in_p + p.poff[l - 1]);
-        int k = 0;
-        for (; k + 4 <= K; k += 4) {
-          const float w0 = __ldg(wt + (size_t)(k + 0) * N), w1 = __ldg(wt + (size_t)(k + 1) * N);
-          const float w2 = __ldg(wt + (size_t)(k + 2) * N), w3 = __ldg(wt + (size_t)(k + 3) * N);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float4 av = *reinterpret_cast<const float4*>(a + r * p.a_stride + k);
-            acc[r] = fmaf(av.x, w0, acc[r]);
-            acc[r] = fmaf(av.y, w1, acc[r]);
-            acc[r] = fmaf(av.z, w2, acc[r]);
-            acc[r] = fmaf(av.w, w3, acc[r]);
-          }
-        }
-        for (; k < K; ++k) {
-          const float w0 = __ldg(wt + (size_t)k * N);
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fmaf(a[r * p.a_stride + k], w0, acc[r]);
-        }
+        dot_strided<R>(wt, (size_t)N, 0, K, a, p.a_stride, acc);
       }
       if (!is_out) {
         const float ce = 0.5f * nd.c[l], gc = nd.gc[l];
@@ -217,24 +238,8 @@ __global__ void __launch_bounds__(kThreads) infer_rows_kernel(const __grid_const
         const int Nup = (l + 1 < L) ? nd.dims[l + 1] : nd.d_out;
         const float* __restrict__ w = p.W[l + 1] + k;                     // [Nup][dl]
         const float* g = gs + p.poff[l + 1];
-        int j = (l + 1 == L) ? (nd.mask_start & ~3) : 0;                  // masked-out e_out are exactly 0
-        for (; j + 4 <= Nup; j += 4) {
-          const float w0 = __ldg(w + (size_t)(j + 0) * dl), w1 = __ldg(w + (size_t)(j + 1) * dl);
-          const float w2 = __ldg(w + (size_t)(j + 2) * dl), w3 = __ldg(w + (size_t)(j + 3) * dl);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float4 gv = *reinterpret_cast<const float4*>(g + r * p.g_stride + j);
-            bp[r] = fmaf(gv.x, w0, bp[r]);
-            bp[r] = fmaf(gv.y, w1, bp[r]);
-            bp[r] = fmaf(gv.z, w2, bp[r]);
-            bp[r] = fmaf(gv.w, w3, bp[r]);
-          }
-        }
-        for (; j < Nup; ++j) {
-          const float w0 = __ldg(w + (size_t)j * dl);
-#pragma unroll
-          for (int r = 0; r < R; ++r) bp[r] = fmaf(g[r * p.g_stride + j], w0, bp[r]);
-        }
+        const int j0 = (l + 1 == L) ? (nd.mask_start & ~3) : 0;           // masked-out e_out are exactly 0
+        dot_strided<R>(w, (size_t)dl, j0, Nup, g, p.g_stride, bp);
       }
       float nrm[4];
       uint64_t cur_q = ~0ull;
@@ -351,6 +356,11 @@ struct Layout {
 
 int choose_rows(int B, size_t floats_per_row, size_t smem_limit) {
   const int cand[5] = {16, 8, 4, 2, 1};
+  if (const char* env = getenv("MCPC_ROWS")) {       // tuning override: rows per CTA
+    const int R = atoi(env);
+    for (int i = 0; i < 5; ++i)
+      if (cand[i] == R && (size_t)R * floats_per_row * sizeof(float) <= smem_limit) return R;
+  }
   for (int i = 0; i < 5; ++i) {
     const int R = cand[i];
     if ((size_t)R * floats_per_row * sizeof(float) > smem_limit) continue;
