@@ -137,6 +137,12 @@ int mcpc_weight_grad(const McpcNet* net, const McpcGradIO* io, int32_t B, int32_
 int mcpc_fill_noise(uint64_t seed, int32_t t_begin, int32_t n_steps, uint64_t chain_offset, int32_t B,
                     int32_t n_units, float noise_scale, float* out, void* stream);
 
+/* Validation only: known-answer test of the tcgen05/TMEM/bulk-copy primitives of the bf16 path.
+ * Wt [128, Kin], Bx [N, Kin], G [N, 128] -> D1 [128, N] = Wt Bx^T,  D2 [128, N]: D2[m][n] = sum_j Wt[j][m] G[n][j]
+ * (rows m >= Kin undefined).  ws: >= 128*Kin*2 bytes of device scratch. */
+int mcpc_debug_umma(const float* Wt, const float* Bx, const float* G, int32_t Kin, int32_t N, float* D1, float* D2,
+                    void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,7 +93,7 @@ _lib = None
 _lock = threading.Lock()
 LIB_NAME = "libmcpc_b200.so"
 EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_infer", "mcpc_weight_grad",
-           "mcpc_fill_noise")
+           "mcpc_fill_noise", "mcpc_debug_umma")
 
 
 def lib_path():
@@ -128,6 +128,9 @@ def load():
         lib.mcpc_fill_noise.restype = C.c_int
         lib.mcpc_fill_noise.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                         C.c_float, C.c_void_p, C.c_void_p]
+        lib.mcpc_debug_umma.restype = C.c_int
+        lib.mcpc_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
         got = lib.mcpc_version()
         if got != ABI_VERSION:
             raise NativeError(f"{LIB_NAME} ABI version {got}, python binding expects {ABI_VERSION}")

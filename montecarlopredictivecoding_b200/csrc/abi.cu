@@ -175,4 +175,13 @@ int mcpc_fill_noise(uint64_t seed, int32_t t_begin, int32_t n_steps, uint64_t ch
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mcpc_debug_umma(const float* Wt, const float* Bx, const float* G, int32_t Kin, int32_t N, float* D1, float* D2,
+                    void* ws, void* stream) {
+  if (Wt == nullptr || Bx == nullptr || G == nullptr || D1 == nullptr || D2 == nullptr || ws == nullptr) {
+    set_error("mcpc_debug_umma: NULL argument");
+    return MCPC_ERR_INVALID;
+  }
+  return launch_umma_probe(Wt, Bx, G, Kin, N, D1, D2, ws, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -61,4 +61,7 @@ int launch_weight_grad_fp32(const NetDev& nd, const McpcGradIO* io, int B, int n
 int launch_fill_noise(uint64_t seed, int t_begin, int n_steps, uint64_t chain_offset, int B, int n_units,
                       float noise_scale, float* out, cudaStream_t stream);
 
+int launch_umma_probe(const float* Wt, const float* Bx, const float* G, int Kin, int N, float* D1, float* D2, void* ws,
+                      cudaStream_t stream);
+
 }  // namespace mcpc
