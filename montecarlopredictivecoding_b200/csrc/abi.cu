@@ -97,6 +97,7 @@ int mcpc_workspace_bytes(const McpcNet* net, int32_t B, int32_t n_steps, int32_t
     return MCPC_ERR_INVALID;
   }
   if (precision == MCPC_PREC_FP32) return infer_rows_workspace(nd, B, n_steps, out_bytes);
+  if (precision == MCPC_PREC_BF16) return infer_tc_workspace(nd, B, n_steps, out_bytes);
   set_error("precision %d not implemented", precision);
   return MCPC_ERR_UNSUPPORTED;
 }
@@ -146,6 +147,7 @@ int mcpc_infer(const McpcNet* net, const McpcIO* io, const McpcOpts* o, int32_t 
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (o->precision == MCPC_PREC_FP32) return launch_infer_rows(nd, io, o, B, workspace, workspace_bytes, s);
+  if (o->precision == MCPC_PREC_BF16) return launch_infer_tc(nd, io, o, B, workspace, workspace_bytes, s);
   set_error("precision %d not implemented", o->precision);
   return MCPC_ERR_UNSUPPORTED;
 }
@@ -160,7 +162,8 @@ int mcpc_weight_grad(const McpcNet* net, const McpcGradIO* io, int32_t B, int32_
     return MCPC_ERR_INVALID;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (precision == MCPC_PREC_FP32) return launch_weight_grad_fp32(nd, io, B, n_save, s);
+  // both precisions save fp32 operands; the bf16 inference path reuses the fp32 contraction for now
+  if (precision == MCPC_PREC_FP32 || precision == MCPC_PREC_BF16) return launch_weight_grad_fp32(nd, io, B, n_save, s);
   set_error("precision %d not implemented", precision);
   return MCPC_ERR_UNSUPPORTED;
 }

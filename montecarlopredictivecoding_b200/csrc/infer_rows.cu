@@ -515,6 +515,15 @@ int launch_infer_rows(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   return MCPC_OK;
 }
 
+int launch_reduce_partials(const float* partials, int n_steps, int n_tiles, double* energy, double* loss,
+                           cudaStream_t stream) {
+  dim3 block(32, 4);
+  reduce_partials_kernel<<<(n_steps + 3) / 4, block, 0, stream>>>(partials, n_steps, n_tiles, energy, loss);
+  MCPC_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return MCPC_OK;
+}
+
 int launch_fill_noise(uint64_t seed, int t_begin, int n_steps, uint64_t chain_offset, int B, int n_units,
                       float noise_scale, float* out, cudaStream_t stream) {
   const size_t total = (size_t)n_steps * B * n_units;

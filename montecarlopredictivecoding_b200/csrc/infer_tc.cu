@@ -1,0 +1,718 @@
+// mcpc_infer, MCPC_PREC_BF16: persistent tensor-core Langevin / PC inference kernel for sm_100a.
+//
+// One CTA owns NR chains (batch rows) for ALL n_steps steps.  The contractions run on the 5th-gen tensor
+// cores in "swapped" orientation -- units on the 128-lane M axis, chains on the N axis -- so a small
+// batch tile still fills the MMA:
+//     phase A   mu_l^T  [128 units x NR] = W_l tile [128 x K]   . act(x_{l-1})^T      (A K-major)
+//     phase B   bp_l^T  [128 units x NR] += (W_{l+1} tile)^T    . G_{l+1}^T           (A MN-major view of the SAME tile)
+// Weight tiles (bf16, canonical no-swizzle layout, packed once per launch by pack_weights_kernel) are
+// resident in shared memory as far as they fit; the rest streams through a 2-slot ring with bulk async
+// copies (UBLKCP) every step.  The latents never leave the SM: the fp32 master copy of x, the fp32
+// own-layer error and all accumulators live in TMEM (lane = unit, column = chain), the bf16 operand
+// copies in shared memory.
+//
+// Warp roles (192 threads): warps 0-3 = epilogue (thread <-> TMEM lane <-> unit), warp 4 = MMA issuer
+// (one elected lane, tcgen05.mma) + TMEM allocator, warp 5 = weight-tile loader.  Per step and per weight
+// tile t:  MMA_A(t) -> epilogue(t): eps, energy / loss, G (bf16 -> smem)  -> MMA_B(t); then the update
+// epilogue applies  x <- x - lr*grad (SGD | Adam)  and  x <- x - lr*noise (Philox)  and re-emits act(x).
+// All hand-offs are mbarriers; the tensor pipe never waits on a __syncthreads.
+//
+// Reference semantics: predictive_coding/pc_trainer.py:733-918 + utils/model.py:35-44 (see infer_rows.cu
+// for the fp32 restatement this kernel is validated against).
+#include <cstdlib>
+
+#include "mcpc_common.cuh"
+#include "philox.cuh"
+#include "umma.cuh"
+
+namespace mcpc {
+namespace {
+
+using namespace umma;
+
+constexpr int kMaxTiles = 32;         // weight tiles (128 output units each) per network
+constexpr int kMaxHT = 8;             // hidden unit tiles (128 latent units each)
+constexpr int kEpiThreads = 128;
+constexpr int kThreadsTc = 192;
+constexpr uint32_t kSmemBudget = 225 * 1024;
+
+struct Tile {
+  int lin;          // Linear index: 1..L-1 hidden, L = output Linear
+  int out_tile;     // which block of 128 output units
+  int Kp;           // in-features padded to 16 (phase-A K extent)
+  int sbo;          // (Kp/8)*128: byte stride between 8-row groups
+  int bytes;        // 128*Kp*2
+  int smem_off;     // byte offset of the tile (resident) or of its ring slot (streamed)
+  int slot;         // -1 resident, else ring slot
+  int h_out;        // hidden unit-tile index of the units this tile predicts (-1 for output tiles)
+  size_t gsrc;      // byte offset inside the packed-weights workspace
+};
+
+struct TcParams {
+  NetDev net;
+  int n_hid_tiles, n_out_tiles;
+  Tile tiles[kMaxTiles];
+  int HT;                       // hidden unit tiles in total
+  int h_layer[kMaxHT];          // layer of hidden unit tile h
+  int h_index[kMaxHT];          // its index inside the layer
+  int h_off[kMaxL + 1];         // first hidden unit tile of layer l
+  int ut[kMaxL];                // unit tiles per layer
+  int act_off[kMaxL];           // byte offset of layer l's bf16 activation operand [NR x Kp_act[l]]
+  int act_kp[kMaxL];            // pad16(d_l)
+  int gbuf_off[2];              // byte offsets of the two bf16 G operand buffers [NR x 128]
+  int n_resident_bytes;
+  const uint8_t* packed;        // packed bf16 weight tiles
+  const float* b[kMaxL + 1];
+  float* x[kMaxL];
+  float* m[kMaxL];
+  float* v[kMaxL];
+  float* xgrad[kMaxL];
+  float* traj_x[kMaxL];
+  float* traj_out;
+  float* save_g;
+  float* save_f;
+  const float* target;
+  const float* noise;
+  float* partials;
+  int B, n_ctas, n_steps, t_begin;
+  int optimizer, update_x;
+  float lr, adam_eps, one_minus_b1, one_minus_b2, beta2f;
+  double lr_d, beta1, beta2, b1_pow0, b2_pow0;
+  int noise_mode;
+  float noise_scale;
+  uint64_t seed, chain_offset;
+  int traj_every, save_begin, save_end;
+};
+
+struct Barriers {
+  uint64_t w_res;            // resident tiles landed
+  uint64_t w_full[2], w_empty[2];
+  uint64_t dA_full[2], dA_empty[2];
+  uint64_t g_full[2], g_empty[2];
+  uint64_t acts_ready, bp_full;
+};
+
+__device__ __forceinline__ float warp_sum_tc(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// fp32 W [rows x cols] (nn.Linear layout) -> bf16 tiles of 128 output units in canonical K-major order
+__global__ void pack_weights_kernel(const float* __restrict__ W, int rows, int cols, int Kp, int n_tiles,
+                                    uint8_t* __restrict__ out) {
+  const uint32_t sbo = (uint32_t)(Kp / 8) * 128u;
+  const int per_tile = 128 * Kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles * per_tile; i += gridDim.x * blockDim.x) {
+    const int t = i / per_tile, j = i % per_tile;
+    const int r = j / Kp, k = j % Kp;
+    const int row = t * 128 + r;
+    const float val = (row < rows && k < cols) ? W[(size_t)row * cols + k] : 0.0f;
+    *reinterpret_cast<__nv_bfloat16*>(out + (size_t)t * per_tile * 2 + kmajor_off(r, k, 128u, sbo)) = __float2bfloat16(val);
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ Barriers bars;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_red[2][4][2];
+
+  const NetDev& nd = p.net;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = nd.L, HT = p.HT;
+  const int row0 = blockIdx.x * NR;
+  constexpr int NC = NR / 16;                 // 16-column chunks per accumulator
+
+  if (tid == 0) {
+    mbar_init(&bars.w_res, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.w_full[i], 1);
+      mbar_init(&bars.w_empty[i], 1);
+      mbar_init(&bars.dA_full[i], 1);
+      mbar_init(&bars.dA_empty[i], kEpiThreads);
+      mbar_init(&bars.g_full[i], kEpiThreads);
+      mbar_init(&bars.g_empty[i], 1);
+    }
+    mbar_init(&bars.acts_ready, kEpiThreads);
+    mbar_init(&bars.bp_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(&tmem_base_s, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  // TMEM column map (fp32 columns): [dA0 | dA1 | bp_h ... | x_h ... | gown_h ...], NR columns each
+  const uint32_t col_dA = 0, col_bp = 2 * NR, col_x = (2 + HT) * NR, col_g = (2 + 2 * HT) * NR;
+
+  const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;
+
+  // =====================================================================================================
+  if (warp == 5) {
+    // ---------------- weight loader ----------------
+    if (lane == 0) {
+      uint32_t res_bytes = 0;
+      for (int t = 0; t < n_tiles_all; ++t)
+        if (p.tiles[t].slot < 0) res_bytes += (uint32_t)p.tiles[t].bytes;
+      if (res_bytes > 0) {
+        mbar_expect_tx(&bars.w_res, res_bytes);
+        for (int t = 0; t < n_tiles_all; ++t)
+          if (p.tiles[t].slot < 0)
+            bulk_g2s(smem + p.tiles[t].smem_off, p.packed + p.tiles[t].gsrc, (uint32_t)p.tiles[t].bytes, &bars.w_res);
+      } else {
+        mbar_arrive(&bars.w_res);
+      }
+      uint32_t empty_phase[2] = {1, 1};       // a fresh barrier passes a wait on the preceding phase
+      for (int ts = 0; ts < p.n_steps; ++ts) {
+        const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+        const int nt = p.n_hid_tiles + (need_out ? p.n_out_tiles : 0);
+        for (int t = 0; t < nt; ++t) {
+          const Tile& T = p.tiles[t];
+          if (T.slot < 0) continue;
+          mbar_wait(&bars.w_empty[T.slot], empty_phase[T.slot]);
+          empty_phase[T.slot] ^= 1;
+          mbar_expect_tx(&bars.w_full[T.slot], (uint32_t)T.bytes);
+          bulk_g2s(smem + T.smem_off, p.packed + T.gsrc, (uint32_t)T.bytes, &bars.w_full[T.slot]);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t id_a = idesc_bf16(128, NR, false, false);
+      const uint32_t id_b = idesc_bf16(128, NR, true, false);
+      const uint32_t smem_base = smem_u32(smem);
+      uint32_t ph_wfull[2] = {0, 0}, ph_dAe[2] = {1, 1}, ph_gfull[2] = {0, 0};
+      uint32_t ph_acts = 0;
+      uint32_t bp_started = 0;               // bit h: accumulator bp_h already written in this step
+      mbar_wait(&bars.w_res, 0);
+
+      auto phaseB = [&](int t) {
+        const Tile& T = p.tiles[t];
+        const int gb = t & 1;
+        const bool has_b = (T.lin < L) || nd.top_has_grad;      // readout-only output tiles feed nothing back
+        if (has_b) {
+          mbar_wait(&bars.g_full[gb], ph_gfull[gb]);
+          ph_gfull[gb] ^= 1;
+          fence_after_sync();
+          const int in_layer = T.lin - 1;
+          for (int u = 0; u < p.ut[in_layer]; ++u) {
+            const int h = p.h_off[in_layer] + u;
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t ad = smem_desc(smem_base + T.smem_off + u * 2048 + ks * 2 * T.sbo, (uint32_t)T.sbo, 128u);
+              const uint64_t bd = smem_desc(smem_base + p.gbuf_off[gb] + ks * 256, 128u, 2048u);
+              mma_bf16_ss(tmem + col_bp + h * NR, ad, bd, id_b, ((bp_started >> h) & 1u) || ks > 0);
+            }
+            bp_started |= 1u << h;
+          }
+          mma_commit(&bars.g_empty[gb]);
+        }
+        if (T.slot >= 0) mma_commit(&bars.w_empty[T.slot]);
+      };
+
+      for (int ts = 0; ts < p.n_steps; ++ts) {
+        const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+        const int nt = p.n_hid_tiles + (need_out ? p.n_out_tiles : 0);
+        bp_started = 0;
+        mbar_wait(&bars.acts_ready, ph_acts);
+        ph_acts ^= 1;
+        fence_after_sync();
+        for (int t = 0; t < nt; ++t) {
+          const Tile& T = p.tiles[t];
+          if (T.slot >= 0) {
+            mbar_wait(&bars.w_full[T.slot], ph_wfull[T.slot]);
+            ph_wfull[T.slot] ^= 1;
+          }
+          const int db = t & 1;
+          mbar_wait(&bars.dA_empty[db], ph_dAe[db]);
+          ph_dAe[db] ^= 1;
+          fence_after_sync();
+          const int in_layer = T.lin - 1;
+          const uint32_t act_sbo = (uint32_t)(p.act_kp[in_layer] / 8) * 128u;
+          for (int ks = 0; ks < T.Kp / 16; ++ks) {
+            const uint64_t ad = smem_desc(smem_base + T.smem_off + ks * 256, 128u, (uint32_t)T.sbo);
+            const uint64_t bd = smem_desc(smem_base + p.act_off[in_layer] + ks * 256, 128u, act_sbo);
+            mma_bf16_ss(tmem + col_dA + db * NR, ad, bd, id_a, ks > 0);
+          }
+          mma_commit(&bars.dA_full[db]);
+          if (t > 0) phaseB(t - 1);
+        }
+        if (nt > 0) phaseB(nt - 1);
+        mma_commit(&bars.bp_full);
+      }
+    }
+  } else {
+    // ---------------- epilogue: thread <-> TMEM lane <-> unit ----------------
+    const int ln = warp * 32 + lane;                                   // lane / unit index inside a tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    // zero the bf16 operand buffers (padding columns must stay finite), then load the latents
+    for (int i = tid * 16; i < p.gbuf_off[1] + NR * 256 - p.act_off[0]; i += kEpiThreads * 16)
+      *reinterpret_cast<uint4*>(smem + p.act_off[0] + i) = make_uint4(0, 0, 0, 0);
+    epi_bar();
+    for (int h = 0; h < HT; ++h) {
+      const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
+      const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float xv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int row = row0 + c * 16 + i;
+          xv[i] = (u < dl && row < p.B) ? p.x[l][(size_t)row * dl + u] : 0.0f;
+          if (u < dl)
+            *reinterpret_cast<__nv_bfloat16*>(smem + p.act_off[l] + kmajor_off(c * 16 + i, u, 128u, asbo)) =
+                __float2bfloat16(act_apply(nd.act[l], xv[i]));
+        }
+        tmem_st16(lane_addr + col_x + h * NR + c * 16, xv);
+      }
+    }
+    tmem_st_wait();
+    fence_async_smem();
+    fence_before_sync();
+    mbar_arrive(&bars.acts_ready);
+
+    uint32_t ph_dAf[2] = {0, 0}, ph_ge[2] = {1, 1}, ph_bp = 0;
+    double b1p = p.b1_pow0, b2p = p.b2_pow0;
+
+    for (int ts = 0; ts < p.n_steps; ++ts) {
+      const int t_abs = p.t_begin + ts;
+      const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
+      const int slot = ts - p.save_begin;
+      const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+      const int rec = do_traj ? ts / p.traj_every : 0;
+      const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+      const int nt = p.n_hid_tiles + (need_out ? p.n_out_tiles : 0);
+      const bool last = (ts == p.n_steps - 1);
+      float e_part = 0.0f, l_part = 0.0f;
+
+      // ---------- per-tile epilogue: errors of the units this tile predicts ----------
+      for (int t = 0; t < nt; ++t) {
+        const Tile& T = p.tiles[t];
+        const int db = t & 1, gb = t & 1;
+        const bool is_out = (T.lin == L);
+        const bool has_b = !is_out || nd.top_has_grad;
+        const int dl = is_out ? nd.d_out : nd.dims[T.lin];
+        const int u = T.out_tile * 128 + ln;
+        const bool uvalid = u < dl;
+        const float bias = (uvalid && p.b[T.lin] != nullptr) ? __ldg(p.b[T.lin] + u) : 0.0f;
+        mbar_wait(&bars.dA_full[db], ph_dAf[db]);
+        ph_dAf[db] ^= 1;
+        if (has_b) {
+          mbar_wait(&bars.g_empty[gb], ph_ge[gb]);
+          ph_ge[gb] ^= 1;
+        }
+        fence_after_sync();
+        uint8_t* gbuf = smem + p.gbuf_off[gb];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float d[16];
+          tmem_ld16(lane_addr + col_dA + db * NR + c * 16, d);
+          if (!is_out) {
+            const int h = T.h_out;
+            const float ce = 0.5f * nd.c[T.lin], gc = nd.gc[T.lin];
+            float xv[16], gv[16];
+            tmem_ld16(lane_addr + col_x + h * NR + c * 16, xv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + c * 16 + i;
+              const float eps = xv[i] - (d[i] + bias);
+              const float G = uvalid ? -gc * eps : 0.0f;
+              gv[i] = G;
+              if (uvalid && row < p.B) {
+                e_part = fmaf(ce * eps, eps, e_part);
+                if (do_save) p.save_g[((size_t)slot * p.B + row) * nd.NG + nd.off[T.lin] + u] = G;
+              }
+              *reinterpret_cast<__nv_bfloat16*>(gbuf + kmajor_off(c * 16 + i, ln, 128u, 2048u)) = __float2bfloat16(G);
+            }
+            tmem_st16(lane_addr + col_g + h * NR + c * 16, gv);
+          } else {
+            const bool in_mask = u >= nd.mask_start;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + c * 16 + i;
+              const float o = d[i] + bias;
+              float e_out = 0.0f;
+              if (uvalid && row < p.B) {
+                if (in_mask && nd.top >= MCPC_TOP_GAUSS) {
+                  const float y = __ldg(p.target + (size_t)row * nd.d_out + u);
+                  if (nd.top == MCPC_TOP_GAUSS) {
+                    const float dd = o - y;
+                    l_part = fmaf(0.5f * nd.inv_var * dd, dd, l_part);
+                    e_out = dd * nd.inv_var;
+                  } else {
+                    const float z = __expf(-fabsf(o));
+                    l_part += fmaxf(o, 0.0f) - o * y + __logf(1.0f + z);
+                    e_out = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - y;
+                  }
+                }
+                if (do_traj && p.traj_out != nullptr) p.traj_out[((size_t)rec * p.B + row) * nd.d_out + u] = o;
+                if (do_save) p.save_g[((size_t)slot * p.B + row) * nd.NG + nd.SD + u] = e_out;
+              }
+              if (has_b)
+                *reinterpret_cast<__nv_bfloat16*>(gbuf + kmajor_off(c * 16 + i, ln, 128u, 2048u)) = __float2bfloat16(e_out);
+            }
+          }
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        mbar_arrive(&bars.dA_empty[db]);
+        if (has_b) {
+          fence_async_smem();
+          mbar_arrive(&bars.g_full[gb]);
+        }
+      }
+
+      // ---------- update epilogue: latent gradient, optimizer step, Langevin noise ----------
+      mbar_wait(&bars.bp_full, ph_bp);
+      ph_bp ^= 1;
+      fence_after_sync();
+      float step_size = 0.0f, bc2_sqrt = 1.0f;
+      if (p.optimizer == MCPC_OPT_ADAM && p.update_x) {
+        b1p *= p.beta1;
+        b2p *= p.beta2;
+        step_size = (float)(p.lr_d / (1.0 - b1p));
+        bc2_sqrt = (float)sqrt(1.0 - b2p);
+      }
+      for (int h = 0; h < HT; ++h) {
+        const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
+        const bool uvalid = u < dl;
+        const bool has_above = (l + 1 < L) || nd.top_has_grad;
+        const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
+        const int gu = nd.off[l] + u;                    // global unit index (Philox counter, noise / save column)
+        const float b0 = (l == 0 && uvalid && p.b[0] != nullptr) ? __ldg(p.b[0] + u) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float xv[16], bp[16], gown[16];
+          tmem_ld16(lane_addr + col_x + h * NR + c * 16, xv);
+          if (has_above) {
+            tmem_ld16(lane_addr + col_bp + h * NR + c * 16, bp);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bp[i] = 0.0f;
+          }
+          if (l > 0) {
+            tmem_ld16(lane_addr + col_g + h * NR + c * 16, gown);
+          } else {
+            // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
+            const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + c * 16 + i;
+              const float eps = xv[i] - b0;
+              gown[i] = -gc * eps;
+              if (uvalid && row < p.B) {
+                e_part = fmaf(ce * eps, eps, e_part);
+                if (do_save) p.save_g[((size_t)slot * p.B + row) * nd.NG + u] = gown[i];
+              }
+            }
+          }
+          if (uvalid) {
+            float nrm[4];
+            uint64_t cur_q = ~0ull;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + c * 16 + i;
+              if (row >= p.B) break;
+              float x = xv[i];
+              const float a = act_apply(nd.act[l], x);
+              const float grad = fmaf(act_deriv(nd.act[l], x, a), bp[i], -gown[i]);
+              if (do_traj && p.traj_x[l] != nullptr) p.traj_x[l][((size_t)rec * p.B + row) * dl + u] = x;
+              if (do_save) p.save_f[((size_t)slot * p.B + row) * nd.SD + gu] = a;
+              if (last && p.xgrad[l] != nullptr) p.xgrad[l][(size_t)row * dl + u] = grad;
+              if (p.update_x) {
+                if (p.optimizer == MCPC_OPT_SGD) {
+                  x = fmaf(-p.lr, grad, x);
+                } else {
+                  const size_t si = (size_t)row * dl + u;
+                  float mv = p.m[l][si], vv = p.v[l][si];
+                  mv = fmaf(p.one_minus_b1, grad - mv, mv);
+                  vv = vv * p.beta2f;
+                  vv = fmaf(p.one_minus_b2 * grad, grad, vv);
+                  p.m[l][si] = mv;
+                  p.v[l][si] = vv;
+                  x = fmaf(-step_size, mv / (sqrtf(vv) / bc2_sqrt + p.adam_eps), x);
+                }
+              }
+              if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
+                x = fmaf(-p.lr, p.noise[((size_t)ts * p.B + row) * nd.SD + gu], x);
+              } else if (p.noise_mode == MCPC_NOISE_PHILOX) {
+                const uint64_t chain = p.chain_offset + (uint64_t)row;
+                if ((chain >> 2) != cur_q) {
+                  cur_q = chain >> 2;
+                  langevin_normals4(p.seed, (uint32_t)gu, (uint32_t)t_abs, cur_q, nrm);
+                }
+                x = fmaf(-p.lr, p.noise_scale * nrm[chain & 3], x);
+              }
+              xv[i] = x;
+              *reinterpret_cast<__nv_bfloat16*>(smem + p.act_off[l] + kmajor_off(c * 16 + i, u, 128u, asbo)) =
+                  __float2bfloat16(act_apply(nd.act[l], x));
+            }
+            tmem_st16(lane_addr + col_x + h * NR + c * 16, xv);
+          }
+        }
+      }
+      tmem_st_wait();
+      fence_async_smem();
+      fence_before_sync();
+      mbar_arrive(&bars.acts_ready);
+
+      // ---------- per-step scalars ----------
+      e_part = warp_sum_tc(e_part);
+      l_part = warp_sum_tc(l_part);
+      float (*red)[2] = s_red[ts & 1];
+      if (lane == 0) { red[warp][0] = e_part; red[warp][1] = l_part; }
+      epi_bar();
+      if (tid < 2) p.partials[((size_t)ts * p.n_ctas + blockIdx.x) * 2 + tid] =
+          red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    }
+
+    // ---------- write the latents back ----------
+    for (int h = 0; h < HT; ++h) {
+      const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float xv[16];
+        tmem_ld16(lane_addr + col_x + h * NR + c * 16, xv);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int row = row0 + c * 16 + i;
+          if (u < dl && row < p.B) p.x[l][(size_t)row * dl + u] = xv[i];
+        }
+      }
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+inline int pad16(int v) { return (v + 15) & ~15; }
+
+// Fills the tile table + shared-memory plan.  Returns MCPC_OK or MCPC_ERR_UNSUPPORTED (message set).
+int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* packed_bytes) {
+  if (nd.L < 1) return MCPC_ERR_INVALID;
+  int HT = 0;
+  for (int l = 0; l < nd.L; ++l) {
+    p->ut[l] = (nd.dims[l] + 127) / 128;
+    p->h_off[l] = HT;
+    for (int i = 0; i < p->ut[l]; ++i) {
+      if (HT >= kMaxHT) {
+        set_error("bf16 path: more than %d hidden unit tiles (128 units each)", kMaxHT);
+        return MCPC_ERR_UNSUPPORTED;
+      }
+      p->h_layer[HT] = l;
+      p->h_index[HT] = i;
+      ++HT;
+    }
+  }
+  p->h_off[nd.L] = HT;
+  p->HT = HT;
+  if ((2 + 3 * HT) * NR > 512) {
+    set_error("bf16 path: %d hidden unit tiles x %d chains per CTA do not fit the 512 TMEM columns", HT, NR);
+    return MCPC_ERR_UNSUPPORTED;
+  }
+  // operand buffers first, weights after them
+  uint32_t off = 0;
+  for (int l = 0; l < nd.L; ++l) {
+    p->act_kp[l] = pad16(nd.dims[l]);
+    p->act_off[l] = (int)off;
+    off += (uint32_t)NR * p->act_kp[l] * 2;
+  }
+  for (int i = 0; i < 2; ++i) {
+    p->gbuf_off[i] = (int)off;
+    off += (uint32_t)NR * 128 * 2;
+  }
+  off = (off + 1023u) & ~1023u;
+  // tile table: hidden Linears 1..L-1 first, then the output Linear
+  int nt = 0;
+  size_t gsrc = 0;
+  uint32_t max_tile = 0;
+  for (int lin = 1; lin <= nd.L; ++lin) {
+    if (lin == nd.L && nd.d_out == 0) break;
+    const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
+    const int Kp = pad16(nd.dims[lin - 1]);
+    if (Kp > 1024) {
+      set_error("bf16 path: layer width %d too large for one weight tile", nd.dims[lin - 1]);
+      return MCPC_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < (rows + 127) / 128; ++i) {
+      if (nt >= kMaxTiles) {
+        set_error("bf16 path: more than %d weight tiles", kMaxTiles);
+        return MCPC_ERR_UNSUPPORTED;
+      }
+      Tile& T = p->tiles[nt++];
+      T.lin = lin;
+      T.out_tile = i;
+      T.Kp = Kp;
+      T.sbo = (Kp / 8) * 128;
+      T.bytes = 128 * Kp * 2;
+      T.h_out = (lin < nd.L) ? p->h_off[lin] + i : -1;
+      T.gsrc = gsrc;
+      T.slot = -1;
+      gsrc += (size_t)T.bytes;
+      if ((uint32_t)T.bytes > max_tile) max_tile = (uint32_t)T.bytes;
+    }
+    if (lin < nd.L) p->n_hid_tiles = nt;
+  }
+  if (nd.d_out == 0 || nd.L == 0) p->n_hid_tiles = nt;
+  p->n_out_tiles = nt - p->n_hid_tiles;
+  *packed_bytes = gsrc;
+  // residency: everything if it fits, else as many leading tiles as fit beside a 2-slot ring
+  const uint32_t slack = 4096;             // MN-major reads of narrow tiles overrun their 128 x Kp footprint
+  uint32_t total = 0;
+  for (int t = 0; t < nt; ++t) total += (uint32_t)p->tiles[t].bytes;
+  if (off + total + slack <= kSmemBudget) {
+    for (int t = 0; t < nt; ++t) {
+      p->tiles[t].smem_off = (int)off;
+      off += (uint32_t)p->tiles[t].bytes;
+    }
+  } else {
+    const uint32_t ring = 2 * max_tile;
+    if (off + ring + slack > kSmemBudget) {
+      set_error("bf16 path: weight tiles of %u B do not fit shared memory", max_tile);
+      return MCPC_ERR_UNSUPPORTED;
+    }
+    const uint32_t ring_off = off;
+    off += ring;
+    int next_slot = 0;
+    for (int t = 0; t < nt; ++t) {
+      Tile& T = p->tiles[t];
+      if (off + (uint32_t)T.bytes + slack <= kSmemBudget) {
+        T.smem_off = (int)off;
+        off += (uint32_t)T.bytes;
+      } else {
+        T.slot = next_slot;
+        T.smem_off = (int)(ring_off + next_slot * max_tile);
+        next_slot ^= 1;
+      }
+    }
+    // a streamed tile must find its slot free again before the same slot is needed twice in one step:
+    // with 2 slots used round-robin in tile order that holds by construction.
+  }
+  *smem_bytes = off + slack;
+  return MCPC_OK;
+}
+
+int choose_nr(int B) {
+  if (const char* env = getenv("MCPC_TC_ROWS")) {
+    const int v = atoi(env);
+    if (v == 16 || v == 32) return v;
+  }
+  return (B + 15) / 16 >= 2 * 148 ? 32 : 16;
+}
+
+}  // namespace
+
+int infer_tc_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes) {
+  TcParams p{};
+  size_t smem = 0, packed = 0;
+  int NR = choose_nr(B);
+  int rc = plan_tc(nd, NR, &p, &smem, &packed);
+  if (rc != MCPC_OK && NR == 32) {
+    NR = 16;
+    rc = plan_tc(nd, NR, &p, &smem, &packed);
+  }
+  if (rc != MCPC_OK) return rc;
+  const int n_ctas = (B + NR - 1) / NR;
+  *bytes = ((packed + 255) & ~(size_t)255) + (size_t)n_steps * n_ctas * 2 * sizeof(float) + 512;
+  return MCPC_OK;
+}
+
+int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B, void* ws, size_t ws_bytes,
+                    cudaStream_t stream) {
+  if (io->inputs != nullptr) {
+    set_error("bf16 path: non-zero `inputs` are not implemented (Linear_0 is bias-only); use MCPC_PREC_FP32");
+    return MCPC_ERR_UNSUPPORTED;
+  }
+  TcParams p{};
+  size_t smem = 0, packed = 0;
+  int NR = choose_nr(B);
+  int rc = plan_tc(nd, NR, &p, &smem, &packed);
+  if (rc != MCPC_OK && NR == 32) {
+    NR = 16;
+    p = TcParams{};
+    rc = plan_tc(nd, NR, &p, &smem, &packed);
+  }
+  if (rc != MCPC_OK) return rc;
+  p.net = nd;
+  p.B = B;
+  p.n_ctas = (B + NR - 1) / NR;
+  size_t need = 0;
+  infer_tc_workspace(nd, B, o->n_steps, &need);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("workspace too small: %zu B given, %zu B needed", ws_bytes, need);
+    return MCPC_ERR_WORKSPACE;
+  }
+  uint8_t* wsb = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  p.packed = wsb;
+  p.partials = reinterpret_cast<float*>(wsb + ((packed + 255) & ~(size_t)255));
+  // pack the weights (fp32 nn.Linear layout -> bf16 canonical tiles); they change once per learning step
+  for (int t = 0; t < p.n_hid_tiles + p.n_out_tiles;) {
+    const Tile& T = p.tiles[t];
+    const int lin = T.lin;
+    const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
+    const int n_lin_tiles = (rows + 127) / 128;
+    pack_weights_kernel<<<2 * n_lin_tiles > 64 ? 64 : 2 * n_lin_tiles + 2, 256, 0, stream>>>(
+        io->W[lin], rows, nd.dims[lin - 1], T.Kp, n_lin_tiles, wsb + T.gsrc);
+    count_launch();
+    t += n_lin_tiles;
+  }
+  for (int l = 0; l <= nd.L; ++l) p.b[l] = io->b[l];
+  for (int l = 0; l < nd.L; ++l) {
+    p.x[l] = io->x[l];
+    p.m[l] = io->adam_m[l];
+    p.v[l] = io->adam_v[l];
+    p.xgrad[l] = io->x_grad[l];
+    p.traj_x[l] = io->traj_x[l];
+  }
+  p.traj_out = io->traj_out;
+  p.save_g = reinterpret_cast<float*>(io->save_g);
+  p.save_f = reinterpret_cast<float*>(io->save_f);
+  p.target = io->target;
+  p.noise = io->noise;
+  p.n_steps = o->n_steps;
+  p.t_begin = o->t_begin;
+  p.optimizer = o->optimizer;
+  p.update_x = o->update_x;
+  p.lr = (float)o->lr;
+  p.lr_d = o->lr;
+  p.beta1 = o->adam_beta1;
+  p.beta2 = o->adam_beta2;
+  p.one_minus_b1 = (float)(1.0 - o->adam_beta1);
+  p.one_minus_b2 = (float)(1.0 - o->adam_beta2);
+  p.beta2f = (float)o->adam_beta2;
+  p.adam_eps = (float)o->adam_eps;
+  p.b1_pow0 = pow(o->adam_beta1, (double)o->adam_step0);
+  p.b2_pow0 = pow(o->adam_beta2, (double)o->adam_step0);
+  p.noise_mode = o->noise_mode;
+  p.noise_scale = (float)o->noise_scale;
+  p.seed = o->seed;
+  p.chain_offset = o->chain_offset;
+  bool any_traj = io->traj_out != nullptr;
+  for (int l = 0; l < nd.L; ++l) any_traj = any_traj || io->traj_x[l] != nullptr;
+  p.traj_every = any_traj ? (o->traj_every > 0 ? o->traj_every : 1) : 0;
+  p.save_begin = o->save_begin;
+  p.save_end = o->save_end;
+  if (NR == 32) {
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infer_tc_kernel<32><<<p.n_ctas, kThreadsTc, smem, stream>>>(p);
+  } else {
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infer_tc_kernel<16><<<p.n_ctas, kThreadsTc, smem, stream>>>(p);
+  }
+  MCPC_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  if (io->energy != nullptr || io->loss != nullptr) {
+    rc = launch_reduce_partials(p.partials, o->n_steps, p.n_ctas, io->energy, io->loss, stream);
+    if (rc != MCPC_OK) return rc;
+  }
+  return MCPC_OK;
+}
+
+}  // namespace mcpc

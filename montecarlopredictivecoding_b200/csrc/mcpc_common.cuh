@@ -61,6 +61,11 @@ int launch_weight_grad_fp32(const NetDev& nd, const McpcGradIO* io, int B, int n
 int launch_fill_noise(uint64_t seed, int t_begin, int n_steps, uint64_t chain_offset, int B, int n_units,
                       float noise_scale, float* out, cudaStream_t stream);
 
+int launch_reduce_partials(const float* partials, int n_steps, int n_tiles, double* energy, double* loss,
+                           cudaStream_t stream);
+int infer_tc_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes);
+int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B, void* ws, size_t ws_bytes,
+                    cudaStream_t stream);
 int launch_umma_probe(const float* Wt, const float* Bx, const float* G, int Kin, int N, float* D1, float* D2, void* ws,
                       cudaStream_t stream);
 

@@ -1,0 +1,85 @@
+"""MCPC_PREC_BF16 (tcgen05 tensor-core path) against (i) the golden vectors of the fp32 reference under the
+stated bf16 bound and (ii) the oracle run with bf16-rounded contraction operands (tight).
+
+Stated bound (north star: "a stated bf16/tf32 bound over T steps"): bf16 operands carry 2^-9 relative
+rounding; with supplied noise the latents of the recorded cases stay within 3e-2 (max-norm relative)
+of the fp32 reference over their horizons, energies / losses within 1e-2, weight updates within 5e-4
+absolute.  Against the bf16-emulating oracle the same quantities agree to 2e-3 (differences come from
+fp32 accumulation order flipping individual bf16 roundings)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from golden_util import orc, rel_err
+from trainer_replay import replay
+
+from montecarlopredictivecoding_b200 import mcpc_utils as mu
+from montecarlopredictivecoding_b200 import predictive_coding as pc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+BF16_CASES = ["mcpc_relu_bce_learn", "mcpc_ml_checkpoint", "pc_tanh_adam_mask", "fig2_linear", "free_output_layer",
+              "gauss_mask_one_sample", "zero_fn_sampling", "update_p_all"]
+
+
+@pytest.mark.parametrize("name", BF16_CASES)
+def test_golden_case_bf16_bound(name):
+    worst = replay(name, torch.device(DEV), precision="bf16", tol_x=3e-2, tol_s=1e-2, tol_g=2e-2, tol_w=5e-4)
+    print(name, {k: f"{v:.2e}" for k, v in worst.items()})
+
+
+def test_nonzero_inputs_are_refused_in_bf16():
+    with pytest.raises(NotImplementedError):
+        replay("mcpc_tanh_bce_learn_inputs", torch.device(DEV), precision="bf16", tol_x=1, tol_s=1, tol_g=1, tol_w=1)
+
+
+@pytest.mark.parametrize("act,top,B", [("relu", "bernoulli", 1024), ("tanh", "gauss", 200), ("relu", "zero", 4096)])
+def test_bf16_kernel_vs_bf16_oracle(act, top, B):
+    dev = torch.device(DEV)
+    mixing, sampling, lr = 3, 5, 0.03
+    T = mixing + sampling
+    torch.manual_seed(1)
+    cfg = {"input_size": 20, "hidden_size": 128, "hidden2_size": 128, "output_size": 784, "activation_fn": act}
+    model = mu.get_model(cfg, use_cuda=False).to(dev)
+    tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": lr}, update_p_at="last",
+                      accumulate_p_at=list(range(mixing, T)), optimizer_p_fn=optim.SGD, optimizer_p_kwargs={"lr": 0.0},
+                      plot_progress_at=[])
+    tr.set_precision("bf16")
+    tr.set_noise_seed(31337)
+    y = (torch.rand(B, 784, device=dev) < 0.5).float() if top != "gauss" else torch.randn(B, 784, device=dev)
+    x0 = [torch.randn(B, d, device=dev) for d in (20, 128, 128)]
+    pcs = [m for m in model if isinstance(m, pc.PCLayer)]
+    lins = [m for m in model if isinstance(m, nn.Linear)]
+    for layer, v in zip(pcs, x0):
+        layer._sample_x_fn = (lambda inputs, v=v: v.clone())
+    loss_fn = {"bernoulli": mu.bernoulli_fn, "gauss": mu.fe_fn, "zero": mu.zero_fn}[top]
+    kw = {} if top == "zero" else {"loss_fn_kwargs": {"_target": y, "_var": 1.0}}
+    res = tr.train_on_batch(torch.zeros(B, 20, device=dev), loss_fn=loss_fn, callback_after_t=mu.random_step,
+                            callback_after_t_kwargs={"_pc_trainer": tr}, is_log_progress=False,
+                            is_return_results_every_t=True, is_return_outputs=True, **kw)
+    assert tr.last_call_info["precision"] == 1
+    nz = tr._get_engine().fill_noise(31337, 0, T, 0, B, 276, float(np.sqrt(2.0 / lr)), dev).cpu().numpy()
+    offs = [0, 20, 148, 276]
+    noise = [[nz[t][:, offs[l]:offs[l + 1]] for l in range(3)] for t in range(T)]
+    net = orc.OracleNet(W=[l.weight.detach().cpu().numpy() for l in lins], b=[l.bias.detach().cpu().numpy() for l in lins],
+                        n_layers=3, act=[orc.ACT_RELU if act == "relu" else orc.ACT_TANH] * 3, energy_scale=[1.0] * 3,
+                        top={"bernoulli": orc.TOP_BERNOULLI, "gauss": orc.TOP_GAUSS, "zero": orc.TOP_ZERO}[top],
+                        bf16_operands=True)
+    ref = orc.infer(net, [v.cpu().numpy() for v in x0], np.zeros((B, 20), np.float32), y.cpu().numpy(), T,
+                    optimizer="sgd", lr=lr, noise=noise, acc_begin=mixing, acc_end=T, record_traj=True)
+    errs = {f"x{l}": rel_err(pcs[l].get_x().detach().cpu().numpy(), ref.xs[l]) for l in range(3)}
+    errs["energy"] = rel_err(res["energy"], ref.energy)
+    if top != "zero":
+        errs["loss"] = rel_err(res["loss"], ref.loss)
+    errs["out"] = rel_err(torch.stack(res["outputs"]).cpu().numpy(), np.stack(ref.traj_out))
+    div = sampling * B
+    if top != "zero":
+        errs["gW_out"] = rel_err(lins[3].weight.grad.cpu().numpy(), ref.gW[3] / div)
+    errs["gW_2"] = rel_err(lins[2].weight.grad.cpu().numpy(), ref.gW[2] / div)
+    errs["gb_0"] = rel_err(lins[0].bias.grad.cpu().numpy(), ref.gb[0] / div)
+    print(act, top, B, {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < 2e-3, (k, v)
