@@ -180,13 +180,18 @@ __global__ void __launch_bounds__(kThreads) infer_rows_kernel(const __grid_const
         }
       } else {
         const bool in_mask = j >= nd.mask_start;
+        float yv[R];
+        if (in_mask && nd.top >= MCPC_TOP_GAUSS) {       // independent loads, not serialised behind the stores below
+#pragma unroll
+          for (int r = 0; r < R; ++r) yv[r] = (r < nvalid) ? __ldg(p.target + (size_t)(row0 + r) * nd.d_out + j) : 0.0f;
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const float o = acc[r];
           float e_out = 0.0f;
           if (r < nvalid) {
             if (in_mask && nd.top >= MCPC_TOP_GAUSS) {
-              const float y = p.target[(size_t)(row0 + r) * nd.d_out + j];
+              const float y = yv[r];
               if (nd.top == MCPC_TOP_GAUSS) {
                 const float d = o - y;
                 l_part = fmaf(0.5f * nd.inv_var * d, d, l_part);

@@ -32,8 +32,6 @@ using namespace umma;
 
 constexpr int kMaxTiles = 32;         // weight tiles (128 output units each) per network
 constexpr int kMaxHT = 8;             // hidden unit tiles (128 latent units each)
-constexpr int kEpiThreads = 128;
-constexpr int kThreadsTc = 192;
 constexpr uint32_t kSmemBudget = 225 * 1024;
 
 struct Tile {
@@ -82,6 +80,7 @@ struct TcParams {
   float noise_scale;
   uint64_t seed, chain_offset;
   int traj_every, save_begin, save_end;
+  long long* dbg;               // optional timing trace of CTA 0 (MCPC_TC_TIMING=1), 64 slots per step
 };
 
 struct Barriers {
@@ -98,6 +97,7 @@ __device__ __forceinline__ float warp_sum_tc(float v) {
   return v;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+#define TC_STAMP(cond, ts, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (cond) && (ts) < 8) p.dbg[(ts) * 64 + (idx)] = clock64(); } while (0)
 
 // fp32 W [rows x cols] (nn.Linear layout) -> bf16 tiles of 128 output units in canonical K-major order
 __global__ void pack_weights_kernel(const float* __restrict__ W, int rows, int cols, int Kp, int n_tiles,
@@ -113,18 +113,43 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, int rows, int c
   }
 }
 
-template <int NR>
-__global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// activation / derivative of the tensor-core path (bf16 operands: MUFU tanh.approx is far below their rounding)
+__device__ __forceinline__ float act_tc(int kind, float x) {
+  return kind == MCPC_ACT_RELU ? fmaxf(x, 0.0f) : (kind == MCPC_ACT_TANH ? tanh_fast(x) : x);
+}
+__device__ __forceinline__ float dact_tc(int kind, float x, float a) {
+  return kind == MCPC_ACT_RELU ? (x > 0.0f ? 1.0f : 0.0f) : (kind == MCPC_ACT_TANH ? fmaf(-a, a, 1.0f) : 1.0f);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
+  return k == 0 ? n[0] : (k == 1 ? n[1] : (k == 2 ? n[2] : n[3]));
+}
+
+// NR chains per CTA; every epilogue thread owns one unit (TMEM lane) and RPT of the NR chains (columns), so
+// NR/RPT warps share each 32-lane quarter of TMEM: 4*NR/RPT epilogue warps + MMA warp + loader warp.
+template <int NR, int RPT>
+__global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int CS = NR / RPT;               // column groups
+  constexpr int kEpi = 128 * CS;             // epilogue threads
+  constexpr int kMmaWarp = 4 * CS, kLoadWarp = 4 * CS + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Barriers bars;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_red[2][4][2];
+  __shared__ float s_red[2][4 * CS][2];
 
   const NetDev& nd = p.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = nd.L, HT = p.HT;
   const int row0 = blockIdx.x * NR;
-  constexpr int NC = NR / 16;                 // 16-column chunks per accumulator
 
   if (tid == 0) {
     mbar_init(&bars.w_res, 1);
@@ -132,26 +157,25 @@ __global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_co
       mbar_init(&bars.w_full[i], 1);
       mbar_init(&bars.w_empty[i], 1);
       mbar_init(&bars.dA_full[i], 1);
-      mbar_init(&bars.dA_empty[i], kEpiThreads);
-      mbar_init(&bars.g_full[i], kEpiThreads);
+      mbar_init(&bars.dA_empty[i], kEpi);
+      mbar_init(&bars.g_full[i], kEpi);
       mbar_init(&bars.g_empty[i], 1);
     }
-    mbar_init(&bars.acts_ready, kEpiThreads);
+    mbar_init(&bars.acts_ready, kEpi);
     mbar_init(&bars.bp_full, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_base_s, 512);
+  if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   // TMEM column map (fp32 columns): [dA0 | dA1 | bp_h ... | x_h ... | gown_h ...], NR columns each
   const uint32_t col_dA = 0, col_bp = 2 * NR, col_x = (2 + HT) * NR, col_g = (2 + 2 * HT) * NR;
-
   const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;
 
   // =====================================================================================================
-  if (warp == 5) {
+  if (warp == kLoadWarp) {
     // ---------------- weight loader ----------------
     if (lane == 0) {
       uint32_t res_bytes = 0;
@@ -165,7 +189,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_co
       } else {
         mbar_arrive(&bars.w_res);
       }
-      uint32_t empty_phase[2] = {1, 1};       // a fresh barrier passes a wait on the preceding phase
+      uint32_t empty_phase = 3;                // bit s: parity to wait for on w_empty[s] (fresh barrier: previous phase)
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
         const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
@@ -173,21 +197,23 @@ __global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_co
         for (int t = 0; t < nt; ++t) {
           const Tile& T = p.tiles[t];
           if (T.slot < 0) continue;
-          mbar_wait(&bars.w_empty[T.slot], empty_phase[T.slot]);
-          empty_phase[T.slot] ^= 1;
+          mbar_wait(&bars.w_empty[T.slot], (empty_phase >> T.slot) & 1u);
+          empty_phase ^= 1u << T.slot;
           mbar_expect_tx(&bars.w_full[T.slot], (uint32_t)T.bytes);
           bulk_g2s(smem + T.smem_off, p.packed + T.gsrc, (uint32_t)T.bytes, &bars.w_full[T.slot]);
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // The whole warp runs the control flow (converged, so descriptors stay in uniform registers); one
+    // elected lane issues tcgen05.mma / tcgen05.commit.  Issuing from inside `if (lane == 0)` costs ~170
+    // cycles per instruction (warp-uniformisation loop), converged + elect.sync ~10x less.
+    {
       const uint32_t id_a = idesc_bf16(128, NR, false, false);
       const uint32_t id_b = idesc_bf16(128, NR, true, false);
       const uint32_t smem_base = smem_u32(smem);
-      uint32_t ph_wfull[2] = {0, 0}, ph_dAe[2] = {1, 1}, ph_gfull[2] = {0, 0};
-      uint32_t ph_acts = 0;
+      uint32_t ph_wfull = 0, ph_dAe = 3, ph_gfull = 0, ph_acts = 0;
       uint32_t bp_started = 0;               // bit h: accumulator bp_h already written in this step
       mbar_wait(&bars.w_res, 0);
 
@@ -196,22 +222,32 @@ __global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_co
         const int gb = t & 1;
         const bool has_b = (T.lin < L) || nd.top_has_grad;      // readout-only output tiles feed nothing back
         if (has_b) {
-          mbar_wait(&bars.g_full[gb], ph_gfull[gb]);
-          ph_gfull[gb] ^= 1;
+          mbar_wait(&bars.g_full[gb], (ph_gfull >> gb) & 1u);
+          ph_gfull ^= 1u << gb;
           fence_after_sync();
           const int in_layer = T.lin - 1;
+          const uint64_t bd0 = smem_desc(smem_base + p.gbuf_off[gb], 128u, 2048u);
+          const uint32_t a_step = (uint32_t)(2 * T.sbo) >> 4;    // descriptor start-address field is in 16 B units
           for (int u = 0; u < p.ut[in_layer]; ++u) {
             const int h = p.h_off[in_layer] + u;
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t ad = smem_desc(smem_base + T.smem_off + u * 2048 + ks * 2 * T.sbo, (uint32_t)T.sbo, 128u);
-              const uint64_t bd = smem_desc(smem_base + p.gbuf_off[gb] + ks * 256, 128u, 2048u);
-              mma_bf16_ss(tmem + col_bp + h * NR, ad, bd, id_b, ((bp_started >> h) & 1u) || ks > 0);
+            const uint64_t ad0 = smem_desc(smem_base + T.smem_off + u * 2048, (uint32_t)T.sbo, 128u);
+            const uint32_t dcol = tmem + col_bp + h * NR;
+            const bool acc0 = (bp_started >> h) & 1u;
+            if (elect_one()) {
+              mma_bf16_ss(dcol, ad0, bd0, id_b, acc0);
+#pragma unroll
+              for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * 16), id_b, true);
             }
+            __syncwarp();
             bp_started |= 1u << h;
           }
-          mma_commit(&bars.g_empty[gb]);
+          if (elect_one()) mma_commit(&bars.g_empty[gb]);
+          __syncwarp();
         }
-        if (T.slot >= 0) mma_commit(&bars.w_empty[T.slot]);
+        if (T.slot >= 0) {
+          if (elect_one()) mma_commit(&bars.w_empty[T.slot]);
+          __syncwarp();
+        }
       };
 
       for (int ts = 0; ts < p.n_steps; ++ts) {
@@ -222,61 +258,84 @@ __global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_co
         mbar_wait(&bars.acts_ready, ph_acts);
         ph_acts ^= 1;
         fence_after_sync();
+        TC_STAMP(lane == 0, ts, 0);
         for (int t = 0; t < nt; ++t) {
           const Tile& T = p.tiles[t];
           if (T.slot >= 0) {
-            mbar_wait(&bars.w_full[T.slot], ph_wfull[T.slot]);
-            ph_wfull[T.slot] ^= 1;
+            mbar_wait(&bars.w_full[T.slot], (ph_wfull >> T.slot) & 1u);
+            ph_wfull ^= 1u << T.slot;
           }
           const int db = t & 1;
-          mbar_wait(&bars.dA_empty[db], ph_dAe[db]);
-          ph_dAe[db] ^= 1;
+          mbar_wait(&bars.dA_empty[db], (ph_dAe >> db) & 1u);
+          ph_dAe ^= 1u << db;
           fence_after_sync();
           const int in_layer = T.lin - 1;
           const uint32_t act_sbo = (uint32_t)(p.act_kp[in_layer] / 8) * 128u;
-          for (int ks = 0; ks < T.Kp / 16; ++ks) {
-            const uint64_t ad = smem_desc(smem_base + T.smem_off + ks * 256, 128u, (uint32_t)T.sbo);
-            const uint64_t bd = smem_desc(smem_base + p.act_off[in_layer] + ks * 256, 128u, act_sbo);
-            mma_bf16_ss(tmem + col_dA + db * NR, ad, bd, id_a, ks > 0);
+          const uint64_t ad0 = smem_desc(smem_base + T.smem_off, 128u, (uint32_t)T.sbo);
+          const uint64_t bd0 = smem_desc(smem_base + p.act_off[in_layer], 128u, act_sbo);
+          const uint32_t dcol = tmem + col_dA + db * NR;
+          const int nk = T.Kp / 16;
+          if (elect_one()) {
+            mma_bf16_ss(dcol, ad0, bd0, id_a, false);
+            for (int k8 = 0; k8 < nk; k8 += 8) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const int ks = k8 + kk;
+                if (ks > 0 && ks < nk) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), id_a, true);
+              }
+            }
+            mma_commit(&bars.dA_full[db]);
           }
-          mma_commit(&bars.dA_full[db]);
+          __syncwarp();
+          TC_STAMP(lane == 0, ts, 1 + t);
           if (t > 0) phaseB(t - 1);
+          TC_STAMP(lane == 0, ts, 11 + t);
         }
         if (nt > 0) phaseB(nt - 1);
-        mma_commit(&bars.bp_full);
+        if (elect_one()) mma_commit(&bars.bp_full);
+        __syncwarp();
+        TC_STAMP(lane == 0, ts, 21);
       }
     }
   } else {
-    // ---------------- epilogue: thread <-> TMEM lane <-> unit ----------------
-    const int ln = warp * 32 + lane;                                   // lane / unit index inside a tile
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---------------- epilogue: thread <-> (TMEM lane = unit, RPT of the NR chains) ----------------
+    const int q = warp & 3, cg = warp >> 2;
+    const int ln = q * 32 + lane;                                      // unit index inside a 128-unit tile
+    const int cbase = cg * RPT;                                        // first chain (column) of this thread
+    const int rb = row0 + cbase;                                       // its global row
+    const int nrow = max(0, min(RPT, p.B - rb));                       // valid chains of this thread
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase;
+    // byte offset of (chain cbase, unit ln) inside a [NR x 128] K-major operand (LBO 128, SBO 2048); chain i adds
+    // (i>>3)*SBO + (i&7)*16
+    const uint32_t g_thread_off = (uint32_t)(cbase >> 3) * 2048u + (uint32_t)(cbase & 7) * 16u + (uint32_t)(ln >> 3) * 128u +
+                                  (uint32_t)(ln & 7) * 2u;
+    auto bar_epi = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory"); };
+
     // zero the bf16 operand buffers (padding columns must stay finite), then load the latents
-    for (int i = tid * 16; i < p.gbuf_off[1] + NR * 256 - p.act_off[0]; i += kEpiThreads * 16)
+    for (int i = tid * 16; i < p.gbuf_off[1] + NR * 256 - p.act_off[0]; i += kEpi * 16)
       *reinterpret_cast<uint4*>(smem + p.act_off[0] + i) = make_uint4(0, 0, 0, 0);
-    epi_bar();
+    bar_epi();
     for (int h = 0; h < HT; ++h) {
       const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
       const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
+      uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
+                      (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
+      float xv[RPT];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        float xv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int row = row0 + c * 16 + i;
-          xv[i] = (u < dl && row < p.B) ? p.x[l][(size_t)row * dl + u] : 0.0f;
-          if (u < dl)
-            *reinterpret_cast<__nv_bfloat16*>(smem + p.act_off[l] + kmajor_off(c * 16 + i, u, 128u, asbo)) =
-                __float2bfloat16(act_apply(nd.act[l], xv[i]));
-        }
-        tmem_st16(lane_addr + col_x + h * NR + c * 16, xv);
+      for (int i = 0; i < RPT; ++i) {
+        xv[i] = (u < dl && i < nrow) ? p.x[l][(size_t)(rb + i) * dl + u] : 0.0f;
+        if (u < dl)
+          *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(nd.act[l], xv[i]));
       }
+      __syncwarp();
+      tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
     }
     tmem_st_wait();
     fence_async_smem();
     fence_before_sync();
     mbar_arrive(&bars.acts_ready);
 
-    uint32_t ph_dAf[2] = {0, 0}, ph_ge[2] = {1, 1}, ph_bp = 0;
+    uint32_t ph_dAf = 0, ph_ge = 3, ph_bp = 0;
     double b1p = p.b1_pow0, b2p = p.b2_pow0;
 
     for (int ts = 0; ts < p.n_steps; ++ts) {
@@ -289,6 +348,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_co
       const int nt = p.n_hid_tiles + (need_out ? p.n_out_tiles : 0);
       const bool last = (ts == p.n_steps - 1);
       float e_part = 0.0f, l_part = 0.0f;
+      // row-major [slot][row] bases of this thread's first chain in the save / trajectory tensors
+      float* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * nd.NG : nullptr;
+      float* sf_row = do_save ? p.save_f + ((size_t)slot * p.B + rb) * nd.SD : nullptr;
+      TC_STAMP(tid == 0, ts, 32);
 
       // ---------- per-tile epilogue: errors of the units this tile predicts ----------
       for (int t = 0; t < nt; ++t) {
@@ -300,62 +363,69 @@ __global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_co
         const int u = T.out_tile * 128 + ln;
         const bool uvalid = u < dl;
         const float bias = (uvalid && p.b[T.lin] != nullptr) ? __ldg(p.b[T.lin] + u) : 0.0f;
-        mbar_wait(&bars.dA_full[db], ph_dAf[db]);
-        ph_dAf[db] ^= 1;
+        // targets of this tile: independent loads issued before the wait on the tensor pipe (a load inside
+        // the element loop would be serialised behind the save/trajectory stores it may alias)
+        float yv[RPT];
+        const bool use_y = is_out && uvalid && (u >= nd.mask_start) && nd.top >= MCPC_TOP_GAUSS;
+        if (use_y) {
+          const float* yp = p.target + (size_t)rb * nd.d_out + u;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) yv[i] = (i < nrow) ? __ldg(yp + (size_t)i * nd.d_out) : 0.0f;
+        }
+        mbar_wait(&bars.dA_full[db], (ph_dAf >> db) & 1u);
+        ph_dAf ^= 1u << db;
         if (has_b) {
-          mbar_wait(&bars.g_empty[gb], ph_ge[gb]);
-          ph_ge[gb] ^= 1;
+          mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
+          ph_ge ^= 1u << gb;
         }
         fence_after_sync();
-        uint8_t* gbuf = smem + p.gbuf_off[gb];
+        TC_STAMP(tid == 0, ts, 33 + t);
+        uint8_t* gptr = smem + p.gbuf_off[gb] + g_thread_off;
+        float d[RPT];
+        tmem_ld<RPT>(lane_addr + col_dA + db * NR, d);
+        if (!is_out) {
+          const int h = T.h_out;
+          const float ce = 0.5f * nd.c[T.lin], gc = nd.gc[T.lin];
+          float xv[RPT], gv[RPT];
+          tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
+          float* sg = (do_save && uvalid) ? sg_row + nd.off[T.lin] + u : nullptr;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          float d[16];
-          tmem_ld16(lane_addr + col_dA + db * NR + c * 16, d);
-          if (!is_out) {
-            const int h = T.h_out;
-            const float ce = 0.5f * nd.c[T.lin], gc = nd.gc[T.lin];
-            float xv[16], gv[16];
-            tmem_ld16(lane_addr + col_x + h * NR + c * 16, xv);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int row = row0 + c * 16 + i;
-              const float eps = xv[i] - (d[i] + bias);
-              const float G = uvalid ? -gc * eps : 0.0f;
-              gv[i] = G;
-              if (uvalid && row < p.B) {
-                e_part = fmaf(ce * eps, eps, e_part);
-                if (do_save) p.save_g[((size_t)slot * p.B + row) * nd.NG + nd.off[T.lin] + u] = G;
-              }
-              *reinterpret_cast<__nv_bfloat16*>(gbuf + kmajor_off(c * 16 + i, ln, 128u, 2048u)) = __float2bfloat16(G);
+          for (int i = 0; i < RPT; ++i) {
+            const float eps = xv[i] - (d[i] + bias);
+            const float G = uvalid ? -gc * eps : 0.0f;
+            gv[i] = G;
+            if (uvalid && i < nrow) {
+              e_part = fmaf(ce * eps, eps, e_part);
+              if (sg != nullptr) sg[(size_t)i * nd.NG] = G;
             }
-            tmem_st16(lane_addr + col_g + h * NR + c * 16, gv);
-          } else {
-            const bool in_mask = u >= nd.mask_start;
+            *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = __float2bfloat16(G);
+          }
+          tmem_st<RPT>(lane_addr + col_g + h * NR, gv);
+        } else {
+          float* sg = (do_save && uvalid) ? sg_row + nd.SD + u : nullptr;
+          float* to = (do_traj && p.traj_out != nullptr && uvalid) ? p.traj_out + ((size_t)rec * p.B + rb) * nd.d_out + u : nullptr;
+          const bool bern = nd.top == MCPC_TOP_BERNOULLI;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int row = row0 + c * 16 + i;
-              const float o = d[i] + bias;
-              float e_out = 0.0f;
-              if (uvalid && row < p.B) {
-                if (in_mask && nd.top >= MCPC_TOP_GAUSS) {
-                  const float y = __ldg(p.target + (size_t)row * nd.d_out + u);
-                  if (nd.top == MCPC_TOP_GAUSS) {
-                    const float dd = o - y;
-                    l_part = fmaf(0.5f * nd.inv_var * dd, dd, l_part);
-                    e_out = dd * nd.inv_var;
-                  } else {
-                    const float z = __expf(-fabsf(o));
-                    l_part += fmaxf(o, 0.0f) - o * y + __logf(1.0f + z);
-                    e_out = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - y;
-                  }
+          for (int i = 0; i < RPT; ++i) {
+            const float o = d[i] + bias;
+            float e_out = 0.0f;
+            if (uvalid && i < nrow) {
+              if (use_y) {
+                const float y = yv[i];
+                if (!bern) {
+                  const float dd = o - y;
+                  l_part = fmaf(0.5f * nd.inv_var * dd, dd, l_part);
+                  e_out = dd * nd.inv_var;
+                } else {
+                  const float z = __expf(-fabsf(o));
+                  l_part += fmaxf(o, 0.0f) - o * y + __logf(1.0f + z);
+                  e_out = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - y;
                 }
-                if (do_traj && p.traj_out != nullptr) p.traj_out[((size_t)rec * p.B + row) * nd.d_out + u] = o;
-                if (do_save) p.save_g[((size_t)slot * p.B + row) * nd.NG + nd.SD + u] = e_out;
               }
-              if (has_b)
-                *reinterpret_cast<__nv_bfloat16*>(gbuf + kmajor_off(c * 16 + i, ln, 128u, 2048u)) = __float2bfloat16(e_out);
+              if (to != nullptr) to[(size_t)i * nd.d_out] = o;
+              if (sg != nullptr) sg[(size_t)i * nd.NG] = e_out;
             }
+            if (has_b) *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = __float2bfloat16(e_out);
           }
         }
         tmem_st_wait();
@@ -365,132 +435,152 @@ __global__ void __launch_bounds__(kThreadsTc, 1) infer_tc_kernel(const __grid_co
           fence_async_smem();
           mbar_arrive(&bars.g_full[gb]);
         }
+        TC_STAMP(tid == 0, ts, 43 + t);
       }
 
       // ---------- update epilogue: latent gradient, optimizer step, Langevin noise ----------
       mbar_wait(&bars.bp_full, ph_bp);
       ph_bp ^= 1;
       fence_after_sync();
-      float step_size = 0.0f, bc2_sqrt = 1.0f;
-      if (p.optimizer == MCPC_OPT_ADAM && p.update_x) {
+      TC_STAMP(tid == 0, ts, 53);
+      float step_size = 0.0f, inv_bc2_sqrt = 1.0f;
+      const bool adam = (p.optimizer == MCPC_OPT_ADAM);
+      if (adam && p.update_x) {
         b1p *= p.beta1;
         b2p *= p.beta2;
         step_size = (float)(p.lr_d / (1.0 - b1p));
-        bc2_sqrt = (float)sqrt(1.0 - b2p);
+        inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
       }
       for (int h = 0; h < HT; ++h) {
         const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
         const bool uvalid = u < dl;
         const bool has_above = (l + 1 < L) || nd.top_has_grad;
+        const int kind = nd.act[l];
         const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
         const int gu = nd.off[l] + u;                    // global unit index (Philox counter, noise / save column)
-        const float b0 = (l == 0 && uvalid && p.b[0] != nullptr) ? __ldg(p.b[0] + u) : 0.0f;
+        float xv[RPT], bp[RPT], gown[RPT];
+        tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
+        if (has_above) {
+          tmem_ld<RPT>(lane_addr + col_bp + h * NR, bp);
+        } else {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          float xv[16], bp[16], gown[16];
-          tmem_ld16(lane_addr + col_x + h * NR + c * 16, xv);
-          if (has_above) {
-            tmem_ld16(lane_addr + col_bp + h * NR + c * 16, bp);
-          } else {
+          for (int i = 0; i < RPT; ++i) bp[i] = 0.0f;
+        }
+        if (l > 0) {
+          tmem_ld<RPT>(lane_addr + col_g + h * NR, gown);
+        } else {
+          // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
+          const float b0 = (uvalid && p.b[0] != nullptr) ? __ldg(p.b[0] + u) : 0.0f;
+          const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
+          float* sg = (do_save && uvalid) ? sg_row + u : nullptr;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) bp[i] = 0.0f;
-          }
-          if (l > 0) {
-            tmem_ld16(lane_addr + col_g + h * NR + c * 16, gown);
-          } else {
-            // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
-            const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int row = row0 + c * 16 + i;
-              const float eps = xv[i] - b0;
-              gown[i] = -gc * eps;
-              if (uvalid && row < p.B) {
-                e_part = fmaf(ce * eps, eps, e_part);
-                if (do_save) p.save_g[((size_t)slot * p.B + row) * nd.NG + u] = gown[i];
-              }
+          for (int i = 0; i < RPT; ++i) {
+            const float eps = xv[i] - b0;
+            gown[i] = -gc * eps;
+            if (uvalid && i < nrow) {
+              e_part = fmaf(ce * eps, eps, e_part);
+              if (sg != nullptr) sg[(size_t)i * nd.NG] = gown[i];
             }
           }
-          if (uvalid) {
+        }
+        if (uvalid) {
+          float mv[RPT], vv[RPT], nz[RPT];
+          const size_t xoff = (size_t)rb * dl + u;
+          if (adam && p.update_x) {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              mv[i] = (i < nrow) ? p.m[l][xoff + (size_t)i * dl] : 0.0f;
+              vv[i] = (i < nrow) ? p.v[l][xoff + (size_t)i * dl] : 0.0f;
+            }
+          }
+          if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
+            const float* np_ = p.noise + ((size_t)ts * p.B + rb) * nd.SD + gu;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) nz[i] = (i < nrow) ? __ldg(np_ + (size_t)i * nd.SD) : 0.0f;
+          } else if (p.noise_mode == MCPC_NOISE_PHILOX) {
             float nrm[4];
             uint64_t cur_q = ~0ull;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int row = row0 + c * 16 + i;
-              if (row >= p.B) break;
+            for (int i = 0; i < RPT; ++i) {
+              const uint64_t chain = p.chain_offset + (uint64_t)(rb + i);
+              if ((chain >> 2) != cur_q) {
+                cur_q = chain >> 2;
+                langevin_normals4(p.seed, (uint32_t)gu, (uint32_t)t_abs, cur_q, nrm);
+              }
+              nz[i] = p.noise_scale * sel4(nrm, (uint32_t)(chain & 3));
+            }
+          }
+          uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
+                          (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
+          float* tx = (do_traj && p.traj_x[l] != nullptr) ? p.traj_x[l] + ((size_t)rec * p.B + rb) * dl + u : nullptr;
+          float* sf = do_save ? sf_row + gu : nullptr;
+          float* xg = (last && p.xgrad[l] != nullptr) ? p.xgrad[l] + xoff : nullptr;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            if (i < nrow) {
               float x = xv[i];
-              const float a = act_apply(nd.act[l], x);
-              const float grad = fmaf(act_deriv(nd.act[l], x, a), bp[i], -gown[i]);
-              if (do_traj && p.traj_x[l] != nullptr) p.traj_x[l][((size_t)rec * p.B + row) * dl + u] = x;
-              if (do_save) p.save_f[((size_t)slot * p.B + row) * nd.SD + gu] = a;
-              if (last && p.xgrad[l] != nullptr) p.xgrad[l][(size_t)row * dl + u] = grad;
+              const float a = act_tc(kind, x);
+              const float grad = fmaf(dact_tc(kind, x, a), bp[i], -gown[i]);
+              if (tx != nullptr) tx[(size_t)i * dl] = x;
+              if (sf != nullptr) sf[(size_t)i * nd.SD] = a;
+              if (xg != nullptr) xg[(size_t)i * dl] = grad;
               if (p.update_x) {
-                if (p.optimizer == MCPC_OPT_SGD) {
+                if (!adam) {
                   x = fmaf(-p.lr, grad, x);
                 } else {
-                  const size_t si = (size_t)row * dl + u;
-                  float mv = p.m[l][si], vv = p.v[l][si];
-                  mv = fmaf(p.one_minus_b1, grad - mv, mv);
-                  vv = vv * p.beta2f;
-                  vv = fmaf(p.one_minus_b2 * grad, grad, vv);
-                  p.m[l][si] = mv;
-                  p.v[l][si] = vv;
-                  x = fmaf(-step_size, mv / (sqrtf(vv) / bc2_sqrt + p.adam_eps), x);
+                  const float m1 = fmaf(p.one_minus_b1, grad - mv[i], mv[i]);
+                  const float v1 = fmaf(p.one_minus_b2 * grad, grad, vv[i] * p.beta2f);
+                  p.m[l][xoff + (size_t)i * dl] = m1;
+                  p.v[l][xoff + (size_t)i * dl] = v1;
+                  x = fmaf(-step_size, __fdividef(m1, fmaf(sqrtf(v1), inv_bc2_sqrt, p.adam_eps)), x);
                 }
               }
-              if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
-                x = fmaf(-p.lr, p.noise[((size_t)ts * p.B + row) * nd.SD + gu], x);
-              } else if (p.noise_mode == MCPC_NOISE_PHILOX) {
-                const uint64_t chain = p.chain_offset + (uint64_t)row;
-                if ((chain >> 2) != cur_q) {
-                  cur_q = chain >> 2;
-                  langevin_normals4(p.seed, (uint32_t)gu, (uint32_t)t_abs, cur_q, nrm);
-                }
-                x = fmaf(-p.lr, p.noise_scale * nrm[chain & 3], x);
-              }
+              if (p.noise_mode != MCPC_NOISE_NONE) x = fmaf(-p.lr, nz[i], x);
               xv[i] = x;
-              *reinterpret_cast<__nv_bfloat16*>(smem + p.act_off[l] + kmajor_off(c * 16 + i, u, 128u, asbo)) =
-                  __float2bfloat16(act_apply(nd.act[l], x));
+              *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(kind, x));
             }
-            tmem_st16(lane_addr + col_x + h * NR + c * 16, xv);
           }
         }
+        // .sync.aligned: every lane of the warp must execute the store (padding lanes write back their zeros)
+        __syncwarp();
+        tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
       }
       tmem_st_wait();
       fence_async_smem();
       fence_before_sync();
       mbar_arrive(&bars.acts_ready);
+      TC_STAMP(tid == 0, ts, 54);
 
       // ---------- per-step scalars ----------
       e_part = warp_sum_tc(e_part);
       l_part = warp_sum_tc(l_part);
       float (*red)[2] = s_red[ts & 1];
       if (lane == 0) { red[warp][0] = e_part; red[warp][1] = l_part; }
-      epi_bar();
-      if (tid < 2) p.partials[((size_t)ts * p.n_ctas + blockIdx.x) * 2 + tid] =
-          red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+      bar_epi();
+      if (tid < 2) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 4 * CS; ++w) s += red[w][tid];
+        p.partials[((size_t)ts * p.n_ctas + blockIdx.x) * 2 + tid] = s;
+      }
     }
 
     // ---------- write the latents back ----------
     for (int h = 0; h < HT; ++h) {
       const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
+      float xv[RPT];
+      tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        float xv[16];
-        tmem_ld16(lane_addr + col_x + h * NR + c * 16, xv);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int row = row0 + c * 16 + i;
-          if (u < dl && row < p.B) p.x[l][(size_t)row * dl + u] = xv[i];
-        }
-      }
+      for (int i = 0; i < RPT; ++i)
+        if (u < dl && i < nrow) p.x[l][(size_t)(rb + i) * dl + u] = xv[i];
     }
   }
 
   fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
+
 
 inline int pad16(int v) { return (v + 15) & ~15; }
 
@@ -699,15 +789,43 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   p.traj_every = any_traj ? (o->traj_every > 0 ? o->traj_every : 1) : 0;
   p.save_begin = o->save_begin;
   p.save_end = o->save_end;
-  if (NR == 32) {
-    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    infer_tc_kernel<32><<<p.n_ctas, kThreadsTc, smem, stream>>>(p);
-  } else {
-    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    infer_tc_kernel<16><<<p.n_ctas, kThreadsTc, smem, stream>>>(p);
+  const bool timing = getenv("MCPC_TC_TIMING") != nullptr;     // debug only: allocates + synchronises
+  if (timing) {
+    cudaMalloc(&p.dbg, 8 * 64 * sizeof(long long));
+    cudaMemsetAsync(p.dbg, 0, 8 * 64 * sizeof(long long), stream);
   }
+  int rpt = (NR == 32) ? 8 : 4;             // chains per epilogue thread (16 epilogue warps by default)
+  if (const char* env = getenv("MCPC_TC_RPT")) {
+    const int v = atoi(env);
+    if ((v == 4 || v == 8 || v == 16) && NR / v >= 1 && NR / v <= 4) rpt = v;
+  }
+#define MCPC_TC_LAUNCH(NR_, RPT_)                                                                                     \
+  do {                                                                                                                \
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<NR_, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         (int)smem));                                                                 \
+    infer_tc_kernel<NR_, RPT_><<<p.n_ctas, 128 * (NR_ / RPT_) + 64, smem, stream>>>(p);                              \
+  } while (0)
+  if (NR == 32 && rpt == 16) MCPC_TC_LAUNCH(32, 16);
+  else if (NR == 32) MCPC_TC_LAUNCH(32, 8);
+  else if (rpt == 16) MCPC_TC_LAUNCH(16, 16);
+  else if (rpt == 8) MCPC_TC_LAUNCH(16, 8);
+  else MCPC_TC_LAUNCH(16, 4);
+#undef MCPC_TC_LAUNCH
   MCPC_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  if (timing) {
+    long long h[8 * 64];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    for (int ts = 0; ts < 8 && ts < o->n_steps; ++ts) {
+      const long long base = h[ts * 64 + 32];
+      fprintf(stderr, "[tc timing] step %d (cycles rel. to epilogue step start):", ts);
+      for (int i = 0; i < 64; ++i)
+        if (h[ts * 64 + i] != 0) fprintf(stderr, " %d:%lld", i, h[ts * 64 + i] - base);
+      fprintf(stderr, "\n");
+    }
+  }
   if (io->energy != nullptr || io->loss != nullptr) {
     rc = launch_reduce_partials(p.partials, o->n_steps, p.n_ctas, io->energy, io->loss, stream);
     if (rc != MCPC_OK) return rc;

@@ -4,6 +4,8 @@
 // compares both products with torch.
 //     D1[128][N] = Wt[128][Kin] . Bx[N][Kin]^T          (prediction-style: A = tile, K-major)
 //     D2[m][N]   = sum_j Wt[j][m] . G[N][j]             (back-projection-style: A = tile^T, MN-major), m < Kin
+#include <cstdlib>
+
 #include "mcpc_common.cuh"
 #include "umma.cuh"
 
@@ -96,10 +98,106 @@ __global__ void __launch_bounds__(160) umma_probe_kernel(const __nv_bfloat16* __
   if (warp == 4) tmem_dealloc(tmem, 64);
 }
 
+// Cost model of small tcgen05.mma instructions (debug, MCPC_UMMA_TIMING=1): cycles from first issue to the
+// commit barrier for n_mma instructions of shape M x N x 16 spread round-robin over n_acc accumulators.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+// variant: 0 = issued inside `if (lane == 0)`, 1 = converged warp + elect.sync, 2 = as 1 with SWIZZLE_128B
+// descriptors, 3 = as 1 with the A operand in TMEM
+__global__ void __launch_bounds__(160) umma_timing_kernel(int M, int N, int n_mma, int n_acc, int variant, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 4) tmem_alloc(&tmem_base_s, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 4) {
+    const uint32_t id = idesc_bf16(M, N, false, false);
+    uint64_t ad = smem_desc(smem_u32(smem), 128u, 2048u);
+    uint64_t bd = smem_desc(smem_u32(smem) + 32768, 128u, 256u);
+    if (variant == 2) {
+      ad = smem_desc(smem_u32(smem), 16u, 1024u) | ((uint64_t)2 << 61);
+      bd = smem_desc(smem_u32(smem) + 32768, 16u, 1024u) | ((uint64_t)2 << 61);
+    }
+    for (int rep = 0; rep < 3; ++rep) {
+      long long t0 = 0, t1 = 0, t2 = 0;
+      if (variant == 0) {
+        if (lane == 0) {
+          t0 = clock64();
+          for (int i = 0; i < n_mma; ++i)
+            mma_bf16_ss(tmem + (uint32_t)((i % n_acc) * N), ad + (uint64_t)((i & 7) * 16), bd, id, i >= n_acc);
+          mma_commit(&bar);
+          t1 = clock64();
+        }
+      } else {
+        t0 = clock64();
+        if (elect_one()) {
+          if (variant == 3) {
+            for (int i = 0; i < n_mma; ++i)
+              mma_bf16_ts(tmem + (uint32_t)((i % n_acc) * N), tmem + 256 + (uint32_t)((i & 7) * 8), bd, id, i >= n_acc);
+          } else {
+            for (int i = 0; i < n_mma; ++i)
+              mma_bf16_ss(tmem + (uint32_t)((i % n_acc) * N), ad + (uint64_t)((i & 7) * (variant == 2 ? 2 : 16)), bd, id, i >= n_acc);
+          }
+          mma_commit(&bar);
+        }
+        __syncwarp();
+        t1 = clock64();
+      }
+      mbar_wait(&bar, rep & 1);
+      t2 = clock64();
+      if (rep == 2 && lane == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
+
+int launch_umma_timing(cudaStream_t stream) {
+  long long* d = nullptr;
+  cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  const int Ms[2] = {128, 64};
+  const int Ns[5] = {16, 32, 64, 128, 256};
+  for (int variant = 0; variant < 4; ++variant)
+    for (int mi = 0; mi < 2; ++mi)
+      for (int ni = 0; ni < 5; ni += 2)
+        for (int n_acc = 1; n_acc <= 2; ++n_acc) {
+          const int M = Ms[mi], N = Ns[ni];
+          if (n_acc * N > 256 || (variant == 3 && M == 64)) continue;
+          umma_timing_kernel<<<1, 160, 64 * 1024, stream>>>(M, N, 32, n_acc, variant, d);
+          long long h[2];
+          cudaStreamSynchronize(stream);
+          cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+          fprintf(stderr, "[umma timing] variant=%d M=%d N=%d n_acc=%d: issue %lld cyc, complete %lld cyc for 32 MMAs (%.1f cyc/MMA)\n",
+                  variant, M, N, n_acc, h[0], h[1], h[1] / 32.0);
+        }
+  cudaFree(d);
+  return MCPC_OK;
+}
 
 int launch_umma_probe(const float* Wt, const float* Bx, const float* G, int Kin, int N, float* D1, float* D2, void* ws,
                       cudaStream_t stream) {
+  if (getenv("MCPC_UMMA_TIMING") != nullptr) return launch_umma_timing(stream);
   if (Kin % 16 != 0 || Kin < 16 || Kin > 256 || N % 16 != 0 || N < 16 || N > 32) {
     set_error("umma probe: Kin must be a multiple of 16 in [16,256], N in {16,32}");
     return MCPC_ERR_INVALID;

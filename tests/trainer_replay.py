@@ -59,7 +59,7 @@ def make_trainer(model, tr):
 
 
 def replay(name, device, engine_factory=None, precision="fp32", tol_x=1e-5, tol_s=1e-5, tol_g=2e-5, tol_w=2e-6,
-           callback_wrapper=None):
+           callback_wrapper=None, teacher_force=False):
     """Returns a dict of the worst errors seen; asserts against the tolerances."""
     gc = GoldenCase(name)
     model = build_model(gc, device)
@@ -76,6 +76,17 @@ def replay(name, device, engine_factory=None, precision="fp32", tol_x=1e-5, tol_
             trainer._engine = engine_factory()
         trainer.set_precision(precision)
         T = tr["T"]
+        if teacher_force and ci > 0:
+            # start every call from the reference's own state (latents and parameters) so that the bound
+            # measures ONE call, not the drift accumulated over the preceding (chaotic, Adam) calls
+            with torch.no_grad():
+                for l, layer in enumerate(pcs):
+                    layer.get_x().copy_(torch.from_numpy(gc.x0(ci)[l]).to(device))
+                Wb, bb = gc.weights(ci, "before")
+                for lin, w, b_ in zip(lins, Wb, bb):
+                    lin.weight.copy_(torch.from_numpy(w).to(device))
+                    if b_ is not None:
+                        lin.bias.copy_(torch.from_numpy(b_).to(device))
         if call.get("sample_x", True):
             for l, layer in enumerate(pcs):
                 x0 = torch.from_numpy(gc.x0(ci)[l]).to(device)
