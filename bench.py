@@ -46,7 +46,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="chains per GPU")
-    ap.add_argument("--precision", default=os.environ.get("MCPC_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("MCPC_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"],
+                    help="bf16 = tcgen05 tensor-core path (bf16 operands, fp32 master latents + accumulation; stated bound "
+                         "in tests/test_gpu_bf16.py); fp32 = reference-exact CUDA-core path (1e-5 parity)")
     ap.add_argument("--cpu-sample-steps", type=int, default=int(os.environ.get("MCPC_CPU_SAMPLE_STEPS", "30")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -131,7 +133,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
         except OSError:
@@ -244,12 +246,12 @@ def run_ours(args):
 
     import warnings
     warnings.simplefilter("ignore")
+    sampler = ClockSampler(local) if rank == 0 else None      # runs from the warm-up to the end of the timed loops
     for i in range(W):
         map_call(dev_targets[i % n_pool])
         mcpc_call(dev_targets[i % n_pool])
 
     # ---- timed: K MCPC learning calls, inputs resident in HBM --------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.mcpc_launch_count()
     barrier()
     evs = []
@@ -265,7 +267,6 @@ def run_ours(args):
     launches = lib.mcpc_launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     total_s = max_over_ranks(dev_ms * 1e-3)
-    clocks = sampler.stop() if sampler is not None else None
 
     # ---- e2e: targets start in pinned HOST memory, result lists are read back every step ----------
     barrier()
@@ -295,6 +296,27 @@ def run_ours(args):
         t_ev.append((e0, e1))
     barrier()
     full_s = max_over_ranks(sum(a.elapsed_time(b) for a, b in t_ev) * 1e-3) / kk
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- the other precision mode, short run, for the record ----------------------------------------
+    other = "fp32" if args.precision == "bf16" else "bf16"
+    for tr in (map_trainer, mcpc_trainer):
+        tr.set_precision(other)
+    for i in range(2):
+        mcpc_call(dev_targets[i % n_pool])
+    barrier()
+    o_ev = []
+    for i in range(3):
+        flush.fill_(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mcpc_call(dev_targets[i % n_pool])
+        e1.record()
+        o_ev.append((e0, e1))
+    barrier()
+    other_s = max_over_ranks(sum(a.elapsed_time(b) for a, b in o_ev) * 1e-3) / 3
+    for tr in (map_trainer, mcpc_trainer):
+        tr.set_precision(args.precision)
 
     # ---- dominant kernel alone (roofline): events around the mcpc_infer launch of an MCPC call ----
     eng = mcpc_trainer._get_engine()
@@ -332,6 +354,8 @@ def run_ours(args):
             "e2e": {"value": world * B * L * T_MCPC / (e2e_s / K), "unit": "latent-updates/s",
                     "h2d_bytes_per_step": B * D_OUT * 4, "d2h_bytes_per_step": 2 * T_MCPC * 8,
                     "ms_per_step": e2e_s / K * 1e3},
+            "other_precision": {"precision": other, "ms_per_step": other_s * 1e3,
+                                "value": world * B * L * T_MCPC / other_s},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "mcpc_infer (all T steps, one launch)",
