@@ -83,8 +83,9 @@ typedef struct McpcIO {
   double* loss;                           /* [n_steps] loss at the start of each step (0 when TOP_NONE) :777-780 */
   float* traj_x[MCPC_MAX_LAYERS];         /* optional [n_rec, B, d_l]: x_l at the start of step t_k = k*traj_every */
   float* traj_out;                        /* optional [n_rec, B, d_out]: outputs of the same steps (:769-770) */
-  void* save_g;                           /* optional [n_save, B, sum(d_l)+d_out]: d overall / d mu_l and d loss / d out */
-  void* save_f;                           /* optional [n_save, B, sum(d_l)]: act_l(x_l); operands of mcpc_weight_grad */
+  void* save_g;                           /* optional [n_save, B, g_width]: d overall / d mu_l and d loss / d out      */
+  void* save_f;                           /* optional [n_save, B, f_width]: act_l(x_l); operands of mcpc_weight_grad;
+                                             widths / element type from mcpc_save_layout                           */
 } McpcIO;
 
 typedef struct McpcOpts {
@@ -122,6 +123,11 @@ uint64_t mcpc_launch_count(void);
 
 /* Bytes of scratch mcpc_infer needs for (net, B, n_steps). */
 int mcpc_workspace_bytes(const McpcNet* net, int32_t B, int32_t n_steps, int32_t precision, size_t* out_bytes);
+
+/* Row layout of the operands mcpc_infer saves for mcpc_weight_grad: save_g is [n_save, B, *g_width],
+ * save_f is [n_save, B, *f_width], elements of *elem_bytes bytes (fp32: unpadded concatenation; bf16: every
+ * layer's block padded to 8 columns).  Allocate 1024 elements of slack behind each buffer. */
+int mcpc_save_layout(const McpcNet* net, int32_t precision, int32_t* g_width, int32_t* f_width, int32_t* elem_bytes);
 
 /* n_steps fused steps of: forward, energy/loss readout, latent gradient, x-step, Langevin noise
  * (pc_trainer.py:733-918 with utils/model.py:35-44 folded in). */

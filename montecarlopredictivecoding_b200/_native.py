@@ -92,7 +92,7 @@ class NativeError(RuntimeError):
 _lib = None
 _lock = threading.Lock()
 LIB_NAME = "libmcpc_b200.so"
-EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_infer", "mcpc_weight_grad",
+EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer", "mcpc_weight_grad",
            "mcpc_fill_noise", "mcpc_debug_umma")
 
 
@@ -119,6 +119,9 @@ def load():
         lib.mcpc_workspace_bytes.restype = C.c_int
         lib.mcpc_workspace_bytes.argtypes = [C.POINTER(McpcNet), C.c_int32, C.c_int32, C.c_int32,
                                              C.POINTER(C.c_size_t)]
+        lib.mcpc_save_layout.restype = C.c_int
+        lib.mcpc_save_layout.argtypes = [C.POINTER(McpcNet), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32)]
         lib.mcpc_infer.restype = C.c_int
         lib.mcpc_infer.argtypes = [C.POINTER(McpcNet), C.POINTER(McpcIO), C.POINTER(McpcOpts), C.c_int32,
                                    C.c_void_p, C.c_size_t, C.c_void_p]

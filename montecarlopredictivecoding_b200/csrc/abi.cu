@@ -102,6 +102,32 @@ int mcpc_workspace_bytes(const McpcNet* net, int32_t B, int32_t n_steps, int32_t
   return MCPC_ERR_UNSUPPORTED;
 }
 
+int mcpc_save_layout(const McpcNet* net, int32_t precision, int32_t* g_width, int32_t* f_width, int32_t* elem_bytes) {
+  NetDev nd;
+  int rc = check_net(net, &nd);
+  if (rc != MCPC_OK) return rc;
+  if (g_width == nullptr || f_width == nullptr || elem_bytes == nullptr) {
+    set_error("mcpc_save_layout: NULL output");
+    return MCPC_ERR_INVALID;
+  }
+  if (precision == MCPC_PREC_FP32) {
+    *g_width = nd.NG;
+    *f_width = nd.SD;
+    *elem_bytes = 4;
+    return MCPC_OK;
+  }
+  if (precision == MCPC_PREC_BF16) {
+    int g_off[kMaxL + 1], f_off[kMaxL + 1], gw = 0, fw = 0;
+    save_layout_bf16(nd, g_off, &gw, f_off, &fw);
+    *g_width = gw;
+    *f_width = fw;
+    *elem_bytes = 2;
+    return MCPC_OK;
+  }
+  set_error("precision %d not implemented", precision);
+  return MCPC_ERR_UNSUPPORTED;
+}
+
 int mcpc_infer(const McpcNet* net, const McpcIO* io, const McpcOpts* o, int32_t B, void* workspace,
                size_t workspace_bytes, void* stream) {
   NetDev nd;
@@ -162,8 +188,8 @@ int mcpc_weight_grad(const McpcNet* net, const McpcGradIO* io, int32_t B, int32_
     return MCPC_ERR_INVALID;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // both precisions save fp32 operands; the bf16 inference path reuses the fp32 contraction for now
-  if (precision == MCPC_PREC_FP32 || precision == MCPC_PREC_BF16) return launch_weight_grad_fp32(nd, io, B, n_save, s);
+  if (precision == MCPC_PREC_FP32) return launch_weight_grad_fp32(nd, io, B, n_save, s);
+  if (precision == MCPC_PREC_BF16) return launch_weight_grad_tc(nd, io, B, n_save, s);
   set_error("precision %d not implemented", precision);
   return MCPC_ERR_UNSUPPORTED;
 }

@@ -67,8 +67,10 @@ struct TcParams {
   float* xgrad[kMaxL];
   float* traj_x[kMaxL];
   float* traj_out;
-  float* save_g;
-  float* save_f;
+  __nv_bfloat16* save_g;        // bf16 [n_save, B, sg_pitch], layer blocks padded to 8 columns (wgrad_tc.cu)
+  __nv_bfloat16* save_f;        // bf16 [n_save, B, sf_pitch]
+  int sg_off[kMaxL + 1];
+  int sg_pitch, sf_pitch;
   const float* target;
   const float* noise;
   float* partials;
@@ -349,8 +351,8 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
       const bool last = (ts == p.n_steps - 1);
       float e_part = 0.0f, l_part = 0.0f;
       // row-major [slot][row] bases of this thread's first chain in the save / trajectory tensors
-      float* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * nd.NG : nullptr;
-      float* sf_row = do_save ? p.save_f + ((size_t)slot * p.B + rb) * nd.SD : nullptr;
+      __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * p.sg_pitch : nullptr;
+      __nv_bfloat16* sf_row = do_save ? p.save_f + ((size_t)slot * p.B + rb) * p.sf_pitch : nullptr;
       TC_STAMP(tid == 0, ts, 32);
 
       // ---------- per-tile epilogue: errors of the units this tile predicts ----------
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
           const float ce = 0.5f * nd.c[T.lin], gc = nd.gc[T.lin];
           float xv[RPT], gv[RPT];
           tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
-          float* sg = (do_save && uvalid) ? sg_row + nd.off[T.lin] + u : nullptr;
+          __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[T.lin] + u : nullptr;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             const float eps = xv[i] - (d[i] + bias);
@@ -396,13 +398,13 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
             gv[i] = G;
             if (uvalid && i < nrow) {
               e_part = fmaf(ce * eps, eps, e_part);
-              if (sg != nullptr) sg[(size_t)i * nd.NG] = G;
+              if (sg != nullptr) sg[(size_t)i * p.sg_pitch] = __float2bfloat16(G);
             }
             *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = __float2bfloat16(G);
           }
           tmem_st<RPT>(lane_addr + col_g + h * NR, gv);
         } else {
-          float* sg = (do_save && uvalid) ? sg_row + nd.SD + u : nullptr;
+          __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[L] + u : nullptr;
           float* to = (do_traj && p.traj_out != nullptr && uvalid) ? p.traj_out + ((size_t)rec * p.B + rb) * nd.d_out + u : nullptr;
           const bool bern = nd.top == MCPC_TOP_BERNOULLI;
 #pragma unroll
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
                 }
               }
               if (to != nullptr) to[(size_t)i * nd.d_out] = o;
-              if (sg != nullptr) sg[(size_t)i * nd.NG] = e_out;
+              if (sg != nullptr) sg[(size_t)i * p.sg_pitch] = __float2bfloat16(e_out);
             }
             if (has_b) *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = __float2bfloat16(e_out);
           }
@@ -472,14 +474,14 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
           // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
           const float b0 = (uvalid && p.b[0] != nullptr) ? __ldg(p.b[0] + u) : 0.0f;
           const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
-          float* sg = (do_save && uvalid) ? sg_row + u : nullptr;
+          __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + u : nullptr;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             const float eps = xv[i] - b0;
             gown[i] = -gc * eps;
             if (uvalid && i < nrow) {
               e_part = fmaf(ce * eps, eps, e_part);
-              if (sg != nullptr) sg[(size_t)i * nd.NG] = gown[i];
+              if (sg != nullptr) sg[(size_t)i * p.sg_pitch] = __float2bfloat16(gown[i]);
             }
           }
         }
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
           uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
                           (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
           float* tx = (do_traj && p.traj_x[l] != nullptr) ? p.traj_x[l] + ((size_t)rec * p.B + rb) * dl + u : nullptr;
-          float* sf = do_save ? sf_row + gu : nullptr;
+          __nv_bfloat16* sf = do_save ? sf_row + p.sg_off[l] + u : nullptr;
           float* xg = (last && p.xgrad[l] != nullptr) ? p.xgrad[l] + xoff : nullptr;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
               const float a = act_tc(kind, x);
               const float grad = fmaf(dact_tc(kind, x, a), bp[i], -gown[i]);
               if (tx != nullptr) tx[(size_t)i * dl] = x;
-              if (sf != nullptr) sf[(size_t)i * nd.SD] = a;
+              if (sf != nullptr) sf[(size_t)i * p.sf_pitch] = __float2bfloat16(a);
               if (xg != nullptr) xg[(size_t)i * dl] = grad;
               if (p.update_x) {
                 if (!adam) {
@@ -762,8 +764,12 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     p.traj_x[l] = io->traj_x[l];
   }
   p.traj_out = io->traj_out;
-  p.save_g = reinterpret_cast<float*>(io->save_g);
-  p.save_f = reinterpret_cast<float*>(io->save_f);
+  p.save_g = reinterpret_cast<__nv_bfloat16*>(io->save_g);
+  p.save_f = reinterpret_cast<__nv_bfloat16*>(io->save_f);
+  {
+    int f_off[kMaxL + 1];
+    save_layout_bf16(nd, p.sg_off, &p.sg_pitch, f_off, &p.sf_pitch);
+  }
   p.target = io->target;
   p.noise = io->noise;
   p.n_steps = o->n_steps;

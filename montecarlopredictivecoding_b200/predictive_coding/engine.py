@@ -97,6 +97,14 @@ class NativeEngine:
             self._ws[key] = buf
         return buf
 
+    def save_layout(self, plan: NetPlan, top: TopPlan, precision: int):
+        """(g_width, f_width, torch dtype) of the operands saved for the weight update."""
+        net = net_struct(plan, top, 1.0)
+        gw, fw, eb = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        N.check(self._lib.mcpc_save_layout(C.byref(net), precision, C.byref(gw), C.byref(fw), C.byref(eb)),
+                "mcpc_save_layout")
+        return gw.value, fw.value, (torch.float32 if eb.value == 4 else torch.bfloat16)
+
     def infer(self, c: InferCall) -> None:
         plan = c.plan
         dev = c.x[0].device
@@ -120,8 +128,8 @@ class NativeEngine:
         io.energy = _ptr(c.energy, "energy", torch.float64)
         io.loss = _ptr(c.loss, "loss", torch.float64)
         io.traj_out = _ptr(c.traj_out, "traj_out")
-        io.save_g = _ptr(c.save_g, "save_g")
-        io.save_f = _ptr(c.save_f, "save_f")
+        io.save_g = _ptr(c.save_g, "save_g", c.save_g.dtype if c.save_g is not None else torch.float32)
+        io.save_f = _ptr(c.save_f, "save_f", c.save_f.dtype if c.save_f is not None else torch.float32)
         o = N.McpcOpts()
         o.lr = float(c.lr)
         o.adam_beta1, o.adam_beta2 = float(c.betas[0]), float(c.betas[1])
@@ -151,8 +159,8 @@ class NativeEngine:
         dev = save_g.device
         net = net_struct(plan, top, energy_coefficient)
         io = N.McpcGradIO()
-        io.save_g = _ptr(save_g, "save_g")
-        io.save_f = _ptr(save_f, "save_f")
+        io.save_g = _ptr(save_g, "save_g", save_g.dtype)
+        io.save_f = _ptr(save_f, "save_f", save_f.dtype)
         io.inputs = _ptr(inputs, "inputs")
         for i in range(len(gW)):
             io.gW[i] = _ptr(gW[i], "gW")

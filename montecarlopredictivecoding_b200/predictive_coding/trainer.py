@@ -523,10 +523,16 @@ class PCTrainer(object):
         for s in shape:
             n *= int(s)
         buf = self._buffers.get(role)
-        if buf is None or buf.dtype != dtype or buf.device != device or buf.numel() < n:
-            buf = torch.empty(max(n, 1), dtype=dtype, device=device)
+        if buf is None or buf.dtype != dtype or buf.device != device or buf.numel() < n + 1024:
+            buf = torch.zeros(n + 1024, dtype=dtype, device=device)     # 1024 elements of slack (mcpc_save_layout)
             self._buffers[role] = buf
         return buf[:n].view(*shape)
+
+    def _save_layout(self, netp, top):
+        eng = self._get_engine()
+        if hasattr(eng, "save_layout"):
+            return eng.save_layout(netp, top, self._precision)
+        return netp.SD + netp.d_out, netp.SD, torch.float32
 
     def _inputs_or_none(self, inputs):
         """``None`` when inputs are all zero (every script of the reference): Linear_0 then only
@@ -694,7 +700,8 @@ class PCTrainer(object):
                 win_begin = zero_steps[-1] if zero_steps else t0
                 flat, gW, gb = self._ensure_flat_grads(netp, zero=bool(zero_steps))
             # the window may be cut further so the saved operands fit the scratch budget
-            row_bytes = 4 * B * (netp.SD * 2 + netp.d_out)
+            g_w, f_w, s_dtype = self._save_layout(netp, top)
+            row_bytes = (4 if s_dtype == torch.float32 else 2) * B * (g_w + f_w)
             max_save = max(1, self._save_budget_bytes // max(row_bytes, 1))
             cuts = [(t0, t1)]
             if need_grads and (t1 - win_begin) > max_save:
@@ -709,8 +716,8 @@ class PCTrainer(object):
                 save_g = save_f = None
                 if need_grads and c1 > win_begin:
                     sb, se = max(win_begin, c0) - c0, n
-                    save_g = self._buffer("save_g", (se - sb, B, netp.SD + netp.d_out), torch.float32, device)
-                    save_f = self._buffer("save_f", (se - sb, B, netp.SD), torch.float32, device)
+                    save_g = self._buffer("save_g", (se - sb, B, g_w), s_dtype, device)
+                    save_f = self._buffer("save_f", (se - sb, B, f_w), s_dtype, device)
                 rec_in_cut = want_traj and (every_t or c1 == T)
                 call = InferCall(
                     plan=netp, top=top, energy_coefficient=self._energy_coefficient, B=B, W=W, b=b, x=xs,
@@ -781,8 +788,9 @@ class PCTrainer(object):
             save_g = save_f = None
             if need_grads:
                 flat, gW, gb = self._ensure_flat_grads(netp, zero=self._is_zero_grad_step(t))
-                save_g = self._buffer("save_g", (1, B, netp.SD + netp.d_out), torch.float32, device)
-                save_f = self._buffer("save_f", (1, B, netp.SD), torch.float32, device)
+                g_w, f_w, s_dtype = self._save_layout(netp, top)
+                save_g = self._buffer("save_g", (1, B, g_w), s_dtype, device)
+                save_f = self._buffer("save_f", (1, B, f_w), s_dtype, device)
             rec = every_t or t == T - 1
             ri = t if every_t else 0
             call = InferCall(
