@@ -45,6 +45,13 @@ enum { MCPC_NOISE_NONE = 0, MCPC_NOISE_SUPPLIED = 1, MCPC_NOISE_PHILOX = 2 };
  * BF16 = tcgen05 kind::f16 with bf16 operands and fp32 accumulation in TMEM               */
 enum { MCPC_PREC_FP32 = 0, MCPC_PREC_BF16 = 1 };
 
+/* how mcpc_infer executes (net, B, precision) -- see mcpc_infer_mode:
+ *   RESIDENT_*  one persistent launch for all steps, latents on chip; the weight update is a separate
+ *               mcpc_weight_grad over operands saved in save_g / save_f
+ *   STREAMING   networks too wide for one SM: per-step grouped GEMM kernels; the weight update is accumulated
+ *               directly into McpcIO.gW / gb                                                              */
+enum { MCPC_MODE_RESIDENT_FP32 = 0, MCPC_MODE_RESIDENT_BF16 = 1, MCPC_MODE_STREAMING_BF16 = 2 };
+
 enum {
   MCPC_OK = 0,
   MCPC_ERR_INVALID = -1,      /* bad argument (NULL, negative size, unknown enum)            */
@@ -83,6 +90,8 @@ typedef struct McpcIO {
   double* loss;                           /* [n_steps] loss at the start of each step (0 when TOP_NONE) :777-780 */
   float* traj_x[MCPC_MAX_LAYERS];         /* optional [n_rec, B, d_l]: x_l at the start of step t_k = k*traj_every */
   float* traj_out;                        /* optional [n_rec, B, d_out]: outputs of the same steps (:769-770) */
+  float* gW[MCPC_MAX_LAYERS + 1];         /* MODE_STREAMING only: weight-gradient accumulators; the update of the steps */
+  float* gb[MCPC_MAX_LAYERS + 1];         /*   [save_begin, save_end) is ADDED here directly (no save_g/save_f)        */
   void* save_g;                           /* optional [n_save, B, g_width]: d overall / d mu_l and d loss / d out      */
   void* save_f;                           /* optional [n_save, B, f_width]: act_l(x_l); operands of mcpc_weight_grad;
                                              widths / element type from mcpc_save_layout                           */
@@ -128,6 +137,8 @@ int mcpc_workspace_bytes(const McpcNet* net, int32_t B, int32_t n_steps, int32_t
  * save_f is [n_save, B, *f_width], elements of *elem_bytes bytes (fp32: unpadded concatenation; bf16: every
  * layer's block padded to 8 columns).  Allocate 1024 elements of slack behind each buffer. */
 int mcpc_save_layout(const McpcNet* net, int32_t precision, int32_t* g_width, int32_t* f_width, int32_t* elem_bytes);
+
+int mcpc_infer_mode(const McpcNet* net, int32_t B, int32_t precision, int32_t* mode);
 
 /* n_steps fused steps of: forward, energy/loss readout, latent gradient, x-step, Langevin noise
  * (pc_trainer.py:733-918 with utils/model.py:35-44 folded in). */

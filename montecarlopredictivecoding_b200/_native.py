@@ -13,6 +13,7 @@ TOP_NONE, TOP_ZERO, TOP_GAUSS, TOP_BERNOULLI = 0, 1, 2, 3
 OPT_SGD, OPT_ADAM = 0, 1
 NOISE_NONE, NOISE_SUPPLIED, NOISE_PHILOX = 0, 1, 2
 PREC_FP32, PREC_BF16 = 0, 1
+MODE_RESIDENT_FP32, MODE_RESIDENT_BF16, MODE_STREAMING_BF16 = 0, 1, 2
 ABI_VERSION = 1
 
 _FP = C.c_void_p   # device pointers travel as integers
@@ -48,6 +49,8 @@ class McpcIO(C.Structure):
         ("loss", _FP),
         ("traj_x", _FP * MAX_LAYERS),
         ("traj_out", _FP),
+        ("gW", _FP * (MAX_LAYERS + 1)),
+        ("gb", _FP * (MAX_LAYERS + 1)),
         ("save_g", _FP),
         ("save_f", _FP),
     ]
@@ -92,7 +95,7 @@ class NativeError(RuntimeError):
 _lib = None
 _lock = threading.Lock()
 LIB_NAME = "libmcpc_b200.so"
-EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer", "mcpc_weight_grad",
+EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer_mode", "mcpc_infer", "mcpc_weight_grad",
            "mcpc_fill_noise", "mcpc_debug_umma")
 
 
@@ -122,6 +125,8 @@ def load():
         lib.mcpc_save_layout.restype = C.c_int
         lib.mcpc_save_layout.argtypes = [C.POINTER(McpcNet), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32)]
+        lib.mcpc_infer_mode.restype = C.c_int
+        lib.mcpc_infer_mode.argtypes = [C.POINTER(McpcNet), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
         lib.mcpc_infer.restype = C.c_int
         lib.mcpc_infer.argtypes = [C.POINTER(McpcNet), C.POINTER(McpcIO), C.POINTER(McpcOpts), C.c_int32,
                                    C.c_void_p, C.c_size_t, C.c_void_p]

@@ -97,7 +97,8 @@ int mcpc_workspace_bytes(const McpcNet* net, int32_t B, int32_t n_steps, int32_t
     return MCPC_ERR_INVALID;
   }
   if (precision == MCPC_PREC_FP32) return infer_rows_workspace(nd, B, n_steps, out_bytes);
-  if (precision == MCPC_PREC_BF16) return infer_tc_workspace(nd, B, n_steps, out_bytes);
+  if (precision == MCPC_PREC_BF16)
+    return infer_tc_fits(nd, B) ? infer_tc_workspace(nd, B, n_steps, out_bytes) : infer_wide_workspace(nd, B, n_steps, out_bytes);
   set_error("precision %d not implemented", precision);
   return MCPC_ERR_UNSUPPORTED;
 }
@@ -122,6 +123,36 @@ int mcpc_save_layout(const McpcNet* net, int32_t precision, int32_t* g_width, in
     *g_width = gw;
     *f_width = fw;
     *elem_bytes = 2;
+    return MCPC_OK;
+  }
+  set_error("precision %d not implemented", precision);
+  return MCPC_ERR_UNSUPPORTED;
+}
+
+int mcpc_infer_mode(const McpcNet* net, int32_t B, int32_t precision, int32_t* mode) {
+  NetDev nd;
+  int rc = check_net(net, &nd);
+  if (rc != MCPC_OK) return rc;
+  if (mode == nullptr || B < 1) {
+    set_error("mcpc_infer_mode: bad arguments");
+    return MCPC_ERR_INVALID;
+  }
+  if (precision == MCPC_PREC_FP32) {
+    size_t bytes = 0;
+    rc = infer_rows_workspace(nd, B, 1, &bytes);
+    if (rc != MCPC_OK) return rc;
+    *mode = MCPC_MODE_RESIDENT_FP32;
+    return MCPC_OK;
+  }
+  if (precision == MCPC_PREC_BF16) {
+    if (infer_tc_fits(nd, B)) {
+      *mode = MCPC_MODE_RESIDENT_BF16;
+      return MCPC_OK;
+    }
+    size_t bytes = 0;
+    rc = infer_wide_workspace(nd, B, 1, &bytes);
+    if (rc != MCPC_OK) return rc;
+    *mode = MCPC_MODE_STREAMING_BF16;
     return MCPC_OK;
   }
   set_error("precision %d not implemented", precision);
@@ -163,6 +194,10 @@ int mcpc_infer(const McpcNet* net, const McpcIO* io, const McpcOpts* o, int32_t 
     set_error("NOISE_SUPPLIED without a noise tensor");
     return MCPC_ERR_INVALID;
   }
+  if (io->save_g != nullptr && o->precision == MCPC_PREC_BF16 && !infer_tc_fits(nd, B)) {
+    set_error("streaming bf16 path: pass McpcIO.gW/gb instead of save_g/save_f (see mcpc_infer_mode)");
+    return MCPC_ERR_INVALID;
+  }
   if ((io->save_g != nullptr) != (io->save_f != nullptr)) {
     set_error("save_g and save_f must be given together");
     return MCPC_ERR_INVALID;
@@ -173,7 +208,9 @@ int mcpc_infer(const McpcNet* net, const McpcIO* io, const McpcOpts* o, int32_t 
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (o->precision == MCPC_PREC_FP32) return launch_infer_rows(nd, io, o, B, workspace, workspace_bytes, s);
-  if (o->precision == MCPC_PREC_BF16) return launch_infer_tc(nd, io, o, B, workspace, workspace_bytes, s);
+  if (o->precision == MCPC_PREC_BF16)
+    return infer_tc_fits(nd, B) ? launch_infer_tc(nd, io, o, B, workspace, workspace_bytes, s)
+                                : launch_infer_wide(nd, io, o, B, workspace, workspace_bytes, s);
   set_error("precision %d not implemented", o->precision);
   return MCPC_ERR_UNSUPPORTED;
 }

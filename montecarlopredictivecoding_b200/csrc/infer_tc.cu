@@ -701,6 +701,13 @@ int choose_nr(int B) {
 
 }  // namespace
 
+bool infer_tc_fits(const NetDev& nd, int B) {
+  if (getenv("MCPC_FORCE_STREAMING") != nullptr) return false;     // testing hook: exercise the streaming path on small nets
+  TcParams p{};
+  size_t smem = 0, packed = 0;
+  return plan_tc(nd, 16, &p, &smem, &packed) == MCPC_OK;
+}
+
 int infer_tc_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes) {
   TcParams p{};
   size_t smem = 0, packed = 0;

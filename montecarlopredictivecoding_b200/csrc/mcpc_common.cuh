@@ -68,6 +68,10 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
                     cudaStream_t stream);
 void save_layout_bf16(const NetDev& nd, int* g_off, int* g_width, int* f_off, int* f_width);
 int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_save, cudaStream_t stream);
+bool infer_tc_fits(const NetDev& nd, int B);
+int infer_wide_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes);
+int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B, void* ws, size_t ws_bytes,
+                      cudaStream_t stream);
 int launch_umma_probe(const float* Wt, const float* Bx, const float* G, int Kin, int N, float* D1, float* D2, void* ws,
                       cudaStream_t stream);
 

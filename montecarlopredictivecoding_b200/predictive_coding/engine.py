@@ -49,6 +49,9 @@ class InferCall:
     save_begin: int = 0
     save_end: int = 0
     precision: int = N.PREC_FP32
+    # MODE_STREAMING: accumulators of the weight update of steps [save_begin, save_end) (instead of save_g/save_f)
+    gW: Optional[List[Optional[torch.Tensor]]] = None
+    gb: Optional[List[Optional[torch.Tensor]]] = None
 
 
 def net_struct(plan: NetPlan, top: TopPlan, energy_coefficient: float) -> N.McpcNet:
@@ -105,6 +108,13 @@ class NativeEngine:
                 "mcpc_save_layout")
         return gw.value, fw.value, (torch.float32 if eb.value == 4 else torch.bfloat16)
 
+    def infer_mode(self, plan: NetPlan, top: TopPlan, B: int, precision: int) -> int:
+        """N.MODE_*: how mcpc_infer will execute this network (resident one-launch vs streaming per-step GEMMs)."""
+        net = net_struct(plan, top, 1.0)
+        mode = C.c_int32(0)
+        N.check(self._lib.mcpc_infer_mode(C.byref(net), B, precision, C.byref(mode)), "mcpc_infer_mode")
+        return mode.value
+
     def infer(self, c: InferCall) -> None:
         plan = c.plan
         dev = c.x[0].device
@@ -122,6 +132,10 @@ class NativeEngine:
                 io.x_grad[l] = _ptr(c.x_grad[l], "x_grad")
             if c.traj_x and c.traj_x[l] is not None:
                 io.traj_x[l] = _ptr(c.traj_x[l], "traj_x")
+        if c.gW is not None:
+            for i in range(len(c.gW)):
+                io.gW[i] = _ptr(c.gW[i], "gW")
+                io.gb[i] = _ptr(c.gb[i], "gb")
         io.inputs = _ptr(c.inputs, "inputs")
         io.target = _ptr(c.target, "target")
         io.noise = _ptr(c.noise, "noise")

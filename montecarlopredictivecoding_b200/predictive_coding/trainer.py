@@ -687,6 +687,8 @@ class PCTrainer(object):
         seed = (self._seed + 0x9E3779B97F4A7C15 * self._noise_epoch) & 0xFFFFFFFFFFFFFFFF
 
         W, b = self._param_tensors(netp)
+        streaming = hasattr(eng, "infer_mode") and \
+            eng.infer_mode(netp, top, B, self._precision) == N.MODE_STREAMING_BF16
         later_p_updates = sorted(self._update_p_set)
         segs = self._segments(T, split_last=(want_traj and not every_t))
         flat = None
@@ -704,7 +706,7 @@ class PCTrainer(object):
             row_bytes = (4 if s_dtype == torch.float32 else 2) * B * (g_w + f_w)
             max_save = max(1, self._save_budget_bytes // max(row_bytes, 1))
             cuts = [(t0, t1)]
-            if need_grads and (t1 - win_begin) > max_save:
+            if need_grads and not streaming and (t1 - win_begin) > max_save:
                 cuts = [(t0, win_begin + max_save)] if win_begin + max_save > t0 else []
                 s = win_begin + max_save
                 while s < t1:
@@ -716,8 +718,9 @@ class PCTrainer(object):
                 save_g = save_f = None
                 if need_grads and c1 > win_begin:
                     sb, se = max(win_begin, c0) - c0, n
-                    save_g = self._buffer("save_g", (se - sb, B, g_w), s_dtype, device)
-                    save_f = self._buffer("save_f", (se - sb, B, f_w), s_dtype, device)
+                    if not streaming:
+                        save_g = self._buffer("save_g", (se - sb, B, g_w), s_dtype, device)
+                        save_f = self._buffer("save_f", (se - sb, B, f_w), s_dtype, device)
                 rec_in_cut = want_traj and (every_t or c1 == T)
                 call = InferCall(
                     plan=netp, top=top, energy_coefficient=self._energy_coefficient, B=B, W=W, b=b, x=xs,
@@ -730,7 +733,9 @@ class PCTrainer(object):
                     traj_x=[None if (tx is None or not rec_in_cut) else (tx[c0:c1] if every_t else tx) for tx in traj_x],
                     traj_out=None if (traj_out is None or not rec_in_cut) else (traj_out[c0:c1] if every_t else traj_out),
                     traj_every=1, save_g=save_g, save_f=save_f, save_begin=sb, save_end=se,
-                    precision=self._precision)
+                    precision=self._precision,
+                    gW=gW if (streaming and need_grads and se > sb) else None,
+                    gb=gb if (streaming and need_grads and se > sb) else None)
                 eng.infer(call)
                 n_launch += 1
                 if x_opt["kind"] == N.OPT_ADAM and (c0 in self._update_x_set):

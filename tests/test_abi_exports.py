@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_struct_sizes_match_header_layout():
     # sizes computed from the header by hand: any drift between the C structs and the ctypes mirrors shows here
     assert ctypes.sizeof(N.McpcNet) == 4 * (2 + 8 + 1 + 8 + 8 + 1 + 1 + 1 + 1)
-    assert ctypes.sizeof(N.McpcIO) == 8 * (9 + 9 + 8 + 3 + 8 + 8 + 8 + 2 + 8 + 1 + 2)
+    assert ctypes.sizeof(N.McpcIO) == 8 * (9 + 9 + 8 + 3 + 8 + 8 + 8 + 2 + 8 + 1 + 9 + 9 + 2)
     assert ctypes.sizeof(N.McpcOpts) == 8 * 7 + 4 * 10
     assert ctypes.sizeof(N.McpcGradIO) == 8 * (3 + 9 + 9)
 
