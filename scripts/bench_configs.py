@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Secondary measurements (one JSON line per workload) for the configs of BASELINE.json that are not the
+bench.py headline: C1 figure_2 linear model (latency), C3 65,536-chain sampling, C4 deterministic PC (Adam),
+C5 wide 4x4096.  Usage: python scripts/bench_configs.py [c1 c3 c4 c5] [--precision bf16|fp32]"""
+import json
+import os
+import sys
+import warnings
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+warnings.simplefilter("ignore")
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+import torch.optim as optim  # noqa: E402
+
+from montecarlopredictivecoding_b200 import mcpc_utils as mu  # noqa: E402
+from montecarlopredictivecoding_b200 import predictive_coding as pc  # noqa: E402
+
+DEV = torch.device("cuda:0")
+PEAK_TF = 1663.5
+if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")):
+    PEAK_TF = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("bf16_tflops", PEAK_TF)
+
+
+def timed(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return min(ts)
+
+
+def c1(prec):
+    model = nn.Sequential(nn.Linear(1, 1), pc.PCLayer(sample_x_fn=mu.sample_x_fn_cte), nn.Linear(1, 1, bias=False)).to(DEV)
+    model.train()
+    nn.init.constant_(model[0].bias, 0.2)
+    nn.init.constant_(model[2].weight, 2.0)
+    T = 10000
+    tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.02}, update_p_at="never", plot_progress_at=[])
+    tr.set_precision(prec)
+    out = {}
+
+    def run():
+        out["res"] = tr.train_on_batch(torch.zeros(1, 1, device=DEV), loss_fn=mu.fe_fn,
+                                        loss_fn_kwargs={"_target": torch.ones(1, 1, device=DEV), "_var": 1.0},
+                                        callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": tr},
+                                        is_log_progress=False, is_return_representations=True)
+    s = timed(run)
+    reps = torch.stack(out["res"]["representations"][1000:])
+    return {"workload": "C1 figure_2 linear-Gaussian, B=1, T=10000, per-step representations", "precision": prec,
+            "steps_per_s": T / s, "ms": s * 1e3, "posterior_mean": float(reps.mean()), "posterior_var": float(reps.var()),
+            "analytic": [0.44, 0.2]}
+
+
+def ml_model(act="relu", dims=(20, 128, 128)):
+    torch.manual_seed(0)
+    cfg = {"input_size": dims[0], "hidden_size": dims[1], "hidden2_size": dims[2], "output_size": 784, "activation_fn": act}
+    return mu.get_model(cfg, use_cuda=False).to(DEV)
+
+
+def c3(prec, B=65536, T=1000):
+    model = ml_model()
+    tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.1}, update_p_at="never", plot_progress_at=[])
+    tr.set_precision(prec)
+    z = torch.zeros(B, 20, device=DEV)
+    pcs = [m for m in model if isinstance(m, pc.PCLayer)]
+    x0 = [torch.randn(B, d, device=DEV) for d in (20, 128, 128)]
+    for layer, v in zip(pcs, x0):
+        layer._sample_x_fn = (lambda inputs, v=v: v.clone())
+    first = [True]
+
+    def run():
+        tr.train_on_batch(z, loss_fn=mu.zero_fn, callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": tr},
+                          is_sample_x_at_batch_start=first[0], is_log_progress=False, is_return_results_every_t=False)
+        first[0] = False
+    s = timed(run, reps=2)
+    flops = B * T * 4 * (20 * 128 + 128 * 128)
+    return {"workload": f"C3 sampling, {B} chains, T={T}, zero_fn (sensory Linear is readout only)", "precision": prec,
+            "latent_updates_per_s": B * 3 * T / s, "ms": s * 1e3, "us_per_step": s / T * 1e6,
+            "algorithmic_tflops": flops / s / 1e12, "frac_of_bf16_peak": flops / s / 1e12 / PEAK_TF}
+
+
+def c4(prec, B=1024, T=250):
+    model = ml_model("tanh", (25, 128, 128))
+    tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.Adam, optimizer_x_kwargs={"lr": 0.3}, update_p_at="last",
+                      optimizer_p_fn=optim.Adam, optimizer_p_kwargs={"lr": 0.01}, plot_progress_at=[])
+    tr.set_precision(prec)
+    z = torch.zeros(B, 25, device=DEV)
+    y = (torch.rand(B, 784, device=DEV) < 0.5).float()
+
+    def run():
+        tr.train_on_batch(z, loss_fn=mu.bernoulli_fn_mask, loss_fn_kwargs={"_target": y, "_var": 1.0}, is_log_progress=False,
+                          is_return_results_every_t=False)
+    s = timed(run)
+    return {"workload": f"C4 deterministic PC (pc_ml shape 25-128-128->784 tanh), Adam lr 0.3, T={T}, masked BCE, B={B}",
+            "precision": prec, "latent_updates_per_s": B * 3 * T / s, "ms": s * 1e3, "us_per_step": s / T * 1e6,
+            "images_per_s": B / s}
+
+
+def c5(prec, B=2048, T=20, width=4096, L=4):
+    torch.manual_seed(0)
+    mods, prev = [], width
+    for _ in range(L):
+        mods += [nn.Linear(prev, width), pc.PCLayer(sample_x_fn=mu.sample_x_fn_normal), nn.Tanh()]
+    mods.append(nn.Linear(width, width))
+    model = nn.Sequential(*mods)
+    model.train()
+    with torch.no_grad():
+        for m in model:
+            if isinstance(m, nn.Linear):
+                m.weight.normal_(0, (1.0 / width) ** 0.5)
+                m.bias.zero_()
+    model.to(DEV)
+    tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.01}, update_p_at="last",
+                      accumulate_p_at=list(range(T)), optimizer_p_fn=optim.SGD, optimizer_p_kwargs={"lr": 1e-4},
+                      plot_progress_at=[])
+    tr.set_precision(prec)
+    z = torch.zeros(B, width, device=DEV)
+    y = torch.randn(B, width, device=DEV)
+    first = [True]
+
+    def run():
+        tr.train_on_batch(z, loss_fn=mu.fe_fn, loss_fn_kwargs={"_target": y, "_var": 1.0}, callback_after_t=mu.random_step,
+                          callback_after_t_kwargs={"_pc_trainer": tr}, is_sample_x_at_batch_start=first[0],
+                          is_log_progress=False, is_return_results_every_t=False)
+        first[0] = False
+    s = timed(run, reps=2)
+    mac = L * width * width          # Linear_0 sees zero inputs; 3 hidden + 1 output contraction of width^2 each ... L total
+    flops = B * T * 6 * mac          # fwd + back-projection + dW every step
+    return {"workload": f"C5 wide {L}x{width}->{width} tanh Gaussian, B={B} per GPU, T={T}, dW every step", "precision": prec,
+            "ms_per_step": s / T * 1e3, "latent_updates_per_s": B * L * T / s, "images_per_s_T100": B / (s / T * 100),
+            "algorithmic_tflops": flops / s / 1e12, "frac_of_bf16_peak": flops / s / 1e12 / PEAK_TF}
+
+
+if __name__ == "__main__":
+    prec = "bf16"
+    if "--precision" in sys.argv:
+        prec = sys.argv[sys.argv.index("--precision") + 1]
+    which = [a for a in sys.argv[1:] if a in ("c1", "c3", "c4", "c5")] or ["c1", "c3", "c4", "c5"]
+    for w in which:
+        try:
+            print(json.dumps({"c1": c1, "c3": c3, "c4": c4, "c5": c5}[w](prec)))
+        except Exception as exc:  # noqa: BLE001
+            print(json.dumps({"workload": w, "error": repr(exc)[:300]}))
+        sys.stdout.flush()
