@@ -51,6 +51,7 @@ def parse():
                          "in tests/test_gpu_bf16.py); fp32 = reference-exact CUDA-core path (1e-5 parity)")
     ap.add_argument("--cpu-sample-steps", type=int, default=int(os.environ.get("MCPC_CPU_SAMPLE_STEPS", "30")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
     return ap.parse_args()
 
 
@@ -365,6 +366,20 @@ def run_ours(args):
                          "note": "4*MAC flops per chain-step x B x T (SURVEY §8d); latents stay on chip, HBM traffic is the "
                                  "saved dW operands only"},
         }
+        if world == 1 and not args.no_other_workloads:
+            # the other configs of BASELINE.json, short runs (scripts/bench_configs.py has the full versions)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "scripts"))
+                import bench_configs as bc
+                del model, map_trainer, mcpc_trainer
+                torch.cuda.empty_cache()
+                line["other_workloads"] = {
+                    "C3_sampling_65536_chains": bc.c3(args.precision, B=65536, T=200),
+                    "C5_wide_4x4096_B2048": bc.c5(args.precision, B=2048, T=10),
+                    "C4_deterministic_pc_adam": bc.c4(args.precision),
+                }
+            except Exception as exc:  # noqa: BLE001
+                line["other_workloads"] = {"error": repr(exc)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             n = max(2, args.cpu_sample_steps)
             cpu_port_run(B, 2)

@@ -221,6 +221,15 @@ CASES = {
                               accumulate_p_at=[4, 5, 6, 7, 8, 9, 10, 11], opt_p="adam", opt_p_kwargs={"lr": 0.01}),
                  langevin=True, sample_x=False),
         ]),
+    # deterministic PC path on the shipped pc_ml_1 checkpoint (table_1.py:214-225): [25,128,128] tanh, Adam lr 0.3,
+    # masked BCE as get_mse_rec runs it (utils/training_evaluation.py:143-174); horizon kept below the chaotic
+    # divergence of Adam trajectories
+    "pc_ml_checkpoint_map": dict(
+        dims=[25, 128, 128], d_out=784, act="tanh", loss="bernoulli_mask", B=16, sampler="uniform",
+        checkpoint="pc_ml_1",
+        calls=[
+            dict(trainer=dict(T=40, opt_x="adam", lr_x=0.3), sample_x=True),
+        ]),
     # deterministic PC path: tanh, Adam on x, masked BCE, PC training with p-step at last (table_1.py:214-225)
     "pc_tanh_adam_mask": dict(
         dims=[5, 16, 16], d_out=24, act="tanh", loss="bernoulli_mask", B=8, sampler="uniform",
