@@ -90,7 +90,9 @@ struct Barriers {
   uint64_t w_full[2], w_empty[2];
   uint64_t dA_full[2], dA_empty[2];
   uint64_t g_full[2], g_empty[2];
-  uint64_t acts_ready, bp_full;
+  uint64_t acts_ready[kMaxL];   // act(x_l) / x_l of the coming step are in place (group U -> MMA warp, group T)
+  uint64_t bp_ready[kMaxL];     // back-projection into layer l complete (MMA warp -> group U)
+  uint64_t g_ready[kMaxL];      // own-layer error of layer l stored in TMEM (group T -> group U)
 };
 
 __device__ __forceinline__ float warp_sum_tc(float v) {
@@ -136,17 +138,24 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
   return k == 0 ? n[0] : (k == 1 ? n[1] : (k == 2 ? n[2] : n[3]));
 }
 
-// NR chains per CTA; every epilogue thread owns one unit (TMEM lane) and RPT of the NR chains (columns), so
-// NR/RPT warps share each 32-lane quarter of TMEM: 4*NR/RPT epilogue warps + MMA warp + loader warp.
-template <int NR, int RPT>
-__global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
-  constexpr int CS = NR / RPT;               // column groups
-  constexpr int kEpi = 128 * CS;             // epilogue threads
-  constexpr int kMmaWarp = 4 * CS, kLoadWarp = 4 * CS + 1;
+// NR chains per CTA.  Warp roles (18 warps):
+//   warps 8-15  group T: per-tile epilogue (errors of the units a weight tile predicts, G operand for phase B)
+//   warps 0-7   group U: latent update of one layer as soon as its back-projection is complete
+//   warp 16     MMA issuer (converged warp, one elected lane issues tcgen05.mma / commit)
+//   warp 17     weight-tile loader (bulk async copies for tiles that are not resident)
+// Every epilogue thread owns one unit (TMEM lane) and RPT = NR/2 of the chains (two warps per 32-lane quarter).
+// Tiles are visited top-down (output tiles first, then Linear L-1 ... 1): the update of layer l only needs the
+// tiles of Linear l+1 (back-projection) and Linear l (own error), so group U works on layer l while the tensor
+// pipe and group T are already busy with the NEXT step's output tiles -- the step is pipelined across layers.
+template <int NR>
+__global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int RPT = NR / 2;
+  constexpr int kGrp = 256;                  // threads per epilogue group
+  constexpr int kMmaWarp = 16, kLoadWarp = 17;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Barriers bars;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_red[2][4 * CS][2];
+  __shared__ float s_red[2][2][8][2];        // [group][step parity][warp][energy, loss]
 
   const NetDev& nd = p.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -159,12 +168,15 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
       mbar_init(&bars.w_full[i], 1);
       mbar_init(&bars.w_empty[i], 1);
       mbar_init(&bars.dA_full[i], 1);
-      mbar_init(&bars.dA_empty[i], kEpi);
-      mbar_init(&bars.g_full[i], kEpi);
+      mbar_init(&bars.dA_empty[i], kGrp);
+      mbar_init(&bars.g_full[i], kGrp);
       mbar_init(&bars.g_empty[i], 1);
     }
-    mbar_init(&bars.acts_ready, kEpi);
-    mbar_init(&bars.bp_full, 1);
+    for (int l = 0; l < kMaxL; ++l) {
+      mbar_init(&bars.acts_ready[l], kGrp);
+      mbar_init(&bars.bp_ready[l], 1);
+      mbar_init(&bars.g_ready[l], kGrp);
+    }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
@@ -174,11 +186,10 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
   const uint32_t tmem = tmem_base_s;
   // TMEM column map (fp32 columns): [dA0 | dA1 | bp_h ... | x_h ... | gown_h ...], NR columns each
   const uint32_t col_dA = 0, col_bp = 2 * NR, col_x = (2 + HT) * NR, col_g = (2 + 2 * HT) * NR;
-  const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;
+  const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;      // table order: output tiles, then Linear L-1 ... 1
 
   // =====================================================================================================
   if (warp == kLoadWarp) {
-    // ---------------- weight loader ----------------
     if (lane == 0) {
       uint32_t res_bytes = 0;
       for (int t = 0; t < n_tiles_all; ++t)
@@ -191,12 +202,11 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
       } else {
         mbar_arrive(&bars.w_res);
       }
-      uint32_t empty_phase = 3;                // bit s: parity to wait for on w_empty[s] (fresh barrier: previous phase)
+      uint32_t empty_phase = 3;
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
         const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
-        const int nt = p.n_hid_tiles + (need_out ? p.n_out_tiles : 0);
-        for (int t = 0; t < nt; ++t) {
+        for (int t = need_out ? 0 : p.n_out_tiles; t < n_tiles_all; ++t) {
           const Tile& T = p.tiles[t];
           if (T.slot < 0) continue;
           mbar_wait(&bars.w_empty[T.slot], (empty_phase >> T.slot) & 1u);
@@ -207,374 +217,457 @@ __global__ void __launch_bounds__(128 * (NR / RPT) + 64, 1) infer_tc_kernel(cons
       }
     }
   } else if (warp == kMmaWarp) {
-    // ---------------- MMA issuer ----------------
-    // The whole warp runs the control flow (converged, so descriptors stay in uniform registers); one
-    // elected lane issues tcgen05.mma / tcgen05.commit.  Issuing from inside `if (lane == 0)` costs ~170
-    // cycles per instruction (warp-uniformisation loop), converged + elect.sync ~10x less.
-    {
-      const uint32_t id_a = idesc_bf16(128, NR, false, false);
-      const uint32_t id_b = idesc_bf16(128, NR, true, false);
-      const uint32_t smem_base = smem_u32(smem);
-      uint32_t ph_wfull = 0, ph_dAe = 3, ph_gfull = 0, ph_acts = 0;
-      uint32_t bp_started = 0;               // bit h: accumulator bp_h already written in this step
-      mbar_wait(&bars.w_res, 0);
+    // ---------------- MMA issuer (converged warp; descriptors stay in uniform registers) ----------------
+    const uint32_t id_a = idesc_bf16(128, NR, false, false);
+    const uint32_t id_b = idesc_bf16(128, NR, true, false);
+    const uint32_t smem_base = smem_u32(smem);
+    uint32_t ph_wfull = 0, ph_dAe = 3, ph_gfull = 0;
+    uint32_t bp_started = 0;
+    mbar_wait(&bars.w_res, 0);
 
-      auto phaseB = [&](int t) {
-        const Tile& T = p.tiles[t];
-        const int gb = t & 1;
-        const bool has_b = (T.lin < L) || nd.top_has_grad;      // readout-only output tiles feed nothing back
-        if (has_b) {
-          mbar_wait(&bars.g_full[gb], (ph_gfull >> gb) & 1u);
-          ph_gfull ^= 1u << gb;
-          fence_after_sync();
-          const int in_layer = T.lin - 1;
-          const uint64_t bd0 = smem_desc(smem_base + p.gbuf_off[gb], 128u, 2048u);
-          const uint32_t a_step = (uint32_t)(2 * T.sbo) >> 4;    // descriptor start-address field is in 16 B units
-          for (int u = 0; u < p.ut[in_layer]; ++u) {
-            const int h = p.h_off[in_layer] + u;
-            const uint64_t ad0 = smem_desc(smem_base + T.smem_off + u * 2048, (uint32_t)T.sbo, 128u);
-            const uint32_t dcol = tmem + col_bp + h * NR;
-            const bool acc0 = (bp_started >> h) & 1u;
-            if (elect_one()) {
-              mma_bf16_ss(dcol, ad0, bd0, id_b, acc0);
-#pragma unroll
-              for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * 16), id_b, true);
-            }
-            __syncwarp();
-            bp_started |= 1u << h;
-          }
-          if (elect_one()) mma_commit(&bars.g_empty[gb]);
-          __syncwarp();
-        }
-        if (T.slot >= 0) {
-          if (elect_one()) mma_commit(&bars.w_empty[T.slot]);
-          __syncwarp();
-        }
-      };
-
-      for (int ts = 0; ts < p.n_steps; ++ts) {
-        const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
-        const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
-        const int nt = p.n_hid_tiles + (need_out ? p.n_out_tiles : 0);
-        bp_started = 0;
-        mbar_wait(&bars.acts_ready, ph_acts);
-        ph_acts ^= 1;
+    auto phaseB = [&](int t, int k, bool last_of_lin) {
+      const Tile& T = p.tiles[t];
+      const int gb = k & 1;
+      const bool has_b = (T.lin < L) || nd.top_has_grad;
+      if (has_b) {
+        mbar_wait(&bars.g_full[gb], (ph_gfull >> gb) & 1u);
+        ph_gfull ^= 1u << gb;
         fence_after_sync();
-        TC_STAMP(lane == 0, ts, 0);
-        for (int t = 0; t < nt; ++t) {
-          const Tile& T = p.tiles[t];
-          if (T.slot >= 0) {
-            mbar_wait(&bars.w_full[T.slot], (ph_wfull >> T.slot) & 1u);
-            ph_wfull ^= 1u << T.slot;
-          }
-          const int db = t & 1;
-          mbar_wait(&bars.dA_empty[db], (ph_dAe >> db) & 1u);
-          ph_dAe ^= 1u << db;
-          fence_after_sync();
-          const int in_layer = T.lin - 1;
-          const uint32_t act_sbo = (uint32_t)(p.act_kp[in_layer] / 8) * 128u;
-          const uint64_t ad0 = smem_desc(smem_base + T.smem_off, 128u, (uint32_t)T.sbo);
-          const uint64_t bd0 = smem_desc(smem_base + p.act_off[in_layer], 128u, act_sbo);
-          const uint32_t dcol = tmem + col_dA + db * NR;
-          const int nk = T.Kp / 16;
+        const int in_layer = T.lin - 1;
+        const uint64_t bd0 = smem_desc(smem_base + p.gbuf_off[gb], 128u, 2048u);
+        const uint32_t a_step = (uint32_t)(2 * T.sbo) >> 4;
+        for (int u = 0; u < p.ut[in_layer]; ++u) {
+          const int h = p.h_off[in_layer] + u;
+          const uint64_t ad0 = smem_desc(smem_base + T.smem_off + u * 2048, (uint32_t)T.sbo, 128u);
+          const uint32_t dcol = tmem + col_bp + h * NR;
+          const bool acc0 = (bp_started >> h) & 1u;
           if (elect_one()) {
-            mma_bf16_ss(dcol, ad0, bd0, id_a, false);
-            for (int k8 = 0; k8 < nk; k8 += 8) {
+            mma_bf16_ss(dcol, ad0, bd0, id_b, acc0);
 #pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {
-                const int ks = k8 + kk;
-                if (ks > 0 && ks < nk) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), id_a, true);
-              }
-            }
-            mma_commit(&bars.dA_full[db]);
+            for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * 16), id_b, true);
           }
           __syncwarp();
-          TC_STAMP(lane == 0, ts, 1 + t);
-          if (t > 0) phaseB(t - 1);
-          TC_STAMP(lane == 0, ts, 11 + t);
+          bp_started |= 1u << h;
         }
-        if (nt > 0) phaseB(nt - 1);
-        if (elect_one()) mma_commit(&bars.bp_full);
+        if (elect_one()) {
+          mma_commit(&bars.g_empty[gb]);
+          if (last_of_lin) mma_commit(&bars.bp_ready[in_layer]);     // back-projection into layer lin-1 is complete
+        }
         __syncwarp();
-        TC_STAMP(lane == 0, ts, 21);
       }
-    }
-  } else {
-    // ---------------- epilogue: thread <-> (TMEM lane = unit, RPT of the NR chains) ----------------
-    const int q = warp & 3, cg = warp >> 2;
-    const int ln = q * 32 + lane;                                      // unit index inside a 128-unit tile
-    const int cbase = cg * RPT;                                        // first chain (column) of this thread
-    const int rb = row0 + cbase;                                       // its global row
-    const int nrow = max(0, min(RPT, p.B - rb));                       // valid chains of this thread
-    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase;
-    // byte offset of (chain cbase, unit ln) inside a [NR x 128] K-major operand (LBO 128, SBO 2048); chain i adds
-    // (i>>3)*SBO + (i&7)*16
-    const uint32_t g_thread_off = (uint32_t)(cbase >> 3) * 2048u + (uint32_t)(cbase & 7) * 16u + (uint32_t)(ln >> 3) * 128u +
-                                  (uint32_t)(ln & 7) * 2u;
-    auto bar_epi = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory"); };
-
-    // zero the bf16 operand buffers (padding columns must stay finite), then load the latents
-    for (int i = tid * 16; i < p.gbuf_off[1] + NR * 256 - p.act_off[0]; i += kEpi * 16)
-      *reinterpret_cast<uint4*>(smem + p.act_off[0] + i) = make_uint4(0, 0, 0, 0);
-    bar_epi();
-    for (int h = 0; h < HT; ++h) {
-      const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
-      const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
-      uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
-                      (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
-      float xv[RPT];
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        xv[i] = (u < dl && i < nrow) ? p.x[l][(size_t)(rb + i) * dl + u] : 0.0f;
-        if (u < dl)
-          *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(nd.act[l], xv[i]));
+      if (T.slot >= 0) {
+        if (elect_one()) mma_commit(&bars.w_empty[T.slot]);
+        __syncwarp();
       }
-      __syncwarp();
-      tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
-    }
-    tmem_st_wait();
-    fence_async_smem();
-    fence_before_sync();
-    mbar_arrive(&bars.acts_ready);
-
-    uint32_t ph_dAf = 0, ph_ge = 3, ph_bp = 0;
-    double b1p = p.b1_pow0, b2p = p.b2_pow0;
+    };
 
     for (int ts = 0; ts < p.n_steps; ++ts) {
-      const int t_abs = p.t_begin + ts;
-      const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
-      const int slot = ts - p.save_begin;
       const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
-      const int rec = do_traj ? ts / p.traj_every : 0;
       const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
-      const int nt = p.n_hid_tiles + (need_out ? p.n_out_tiles : 0);
-      const bool last = (ts == p.n_steps - 1);
-      float e_part = 0.0f, l_part = 0.0f;
-      // row-major [slot][row] bases of this thread's first chain in the save / trajectory tensors
-      __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * p.sg_pitch : nullptr;
-      __nv_bfloat16* sf_row = do_save ? p.save_f + ((size_t)slot * p.B + rb) * p.sf_pitch : nullptr;
-      TC_STAMP(tid == 0, ts, 32);
-
-      // ---------- per-tile epilogue: errors of the units this tile predicts ----------
-      for (int t = 0; t < nt; ++t) {
+      const int t_first = need_out ? 0 : p.n_out_tiles;
+      bp_started = 0;
+      uint32_t acts_waited = 0;
+      TC_STAMP(lane == 0, ts, 0);
+      for (int t = t_first; t < n_tiles_all; ++t) {
         const Tile& T = p.tiles[t];
-        const int db = t & 1, gb = t & 1;
-        const bool is_out = (T.lin == L);
-        const bool has_b = !is_out || nd.top_has_grad;
-        const int dl = is_out ? nd.d_out : nd.dims[T.lin];
-        const int u = T.out_tile * 128 + ln;
-        const bool uvalid = u < dl;
-        const float bias = (uvalid && p.b[T.lin] != nullptr) ? __ldg(p.b[T.lin] + u) : 0.0f;
-        // targets of this tile: independent loads issued before the wait on the tensor pipe (a load inside
-        // the element loop would be serialised behind the save/trajectory stores it may alias)
-        float yv[RPT];
-        const bool use_y = is_out && uvalid && (u >= nd.mask_start) && nd.top >= MCPC_TOP_GAUSS;
-        if (use_y) {
-          const float* yp = p.target + (size_t)rb * nd.d_out + u;
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) yv[i] = (i < nrow) ? __ldg(yp + (size_t)i * nd.d_out) : 0.0f;
+        const int k = t - t_first;
+        const int in_layer = T.lin - 1;
+        if (!((acts_waited >> in_layer) & 1u)) {                    // act(x_{lin-1}) of THIS step: written by group U
+          mbar_wait(&bars.acts_ready[in_layer], ts & 1);
+          acts_waited |= 1u << in_layer;
         }
-        mbar_wait(&bars.dA_full[db], (ph_dAf >> db) & 1u);
-        ph_dAf ^= 1u << db;
-        if (has_b) {
-          mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
-          ph_ge ^= 1u << gb;
+        if (T.slot >= 0) {
+          mbar_wait(&bars.w_full[T.slot], (ph_wfull >> T.slot) & 1u);
+          ph_wfull ^= 1u << T.slot;
         }
+        const int db = k & 1;
+        mbar_wait(&bars.dA_empty[db], (ph_dAe >> db) & 1u);
+        ph_dAe ^= 1u << db;
         fence_after_sync();
-        TC_STAMP(tid == 0, ts, 33 + t);
-        uint8_t* gptr = smem + p.gbuf_off[gb] + g_thread_off;
-        float d[RPT];
-        tmem_ld<RPT>(lane_addr + col_dA + db * NR, d);
-        if (!is_out) {
-          const int h = T.h_out;
-          const float ce = 0.5f * nd.c[T.lin], gc = nd.gc[T.lin];
-          float xv[RPT], gv[RPT];
-          tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
-          __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[T.lin] + u : nullptr;
+        const uint32_t act_sbo = (uint32_t)(p.act_kp[in_layer] / 8) * 128u;
+        const uint64_t ad0 = smem_desc(smem_base + T.smem_off, 128u, (uint32_t)T.sbo);
+        const uint64_t bd0 = smem_desc(smem_base + p.act_off[in_layer], 128u, act_sbo);
+        const uint32_t dcol = tmem + col_dA + db * NR;
+        const int nk = T.Kp / 16;
+        if (elect_one()) {
+          mma_bf16_ss(dcol, ad0, bd0, id_a, false);
+          for (int k8 = 0; k8 < nk; k8 += 8) {
 #pragma unroll
-          for (int i = 0; i < RPT; ++i) {
-            const float eps = xv[i] - (d[i] + bias);
-            const float G = uvalid ? -gc * eps : 0.0f;
-            gv[i] = G;
-            if (uvalid && i < nrow) {
-              e_part = fmaf(ce * eps, eps, e_part);
-              if (sg != nullptr) sg[(size_t)i * p.sg_pitch] = __float2bfloat16(G);
+            for (int kk = 0; kk < 8; ++kk) {
+              const int ks = k8 + kk;
+              if (ks > 0 && ks < nk) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), id_a, true);
             }
-            *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = __float2bfloat16(G);
           }
-          tmem_st<RPT>(lane_addr + col_g + h * NR, gv);
-        } else {
-          __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[L] + u : nullptr;
-          float* to = (do_traj && p.traj_out != nullptr && uvalid) ? p.traj_out + ((size_t)rec * p.B + rb) * nd.d_out + u : nullptr;
-          const bool bern = nd.top == MCPC_TOP_BERNOULLI;
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) {
-            const float o = d[i] + bias;
-            float e_out = 0.0f;
-            if (uvalid && i < nrow) {
-              if (use_y) {
-                const float y = yv[i];
-                if (!bern) {
-                  const float dd = o - y;
-                  l_part = fmaf(0.5f * nd.inv_var * dd, dd, l_part);
-                  e_out = dd * nd.inv_var;
-                } else {
-                  const float z = __expf(-fabsf(o));
-                  l_part += fmaxf(o, 0.0f) - o * y + __logf(1.0f + z);
-                  e_out = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - y;
-                }
-              }
-              if (to != nullptr) to[(size_t)i * nd.d_out] = o;
-              if (sg != nullptr) sg[(size_t)i * p.sg_pitch] = __float2bfloat16(e_out);
-            }
-            if (has_b) *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = __float2bfloat16(e_out);
-          }
+          mma_commit(&bars.dA_full[db]);
         }
-        tmem_st_wait();
-        fence_before_sync();
-        mbar_arrive(&bars.dA_empty[db]);
-        if (has_b) {
-          fence_async_smem();
-          mbar_arrive(&bars.g_full[gb]);
-        }
-        TC_STAMP(tid == 0, ts, 43 + t);
+        __syncwarp();
+        TC_STAMP(lane == 0, ts, 1 + k);
+        if (t > t_first) phaseB(t - 1, k - 1, p.tiles[t - 1].lin != T.lin);
       }
+      if (n_tiles_all > t_first) phaseB(n_tiles_all - 1, n_tiles_all - 1 - t_first, true);
+      TC_STAMP(lane == 0, ts, 21);
+    }
+  } else {
+    // ---------------- epilogue groups ----------------
+    // The SM's warp arbiter favours higher warp ids: the latency-critical tile epilogues (group T) get warps
+    // 8-15, the background layer updates (group U) warps 0-7, the MMA issuer the highest id of all.
+    const int grp = (warp < 8) ? 1 : 0;                                // 0 = tiles (T), 1 = update (U)
+    const int gw = warp & 7;                                           // warp inside the group
+    const int gtid = tid & (kGrp - 1);
+    const int q = warp & 3, cg = (gw >> 2);
+    const int ln = q * 32 + lane;                                      // unit index inside a 128-unit tile
+    const int cbase = cg * RPT;
+    const int rb = row0 + cbase;
+    const int nrow = max(0, min(RPT, p.B - rb));
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase;
+    const uint32_t g_thread_off = (uint32_t)(cbase >> 3) * 2048u + (uint32_t)(cbase & 7) * 16u + (uint32_t)(ln >> 3) * 128u +
+                                  (uint32_t)(ln & 7) * 2u;
 
-      // ---------- update epilogue: latent gradient, optimizer step, Langevin noise ----------
-      mbar_wait(&bars.bp_full, ph_bp);
-      ph_bp ^= 1;
-      fence_after_sync();
-      TC_STAMP(tid == 0, ts, 53);
-      float step_size = 0.0f, inv_bc2_sqrt = 1.0f;
-      const bool adam = (p.optimizer == MCPC_OPT_ADAM);
-      if (adam && p.update_x) {
-        b1p *= p.beta1;
-        b2p *= p.beta2;
-        step_size = (float)(p.lr_d / (1.0 - b1p));
-        inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
-      }
+    if (grp == 1) {
+      // ======================= group U: initial state, then one layer update after the other =======================
+      for (int i = gtid * 16; i < p.gbuf_off[0] - p.act_off[0]; i += kGrp * 16)
+        *reinterpret_cast<uint4*>(smem + p.act_off[0] + i) = make_uint4(0, 0, 0, 0);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       for (int h = 0; h < HT; ++h) {
         const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
-        const bool uvalid = u < dl;
-        const bool has_above = (l + 1 < L) || nd.top_has_grad;
-        const int kind = nd.act[l];
         const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
-        const int gu = nd.off[l] + u;                    // global unit index (Philox counter, noise / save column)
-        float xv[RPT], bp[RPT], gown[RPT];
-        tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
-        if (has_above) {
-          tmem_ld<RPT>(lane_addr + col_bp + h * NR, bp);
-        } else {
+        uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
+                        (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
+        float xv[RPT];
 #pragma unroll
-          for (int i = 0; i < RPT; ++i) bp[i] = 0.0f;
+        for (int i = 0; i < RPT; ++i) {
+          xv[i] = (u < dl && i < nrow) ? p.x[l][(size_t)(rb + i) * dl + u] : 0.0f;
+          if (u < dl)
+            *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(nd.act[l], xv[i]));
         }
-        if (l > 0) {
-          tmem_ld<RPT>(lane_addr + col_g + h * NR, gown);
-        } else {
-          // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
-          const float b0 = (uvalid && p.b[0] != nullptr) ? __ldg(p.b[0] + u) : 0.0f;
-          const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
-          __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + u : nullptr;
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) {
-            const float eps = xv[i] - b0;
-            gown[i] = -gc * eps;
-            if (uvalid && i < nrow) {
-              e_part = fmaf(ce * eps, eps, e_part);
-              if (sg != nullptr) sg[(size_t)i * p.sg_pitch] = __float2bfloat16(gown[i]);
-            }
-          }
-        }
-        if (uvalid) {
-          float mv[RPT], vv[RPT], nz[RPT];
-          const size_t xoff = (size_t)rb * dl + u;
-          if (adam && p.update_x) {
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-              mv[i] = (i < nrow) ? p.m[l][xoff + (size_t)i * dl] : 0.0f;
-              vv[i] = (i < nrow) ? p.v[l][xoff + (size_t)i * dl] : 0.0f;
-            }
-          }
-          if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
-            const float* np_ = p.noise + ((size_t)ts * p.B + rb) * nd.SD + gu;
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) nz[i] = (i < nrow) ? __ldg(np_ + (size_t)i * nd.SD) : 0.0f;
-          } else if (p.noise_mode == MCPC_NOISE_PHILOX) {
-            float nrm[4];
-            uint64_t cur_q = ~0ull;
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-              const uint64_t chain = p.chain_offset + (uint64_t)(rb + i);
-              if ((chain >> 2) != cur_q) {
-                cur_q = chain >> 2;
-                langevin_normals4(p.seed, (uint32_t)gu, (uint32_t)t_abs, cur_q, nrm);
-              }
-              nz[i] = p.noise_scale * sel4(nrm, (uint32_t)(chain & 3));
-            }
-          }
-          uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
-                          (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
-          float* tx = (do_traj && p.traj_x[l] != nullptr) ? p.traj_x[l] + ((size_t)rec * p.B + rb) * dl + u : nullptr;
-          __nv_bfloat16* sf = do_save ? sf_row + p.sg_off[l] + u : nullptr;
-          float* xg = (last && p.xgrad[l] != nullptr) ? p.xgrad[l] + xoff : nullptr;
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) {
-            if (i < nrow) {
-              float x = xv[i];
-              const float a = act_tc(kind, x);
-              const float grad = fmaf(dact_tc(kind, x, a), bp[i], -gown[i]);
-              if (tx != nullptr) tx[(size_t)i * dl] = x;
-              if (sf != nullptr) sf[(size_t)i * p.sf_pitch] = __float2bfloat16(a);
-              if (xg != nullptr) xg[(size_t)i * dl] = grad;
-              if (p.update_x) {
-                if (!adam) {
-                  x = fmaf(-p.lr, grad, x);
-                } else {
-                  const float m1 = fmaf(p.one_minus_b1, grad - mv[i], mv[i]);
-                  const float v1 = fmaf(p.one_minus_b2 * grad, grad, vv[i] * p.beta2f);
-                  p.m[l][xoff + (size_t)i * dl] = m1;
-                  p.v[l][xoff + (size_t)i * dl] = v1;
-                  x = fmaf(-step_size, __fdividef(m1, fmaf(sqrtf(v1), inv_bc2_sqrt, p.adam_eps)), x);
-                }
-              }
-              if (p.noise_mode != MCPC_NOISE_NONE) x = fmaf(-p.lr, nz[i], x);
-              xv[i] = x;
-              *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(kind, x));
-            }
-          }
-        }
-        // .sync.aligned: every lane of the warp must execute the store (padding lanes write back their zeros)
         __syncwarp();
         tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
       }
       tmem_st_wait();
       fence_async_smem();
       fence_before_sync();
-      mbar_arrive(&bars.acts_ready);
-      TC_STAMP(tid == 0, ts, 54);
+      for (int l = 0; l < L; ++l) mbar_arrive(&bars.acts_ready[l]);
 
-      // ---------- per-step scalars ----------
-      e_part = warp_sum_tc(e_part);
-      l_part = warp_sum_tc(l_part);
-      float (*red)[2] = s_red[ts & 1];
-      if (lane == 0) { red[warp][0] = e_part; red[warp][1] = l_part; }
-      bar_epi();
-      if (tid < 2) {
-        float s = 0.0f;
+      double b1p = p.b1_pow0, b2p = p.b2_pow0;
+      const bool adam = (p.optimizer == MCPC_OPT_ADAM);
+      for (int ts = 0; ts < p.n_steps; ++ts) {
+        const int t_abs = p.t_begin + ts;
+        const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
+        const int slot = ts - p.save_begin;
+        const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const int rec = do_traj ? ts / p.traj_every : 0;
+        const bool last = (ts == p.n_steps - 1);
+        float e_part = 0.0f;
+        __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * p.sg_pitch : nullptr;
+        __nv_bfloat16* sf_row = do_save ? p.save_f + ((size_t)slot * p.B + rb) * p.sf_pitch : nullptr;
+        float step_size = 0.0f, inv_bc2_sqrt = 1.0f;
+        if (adam && p.update_x) {
+          b1p *= p.beta1;
+          b2p *= p.beta2;
+          step_size = (float)(p.lr_d / (1.0 - b1p));
+          inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
+        }
+        for (int l = L - 1; l >= 0; --l) {
+          const bool has_above = (l + 1 < L) || nd.top_has_grad;
+          if (has_above) mbar_wait(&bars.bp_ready[l], ts & 1);          // all tiles of Linear l+1 back-projected
+          if (l > 0) mbar_wait(&bars.g_ready[l], ts & 1);               // group T stored the own-layer error of layer l
+          fence_after_sync();
+          TC_STAMP(gtid == 0, ts, 40 + l);
+          const int kind = nd.act[l];
+          const int dl = nd.dims[l];
+          const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
+          for (int hi = 0; hi < p.ut[l]; ++hi) {
+            const int h = p.h_off[l] + hi;
+            const int u = hi * 128 + ln;
+            const bool uvalid = u < dl;
+            const int gu = nd.off[l] + u;
+            float xv[RPT], bp[RPT], gown[RPT];
+            tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
+            if (has_above) {
+              tmem_ld<RPT>(lane_addr + col_bp + h * NR, bp);
+            } else {
 #pragma unroll
-        for (int w = 0; w < 4 * CS; ++w) s += red[w][tid];
-        p.partials[((size_t)ts * p.n_ctas + blockIdx.x) * 2 + tid] = s;
+              for (int i = 0; i < RPT; ++i) bp[i] = 0.0f;
+            }
+            if (l > 0) {
+              tmem_ld<RPT>(lane_addr + col_g + h * NR, gown);
+            } else {
+              // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
+              const float b0 = (uvalid && p.b[0] != nullptr) ? __ldg(p.b[0] + u) : 0.0f;
+              const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
+              __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + u : nullptr;
+#pragma unroll
+              for (int i = 0; i < RPT; ++i) {
+                const float eps = xv[i] - b0;
+                gown[i] = -gc * eps;
+                if (uvalid && i < nrow) {
+                  e_part = fmaf(ce * eps, eps, e_part);
+                  if (sg != nullptr) sg[(size_t)i * p.sg_pitch] = __float2bfloat16(gown[i]);
+                }
+              }
+            }
+            if (uvalid) {
+              float mv[RPT], vv[RPT], nz[RPT];
+#pragma unroll
+              for (int i = 0; i < RPT; ++i) { mv[i] = 0.0f; vv[i] = 0.0f; nz[i] = 0.0f; }
+              const size_t xoff = (size_t)rb * dl + u;
+              if (adam && p.update_x) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                  mv[i] = (i < nrow) ? p.m[l][xoff + (size_t)i * dl] : 0.0f;
+                  vv[i] = (i < nrow) ? p.v[l][xoff + (size_t)i * dl] : 0.0f;
+                }
+              }
+              if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
+                const float* np_ = p.noise + ((size_t)ts * p.B + rb) * nd.SD + gu;
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) nz[i] = (i < nrow) ? __ldg(np_ + (size_t)i * nd.SD) : 0.0f;
+              } else if (p.noise_mode == MCPC_NOISE_PHILOX) {
+                float nrm[4];
+                uint64_t cur_q = ~0ull;
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                  const uint64_t chain = p.chain_offset + (uint64_t)(rb + i);
+                  if ((chain >> 2) != cur_q) {
+                    cur_q = chain >> 2;
+                    langevin_normals4(p.seed, (uint32_t)gu, (uint32_t)t_abs, cur_q, nrm);
+                  }
+                  nz[i] = p.noise_scale * sel4(nrm, (uint32_t)(chain & 3));
+                }
+              }
+              uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
+                              (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
+              float* tx = (do_traj && p.traj_x[l] != nullptr) ? p.traj_x[l] + ((size_t)rec * p.B + rb) * dl + u : nullptr;
+              __nv_bfloat16* sf = do_save ? sf_row + p.sg_off[l] + u : nullptr;
+              float* xg = (last && p.xgrad[l] != nullptr) ? p.xgrad[l] + xoff : nullptr;
+              float av[RPT], gradv[RPT], m1v[RPT], v1v[RPT];
+#pragma unroll
+              for (int i = 0; i < RPT; ++i) {                 // straight-line: RPT independent chains interleave
+                const float x = xv[i];
+                const float a = act_tc(kind, x);
+                av[i] = a;
+                gradv[i] = fmaf(dact_tc(kind, x, a), bp[i], -gown[i]);
+              }
+              if (tx != nullptr) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i)
+                  if (i < nrow) tx[(size_t)i * dl] = xv[i];
+              }
+              if (p.update_x) {
+                if (!adam) {
+#pragma unroll
+                  for (int i = 0; i < RPT; ++i) xv[i] = fmaf(-p.lr, gradv[i], xv[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < RPT; ++i) {
+                    m1v[i] = fmaf(p.one_minus_b1, gradv[i] - mv[i], mv[i]);
+                    v1v[i] = fmaf(p.one_minus_b2 * gradv[i], gradv[i], vv[i] * p.beta2f);
+                    xv[i] = fmaf(-step_size, __fdividef(m1v[i], fmaf(sqrtf(v1v[i]), inv_bc2_sqrt, p.adam_eps)), xv[i]);
+                  }
+#pragma unroll
+                  for (int i = 0; i < RPT; ++i)
+                    if (i < nrow) {
+                      p.m[l][xoff + (size_t)i * dl] = m1v[i];
+                      p.v[l][xoff + (size_t)i * dl] = v1v[i];
+                    }
+                }
+              }
+              if (p.noise_mode != MCPC_NOISE_NONE) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) xv[i] = fmaf(-p.lr, nz[i], xv[i]);
+              }
+#pragma unroll
+              for (int i = 0; i < RPT; ++i) {
+                if (i >= nrow) xv[i] = 0.0f;                  // chains past the batch keep their zeros
+                *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(kind, xv[i]));
+                if (sf != nullptr && i < nrow) sf[(size_t)i * p.sf_pitch] = __float2bfloat16(av[i]);
+                if (xg != nullptr && i < nrow) xg[(size_t)i * dl] = gradv[i];
+              }
+            }
+            __syncwarp();                                    // .sync.aligned store: every lane executes it
+            tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
+          }
+          tmem_st_wait();
+          fence_async_smem();
+          fence_before_sync();
+          mbar_arrive(&bars.acts_ready[l]);                  // act(x_l) / x_l of step ts+1 are in place
+        }
+        TC_STAMP(gtid == 0, ts, 54);
+        // layer-0 energy of this step
+        e_part = warp_sum_tc(e_part);
+        float (*red)[2] = s_red[1][ts & 1];
+        if (lane == 0) { red[gw][0] = e_part; red[gw][1] = 0.0f; }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (gtid < 2) {
+          float s = 0.0f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += red[w][gtid];
+          p.partials[(((size_t)ts * p.n_ctas + blockIdx.x) * 2 + 1) * 2 + gtid] = s;
+        }
       }
-    }
-
-    // ---------- write the latents back ----------
-    for (int h = 0; h < HT; ++h) {
-      const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
-      float xv[RPT];
-      tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
+      // ---------- write the latents back (group U owns x) ----------
+      for (int h = 0; h < HT; ++h) {
+        const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
+        float xv[RPT];
+        tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
 #pragma unroll
-      for (int i = 0; i < RPT; ++i)
-        if (u < dl && i < nrow) p.x[l][(size_t)(rb + i) * dl + u] = xv[i];
+        for (int i = 0; i < RPT; ++i)
+          if (u < dl && i < nrow) p.x[l][(size_t)(rb + i) * dl + u] = xv[i];
+      }
+    } else {
+      // ======================= group T: per-tile epilogues =======================
+      uint32_t ph_dAf = 0, ph_ge = 3;
+      float bias_n = 0.0f, yv_n[RPT];
+      auto prefetch_tile = [&](int t) {
+        const Tile& Tn = p.tiles[t];
+        const bool out_n = (Tn.lin == L);
+        const int un = Tn.out_tile * 128 + ln;
+        const bool uv = un < (out_n ? nd.d_out : nd.dims[Tn.lin]);
+        bias_n = (uv && p.b[Tn.lin] != nullptr) ? __ldg(p.b[Tn.lin] + un) : 0.0f;
+        const bool uy = out_n && uv && (un >= nd.mask_start) && nd.top >= MCPC_TOP_GAUSS;
+        const float* yp = uy ? p.target + (size_t)rb * nd.d_out + un : nullptr;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) yv_n[i] = (uy && i < nrow) ? __ldg(yp + (size_t)i * nd.d_out) : 0.0f;
+      };
+      {
+        const bool traj0 = (p.traj_every > 0);
+        const int t0 = (nd.top_has_grad || (traj0 && p.traj_out != nullptr)) ? 0 : p.n_out_tiles;
+        if (t0 < n_tiles_all) prefetch_tile(t0);
+      }
+      for (int ts = 0; ts < p.n_steps; ++ts) {
+        const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
+        const int slot = ts - p.save_begin;
+        const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const int rec = do_traj ? ts / p.traj_every : 0;
+        const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+        const int t_first = need_out ? 0 : p.n_out_tiles;
+        float e_part = 0.0f, l_part = 0.0f;
+        __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * p.sg_pitch : nullptr;
+        uint32_t x_waited = 0;
+        TC_STAMP(gtid == 0, ts, 32);
+        for (int t = t_first; t < n_tiles_all; ++t) {
+          const Tile& T = p.tiles[t];
+          const int k = t - t_first;
+          const int db = k & 1, gb = k & 1;
+          const bool is_out = (T.lin == L);
+          const bool has_b = !is_out || nd.top_has_grad;
+          const int dl = is_out ? nd.d_out : nd.dims[T.lin];
+          const int u = T.out_tile * 128 + ln;
+          const bool uvalid = u < dl;
+          const bool use_y = is_out && uvalid && (u >= nd.mask_start) && nd.top >= MCPC_TOP_GAUSS;
+          // operands of THIS tile were prefetched one tile ago; issue the loads of the next tile now so their
+          // L2 latency hides behind this tile's work
+          const float bias = bias_n;
+          float yv[RPT];
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) yv[i] = yv_n[i];
+          {
+            int tn = t + 1;
+            if (tn >= n_tiles_all) {
+              const int ts1 = ts + 1;
+              const bool traj1 = (p.traj_every > 0) && (ts1 % p.traj_every == 0);
+              tn = (nd.top_has_grad || (traj1 && p.traj_out != nullptr)) ? 0 : p.n_out_tiles;
+            }
+            if (tn < n_tiles_all) prefetch_tile(tn);
+          }
+          if (!is_out && !((x_waited >> T.lin) & 1u)) {       // x_lin of THIS step was written by group U last step
+            mbar_wait(&bars.acts_ready[T.lin], ts & 1);
+            x_waited |= 1u << T.lin;
+          }
+          mbar_wait(&bars.dA_full[db], (ph_dAf >> db) & 1u);
+          ph_dAf ^= 1u << db;
+          if (has_b) {
+            mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
+            ph_ge ^= 1u << gb;
+          }
+          fence_after_sync();
+          TC_STAMP(gtid == 0 && k == 3, ts, 55);
+          uint8_t* gptr = smem + p.gbuf_off[gb] + g_thread_off;
+          float d[RPT];
+          tmem_ld<RPT>(lane_addr + col_dA + db * NR, d);
+          TC_STAMP(gtid == 0 && k == 3, ts, 56);
+          if (!is_out) {
+            const int h = T.h_out;
+            const float ce = 0.5f * nd.c[T.lin], gc = nd.gc[T.lin];
+            float xv[RPT], gv[RPT];
+            tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
+            __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[T.lin] + u : nullptr;
+            // straight-line math for all RPT chains (independent chains interleave); only the stores are predicated
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              const float eps = xv[i] - (d[i] + bias);
+              gv[i] = uvalid ? -gc * eps : 0.0f;
+              e_part = fmaf((uvalid && i < nrow) ? ce * eps : 0.0f, eps, e_part);
+            }
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              const __nv_bfloat16 gb16 = __float2bfloat16(gv[i]);
+              *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = gb16;
+              if (sg != nullptr && i < nrow) sg[(size_t)i * p.sg_pitch] = gb16;
+            }
+            tmem_st<RPT>(lane_addr + col_g + h * NR, gv);
+            tmem_st_wait();
+          } else {
+            __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[L] + u : nullptr;
+            float* to = (do_traj && p.traj_out != nullptr && uvalid) ? p.traj_out + ((size_t)rec * p.B + rb) * nd.d_out + u : nullptr;
+            const bool bern = nd.top == MCPC_TOP_BERNOULLI;
+            float ov[RPT], ev[RPT];
+            if (bern) {
+#pragma unroll
+              for (int i = 0; i < RPT; ++i) {
+                const float o = d[i] + bias;
+                const float z = __expf(-fabsf(o));
+                const float lv = fmaxf(o, 0.0f) - o * yv[i] + __logf(1.0f + z);
+                const float e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[i];
+                const bool on = use_y && i < nrow;
+                l_part += on ? lv : 0.0f;
+                ev[i] = on ? e : 0.0f;
+                ov[i] = o;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < RPT; ++i) {
+                const float o = d[i] + bias;
+                const float dd = o - yv[i];
+                const bool on = use_y && i < nrow;
+                l_part = fmaf(on ? 0.5f * nd.inv_var * dd : 0.0f, dd, l_part);
+                ev[i] = on ? dd * nd.inv_var : 0.0f;
+                ov[i] = o;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              const __nv_bfloat16 eb16 = __float2bfloat16(ev[i]);
+              if (has_b) *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = eb16;
+              if (to != nullptr && i < nrow) to[(size_t)i * nd.d_out] = ov[i];
+              if (sg != nullptr && i < nrow) sg[(size_t)i * p.sg_pitch] = eb16;
+            }
+          }
+          TC_STAMP(gtid == 0 && k == 3, ts, 57);
+          fence_before_sync();
+          mbar_arrive(&bars.dA_empty[db]);
+          TC_STAMP(gtid == 0 && k == 3, ts, 58);
+          if (has_b) {
+            fence_async_smem();
+            mbar_arrive(&bars.g_full[gb]);
+          }
+          TC_STAMP(gtid == 0 && k == 3, ts, 59);
+          // own-layer errors of layer `lin` are complete after the last tile of Linear lin
+          if (!is_out && (t + 1 == n_tiles_all || p.tiles[t + 1].lin != T.lin)) mbar_arrive(&bars.g_ready[T.lin]);
+          TC_STAMP(gtid == 0, ts, 22 + k);
+        }
+        e_part = warp_sum_tc(e_part);
+        l_part = warp_sum_tc(l_part);
+        float (*red)[2] = s_red[0][ts & 1];
+        if (lane == 0) { red[gw][0] = e_part; red[gw][1] = l_part; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (gtid < 2) {
+          float s = 0.0f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += red[w][gtid];
+          p.partials[(((size_t)ts * p.n_ctas + blockIdx.x) * 2 + 0) * 2 + gtid] = s;
+        }
+      }
     }
   }
 
@@ -621,12 +714,15 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
     off += (uint32_t)NR * 128 * 2;
   }
   off = (off + 1023u) & ~1023u;
-  // tile table: hidden Linears 1..L-1 first, then the output Linear
+  // tile table, in the order a step visits them: output tiles first, then Linear L-1 ... 1 (top-down)
   int nt = 0;
   size_t gsrc = 0;
   uint32_t max_tile = 0;
-  for (int lin = 1; lin <= nd.L; ++lin) {
-    if (lin == nd.L && nd.d_out == 0) break;
+  p->n_out_tiles = 0;
+  for (int pass = 0; pass < nd.L; ++pass) {
+    const int lin = nd.L - pass;
+    if (lin == nd.L && nd.d_out == 0) continue;
+    if (lin < 1) break;
     const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
     const int Kp = pad16(nd.dims[lin - 1]);
     if (Kp > 1024) {
@@ -650,10 +746,9 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
       gsrc += (size_t)T.bytes;
       if ((uint32_t)T.bytes > max_tile) max_tile = (uint32_t)T.bytes;
     }
-    if (lin < nd.L) p->n_hid_tiles = nt;
+    if (lin == nd.L) p->n_out_tiles = nt;
   }
-  if (nd.d_out == 0 || nd.L == 0) p->n_hid_tiles = nt;
-  p->n_out_tiles = nt - p->n_hid_tiles;
+  p->n_hid_tiles = nt - p->n_out_tiles;
   *packed_bytes = gsrc;
   // residency: everything if it fits, else as many leading tiles as fit beside a 2-slot ring
   const uint32_t slack = 4096;             // MN-major reads of narrow tiles overrun their 128 x Kp footprint
@@ -719,7 +814,7 @@ int infer_tc_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes) {
   }
   if (rc != MCPC_OK) return rc;
   const int n_ctas = (B + NR - 1) / NR;
-  *bytes = ((packed + 255) & ~(size_t)255) + (size_t)n_steps * n_ctas * 2 * sizeof(float) + 512;
+  *bytes = ((packed + 255) & ~(size_t)255) + (size_t)n_steps * n_ctas * 4 * sizeof(float) + 512;
   return MCPC_OK;
 }
 
@@ -807,23 +902,13 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     cudaMalloc(&p.dbg, 8 * 64 * sizeof(long long));
     cudaMemsetAsync(p.dbg, 0, 8 * 64 * sizeof(long long), stream);
   }
-  int rpt = (NR == 32) ? 8 : 4;             // chains per epilogue thread (16 epilogue warps by default)
-  if (const char* env = getenv("MCPC_TC_RPT")) {
-    const int v = atoi(env);
-    if ((v == 4 || v == 8 || v == 16) && NR / v >= 1 && NR / v <= 4) rpt = v;
+  if (NR == 32) {
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infer_tc_kernel<32><<<p.n_ctas, 576, smem, stream>>>(p);
+  } else {
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infer_tc_kernel<16><<<p.n_ctas, 576, smem, stream>>>(p);
   }
-#define MCPC_TC_LAUNCH(NR_, RPT_)                                                                                     \
-  do {                                                                                                                \
-    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<NR_, RPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                         (int)smem));                                                                 \
-    infer_tc_kernel<NR_, RPT_><<<p.n_ctas, 128 * (NR_ / RPT_) + 64, smem, stream>>>(p);                              \
-  } while (0)
-  if (NR == 32 && rpt == 16) MCPC_TC_LAUNCH(32, 16);
-  else if (NR == 32) MCPC_TC_LAUNCH(32, 8);
-  else if (rpt == 16) MCPC_TC_LAUNCH(16, 16);
-  else if (rpt == 8) MCPC_TC_LAUNCH(16, 8);
-  else MCPC_TC_LAUNCH(16, 4);
-#undef MCPC_TC_LAUNCH
   MCPC_CUDA_CHECK(cudaGetLastError());
   count_launch();
   if (timing) {
@@ -840,7 +925,7 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     }
   }
   if (io->energy != nullptr || io->loss != nullptr) {
-    rc = launch_reduce_partials(p.partials, o->n_steps, p.n_ctas, io->energy, io->loss, stream);
+    rc = launch_reduce_partials(p.partials, o->n_steps, 2 * p.n_ctas, io->energy, io->loss, stream);
     if (rc != MCPC_OK) return rc;
   }
   return MCPC_OK;
