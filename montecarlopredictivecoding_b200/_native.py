@@ -96,7 +96,7 @@ _lib = None
 _lock = threading.Lock()
 LIB_NAME = "libmcpc_b200.so"
 EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer_mode", "mcpc_infer", "mcpc_weight_grad",
-           "mcpc_fill_noise", "mcpc_debug_umma")
+           "mcpc_fill_noise", "mcpc_debug_umma", "mcpc_debug_tma")
 
 
 def lib_path():
@@ -139,6 +139,9 @@ def load():
         lib.mcpc_debug_umma.restype = C.c_int
         lib.mcpc_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mcpc_debug_tma.restype = C.c_int
+        lib.mcpc_debug_tma.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
         got = lib.mcpc_version()
         if got != ABI_VERSION:
             raise NativeError(f"{LIB_NAME} ABI version {got}, python binding expects {ABI_VERSION}")

@@ -250,4 +250,12 @@ int mcpc_debug_umma(const float* Wt, const float* Bx, const float* G, int32_t Ki
   return launch_umma_probe(Wt, Bx, G, Kin, N, D1, D2, ws, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mcpc_debug_tma(const float* A, const float* B, int32_t N, int32_t a_mn, int32_t b_mn, float* D, void* ws, void* stream) {
+  if (A == nullptr || B == nullptr || D == nullptr || ws == nullptr) {
+    set_error("mcpc_debug_tma: NULL argument");
+    return MCPC_ERR_INVALID;
+  }
+  return launch_tma_probe(A, B, N, a_mn, b_mn, D, ws, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -26,10 +26,11 @@ namespace {
 
 using namespace umma;
 
-constexpr int kWS = 3;                      // pipeline stages
+constexpr int kWS = 4;                      // pipeline stages
 constexpr int kBK = 64;                     // K per stage
-constexpr uint32_t kOpBytes = 128 * kBK * 2;            // a 128-wide bf16 operand stage
-constexpr uint32_t kOpBytesW = (kBK / 8) * 18 * 128;    // wgrad B operand: 128 + 16 (ones block) wide
+constexpr int kBN = 256;                    // output-tile width (N of the MMA)
+constexpr uint32_t kABytes = 128 * kBK * 2;             // A operand stage: 128 (M) x 64 (K) bf16
+constexpr uint32_t kBBytes = kBN * kBK * 2;             // B operand stage: 256 (N) x 64 (K) bf16
 
 struct WideParams {
   NetDev net;
@@ -61,6 +62,7 @@ struct WideParams {
   int noise_mode;
   float noise_scale;
   uint64_t seed, chain_offset;
+  long long* dbg;                         // MCPC_WIDE_TIMING=1: per-role cycle counters of CTA 0 (debug)
 };
 
 struct StepArgs {
@@ -102,7 +104,7 @@ __device__ __forceinline__ float warp_sum_w(float v) {
   return v;
 }
 
-// One stage of one operand.  K-major: [128 mn x 64 k], element (mn,k) at base[(mn0+mn)*ld + k]; smem core matrix
+// One stage of one operand (W = W_TOT wide).  K-major: [W mn x 64 k], element (mn,k) at base[(mn0+mn)*ld + k]; smem core matrix
 // (mn/8, k/8) at (mn/8)*1024 + (k/8)*128.  MN-major: [64 k x W mn], element (k,mn) at base[k*ld + mn0+mn]; smem core
 // matrix (k/8, mn/8) at (k/8)*(W/8*128) + (mn/8)*128.  Lane -> (row-in-group = lane%8, 16-byte chunk = lane/8 + 4j):
 // every 8 lanes fill all 32 banks, every row contributes whole 32-byte sectors.
@@ -111,8 +113,8 @@ __device__ __forceinline__ void load_stage(uint32_t dst, const Operand& op, int 
   const int r8 = lane & 7, cq = lane >> 3;
   if (!MN_MAJOR) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int rg = warp * 4 + g;                          // row group (8 rows) 0..15
+    for (int g = 0; g < W_TOT / 32; ++g) {
+      const int rg = warp * (W_TOT / 32) + g;               // row group (8 rows) 0..W_TOT/8-1
       const int mn = op.mn0 + rg * 8 + r8;
       const bool mn_ok = mn < op.mn_ext;
       const __nv_bfloat16* src_row = op.base + (size_t)(mn_ok ? mn : 0) * op.ld;
@@ -133,7 +135,7 @@ __device__ __forceinline__ void load_stage(uint32_t dst, const Operand& op, int 
       const bool k_ok = k < k_ext;
       const __nv_bfloat16* src_row = op.base + (size_t)(k_ok ? k : 0) * op.ld;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < W_TOT / 32; ++j) {
         const int c = cq + 4 * j;
         const int mn = op.mn0 + c * 8;
         const bool ok = k_ok && mn < op.mn_ext;
@@ -144,71 +146,60 @@ __device__ __forceinline__ void load_stage(uint32_t dst, const Operand& op, int 
 }
 
 struct Pipe {
-  uint64_t full[kWS], empty[kWS], done;
+  uint64_t full[kWS], empty[kWS], acc_full[2], acc_empty[2];
 };
 
-// D[128 x BN_TOT] (TMEM, fp32) = A . B over K = k_ext.  Warps 0-3 produce, warp 4 issues.  Returns after the
-// producers have issued everything; the epilogue waits on pipe.done.
-template <bool A_MN, bool B_MN, int BN_TOT>
-__device__ __forceinline__ void gemm_mainloop(uint8_t* smem, Pipe& pipe, uint32_t tmem, const Operand& A, const Operand& Bo,
-                                              int k_ext, int warp, int lane) {
-  constexpr uint32_t a_bytes = kOpBytes;
-  constexpr uint32_t b_bytes = (BN_TOT == 128) ? kOpBytes : kOpBytesW;
-  constexpr uint32_t stage_bytes = a_bytes + b_bytes;
-  const int n_stage = (k_ext + kBK - 1) / kBK;
-  const uint32_t smem_base = smem_u32(smem);
-  if (warp < 4) {
-    constexpr int D = kWS - 1;
-    for (int s = 0; s < n_stage + D; ++s) {
-      if (s < n_stage) {
-        const int slot = s % kWS;
-        mbar_wait(&pipe.empty[slot], ((s / kWS) & 1) ^ 1);
-        load_stage<A_MN, 128>(smem_base + slot * stage_bytes, A, s * kBK, k_ext, warp, lane);
-        load_stage<B_MN, BN_TOT>(smem_base + slot * stage_bytes + a_bytes, Bo, s * kBK, k_ext, warp, lane);
-      }
-      cp_commit();
-      if (s >= D) {
-        cp_wait<D>();
-        fence_async_smem();
-        mbar_arrive(&pipe.full[(s - D) % kWS]);
-      }
-    }
-  } else {
-    const uint32_t id = idesc_bf16(128, BN_TOT, A_MN, B_MN);
-    constexpr uint32_t lbo_a = A_MN ? 2048u : 128u, sbo_a = A_MN ? 128u : 1024u;
-    constexpr uint32_t lbo_b = B_MN ? (uint32_t)(BN_TOT / 8) * 128u : 128u, sbo_b = B_MN ? 128u : 1024u;
-    constexpr uint32_t adv_a = A_MN ? (2 * 2048u) >> 4 : 16u, adv_b = B_MN ? (2 * lbo_b) >> 4 : 16u;
-    for (int s = 0; s < n_stage; ++s) {
-      const int slot = s % kWS;
-      mbar_wait(&pipe.full[slot], (s / kWS) & 1);
-      fence_after_sync();
-      const uint64_t ad0 = smem_desc(smem_base + slot * stage_bytes, lbo_a, sbo_a);
-      const uint64_t bd0 = smem_desc(smem_base + slot * stage_bytes + a_bytes, lbo_b, sbo_b);
-      if (elect1()) {
-#pragma unroll
-        for (int ks = 0; ks < kBK / 16; ++ks)
-          mma_bf16_ss(tmem, ad0 + (uint64_t)(ks * adv_a), bd0 + (uint64_t)(ks * adv_b), id, s > 0 || ks > 0);
-        mma_commit(&pipe.empty[slot]);
-        if (s == n_stage - 1) mma_commit(&pipe.done);
-      }
-      __syncwarp();
-    }
-  }
+enum { KIND_PREDICT = 0, KIND_UPDATE = 1, KIND_WGRAD = 2 };
+
+struct TileDesc {
+  int idx;          // Linear index (predict / wgrad) or layer index (update)
+  int m0, n0;
+  int k_ext;        // 0: no contraction for this tile
+  Operand A, B;
+};
+
+template <int KIND>
+__device__ __forceinline__ int n_tiles_of(const WideParams& p) {
+  return KIND == KIND_PREDICT ? p.tP_first[p.net.L + 1] : (KIND == KIND_UPDATE ? p.tU_first[p.net.L] : p.tW_first[p.net.L + 1]);
 }
 
-__device__ __forceinline__ void pipe_setup(Pipe& pipe, uint32_t* tmem_slot, uint32_t cols, int tid, int warp) {
-  if (tid == 0) {
-    for (int s = 0; s < kWS; ++s) {
-      mbar_init(&pipe.full[s], 128);
-      mbar_init(&pipe.empty[s], 1);
+template <int KIND>
+__device__ __forceinline__ TileDesc decode_tile(const WideParams& p, int tile) {
+  const NetDev& nd = p.net;
+  TileDesc t{};
+  if (KIND == KIND_PREDICT) {
+    int lin = 0;
+    while (tile >= p.tP_first[lin + 1]) ++lin;
+    const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
+    const int d_i = (lin == 0) ? 0 : nd.dims[lin - 1];            // Linear_0 sees zero inputs: mu_0 = b_0
+    const int ntn = (d_o + kBN - 1) / kBN, local = tile - p.tP_first[lin];
+    t.idx = lin; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = d_i;
+    if (d_i > 0) {
+      t.A = Operand{p.act + p.poff[lin - 1], p.a_pitch, t.m0, p.B};     // act(x_{l-1}) [B x d_i], K-major
+      t.B = Operand{p.Wb[lin], d_i, t.n0, d_o};                         // W_l [d_o x d_i], K-major
     }
-    mbar_init(&pipe.done, 1);
-    fence_mbar_init();
+  } else if (KIND == KIND_UPDATE) {
+    int l = 0;
+    while (tile >= p.tU_first[l + 1]) ++l;
+    const int dl = nd.dims[l];
+    const int ntn = (dl + kBN - 1) / kBN, local = tile - p.tU_first[l];
+    const bool has_above = (l + 1 < nd.L) || nd.top_has_grad;
+    const int d_up = (l + 1 < nd.L) ? nd.dims[l + 1] : nd.d_out;
+    t.idx = l; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = has_above ? d_up : 0;
+    if (has_above) {
+      t.A = Operand{p.Gb + p.poff[l + 1], p.g_pitch, t.m0, p.B};        // G_{l+1} [B x d_up], K-major
+      t.B = Operand{p.Wb[l + 1], dl, t.n0, dl};                         // W_{l+1} [d_up x d_l] as B[k][n]: MN-major
+    }
+  } else {
+    int lin = 1;
+    while (tile >= p.tW_first[lin + 1]) ++lin;
+    const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = nd.dims[lin - 1];
+    const int ntn = (d_i + kBN - 1) / kBN, local = tile - p.tW_first[lin];
+    t.idx = lin; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = p.B;
+    t.A = Operand{p.Gb + p.poff[lin], p.g_pitch, t.m0, d_o};            // G_l as A[k=chain][m]: MN-major
+    t.B = Operand{p.act + p.poff[lin - 1], p.a_pitch, t.n0, d_i};       // act(x_{l-1}) as B[k=chain][n]: MN-major
   }
-  if (warp == 4) tmem_alloc(tmem_slot, cols);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
+  return t;
 }
 
 __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float (&v)[16]) {
@@ -233,290 +224,351 @@ __device__ __forceinline__ void store_f32x16(float* dst, const float (&v)[16]) {
   for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
-// ======================================================================================================
-//  predictions + errors
-// ======================================================================================================
-__global__ void __launch_bounds__(160, 2) wide_predict_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st) {
+// ---- epilogues: thread = TMEM lane = chain (predict / update) or output unit (wgrad); 16 columns at a time ----
+__device__ __forceinline__ void epilogue_predict(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_addr,
+                                                 int row_in_tile, float& e_part, float& l_part) {
+  const NetDev& nd = p.net;
+  const int lin = t.idx;
+  const bool is_out = (lin == nd.L);
+  const int d_o = is_out ? nd.d_out : nd.dims[lin];
+  const int row = t.m0 + row_in_tile;
+  const bool rvalid = row < p.B;
+  const float ce = is_out ? 0.0f : 0.5f * nd.c[lin], gc = is_out ? 0.0f : nd.gc[lin];
+  const bool bern = nd.top == MCPC_TOP_BERNOULLI;
+  for (int c = 0; c < kBN; c += 16) {
+    const int n = t.n0 + c;
+    if (n >= d_o) break;                                  // uniform over the warp
+    float d[16];
+    if (t.k_ext > 0) tmem_ld16(acc_addr + c, d);         // .sync.aligned: every lane executes it
+    else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d[i] = 0.0f;
+    }
+    if (!rvalid) continue;
+    float bias[16];
+    if (p.b[lin] != nullptr) load_f32x16(p.b[lin] + n, bias);
+    else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bias[i] = 0.0f;
+    }
+    float g[16];
+    if (!is_out) {
+      float xv[16];
+      load_f32x16(p.x[lin] + (size_t)row * d_o + n, xv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float eps = xv[i] - (d[i] + bias[i]);
+        e_part = fmaf(ce * eps, eps, e_part);
+        g[i] = -gc * eps;
+      }
+      store_f32x16(p.G32 + (size_t)row * nd.SD + nd.off[lin] + n, g);
+    } else {
+      float yv[16];
+      const bool use_y = nd.top >= MCPC_TOP_GAUSS;
+      if (use_y) load_f32x16(p.target + (size_t)row * d_o + n, yv);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) yv[i] = 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float o = d[i] + bias[i];
+        const bool on = use_y && (n + i >= nd.mask_start);
+        float lv, e;
+        if (bern) {
+          const float z = __expf(-fabsf(o));
+          lv = fmaxf(o, 0.0f) - o * yv[i] + __logf(1.0f + z);
+          e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[i];
+        } else {
+          const float dd = o - yv[i];
+          lv = 0.5f * nd.inv_var * dd * dd;
+          e = dd * nd.inv_var;
+        }
+        l_part += on ? lv : 0.0f;
+        g[i] = on ? e : 0.0f;
+        d[i] = o;
+      }
+      if (st.do_traj && p.traj_out != nullptr) store_f32x16(p.traj_out + ((size_t)st.rec * p.B + row) * d_o + n, d);
+    }
+    store_bf16x16(p.Gb + (size_t)row * p.g_pitch + p.poff[lin] + n, g);
+  }
+}
+
+__device__ __forceinline__ void epilogue_update(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_addr,
+                                                int row_in_tile, int lane) {
+  const NetDev& nd = p.net;
+  const int l = t.idx;
+  const int dl = nd.dims[l];
+  const int row = t.m0 + row_in_tile;
+  const bool rvalid = row < p.B;
+  const int kind = nd.act[l];
+  const bool adam = p.optimizer == MCPC_OPT_ADAM;
+  const uint64_t chain = p.chain_offset + (uint64_t)row;
+  const bool grouped_rng = (p.chain_offset & 3) == 0;             // lanes 4q..4q+3 share one Philox counter
+  for (int c = 0; c < kBN; c += 16) {
+    const int n = t.n0 + c;
+    if (n >= dl) break;                                           // uniform over the warp
+    float bp[16];
+    if (t.k_ext > 0) tmem_ld16(acc_addr + c, bp);
+    else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bp[i] = 0.0f;
+    }
+    float nz[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) nz[i] = 0.0f;
+    if (p.noise_mode == MCPC_NOISE_PHILOX) {
+      if (grouped_rng) {
+        float mine[4][4];                                         // my 4 counters (units n + (lane&3) + 4j) x 4 chains
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          langevin_normals4(p.seed, (uint32_t)(nd.off[l] + n + (lane & 3) + 4 * j), (uint32_t)st.t_abs, chain >> 2, mine[j]);
+        const int kc = (int)(chain & 3);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          // unit n+i was drawn by lane (group base + i%4) as its j = i/4; I take the component of MY chain
+          const int src = (lane & ~3) | (i & 3);
+          const float v0 = __shfl_sync(0xffffffffu, mine[i >> 2][0], src), v1 = __shfl_sync(0xffffffffu, mine[i >> 2][1], src);
+          const float v2 = __shfl_sync(0xffffffffu, mine[i >> 2][2], src), v3 = __shfl_sync(0xffffffffu, mine[i >> 2][3], src);
+          nz[i] = p.noise_scale * (kc == 0 ? v0 : (kc == 1 ? v1 : (kc == 2 ? v2 : v3)));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float q4[4];
+          langevin_normals4(p.seed, (uint32_t)(nd.off[l] + n + i), (uint32_t)st.t_abs, chain >> 2, q4);
+          const int kc = (int)(chain & 3);
+          nz[i] = p.noise_scale * (kc == 0 ? q4[0] : (kc == 1 ? q4[1] : (kc == 2 ? q4[2] : q4[3])));
+        }
+      }
+    }
+    if (!rvalid) continue;
+    if (p.noise_mode == MCPC_NOISE_SUPPLIED) load_f32x16(p.noise + ((size_t)st.ts * p.B + row) * nd.SD + nd.off[l] + n, nz);
+    float xv[16], g[16], a_new[16], gradv[16];
+    float* xp = p.x[l] + (size_t)row * dl + n;
+    load_f32x16(xp, xv);
+    load_f32x16(p.G32 + (size_t)row * nd.SD + nd.off[l] + n, g);
+    float mv[16], vv[16];
+    if (adam && p.update_x) {
+      load_f32x16(p.m[l] + (size_t)row * dl + n, mv);
+      load_f32x16(p.v[l] + (size_t)row * dl + n, vv);
+    }
+    if (st.do_traj && p.traj_x[l] != nullptr) store_f32x16(p.traj_x[l] + ((size_t)st.rec * p.B + row) * dl + n, xv);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float x = xv[i];
+      const float a = act_w(kind, x);
+      const float grad = fmaf(dact_w(kind, x, a), bp[i], -g[i]);
+      gradv[i] = grad;
+      if (p.update_x) {
+        if (!adam) {
+          x = fmaf(-p.lr, grad, x);
+        } else {
+          mv[i] = fmaf(p.one_minus_b1, grad - mv[i], mv[i]);
+          vv[i] = fmaf(p.one_minus_b2 * grad, grad, vv[i] * p.beta2f);
+          x = fmaf(-st.step_size, __fdividef(mv[i], fmaf(sqrtf(vv[i]), st.inv_bc2_sqrt, p.adam_eps)), x);
+        }
+      }
+      x = fmaf(-p.lr, nz[i], x);
+      xv[i] = x;
+      a_new[i] = act_w(kind, x);
+    }
+    if (st.last && p.xgrad[l] != nullptr) store_f32x16(p.xgrad[l] + (size_t)row * dl + n, gradv);
+    if (adam && p.update_x) {
+      store_f32x16(p.m[l] + (size_t)row * dl + n, mv);
+      store_f32x16(p.v[l] + (size_t)row * dl + n, vv);
+    }
+    store_f32x16(xp, xv);
+    store_bf16x16(p.act + (size_t)row * p.a_pitch + p.poff[l] + n, a_new);
+  }
+}
+
+__device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDesc& t, uint32_t acc_addr, int row_in_tile) {
+  const NetDev& nd = p.net;
+  const int lin = t.idx;
+  const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = nd.dims[lin - 1];
+  const int mo = t.m0 + row_in_tile;
+  float* gW = p.gW[lin];
+  for (int c = 0; c < kBN; c += 16) {
+    const int n = t.n0 + c;
+    if (n >= d_i) break;
+    float d[16];
+    tmem_ld16(acc_addr + c, d);
+    if (mo >= d_o || gW == nullptr) continue;
+    float* dst = gW + (size_t)mo * d_i + n;                // exactly one CTA owns each tile: plain read-modify-write
+    float cur[16];
+    load_f32x16(dst, cur);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cur[i] += d[i];
+    store_f32x16(dst, cur);
+  }
+}
+
+// Persistent grouped GEMM: each CTA walks tiles blockIdx.x, +gridDim.x, ...  Warps 0-3 cp.async producers (4-stage ring),
+// warp 4 MMA issuer, warps 5-8 epilogue; two 256-column accumulators in TMEM so the epilogue of tile i overlaps the
+// mainloop of tile i+1.
+template <int KIND>
+__global__ void __launch_bounds__(288, 1) wide_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Pipe pipe;
   __shared__ uint32_t tmem_s;
   __shared__ float s_red[4][2];
-  const NetDev& nd = p.net;
+  constexpr bool A_MN = (KIND == KIND_WGRAD), B_MN = (KIND != KIND_PREDICT);
+  constexpr uint32_t stage_bytes = kABytes + kBBytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int lin = 0;
-  while (blockIdx.x >= (unsigned)p.tP_first[lin + 1]) ++lin;
-  const bool is_out = (lin == nd.L);
-  // Linear_0 sees zero inputs: mu_0 = b_0, no contraction (d_i = 0)
-  const int d_o = is_out ? nd.d_out : nd.dims[lin], d_i = (lin == 0) ? 0 : nd.dims[lin - 1];
-  const int ntn = (d_o + 127) / 128;
-  const int local = blockIdx.x - p.tP_first[lin];
-  const int m0 = (local / ntn) * 128, n0 = (local % ntn) * 128;
+  const int n_tiles = n_tiles_of<KIND>(p);
 
-  pipe_setup(pipe, &tmem_s, 128, tid, warp);
-  const uint32_t tmem = tmem_s;
-  if (d_i > 0) {
-    Operand A{p.act + p.poff[lin - 1], p.a_pitch, m0, p.B};
-    Operand Bo{p.Wb[lin], d_i, n0, d_o};
-    gemm_mainloop<false, false, 128>(smem, pipe, tmem, A, Bo, d_i, warp, lane);
+  if (tid == 0) {
+    for (int s = 0; s < kWS; ++s) {
+      mbar_init(&pipe.full[s], 128);
+      mbar_init(&pipe.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&pipe.acc_full[b], 1);
+      mbar_init(&pipe.acc_empty[b], 128);
+    }
+    fence_mbar_init();
   }
+  if (warp == 4) tmem_alloc(&tmem_s, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_s;
+  const uint32_t smem_base = smem_u32(smem);
 
   if (warp < 4) {
-    if (d_i > 0) {
-      mbar_wait(&pipe.done, 0);
-      fence_after_sync();
-    }
-    const int row = m0 + warp * 32 + lane;
-    const bool rvalid = row < p.B;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    float e_part = 0.0f, l_part = 0.0f;
-    const float ce = is_out ? 0.0f : 0.5f * nd.c[lin], gc = is_out ? 0.0f : nd.gc[lin];
-    const bool bern = nd.top == MCPC_TOP_BERNOULLI;
-    for (int c = 0; c < 128; c += 16) {
-      float d[16];
-      if (d_i > 0) tmem_ld16(lane_addr + c, d);         // .sync.aligned: executed by every lane (d_i is uniform)
-      else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) d[i] = 0.0f;
-      }
-      const int n = n0 + c;
-      if (n >= d_o || !rvalid) continue;
-      float bias[16];
-      if (p.b[lin] != nullptr) load_f32x16(p.b[lin] + n, bias);
-      else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) bias[i] = 0.0f;
-      }
-      float g[16];
-      if (!is_out) {
-        float xv[16];
-        load_f32x16(p.x[lin] + (size_t)row * d_o + n, xv);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float eps = xv[i] - (d[i] + bias[i]);
-          e_part = fmaf(ce * eps, eps, e_part);
-          g[i] = -gc * eps;
+    // ---------------- producers ----------------
+    constexpr int D = kWS - 1;
+    uint32_t issued = 0, signalled = 0;
+    long long c_empty = 0, c_issue = 0, c_land = 0;
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileDesc t = decode_tile<KIND>(p, tile);
+      const int n_stage = (t.k_ext + kBK - 1) / kBK;
+      for (int s = 0; s < n_stage; ++s) {
+        const uint32_t slot = issued % kWS;
+        const long long t0 = prof ? clock64() : 0;
+        mbar_wait(&pipe.empty[slot], ((issued / kWS) & 1u) ^ 1u);
+        const long long t1 = prof ? clock64() : 0;
+        load_stage<A_MN, 128>(smem_base + slot * stage_bytes, t.A, s * kBK, t.k_ext, warp, lane);
+        load_stage<B_MN, kBN>(smem_base + slot * stage_bytes + kABytes, t.B, s * kBK, t.k_ext, warp, lane);
+        cp_commit();
+        const long long t2 = prof ? clock64() : 0;
+        ++issued;
+        if (issued - signalled > (uint32_t)D) {
+          cp_wait<D>();
+          fence_async_smem();
+          mbar_arrive(&pipe.full[signalled % kWS]);
+          ++signalled;
         }
-        store_f32x16(p.G32 + (size_t)row * nd.SD + nd.off[lin] + n, g);
+        if (prof) { c_empty += t1 - t0; c_issue += t2 - t1; c_land += clock64() - t2; }
+      }
+    }
+    if (prof) { p.dbg[KIND * 8 + 0] = c_empty; p.dbg[KIND * 8 + 1] = c_issue; p.dbg[KIND * 8 + 2] = c_land; p.dbg[KIND * 8 + 3] = issued; }
+    cp_wait<0>();
+    fence_async_smem();
+    for (; signalled < issued; ++signalled) mbar_arrive(&pipe.full[signalled % kWS]);
+  } else if (warp == 4) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t id = idesc_bf16(128, kBN, A_MN, B_MN);
+    constexpr uint32_t lbo_a = A_MN ? 2048u : 128u, sbo_a = A_MN ? 128u : 1024u;
+    constexpr uint32_t lbo_b = B_MN ? (uint32_t)(kBN / 8) * 128u : 128u, sbo_b = B_MN ? 128u : 1024u;
+    constexpr uint32_t adv_a = A_MN ? (2 * 2048u) >> 4 : 16u, adv_b = B_MN ? (2 * lbo_b) >> 4 : 16u;
+    uint32_t sc = 0, gi = 0;
+    long long c_acc = 0, c_full = 0;
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+    const long long k0 = clock64();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileDesc t = decode_tile<KIND>(p, tile);
+      const int n_stage = (t.k_ext + kBK - 1) / kBK;
+      if (n_stage == 0) continue;
+      const uint32_t ab = gi & 1u;
+      const long long a0 = clock64();
+      mbar_wait(&pipe.acc_empty[ab], ((gi >> 1) & 1u) ^ 1u);
+      c_acc += clock64() - a0;
+      fence_after_sync();
+      for (int s = 0; s < n_stage; ++s, ++sc) {
+        const uint32_t slot = sc % kWS;
+        const long long f0 = clock64();
+        mbar_wait(&pipe.full[slot], (sc / kWS) & 1u);
+        c_full += clock64() - f0;
+        fence_after_sync();
+        const uint64_t ad0 = smem_desc(smem_base + slot * stage_bytes, lbo_a, sbo_a);
+        const uint64_t bd0 = smem_desc(smem_base + slot * stage_bytes + kABytes, lbo_b, sbo_b);
+        if (elect1()) {
+#pragma unroll
+          for (int ks = 0; ks < kBK / 16; ++ks)
+            mma_bf16_ss(tmem + ab * kBN, ad0 + (uint64_t)(ks * adv_a), bd0 + (uint64_t)(ks * adv_b), id, s > 0 || ks > 0);
+          mma_commit(&pipe.empty[slot]);
+          if (s == n_stage - 1) mma_commit(&pipe.acc_full[ab]);
+        }
+        __syncwarp();
+      }
+      ++gi;
+    }
+    if (prof) { p.dbg[KIND * 8 + 4] = c_acc; p.dbg[KIND * 8 + 5] = c_full; p.dbg[KIND * 8 + 6] = clock64() - k0; }
+  } else {
+    // ---------------- epilogue warps 5..8 (TMEM lane quarter = warp % 4) ----------------
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    uint32_t gi = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileDesc t = decode_tile<KIND>(p, tile);
+      const bool has_gemm = t.k_ext > 0;
+      const uint32_t ab = gi & 1u;
+      if (has_gemm) {
+        mbar_wait(&pipe.acc_full[ab], (gi >> 1) & 1u);
+        fence_after_sync();
+      }
+      const uint32_t acc_addr = tmem + ((uint32_t)(q * 32) << 16) + ab * kBN;
+      if (KIND == KIND_PREDICT) {
+        float e_part = 0.0f, l_part = 0.0f;
+        epilogue_predict(p, st, t, acc_addr, row_in_tile, e_part, l_part);
+        e_part = warp_sum_w(e_part);
+        l_part = warp_sum_w(l_part);
+        if (lane == 0) { s_red[q][0] = e_part; s_red[q][1] = l_part; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q == 1 && lane < 2) p.partials[((size_t)st.ts * p.n_part + tile) * 2 + lane] = s_red[0][lane] + s_red[1][lane] + s_red[2][lane] + s_red[3][lane];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else if (KIND == KIND_UPDATE) {
+        epilogue_update(p, st, t, acc_addr, row_in_tile, lane);
       } else {
-        float yv[16];
-        const bool use_y = nd.top >= MCPC_TOP_GAUSS;
-        if (use_y) load_f32x16(p.target + (size_t)row * d_o + n, yv);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float o = d[i] + bias[i];
-          float e_out = 0.0f;
-          if (use_y && n + i >= nd.mask_start) {
-            if (!bern) {
-              const float dd = o - yv[i];
-              l_part = fmaf(0.5f * nd.inv_var * dd, dd, l_part);
-              e_out = dd * nd.inv_var;
-            } else {
-              const float z = __expf(-fabsf(o));
-              l_part += fmaxf(o, 0.0f) - o * yv[i] + __logf(1.0f + z);
-              e_out = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[i];
-            }
-          }
-          g[i] = e_out;
-          d[i] = o;
-        }
-        if (st.do_traj && p.traj_out != nullptr) store_f32x16(p.traj_out + ((size_t)st.rec * p.B + row) * d_o + n, d);
+        epilogue_wgrad(p, t, acc_addr, row_in_tile);
       }
-      store_bf16x16(p.Gb + (size_t)row * p.g_pitch + p.poff[lin] + n, g);
+      if (has_gemm) {
+        fence_before_sync();
+        mbar_arrive(&pipe.acc_empty[ab]);
+        ++gi;
+      }
     }
-    e_part = warp_sum_w(e_part);
-    l_part = warp_sum_w(l_part);
-    if (lane == 0) { s_red[warp][0] = e_part; s_red[warp][1] = l_part; }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (tid < 2) p.partials[((size_t)st.ts * p.n_part + blockIdx.x) * 2 + tid] = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == 4) tmem_dealloc(tmem, 512);
 }
 
-// ======================================================================================================
-//  back-projection + latent update
-// ======================================================================================================
-__global__ void __launch_bounds__(160, 2) wide_update_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ Pipe pipe;
-  __shared__ uint32_t tmem_s;
+// gb_l[m] += sum over chains of G_l[chain][m]   (all Linears at once: the columns of Gb)
+__global__ void __launch_bounds__(256) wide_bias_kernel(const __grid_constant__ WideParams p) {
+  __shared__ float red[8][33];
   const NetDev& nd = p.net;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = nd.L;
-  int l = 0;
-  while (blockIdx.x >= (unsigned)p.tU_first[l + 1]) ++l;
-  const int dl = nd.dims[l];
-  const int ntn = (dl + 127) / 128;
-  const int local = blockIdx.x - p.tU_first[l];
-  const int m0 = (local / ntn) * 128, n0 = (local % ntn) * 128;
-  const bool has_above = (l + 1 < L) || nd.top_has_grad;
-  const int d_up = (l + 1 < L) ? nd.dims[l + 1] : nd.d_out;
-
-  pipe_setup(pipe, &tmem_s, 128, tid, warp);
-  const uint32_t tmem = tmem_s;
-  if (has_above) {
-    Operand A{p.Gb + p.poff[l + 1], p.g_pitch, m0, p.B};          // G_{l+1} [B x d_up], K-major
-    Operand Bo{p.Wb[l + 1], dl, n0, dl};                           // W_{l+1} [d_up x d_l] read as B[k][n]: MN-major
-    gemm_mainloop<false, true, 128>(smem, pipe, tmem, A, Bo, d_up, warp, lane);
-  }
-
-  if (warp < 4) {
-    if (has_above) {
-      mbar_wait(&pipe.done, 0);
-      fence_after_sync();
-    }
-    const int row = m0 + warp * 32 + lane;
-    const bool rvalid = row < p.B;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    const int kind = nd.act[l];
-    const bool adam = p.optimizer == MCPC_OPT_ADAM;
-    const uint64_t chain = p.chain_offset + (uint64_t)row;
-    const bool grouped_rng = (p.chain_offset & 3) == 0;             // lanes 4q..4q+3 share one Philox counter
-    for (int c = 0; c < 128; c += 16) {
-      float bp[16];
-      if (has_above) tmem_ld16(lane_addr + c, bp);
-      else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) bp[i] = 0.0f;
-      }
-      const int n = n0 + c;
-      const bool cvalid = n < dl;                                   // uniform over the warp
-      // ---- Langevin noise for units n..n+15 of this chain (warp-cooperative: 4 lanes share a counter) ----
-      float nz[16];
-      if (p.noise_mode == MCPC_NOISE_PHILOX && cvalid) {
-        if (grouped_rng) {
-          float mine[4][4];                                         // my 4 counters (units n + (lane&3) + 4j) x 4 chains
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            langevin_normals4(p.seed, (uint32_t)(nd.off[l] + n + (lane & 3) + 4 * j), (uint32_t)st.t_abs, chain >> 2, mine[j]);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            // unit n+i was computed by lane (group base + i%4) as its j = i/4; I need the component of MY chain
-            const int src = (lane & ~3) | (i & 3);
-            float v0 = __shfl_sync(0xffffffffu, mine[i >> 2][0], src), v1 = __shfl_sync(0xffffffffu, mine[i >> 2][1], src);
-            float v2 = __shfl_sync(0xffffffffu, mine[i >> 2][2], src), v3 = __shfl_sync(0xffffffffu, mine[i >> 2][3], src);
-            const int k = (int)(chain & 3);
-            nz[i] = p.noise_scale * (k == 0 ? v0 : (k == 1 ? v1 : (k == 2 ? v2 : v3)));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float q4[4];
-            langevin_normals4(p.seed, (uint32_t)(nd.off[l] + n + i), (uint32_t)st.t_abs, chain >> 2, q4);
-            const int k = (int)(chain & 3);
-            nz[i] = p.noise_scale * (k == 0 ? q4[0] : (k == 1 ? q4[1] : (k == 2 ? q4[2] : q4[3])));
-          }
-        }
-      }
-      if (!cvalid || !rvalid) continue;
-      if (p.noise_mode == MCPC_NOISE_SUPPLIED) load_f32x16(p.noise + ((size_t)st.ts * p.B + row) * nd.SD + nd.off[l] + n, nz);
-      float xv[16], g[16], a_new[16];
-      float* xp = p.x[l] + (size_t)row * dl + n;
-      load_f32x16(xp, xv);
-      load_f32x16(p.G32 + (size_t)row * nd.SD + nd.off[l] + n, g);
-      float mv[16], vv[16];
-      if (adam && p.update_x) {
-        load_f32x16(p.m[l] + (size_t)row * dl + n, mv);
-        load_f32x16(p.v[l] + (size_t)row * dl + n, vv);
-      }
-      if (st.do_traj && p.traj_x[l] != nullptr) store_f32x16(p.traj_x[l] + ((size_t)st.rec * p.B + row) * dl + n, xv);
-      float gradv[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = xv[i];
-        const float a = act_w(kind, x);
-        const float grad = fmaf(dact_w(kind, x, a), bp[i], -g[i]);
-        gradv[i] = grad;
-        if (p.update_x) {
-          if (!adam) {
-            x = fmaf(-p.lr, grad, x);
-          } else {
-            mv[i] = fmaf(p.one_minus_b1, grad - mv[i], mv[i]);
-            vv[i] = fmaf(p.one_minus_b2 * grad, grad, vv[i] * p.beta2f);
-            x = fmaf(-st.step_size, __fdividef(mv[i], fmaf(sqrtf(vv[i]), st.inv_bc2_sqrt, p.adam_eps)), x);
-          }
-        }
-        if (p.noise_mode != MCPC_NOISE_NONE) x = fmaf(-p.lr, nz[i], x);
-        xv[i] = x;
-        a_new[i] = act_w(kind, x);
-      }
-      if (st.last && p.xgrad[l] != nullptr) store_f32x16(p.xgrad[l] + (size_t)row * dl + n, gradv);
-      if (adam && p.update_x) {
-        store_f32x16(p.m[l] + (size_t)row * dl + n, mv);
-        store_f32x16(p.v[l] + (size_t)row * dl + n, vv);
-      }
-      store_f32x16(xp, xv);
-      store_bf16x16(p.act + (size_t)row * p.a_pitch + p.poff[l] + n, a_new);
-    }
-  }
-  fence_before_sync();
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rg = threadIdx.x >> 5;
+  float s = 0.0f;
+  if (c < p.g_pitch)
+    for (int r = rg; r < p.B; r += 8) s += __bfloat162float(p.Gb[(size_t)r * p.g_pitch + c]);
+  red[rg][threadIdx.x & 31] = s;
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
-}
-
-// ======================================================================================================
-//  local weight update of one step
-// ======================================================================================================
-__global__ void __launch_bounds__(160, 2) wide_wgrad_kernel(const __grid_constant__ WideParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ Pipe pipe;
-  __shared__ uint32_t tmem_s;
-  const NetDev& nd = p.net;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int lin = 0;
-  while (blockIdx.x >= (unsigned)p.tW_first[lin + 1]) ++lin;
-  const bool is_out = (lin == nd.L);
-  const int d_o = is_out ? nd.d_out : nd.dims[lin];
-  const int d_i = (lin == 0) ? 0 : nd.dims[lin - 1];
-  const int ntn = (d_i == 0) ? 1 : (d_i + 127) / 128;
-  const int local = blockIdx.x - p.tW_first[lin];
-  const int m0 = (local / ntn) * 128, n0 = (local % ntn) * 128;
-  constexpr uint32_t stage_bytes = kOpBytes + kOpBytesW;
-
-  pipe_setup(pipe, &tmem_s, 256, tid, warp);
-  const uint32_t tmem = tmem_s;
-  // the ones block (columns 128..143 of the B operand of every stage): column 128 = 1, the rest 0
-  for (int i = tid; i < kWS * kBK * 2; i += blockDim.x) {
-    const int s = i / (kBK * 2), r = (i / 2) % kBK, g = i & 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (g == 0) v.x = 0x00003F80u;
-    *reinterpret_cast<uint4*>(smem + s * stage_bytes + kOpBytes + (r >> 3) * (18 * 128) + (16 + g) * 128 + (r & 7) * 16) = v;
-  }
-  fence_async_smem();
-  __syncthreads();
-  Operand A{p.Gb + p.poff[lin], p.g_pitch, m0, d_o};                                   // G_l read as A[k=row][m]: MN-major
-  Operand Bo{p.act + (lin == 0 ? 0 : p.poff[lin - 1]), p.a_pitch, n0, d_i};           // act(x_{l-1}) as B[k=row][n]: MN-major
-  gemm_mainloop<true, true, 144>(smem, pipe, tmem, A, Bo, p.B, warp, lane);
-
-  if (warp < 4) {
-    mbar_wait(&pipe.done, 0);
-    fence_after_sync();
-    const int mo = m0 + warp * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    float* gW = (lin == 0) ? nullptr : p.gW[lin];
-    for (int c = 0; c < 144; c += 16) {
-      float d[16];
-      tmem_ld16(lane_addr + c, d);
-      if (mo >= d_o) continue;
-      if (c < 128) {
-        const int n = n0 + c;
-        if (gW != nullptr && n < d_i) {
-          float* dst = gW + (size_t)mo * d_i + n;          // this CTA is the only writer of its tile: plain RMW
-          float cur[16];
-          load_f32x16(dst, cur);
+  if (rg == 0 && c < p.g_pitch) {
+    float tot = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) cur[i] += d[i];
-          store_f32x16(dst, cur);
-        }
-      } else if (n0 == 0 && p.gb[lin] != nullptr) {
-        p.gb[lin][mo] += d[0];
-      }
-    }
+    for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x & 31];
+    int lin = 0;
+    while (lin < nd.L && c >= p.poff[lin + 1]) ++lin;
+    const int m = c - p.poff[lin];
+    const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
+    const bool live = (lin < nd.L) || nd.top_has_grad;
+    if (m < d_o && live && p.gb[lin] != nullptr) p.gb[lin][m] += tot;
   }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
 __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
@@ -569,7 +621,7 @@ int wide_layout(const NetDev& nd, int B, int n_steps, WideLayout* lay) {
   o += align256((size_t)B * nd.SD * 4);
   const int mt = (B + 127) / 128;
   int n_part = 0;
-  for (int l = 0; l < n_lin; ++l) n_part += mt * (((l == nd.L ? nd.d_out : nd.dims[l]) + 127) / 128);
+  for (int l = 0; l < n_lin; ++l) n_part += mt * (((l == nd.L ? nd.d_out : nd.dims[l]) + kBN - 1) / kBN);
   lay->n_part = n_part;
   lay->part_off = o;
   o += align256((size_t)n_steps * n_part * 2 * sizeof(float));
@@ -651,46 +703,60 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.noise_scale = (float)o->noise_scale;
   p.seed = o->seed;
   p.chain_offset = o->chain_offset;
-  // tile tables
+  // tile tables (128 chains / output units x kBN columns per tile)
   int t = 0;
   for (int l = 0; l <= nd.L; ++l) {
     p.tP_first[l] = t;
-    if (l < nd.L || nd.d_out > 0) t += p.mt * (((l == nd.L ? nd.d_out : nd.dims[l]) + 127) / 128);
+    if (l < nd.L || nd.d_out > 0) t += p.mt * (((l == nd.L ? nd.d_out : nd.dims[l]) + kBN - 1) / kBN);
   }
   p.tP_first[nd.L + 1] = t;
   const int n_predict = t;
   t = 0;
   for (int l = 0; l < nd.L; ++l) {
     p.tU_first[l] = t;
-    t += p.mt * ((nd.dims[l] + 127) / 128);
+    t += p.mt * ((nd.dims[l] + kBN - 1) / kBN);
   }
   p.tU_first[nd.L] = t;
   const int n_update = t;
   t = 0;
   bool any_grad = false;
-  for (int l = 0; l <= nd.L; ++l) {
+  p.tW_first[0] = p.tW_first[1] = 0;
+  for (int l = 1; l <= nd.L; ++l) {
     p.tW_first[l] = t;
     const bool is_out = (l == nd.L);
     if (is_out && (nd.d_out == 0 || !nd.top_has_grad)) continue;
-    if (p.gW[l] == nullptr && p.gb[l] == nullptr) continue;
-    any_grad = true;
+    if (p.gW[l] == nullptr) continue;
     const int d_o = is_out ? nd.d_out : nd.dims[l];
-    const int d_i = (l == 0) ? 0 : nd.dims[l - 1];
-    t += ((d_o + 127) / 128) * (d_i == 0 ? 1 : (d_i + 127) / 128);
+    t += ((d_o + 127) / 128) * ((nd.dims[l - 1] + kBN - 1) / kBN);
   }
   p.tW_first[nd.L + 1] = t;
   const int n_wgrad = t;
+  for (int l = 0; l <= nd.L; ++l) any_grad = any_grad || p.gW[l] != nullptr || p.gb[l] != nullptr;
+  if (p.n_part != n_predict) {
+    set_error("internal: partial-slot count mismatch (%d vs %d)", p.n_part, n_predict);
+    return MCPC_ERR_INVALID;
+  }
 
   bool any_traj = io->traj_out != nullptr;
   for (int l = 0; l < nd.L; ++l) any_traj = any_traj || io->traj_x[l] != nullptr;
   const int traj_every = any_traj ? (o->traj_every > 0 ? o->traj_every : 1) : 0;
 
-  const size_t smem_g = (size_t)kWS * 2 * kOpBytes + 1024;
-  const size_t smem_w = (size_t)kWS * (kOpBytes + kOpBytesW) + 1024;
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+  const size_t smem_g = (size_t)kWS * (kABytes + kBBytes) + 1024;
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  int n_sm = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
 
+  const bool timing = getenv("MCPC_WIDE_TIMING") != nullptr;      // debug only: allocates + synchronises
+  if (timing) {
+    cudaMalloc(&p.dbg, 32 * sizeof(long long));
+    cudaMemsetAsync(p.dbg, 0, 32 * sizeof(long long), stream);
+  }
   init_act_kernel<<<1184, 256, 0, stream>>>(p);
   count_launch();
   double b1p = pow(o->adam_beta1, (double)o->adam_step0), b2p = pow(o->adam_beta2, (double)o->adam_step0);
@@ -708,19 +774,34 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
       st.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
     }
     if (n_predict > 0) {
-      wide_predict_kernel<<<n_predict, 160, smem_g, stream>>>(p, st);
+      wide_kernel<KIND_PREDICT><<<n_predict < n_sm ? n_predict : n_sm, 288, smem_g, stream>>>(p, st);
       count_launch();
     }
-    // wgrad reads G (this step's errors) and act(x) of the state BEFORE the update: it runs between the two
+    // the weight update reads G (this step's errors) and act(x) of the state BEFORE the update: it runs between the two
     const bool acc = any_grad && ts >= o->save_begin && ts < o->save_end;
     if (acc) {
-      wide_wgrad_kernel<<<n_wgrad, 160, smem_w, stream>>>(p);
+      if (n_wgrad > 0) {
+        wide_kernel<KIND_WGRAD><<<n_wgrad < n_sm ? n_wgrad : n_sm, 288, smem_g, stream>>>(p, st);
+        count_launch();
+      }
+      wide_bias_kernel<<<(p.g_pitch + 31) / 32, 256, 0, stream>>>(p);
       count_launch();
     }
-    wide_update_kernel<<<n_update, 160, smem_g, stream>>>(p, st);
+    wide_kernel<KIND_UPDATE><<<n_update < n_sm ? n_update : n_sm, 288, smem_g, stream>>>(p, st);
     count_launch();
   }
   MCPC_CUDA_CHECK(cudaGetLastError());
+  if (timing) {
+    long long h[32];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    const char* names[3] = {"predict", "update", "wgrad"};
+    for (int k = 0; k < 3; ++k)
+      fprintf(stderr, "[wide timing] %s (CTA 0, last launch): producer wait-empty %lld, issue %lld, wait-landed %lld cyc over %lld stages; "
+                      "mma wait-acc %lld, wait-full %lld, total %lld cyc\n", names[k], h[k * 8], h[k * 8 + 1], h[k * 8 + 2], h[k * 8 + 3],
+              h[k * 8 + 4], h[k * 8 + 5], h[k * 8 + 6]);
+  }
   if (io->energy != nullptr || io->loss != nullptr) return launch_reduce_partials(p.partials, o->n_steps, p.n_part, io->energy, io->loss, stream);
   return MCPC_OK;
 }
