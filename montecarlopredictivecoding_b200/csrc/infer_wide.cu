@@ -8,17 +8,19 @@
 //   wide_update_kernel    for every PCLayer l: bp = G_{l+1} W_{l+1};  grad = -G_l + act'(x_l) * bp;
 //                         x <- SGD | Adam step; x <- x - lr * noise (Philox);  act(x) re-emitted as bf16
 //
-// All three share one mainloop: 128 x 128 (x144 for wgrad: a block of ones makes the bias gradient a column
-// of the accumulator) output tile per CTA, K in stages of 64, operands scattered from row-major global
-// memory into the canonical no-swizzle UMMA layouts with 16-byte cp.async (K-major or MN-major as the
-// operand's storage order dictates -- no transposed copies of anything), 3-stage ring, accumulator in TMEM,
-// two CTAs per SM so one tile's epilogue overlaps the other's mainloop.  Chains on the M axis: thread =
-// TMEM lane = chain in the epilogues.
+// All three share one persistent mainloop: 128 x 256 output tile, K in stages of 64, operands brought in by TMA
+// (cp.async.bulk.tensor with SWIZZLE_128B tensor maps over the row-major global matrices; K-major or MN-major
+// as the operand's storage order dictates -- no transposed copies of anything), 4-stage mbarrier ring, two
+// 256-column accumulators in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.  Warp roles:
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (thread = TMEM lane = chain, or output unit for wgrad).
+// (A first version scattered operands with 16-byte cp.async: it was bound by the L1TEX wavefront rate -- 8 cache
+// lines per instruction, ~2000 cycles to issue one stage -- see DESIGN.md.)
 // Reference semantics: predictive_coding/pc_trainer.py:733-918 + utils/model.py:35-44.
 #include <cstdlib>
 
 #include "mcpc_common.cuh"
 #include "philox.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 
 namespace mcpc {
@@ -70,18 +72,6 @@ struct StepArgs {
   float step_size, inv_bc2_sqrt;          // Adam bias corrections of this step
 };
 
-struct Operand {
-  const __nv_bfloat16* base;   // element (0,0) of the tile's rows/columns is base[mn0 ...] -- see load_stage
-  int ld;                      // leading dimension (elements)
-  int mn0, mn_ext;             // first M/N index of the tile, extent of the M/N dimension
-};
-
-__device__ __forceinline__ void cp16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ bool elect1() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
@@ -104,46 +94,14 @@ __device__ __forceinline__ float warp_sum_w(float v) {
   return v;
 }
 
-// One stage of one operand (W = W_TOT wide).  K-major: [W mn x 64 k], element (mn,k) at base[(mn0+mn)*ld + k]; smem core matrix
-// (mn/8, k/8) at (mn/8)*1024 + (k/8)*128.  MN-major: [64 k x W mn], element (k,mn) at base[k*ld + mn0+mn]; smem core
-// matrix (k/8, mn/8) at (k/8)*(W/8*128) + (mn/8)*128.  Lane -> (row-in-group = lane%8, 16-byte chunk = lane/8 + 4j):
-// every 8 lanes fill all 32 banks, every row contributes whole 32-byte sectors.
-template <bool MN_MAJOR, int W_TOT>
-__device__ __forceinline__ void load_stage(uint32_t dst, const Operand& op, int k0, int k_ext, int warp, int lane) {
-  const int r8 = lane & 7, cq = lane >> 3;
-  if (!MN_MAJOR) {
-#pragma unroll
-    for (int g = 0; g < W_TOT / 32; ++g) {
-      const int rg = warp * (W_TOT / 32) + g;               // row group (8 rows) 0..W_TOT/8-1
-      const int mn = op.mn0 + rg * 8 + r8;
-      const bool mn_ok = mn < op.mn_ext;
-      const __nv_bfloat16* src_row = op.base + (size_t)(mn_ok ? mn : 0) * op.ld;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = cq + 4 * h;
-        const int k = k0 + c * 8;
-        const bool ok = mn_ok && k < k_ext;
-        cp16(dst + rg * 1024 + c * 128 + r8 * 16, src_row + (ok ? k : 0), ok ? 16u : 0u);
-      }
-    }
-  } else {
-    constexpr uint32_t kg_stride = (uint32_t)(W_TOT / 8) * 128u;
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int kg = warp * 2 + g;                          // k group (8 k) 0..7
-      const int k = k0 + kg * 8 + r8;
-      const bool k_ok = k < k_ext;
-      const __nv_bfloat16* src_row = op.base + (size_t)(k_ok ? k : 0) * op.ld;
-#pragma unroll
-      for (int j = 0; j < W_TOT / 32; ++j) {
-        const int c = cq + 4 * j;
-        const int mn = op.mn0 + c * 8;
-        const bool ok = k_ok && mn < op.mn_ext;
-        cp16(dst + kg * kg_stride + c * 128 + r8 * 16, src_row + (ok ? mn : 0), ok ? 16u : 0u);
-      }
-    }
-  }
-}
+// Tensor maps over the row-major bf16 matrices, one per layer block so that out-of-range K / M / N are zero-filled:
+//   *_k : box 64 (inner = contraction index) x 128|256 rows  -> K-major operand stage
+//   *_mn: box 64 (inner = M/N index) x 64 rows (contraction) -> MN-major operand stage, one box per 64 units
+struct WideMaps {
+  CUtensorMap act_k[kMaxL], act_mn[kMaxL];
+  CUtensorMap gb_k[kMaxL + 1], gb_mn[kMaxL + 1];
+  CUtensorMap w_k[kMaxL + 1], w_mn[kMaxL + 1];
+};
 
 struct Pipe {
   uint64_t full[kWS], empty[kWS], acc_full[2], acc_empty[2];
@@ -155,7 +113,8 @@ struct TileDesc {
   int idx;          // Linear index (predict / wgrad) or layer index (update)
   int m0, n0;
   int k_ext;        // 0: no contraction for this tile
-  Operand A, B;
+  const CUtensorMap* mapA;
+  const CUtensorMap* mapB;
 };
 
 template <int KIND>
@@ -164,7 +123,7 @@ __device__ __forceinline__ int n_tiles_of(const WideParams& p) {
 }
 
 template <int KIND>
-__device__ __forceinline__ TileDesc decode_tile(const WideParams& p, int tile) {
+__device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const WideMaps& mp, int tile) {
   const NetDev& nd = p.net;
   TileDesc t{};
   if (KIND == KIND_PREDICT) {
@@ -175,8 +134,8 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, int tile) {
     const int ntn = (d_o + kBN - 1) / kBN, local = tile - p.tP_first[lin];
     t.idx = lin; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = d_i;
     if (d_i > 0) {
-      t.A = Operand{p.act + p.poff[lin - 1], p.a_pitch, t.m0, p.B};     // act(x_{l-1}) [B x d_i], K-major
-      t.B = Operand{p.Wb[lin], d_i, t.n0, d_o};                         // W_l [d_o x d_i], K-major
+      t.mapA = &mp.act_k[lin - 1];                                // act(x_{l-1}) [B x d_i], K-major
+      t.mapB = &mp.w_k[lin];                                      // W_l [d_o x d_i], K-major
     }
   } else if (KIND == KIND_UPDATE) {
     int l = 0;
@@ -187,17 +146,17 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, int tile) {
     const int d_up = (l + 1 < nd.L) ? nd.dims[l + 1] : nd.d_out;
     t.idx = l; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = has_above ? d_up : 0;
     if (has_above) {
-      t.A = Operand{p.Gb + p.poff[l + 1], p.g_pitch, t.m0, p.B};        // G_{l+1} [B x d_up], K-major
-      t.B = Operand{p.Wb[l + 1], dl, t.n0, dl};                         // W_{l+1} [d_up x d_l] as B[k][n]: MN-major
+      t.mapA = &mp.gb_k[l + 1];                                   // G_{l+1} [B x d_up], K-major
+      t.mapB = &mp.w_mn[l + 1];                                   // W_{l+1} [d_up x d_l] as B[k][n]: MN-major
     }
   } else {
     int lin = 1;
     while (tile >= p.tW_first[lin + 1]) ++lin;
-    const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = nd.dims[lin - 1];
+    const int d_i = nd.dims[lin - 1];
     const int ntn = (d_i + kBN - 1) / kBN, local = tile - p.tW_first[lin];
     t.idx = lin; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = p.B;
-    t.A = Operand{p.Gb + p.poff[lin], p.g_pitch, t.m0, d_o};            // G_l as A[k=chain][m]: MN-major
-    t.B = Operand{p.act + p.poff[lin - 1], p.a_pitch, t.n0, d_i};       // act(x_{l-1}) as B[k=chain][n]: MN-major
+    t.mapA = &mp.gb_mn[lin];                                      // G_l as A[k=chain][m]: MN-major
+    t.mapB = &mp.act_mn[lin - 1];                                 // act(x_{l-1}) as B[k=chain][n]: MN-major
   }
   return t;
 }
@@ -226,7 +185,7 @@ __device__ __forceinline__ void store_f32x16(float* dst, const float (&v)[16]) {
 
 // ---- epilogues: thread = TMEM lane = chain (predict / update) or output unit (wgrad); 16 columns at a time ----
 __device__ __forceinline__ void epilogue_predict(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_addr,
-                                                 int row_in_tile, float& e_part, float& l_part) {
+                                                 int row_in_tile, int c_begin, int c_end, float& e_part, float& l_part) {
   const NetDev& nd = p.net;
   const int lin = t.idx;
   const bool is_out = (lin == nd.L);
@@ -235,7 +194,7 @@ __device__ __forceinline__ void epilogue_predict(const WideParams& p, const Step
   const bool rvalid = row < p.B;
   const float ce = is_out ? 0.0f : 0.5f * nd.c[lin], gc = is_out ? 0.0f : nd.gc[lin];
   const bool bern = nd.top == MCPC_TOP_BERNOULLI;
-  for (int c = 0; c < kBN; c += 16) {
+  for (int c = c_begin; c < c_end; c += 16) {
     const int n = t.n0 + c;
     if (n >= d_o) break;                                  // uniform over the warp
     float d[16];
@@ -295,7 +254,7 @@ __device__ __forceinline__ void epilogue_predict(const WideParams& p, const Step
 }
 
 __device__ __forceinline__ void epilogue_update(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_addr,
-                                                int row_in_tile, int lane) {
+                                                int row_in_tile, int c_begin, int c_end, int lane) {
   const NetDev& nd = p.net;
   const int l = t.idx;
   const int dl = nd.dims[l];
@@ -305,7 +264,7 @@ __device__ __forceinline__ void epilogue_update(const WideParams& p, const StepA
   const bool adam = p.optimizer == MCPC_OPT_ADAM;
   const uint64_t chain = p.chain_offset + (uint64_t)row;
   const bool grouped_rng = (p.chain_offset & 3) == 0;             // lanes 4q..4q+3 share one Philox counter
-  for (int c = 0; c < kBN; c += 16) {
+  for (int c = c_begin; c < c_end; c += 16) {
     const int n = t.n0 + c;
     if (n >= dl) break;                                           // uniform over the warp
     float bp[16];
@@ -323,14 +282,23 @@ __device__ __forceinline__ void epilogue_update(const WideParams& p, const StepA
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           langevin_normals4(p.seed, (uint32_t)(nd.off[l] + n + (lane & 3) + 4 * j), (uint32_t)st.t_abs, chain >> 2, mine[j]);
-        const int kc = (int)(chain & 3);
+        // 4x4 transpose across the 4 lanes of a group: afterwards mine[j][a] = normal of MY chain for unit n + 4j + a
+        const int a = lane & 3;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          // unit n+i was drawn by lane (group base + i%4) as its j = i/4; I take the component of MY chain
-          const int src = (lane & ~3) | (i & 3);
-          const float v0 = __shfl_sync(0xffffffffu, mine[i >> 2][0], src), v1 = __shfl_sync(0xffffffffu, mine[i >> 2][1], src);
-          const float v2 = __shfl_sync(0xffffffffu, mine[i >> 2][2], src), v3 = __shfl_sync(0xffffffffu, mine[i >> 2][3], src);
-          nz[i] = p.noise_scale * (kc == 0 ? v0 : (kc == 1 ? v1 : (kc == 2 ? v2 : v3)));
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int sft = 1; sft <= 2; sft <<= 1) {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              if ((c4 & sft) == 0) {
+                const float send = (a & sft) ? mine[j][c4] : mine[j][c4 | sft];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, sft);
+                if (a & sft) mine[j][c4] = recv; else mine[j][c4 | sft] = recv;
+              }
+            }
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) nz[4 * j + c4] = p.noise_scale * mine[j][c4];
         }
       } else {
 #pragma unroll
@@ -383,13 +351,14 @@ __device__ __forceinline__ void epilogue_update(const WideParams& p, const StepA
   }
 }
 
-__device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDesc& t, uint32_t acc_addr, int row_in_tile) {
+__device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDesc& t, uint32_t acc_addr, int row_in_tile,
+                                               int c_begin, int c_end) {
   const NetDev& nd = p.net;
   const int lin = t.idx;
   const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = nd.dims[lin - 1];
   const int mo = t.m0 + row_in_tile;
   float* gW = p.gW[lin];
-  for (int c = 0; c < kBN; c += 16) {
+  for (int c = c_begin; c < c_end; c += 16) {
     const int n = t.n0 + c;
     if (n >= d_i) break;
     float d[16];
@@ -408,11 +377,12 @@ __device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDe
 // warp 4 MMA issuer, warps 5-8 epilogue; two 256-column accumulators in TMEM so the epilogue of tile i overlaps the
 // mainloop of tile i+1.
 template <int KIND>
-__global__ void __launch_bounds__(288, 1) wide_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st) {
+__global__ void __launch_bounds__(320, 1) wide_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st,
+                                                      const __grid_constant__ WideMaps mp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Pipe pipe;
   __shared__ uint32_t tmem_s;
-  __shared__ float s_red[4][2];
+  __shared__ float s_red[8][2];
   constexpr bool A_MN = (KIND == KIND_WGRAD), B_MN = (KIND != KIND_PREDICT);
   constexpr uint32_t stage_bytes = kABytes + kBBytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -420,66 +390,68 @@ __global__ void __launch_bounds__(288, 1) wide_kernel(const __grid_constant__ Wi
 
   if (tid == 0) {
     for (int s = 0; s < kWS; ++s) {
-      mbar_init(&pipe.full[s], 128);
+      mbar_init(&pipe.full[s], 1);
       mbar_init(&pipe.empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&pipe.acc_full[b], 1);
-      mbar_init(&pipe.acc_empty[b], 128);
+      mbar_init(&pipe.acc_empty[b], 256);
     }
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_s, 512);
+  if (warp == 1) tmem_alloc(&tmem_s, 512);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_s;
   const uint32_t smem_base = smem_u32(smem);
 
-  if (warp < 4) {
-    // ---------------- producers ----------------
-    constexpr int D = kWS - 1;
-    uint32_t issued = 0, signalled = 0;
-    long long c_empty = 0, c_issue = 0, c_land = 0;
-    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileDesc t = decode_tile<KIND>(p, tile);
-      const int n_stage = (t.k_ext + kBK - 1) / kBK;
-      for (int s = 0; s < n_stage; ++s) {
-        const uint32_t slot = issued % kWS;
-        const long long t0 = prof ? clock64() : 0;
-        mbar_wait(&pipe.empty[slot], ((issued / kWS) & 1u) ^ 1u);
-        const long long t1 = prof ? clock64() : 0;
-        load_stage<A_MN, 128>(smem_base + slot * stage_bytes, t.A, s * kBK, t.k_ext, warp, lane);
-        load_stage<B_MN, kBN>(smem_base + slot * stage_bytes + kABytes, t.B, s * kBK, t.k_ext, warp, lane);
-        cp_commit();
-        const long long t2 = prof ? clock64() : 0;
-        ++issued;
-        if (issued - signalled > (uint32_t)D) {
-          cp_wait<D>();
-          fence_async_smem();
-          mbar_arrive(&pipe.full[signalled % kWS]);
-          ++signalled;
+  if (warp == 0) {
+    // ---------------- TMA producer: one elected lane, one mbarrier transaction per 48 KB stage ----------------
+    if (lane == 0) {
+      uint32_t issued = 0;
+      long long c_empty = 0, c_issue = 0;
+      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileDesc t = decode_tile<KIND>(p, mp, tile);
+        const int n_stage = (t.k_ext + kBK - 1) / kBK;
+        for (int s = 0; s < n_stage; ++s, ++issued) {
+          const uint32_t slot = issued % kWS;
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait(&pipe.empty[slot], ((issued / kWS) & 1u) ^ 1u);
+          const long long t1 = prof ? clock64() : 0;
+          uint8_t* sa = smem + slot * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&pipe.full[slot], stage_bytes);
+          const int k0 = s * kBK;
+          if (!A_MN) tma_load_2d(sa, t.mapA, k0, t.m0, &pipe.full[slot]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d(sa + j * 8192, t.mapA, t.m0 + j * 64, k0, &pipe.full[slot]);
+          }
+          if (!B_MN) tma_load_2d(sb, t.mapB, k0, t.n0, &pipe.full[slot]);
+          else {
+#pragma unroll
+            for (int j = 0; j < kBN / 64; ++j) tma_load_2d(sb + j * 8192, t.mapB, t.n0 + j * 64, k0, &pipe.full[slot]);
+          }
+          if (prof) { c_empty += t1 - t0; c_issue += clock64() - t1; }
         }
-        if (prof) { c_empty += t1 - t0; c_issue += t2 - t1; c_land += clock64() - t2; }
       }
+      if (prof) { p.dbg[KIND * 8 + 0] = c_empty; p.dbg[KIND * 8 + 1] = c_issue; p.dbg[KIND * 8 + 2] = 0; p.dbg[KIND * 8 + 3] = issued; }
     }
-    if (prof) { p.dbg[KIND * 8 + 0] = c_empty; p.dbg[KIND * 8 + 1] = c_issue; p.dbg[KIND * 8 + 2] = c_land; p.dbg[KIND * 8 + 3] = issued; }
-    cp_wait<0>();
-    fence_async_smem();
-    for (; signalled < issued; ++signalled) mbar_arrive(&pipe.full[signalled % kWS]);
-  } else if (warp == 4) {
+  } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     const uint32_t id = idesc_bf16(128, kBN, A_MN, B_MN);
-    constexpr uint32_t lbo_a = A_MN ? 2048u : 128u, sbo_a = A_MN ? 128u : 1024u;
-    constexpr uint32_t lbo_b = B_MN ? (uint32_t)(kBN / 8) * 128u : 128u, sbo_b = B_MN ? 128u : 1024u;
-    constexpr uint32_t adv_a = A_MN ? (2 * 2048u) >> 4 : 16u, adv_b = B_MN ? (2 * lbo_b) >> 4 : 16u;
+    // SWIZZLE_128B operand descriptors (tma.cuh): K-major LBO field 1 / SBO 1024, 32 B per K step;
+    // MN-major LBO 8192 (next 64 units) / SBO 1024 (next 8 k-rows), 2048 B per K step
+    constexpr uint32_t lbo_a = A_MN ? 8192u : 16u, lbo_b = B_MN ? 8192u : 16u;
+    constexpr uint32_t adv_a = A_MN ? (2048u >> 4) : (32u >> 4), adv_b = B_MN ? (2048u >> 4) : (32u >> 4);
     uint32_t sc = 0, gi = 0;
     long long c_acc = 0, c_full = 0;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
     const long long k0 = clock64();
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileDesc t = decode_tile<KIND>(p, tile);
+      const TileDesc t = decode_tile<KIND>(p, mp, tile);
       const int n_stage = (t.k_ext + kBK - 1) / kBK;
       if (n_stage == 0) continue;
       const uint32_t ab = gi & 1u;
@@ -493,8 +465,8 @@ __global__ void __launch_bounds__(288, 1) wide_kernel(const __grid_constant__ Wi
         mbar_wait(&pipe.full[slot], (sc / kWS) & 1u);
         c_full += clock64() - f0;
         fence_after_sync();
-        const uint64_t ad0 = smem_desc(smem_base + slot * stage_bytes, lbo_a, sbo_a);
-        const uint64_t bd0 = smem_desc(smem_base + slot * stage_bytes + kABytes, lbo_b, sbo_b);
+        const uint64_t ad0 = smem_desc_sw128(smem_base + slot * stage_bytes, lbo_a, 1024u);
+        const uint64_t bd0 = smem_desc_sw128(smem_base + slot * stage_bytes + kABytes, lbo_b, 1024u);
         if (elect1()) {
 #pragma unroll
           for (int ks = 0; ks < kBK / 16; ++ks)
@@ -508,12 +480,14 @@ __global__ void __launch_bounds__(288, 1) wide_kernel(const __grid_constant__ Wi
     }
     if (prof) { p.dbg[KIND * 8 + 4] = c_acc; p.dbg[KIND * 8 + 5] = c_full; p.dbg[KIND * 8 + 6] = clock64() - k0; }
   } else {
-    // ---------------- epilogue warps 5..8 (TMEM lane quarter = warp % 4) ----------------
+    // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----------------
     const int q = warp & 3;
+    const int ew = warp - 2;                               // 0..7
+    const int c_begin = (ew >> 2) * (kBN / 2), c_end = c_begin + kBN / 2;
     const int row_in_tile = q * 32 + lane;
     uint32_t gi = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileDesc t = decode_tile<KIND>(p, tile);
+      const TileDesc t = decode_tile<KIND>(p, mp, tile);
       const bool has_gemm = t.k_ext > 0;
       const uint32_t ab = gi & 1u;
       if (has_gemm) {
@@ -523,17 +497,22 @@ __global__ void __launch_bounds__(288, 1) wide_kernel(const __grid_constant__ Wi
       const uint32_t acc_addr = tmem + ((uint32_t)(q * 32) << 16) + ab * kBN;
       if (KIND == KIND_PREDICT) {
         float e_part = 0.0f, l_part = 0.0f;
-        epilogue_predict(p, st, t, acc_addr, row_in_tile, e_part, l_part);
+        epilogue_predict(p, st, t, acc_addr, row_in_tile, c_begin, c_end, e_part, l_part);
         e_part = warp_sum_w(e_part);
         l_part = warp_sum_w(l_part);
-        if (lane == 0) { s_red[q][0] = e_part; s_red[q][1] = l_part; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (q == 1 && lane < 2) p.partials[((size_t)st.ts * p.n_part + tile) * 2 + lane] = s_red[0][lane] + s_red[1][lane] + s_red[2][lane] + s_red[3][lane];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (lane == 0) { s_red[ew][0] = e_part; s_red[ew][1] = l_part; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ew == 0 && lane < 2) {
+          float sum = 0.0f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += s_red[w][lane];
+          p.partials[((size_t)st.ts * p.n_part + tile) * 2 + lane] = sum;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       } else if (KIND == KIND_UPDATE) {
-        epilogue_update(p, st, t, acc_addr, row_in_tile, lane);
+        epilogue_update(p, st, t, acc_addr, row_in_tile, c_begin, c_end, lane);
       } else {
-        epilogue_wgrad(p, t, acc_addr, row_in_tile);
+        epilogue_wgrad(p, t, acc_addr, row_in_tile, c_begin, c_end);
       }
       if (has_gemm) {
         fence_before_sync();
@@ -544,7 +523,7 @@ __global__ void __launch_bounds__(288, 1) wide_kernel(const __grid_constant__ Wi
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // gb_l[m] += sum over chains of G_l[chain][m]   (all Linears at once: the columns of Gb)
@@ -741,6 +720,21 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   for (int l = 0; l < nd.L; ++l) any_traj = any_traj || io->traj_x[l] != nullptr;
   const int traj_every = any_traj ? (o->traj_every > 0 ? o->traj_every : 1) : 0;
 
+  // tensor maps: one per layer block (base offset = the block's first column) so TMA zero-fills past its extent
+  WideMaps mp;
+  for (int l = 0; l < nd.L; ++l) {
+    rc = make_tmap_bf16(&mp.act_k[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, 128);
+    if (rc == MCPC_OK) rc = make_tmap_bf16(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, 64);
+    if (rc != MCPC_OK) return rc;
+  }
+  for (int l = 0; l < n_lin; ++l) {
+    const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
+    rc = make_tmap_bf16(&mp.gb_k[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 128);
+    if (rc == MCPC_OK) rc = make_tmap_bf16(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 64);
+    if (rc == MCPC_OK && l >= 1) rc = make_tmap_bf16(&mp.w_k[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, 256);
+    if (rc == MCPC_OK && l >= 1) rc = make_tmap_bf16(&mp.w_mn[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, 64);
+    if (rc != MCPC_OK) return rc;
+  }
   const size_t smem_g = (size_t)kWS * (kABytes + kBBytes) + 1024;
   MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
@@ -750,6 +744,10 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* env = getenv("MCPC_WIDE_CTAS")) {        // testing hook: few persistent CTAs => many tiles per CTA
+      const int v = atoi(env);
+      if (v >= 1 && v <= n_sm) n_sm = v;
+    }
   }
 
   const bool timing = getenv("MCPC_WIDE_TIMING") != nullptr;      // debug only: allocates + synchronises
@@ -774,20 +772,20 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
       st.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
     }
     if (n_predict > 0) {
-      wide_kernel<KIND_PREDICT><<<n_predict < n_sm ? n_predict : n_sm, 288, smem_g, stream>>>(p, st);
+      wide_kernel<KIND_PREDICT><<<n_predict < n_sm ? n_predict : n_sm, 320, smem_g, stream>>>(p, st, mp);
       count_launch();
     }
     // the weight update reads G (this step's errors) and act(x) of the state BEFORE the update: it runs between the two
     const bool acc = any_grad && ts >= o->save_begin && ts < o->save_end;
     if (acc) {
       if (n_wgrad > 0) {
-        wide_kernel<KIND_WGRAD><<<n_wgrad < n_sm ? n_wgrad : n_sm, 288, smem_g, stream>>>(p, st);
+        wide_kernel<KIND_WGRAD><<<n_wgrad < n_sm ? n_wgrad : n_sm, 320, smem_g, stream>>>(p, st, mp);
         count_launch();
       }
       wide_bias_kernel<<<(p.g_pitch + 31) / 32, 256, 0, stream>>>(p);
       count_launch();
     }
-    wide_kernel<KIND_UPDATE><<<n_update < n_sm ? n_update : n_sm, 288, smem_g, stream>>>(p, st);
+    wide_kernel<KIND_UPDATE><<<n_update < n_sm ? n_update : n_sm, 320, smem_g, stream>>>(p, st, mp);
     count_launch();
   }
   MCPC_CUDA_CHECK(cudaGetLastError());
@@ -798,7 +796,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
     cudaFree(p.dbg);
     const char* names[3] = {"predict", "update", "wgrad"};
     for (int k = 0; k < 3; ++k)
-      fprintf(stderr, "[wide timing] %s (CTA 0, last launch): producer wait-empty %lld, issue %lld, wait-landed %lld cyc over %lld stages; "
+      fprintf(stderr, "[wide timing] %s (CTA 0, last launch): producer wait-empty %lld, issue %lld, (%lld) cyc over %lld stages; "
                       "mma wait-acc %lld, wait-full %lld, total %lld cyc\n", names[k], h[k * 8], h[k * 8 + 1], h[k * 8 + 2], h[k * 8 + 3],
               h[k * 8 + 4], h[k * 8 + 5], h[k * 8 + 6]);
   }

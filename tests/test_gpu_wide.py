@@ -39,9 +39,13 @@ def _model(dims, d_out, act, dev, seed=0):
     return m.to(dev)
 
 
-@pytest.mark.parametrize("act,top,opt,B", [("tanh", "gauss", "sgd", 200), ("relu", "bernoulli", "sgd", 256),
-                                           ("tanh", "gauss", "adam", 130)])
-def test_streaming_path_vs_bf16_oracle(act, top, opt, B):
+@pytest.mark.parametrize("act,top,opt,B,ctas", [("tanh", "gauss", "sgd", 200, 0), ("relu", "bernoulli", "sgd", 256, 0),
+                                                ("tanh", "gauss", "adam", 130, 0), ("relu", "bernoulli", "sgd", 392, 2)])
+def test_streaming_path_vs_bf16_oracle(act, top, opt, B, ctas, monkeypatch):
+    # ctas > 0: only that many persistent CTAs, so each walks several tiles (ring wrap-around, accumulator
+    # double buffering across tiles)
+    if ctas:
+        monkeypatch.setenv("MCPC_WIDE_CTAS", str(ctas))
     dev = torch.device(DEV)
     dims, d_out = [128, 256, 144], 272
     mixing, sampling, lr = 2, 4, 0.02
