@@ -64,6 +64,7 @@ struct WideParams {
   int noise_mode;
   float noise_scale;
   uint64_t seed, chain_offset;
+  int mn3;                                // MN-major operands come in through 3-D tensor maps (all widths % 64 == 0)
   long long* dbg;                         // MCPC_WIDE_TIMING=1: per-role cycle counters of CTA 0 (debug)
 };
 
@@ -425,11 +426,13 @@ __global__ void __launch_bounds__(320, 1) wide_kernel(const __grid_constant__ Wi
           mbar_expect_tx(&pipe.full[slot], stage_bytes);
           const int k0 = s * kBK;
           if (!A_MN) tma_load_2d(sa, t.mapA, k0, t.m0, &pipe.full[slot]);
+          else if (p.mn3) tma_load_3d(sa, t.mapA, 0, k0, t.m0 / 64, &pipe.full[slot]);
           else {
 #pragma unroll
             for (int j = 0; j < 2; ++j) tma_load_2d(sa + j * 8192, t.mapA, t.m0 + j * 64, k0, &pipe.full[slot]);
           }
           if (!B_MN) tma_load_2d(sb, t.mapB, k0, t.n0, &pipe.full[slot]);
+          else if (p.mn3) tma_load_3d(sb, t.mapB, 0, k0, t.n0 / 64, &pipe.full[slot]);
           else {
 #pragma unroll
             for (int j = 0; j < kBN / 64; ++j) tma_load_2d(sb + j * 8192, t.mapB, t.n0 + j * 64, k0, &pipe.full[slot]);
@@ -722,17 +725,26 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
 
   // tensor maps: one per layer block (base offset = the block's first column) so TMA zero-fills past its extent
   WideMaps mp;
+  bool mn3 = (nd.d_out % 64 == 0);
+  for (int l = 0; l < nd.L; ++l) mn3 = mn3 && (nd.dims[l] % 64 == 0);
+  p.mn3 = mn3 ? 1 : 0;
   for (int l = 0; l < nd.L; ++l) {
     rc = make_tmap_bf16(&mp.act_k[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, 128);
-    if (rc == MCPC_OK) rc = make_tmap_bf16(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, 64);
+    if (rc == MCPC_OK)
+      rc = mn3 ? make_tmap_bf16_mn3(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, kBN / 64)   // wgrad B operand
+               : make_tmap_bf16(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, 64);
     if (rc != MCPC_OK) return rc;
   }
   for (int l = 0; l < n_lin; ++l) {
     const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
     rc = make_tmap_bf16(&mp.gb_k[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 128);
-    if (rc == MCPC_OK) rc = make_tmap_bf16(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 64);
+    if (rc == MCPC_OK)
+      rc = mn3 ? make_tmap_bf16_mn3(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 2)                   // wgrad A operand
+               : make_tmap_bf16(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 64);
     if (rc == MCPC_OK && l >= 1) rc = make_tmap_bf16(&mp.w_k[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, 256);
-    if (rc == MCPC_OK && l >= 1) rc = make_tmap_bf16(&mp.w_mn[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, 64);
+    if (rc == MCPC_OK && l >= 1)
+      rc = mn3 ? make_tmap_bf16_mn3(&mp.w_mn[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, kBN / 64)       // update B operand
+               : make_tmap_bf16(&mp.w_mn[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, 64);
     if (rc != MCPC_OK) return rc;
   }
   const size_t smem_g = (size_t)kWS * (kABytes + kBBytes) + 1024;

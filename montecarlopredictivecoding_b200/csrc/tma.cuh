@@ -56,6 +56,31 @@ inline int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uin
   return MCPC_OK;
 }
 
+// The same row-major matrix [k rows][n columns] viewed as 3-D (64 columns, k, column block): ONE box of
+// 64 x box_k x box_blocks lands as `box_blocks` consecutive MN-major operand blocks of 8 KB (n must be a
+// multiple of 64 so that no block straddles the end of the matrix).
+inline int make_tmap_bf16_mn3(CUtensorMap* tm, const void* base, uint64_t n_cols, uint64_t k_rows, uint64_t pitch,
+                              uint32_t box_k, uint32_t box_blocks) {
+  TmapEncodeFn fn = tmap_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return MCPC_ERR_CUDA;
+  }
+  const cuuint64_t gdim[3] = {64, k_rows, n_cols / 64};
+  const cuuint64_t gstride[2] = {pitch * 2, 128};
+  const cuuint32_t box[3] = {64, box_k, box_blocks};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed (%d) for cols=%llu rows=%llu pitch=%llu", (int)r,
+              (unsigned long long)n_cols, (unsigned long long)k_rows, (unsigned long long)pitch);
+    return MCPC_ERR_CUDA;
+  }
+  return MCPC_OK;
+}
+
 namespace umma {
 
 // shared-memory matrix descriptor with layout type SWIZZLE_128B (= 2 in bits [61,64))
@@ -67,6 +92,11 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int c_inner, int c_outer, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                :: "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               :: "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {

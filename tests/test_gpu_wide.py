@@ -40,7 +40,8 @@ def _model(dims, d_out, act, dev, seed=0):
 
 
 @pytest.mark.parametrize("act,top,opt,B,ctas", [("tanh", "gauss", "sgd", 200, 0), ("relu", "bernoulli", "sgd", 256, 0),
-                                                ("tanh", "gauss", "adam", 130, 0), ("relu", "bernoulli", "sgd", 392, 2)])
+                                                ("tanh", "gauss", "adam", 130, 0), ("relu", "bernoulli", "sgd", 392, 2),
+                                                ("tanh", "gauss", "sgd", 300, 64)])
 def test_streaming_path_vs_bf16_oracle(act, top, opt, B, ctas, monkeypatch):
     # ctas > 0: only that many persistent CTAs, so each walks several tiles (ring wrap-around, accumulator
     # double buffering across tiles)
@@ -48,6 +49,8 @@ def test_streaming_path_vs_bf16_oracle(act, top, opt, B, ctas, monkeypatch):
         monkeypatch.setenv("MCPC_WIDE_CTAS", str(ctas))
     dev = torch.device(DEV)
     dims, d_out = [128, 256, 144], 272
+    if ctas == 64:          # all widths multiples of 64: MN-major operands come in through the 3-D tensor maps
+        dims, d_out = [128, 320, 192], 576
     mixing, sampling, lr = 2, 4, 0.02
     T = mixing + sampling
     model = _model(dims, d_out, act, dev)
