@@ -17,7 +17,13 @@ import torch.optim as optim  # noqa: E402
 from montecarlopredictivecoding_b200 import mcpc_utils as mu  # noqa: E402
 from montecarlopredictivecoding_b200 import predictive_coding as pc  # noqa: E402
 
-DEV = torch.device("cuda:0")
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+torch.cuda.set_device(LOCAL)
+DEV = torch.device("cuda", LOCAL)
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=DEV)
 PEAK_TF = 1663.5
 if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")):
     PEAK_TF = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("bf16_tflops", PEAK_TF)
@@ -123,6 +129,8 @@ def c5(prec, B=2048, T=20, width=4096, L=4):
                       accumulate_p_at=list(range(T)), optimizer_p_fn=optim.SGD, optimizer_p_kwargs={"lr": 1e-4},
                       plot_progress_at=[])
     tr.set_precision(prec)
+    if WORLD > 1:
+        tr.set_data_parallel()            # chains sharded: B per GPU, one NCCL all-reduce of the 268 MB dW per call
     z = torch.zeros(B, width, device=DEV)
     y = torch.randn(B, width, device=DEV)
     first = [True]
@@ -136,7 +144,8 @@ def c5(prec, B=2048, T=20, width=4096, L=4):
     mac = L * width * width          # Linear_0 sees zero inputs; 3 hidden + 1 output contraction of width^2 each ... L total
     flops = B * T * 6 * mac          # fwd + back-projection + dW every step
     return {"workload": f"C5 wide {L}x{width}->{width} tanh Gaussian, B={B} per GPU, T={T}, dW every step", "precision": prec,
-            "ms_per_step": s / T * 1e3, "latent_updates_per_s": B * L * T / s, "images_per_s_T100": B / (s / T * 100),
+            "n_gpus": WORLD, "ms_per_call": s * 1e3,
+            "ms_per_step": s / T * 1e3, "latent_updates_per_s": WORLD * B * L * T / s, "images_per_s_T100": WORLD * B / (s / T * 100),
             "algorithmic_tflops": flops / s / 1e12, "frac_of_bf16_peak": flops / s / 1e12 / PEAK_TF}
 
 
@@ -147,7 +156,11 @@ if __name__ == "__main__":
     which = [a for a in sys.argv[1:] if a in ("c1", "c3", "c4", "c5")] or ["c1", "c3", "c4", "c5"]
     for w in which:
         try:
-            print(json.dumps({"c1": c1, "c3": c3, "c4": c4, "c5": c5}[w](prec)))
+            out = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[w](prec)
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps(out))
         except Exception as exc:  # noqa: BLE001
             print(json.dumps({"workload": w, "error": repr(exc)[:300]}))
         sys.stdout.flush()
+    if WORLD > 1:
+        dist.destroy_process_group()
