@@ -103,7 +103,8 @@ def run_call(model, trainer, spec, call, inputs, target, out, prefix):
 
     kwargs = dict(inputs=inputs, is_log_progress=False, is_return_results_every_t=True,
                   is_checking_after_callback_after_t=False, is_return_outputs=True, is_return_xs=True,
-                  is_sample_x_at_batch_start=call.get("sample_x", True))
+                  is_sample_x_at_batch_start=call.get("sample_x", True),
+                  is_reset_optimizer_x_at_batch_start=call.get("reset_opt_x", True))
     loss_fn = LOSSES[call.get("loss", spec.get("loss", "none"))]
     if loss_fn is not None:
         kwargs["loss_fn"] = loss_fn
@@ -184,9 +185,12 @@ def run_case(name, spec):
         target = torch.randn(B, d_t)
     out = {"inputs": inputs.numpy().copy(), "target": target.numpy().copy()}
     # trainers are created up-front like the scripts do (figure_2.py:67-69)
-    trainers = [make_trainer(model, c["trainer"]) for c in spec["calls"]]
+    trainers = []
+    for c in spec["calls"]:
+        trainers.append(trainers[c["trainer_of"]] if "trainer_of" in c else make_trainer(model, c["trainer"]))
     for ci, call in enumerate(spec["calls"]):
-        run_call(model, trainers[ci], spec, call, inputs, target, out, f"c{ci}_")
+        rows = call.get("rows", B)      # a call may use only the first `rows` chains (batch-size change)
+        run_call(model, trainers[ci], spec, call, inputs[:rows], target[:rows], out, f"c{ci}_")
     out["spec_json"] = np.frombuffer(json.dumps(spec).encode(), dtype=np.uint8)
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
@@ -274,6 +278,22 @@ CASES = {
         calls=[
             dict(trainer=dict(T=5, opt_x="sgd", lr_x=0.05, update_p_at="all", opt_p="sgd",
                               opt_p_kwargs={"lr": 0.02}, energy_coefficient=0.5), langevin=True, sample_x=True),
+        ]),
+    # schedules given as 'last_half' (pc_trainer.py:1094-1095): x frozen for the first half, p-steps inside the loop
+    "last_half_schedules": dict(
+        dims=[4, 10], d_out=8, act="tanh", loss="gauss", var=1.0, B=6, sampler="normal", target="normal",
+        calls=[
+            dict(trainer=dict(T=8, opt_x="sgd", lr_x=0.05, update_x_at="last_half", update_p_at="last_half",
+                              opt_p="sgd", opt_p_kwargs={"lr": 0.02})),
+        ]),
+    # one trainer used for consecutive calls: Adam-on-x state carried over (is_reset_optimizer_x_at_batch_start=False),
+    # then a smaller batch on the same trainer (latents re-sampled, optimizer_x re-created, pc_trainer.py:742-752)
+    "adam_carryover_batch_resize": dict(
+        dims=[5, 12], d_out=10, act="relu", loss="bernoulli", B=8, sampler="uniform",
+        calls=[
+            dict(trainer=dict(T=6, opt_x="adam", lr_x=0.1), sample_x=True),
+            dict(trainer=dict(T=6, opt_x="adam", lr_x=0.1), trainer_of=0, sample_x=False, reset_opt_x=False),
+            dict(trainer=dict(T=6, opt_x="adam", lr_x=0.1), trainer_of=0, sample_x=True, rows=5),
         ]),
 }
 

@@ -65,6 +65,10 @@ class GoldenCase:
                             top=top, top_var=self.spec.get("var", 1.0), mask_start_col=ms)
         return net.cast(dtype)
 
+    def rows(self, ci):
+        """Number of chains call ``ci`` ran with (a call may use only the first rows of inputs/target)."""
+        return self.calls[ci].get("rows", self.B)
+
     def x0(self, ci):
         return [self.z[f"c{ci}_traj_x{l}"][0] for l in range(self.L)]
 
@@ -94,6 +98,8 @@ class GoldenCase:
                 return list(range(T))
             if v == "last":
                 return [T - 1]
+            if v == "last_half":
+                return list(range(T // 2, T))
             if v == "never":
                 return []
             return list(v)

@@ -65,9 +65,11 @@ def replay(name, device, engine_factory=None, precision="fp32", tol_x=1e-5, tol_
     model = build_model(gc, device)
     lins = [m for m in model if isinstance(m, nn.Linear)]
     pcs = [m for m in model if isinstance(m, pc.PCLayer)]
-    trainers = [make_trainer(model, c["trainer"]) for c in gc.calls]
-    inputs = torch.from_numpy(gc.inputs).to(device)
-    target = torch.from_numpy(gc.target).to(device)
+    trainers = []
+    for c in gc.calls:
+        trainers.append(trainers[c["trainer_of"]] if "trainer_of" in c else make_trainer(model, c["trainer"]))
+    inputs_all = torch.from_numpy(gc.inputs).to(device)
+    target_all = torch.from_numpy(gc.target).to(device)
     worst = {"x": 0.0, "scalar": 0.0, "grad": 0.0, "w": 0.0}
     for ci, call in enumerate(gc.calls):
         tr = call["trainer"]
@@ -76,6 +78,7 @@ def replay(name, device, engine_factory=None, precision="fp32", tol_x=1e-5, tol_
             trainer._engine = engine_factory()
         trainer.set_precision(precision)
         T = tr["T"]
+        inputs, target = inputs_all[:gc.rows(ci)], target_all[:gc.rows(ci)]
         if teacher_force and ci > 0:
             # start every call from the reference's own state (latents and parameters) so that the bound
             # measures ONE call, not the drift accumulated over the preceding (chaotic, Adam) calls
@@ -93,7 +96,8 @@ def replay(name, device, engine_factory=None, precision="fp32", tol_x=1e-5, tol_
                 layer._sample_x_fn = (lambda inputs, v=x0: v.clone())
         kwargs = dict(inputs=inputs, is_log_progress=False, is_return_results_every_t=True,
                       is_checking_after_callback_after_t=False, is_return_outputs=True, is_return_xs=True,
-                      is_sample_x_at_batch_start=call.get("sample_x", True))
+                      is_sample_x_at_batch_start=call.get("sample_x", True),
+                      is_reset_optimizer_x_at_batch_start=call.get("reset_opt_x", True))
         lk = gc.loss_kind(ci)
         if LOSSES[lk] is not None:
             kwargs["loss_fn"] = LOSSES[lk]
