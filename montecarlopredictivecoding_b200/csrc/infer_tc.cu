@@ -50,6 +50,7 @@ struct TcParams {
   NetDev net;
   int n_hid_tiles, n_out_tiles;
   Tile tiles[kMaxTiles];
+  int y_tmem;                   // targets of the output tiles are kept in TMEM (they fit beside the accumulators)
   int HT;                       // hidden unit tiles in total
   int h_layer[kMaxHT];          // layer of hidden unit tile h
   int h_index[kMaxHT];          // its index inside the layer
@@ -143,25 +144,33 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
 //   warps 0-7   group U: latent update of one layer as soon as its back-projection is complete
 //   warp 16     MMA issuer (converged warp, one elected lane issues tcgen05.mma / commit)
 //   warp 17     weight-tile loader (bulk async copies for tiles that are not resident)
-// Every epilogue thread owns one unit (TMEM lane) and RPT = NR/2 of the chains (two warps per 32-lane quarter).
+// Every epilogue thread owns one unit (TMEM lane) and RPT = RV/2 of the chains (two warps per 32-lane quarter).
+// RV <= NR is the number of chains the CTA really holds: the epilogues are issue-bound (not the tensor pipe), so a
+// batch that would leave SMs idle at RV = NR = 16 runs with RV = 8 on twice as many SMs; the MMA stays N = 16 (the
+// minimum at M = 128) and simply carries 8 zero columns.
 // Tiles are visited top-down (output tiles first, then Linear L-1 ... 1): the update of layer l only needs the
 // tiles of Linear l+1 (back-projection) and Linear l (own error), so group U works on layer l while the tensor
 // pipe and group T are already busy with the NEXT step's output tiles -- the step is pipelined across layers.
-template <int NR>
+template <int NR, int RV>
 __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
-  constexpr int RPT = NR / 2;
+  constexpr int RPT = RV / 2;
   constexpr int kGrp = 256;                  // threads per epilogue group
   constexpr int kMmaWarp = 16, kLoadWarp = 17;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Barriers bars;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_red[2][2][8][2];        // [group][step parity][warp][energy, loss]
+  __shared__ int2 s_tile[kMaxTiles];         // x = lin | out_tile << 8 | (h_out + 1) << 16, y = number of units of that Linear
 
   const NetDev& nd = p.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = nd.L, HT = p.HT;
-  const int row0 = blockIdx.x * NR;
+  const int row0 = blockIdx.x * RV;
 
+  if (tid < p.n_hid_tiles + p.n_out_tiles) {
+    const Tile& T = p.tiles[tid];
+    s_tile[tid] = make_int2(T.lin | (T.out_tile << 8) | ((T.h_out + 1) << 16), T.lin == nd.L ? nd.d_out : nd.dims[T.lin]);
+  }
   if (tid == 0) {
     mbar_init(&bars.w_res, 1);
     for (int i = 0; i < 2; ++i) {
@@ -185,7 +194,9 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   // TMEM column map (fp32 columns): [dA0 | dA1 | bp_h ... | x_h ... | gown_h ...], NR columns each
+  // then one bias column per weight tile (32 reserved) and, if p.y_tmem, NR target columns per output tile
   const uint32_t col_dA = 0, col_bp = 2 * NR, col_x = (2 + HT) * NR, col_g = (2 + 2 * HT) * NR;
+  const uint32_t col_bias = (2 + 3 * HT) * NR, col_y = col_bias + 32;
   const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;      // table order: output tiles, then Linear L-1 ... 1
 
   // =====================================================================================================
@@ -290,14 +301,16 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
         const uint32_t dcol = tmem + col_dA + db * NR;
         const int nk = T.Kp / 16;
         if (elect_one()) {
-          mma_bf16_ss(dcol, ad0, bd0, id_a, false);
-          for (int k8 = 0; k8 < nk; k8 += 8) {
+          // groups of 8 K-steps fully unrolled: every MMA then reads its own pre-computed uniform registers and the
+          // instructions issue back to back (46 instead of 91 cycles each, scripts/umma_timing.py variants 6 / 1)
+          int ks = 0;
+          for (; ks + 8 <= nk; ks += 8) {
+            const uint64_t a8 = ad0 + (uint64_t)(ks * 16), b8 = bd0 + (uint64_t)(ks * 16);
+            mma_bf16_ss(dcol, a8, b8, id_a, ks > 0);
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const int ks = k8 + kk;
-              if (ks > 0 && ks < nk) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), id_a, true);
-            }
+            for (int kk = 1; kk < 8; ++kk) mma_bf16_ss(dcol, a8 + (uint64_t)(kk * 16), b8 + (uint64_t)(kk * 16), id_a, true);
           }
+          for (; ks < nk; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), id_a, ks > 0);
           mma_commit(&bars.dA_full[db]);
         }
         __syncwarp();
@@ -319,13 +332,15 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
     const int cbase = cg * RPT;
     const int rb = row0 + cbase;
     const int nrow = max(0, min(RPT, p.B - rb));
-    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_addr = lane_base + (uint32_t)cbase;
     const uint32_t g_thread_off = (uint32_t)(cbase >> 3) * 2048u + (uint32_t)(cbase & 7) * 16u + (uint32_t)(ln >> 3) * 128u +
                                   (uint32_t)(ln & 7) * 2u;
 
     if (grp == 1) {
       // ======================= group U: initial state, then one layer update after the other =======================
-      for (int i = gtid * 16; i < p.gbuf_off[0] - p.act_off[0]; i += kGrp * 16)
+      // activation AND G operand buffers: chains RV..NR-1 (if any) stay zero for the whole run
+      for (int i = gtid * 16; i < p.gbuf_off[1] + NR * 128 * 2 - p.act_off[0]; i += kGrp * 16)
         *reinterpret_cast<uint4*>(smem + p.act_off[0] + i) = make_uint4(0, 0, 0, 0);
       asm volatile("bar.sync 2, 256;" ::: "memory");
       for (int h = 0; h < HT; ++h) {
@@ -517,22 +532,37 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
     } else {
       // ======================= group T: per-tile epilogues =======================
       uint32_t ph_dAf = 0, ph_ge = 3;
-      float bias_n = 0.0f, yv_n[RPT];
-      auto prefetch_tile = [&](int t) {
-        const Tile& Tn = p.tiles[t];
-        const bool out_n = (Tn.lin == L);
-        const int un = Tn.out_tile * 128 + ln;
-        const bool uv = un < (out_n ? nd.d_out : nd.dims[Tn.lin]);
-        bias_n = (uv && p.b[Tn.lin] != nullptr) ? __ldg(p.b[Tn.lin] + un) : 0.0f;
-        const bool uy = out_n && uv && (un >= nd.mask_start) && nd.top >= MCPC_TOP_GAUSS;
-        const float* yp = uy ? p.target + (size_t)rb * nd.d_out + un : nullptr;
+      const float qnan = __int_as_float(0x7fc00000);
+      // Per-tile constants live in TMEM, not in global memory: one bias column per tile and, when they fit, the
+      // targets of every output tile (NaN = "this element carries no loss": masked, past the batch, padding).
+      // The tile loop then needs no global load and no per-element mask logic.
+      auto target_of = [&](int t, float (&yv)[RPT]) {
+        const int2 ti = s_tile[t];
+        const int un = ((ti.x >> 8) & 0xff) * 128 + ln;
+        const bool uy = ((ti.x & 0xff) == L) && un < ti.y && un >= nd.mask_start && nd.top >= MCPC_TOP_GAUSS;
+        const float* yp = p.target + (size_t)rb * nd.d_out + un;
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) yv_n[i] = (uy && i < nrow) ? __ldg(yp + (size_t)i * nd.d_out) : 0.0f;
+        for (int i = 0; i < RPT; ++i) yv[i] = (uy && i < nrow) ? __ldg(yp + (size_t)i * nd.d_out) : qnan;
       };
-      {
+      for (int t = 0; t < n_tiles_all; ++t) {
+        const int2 ti = s_tile[t];
+        const int lin = ti.x & 0xff, un = ((ti.x >> 8) & 0xff) * 128 + ln;
+        const float bv = (un < ti.y && p.b[lin] != nullptr) ? __ldg(p.b[lin] + un) : 0.0f;
+        __syncwarp();
+        tmem_st1(lane_base + col_bias + (uint32_t)t, bv);           // both warps of a lane quarter write the same value
+        if (p.y_tmem && lin == L) {
+          float yv[RPT];
+          target_of(t, yv);
+          __syncwarp();
+          tmem_st<RPT>(lane_addr + col_y + (uint32_t)t * NR, yv);
+        }
+      }
+      tmem_st_wait();
+      float yv_n[RPT];
+      if (!p.y_tmem) {
         const bool traj0 = (p.traj_every > 0);
         const int t0 = (nd.top_has_grad || (traj0 && p.traj_out != nullptr)) ? 0 : p.n_out_tiles;
-        if (t0 < n_tiles_all) prefetch_tile(t0);
+        if (t0 < p.n_out_tiles) target_of(t0, yv_n);
       }
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
@@ -546,36 +576,35 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
         uint32_t x_waited = 0;
         TC_STAMP(gtid == 0, ts, 32);
         for (int t = t_first; t < n_tiles_all; ++t) {
-          const Tile& T = p.tiles[t];
+          const int2 ti = s_tile[t];
+          const int lin = ti.x & 0xff, h = ((ti.x >> 16) & 0xff) - 1, dl = ti.y;
           const int k = t - t_first;
           const int db = k & 1, gb = k & 1;
-          const bool is_out = (T.lin == L);
+          const bool is_out = (lin == L);
           const bool has_b = !is_out || nd.top_has_grad;
-          const int dl = is_out ? nd.d_out : nd.dims[T.lin];
-          const int u = T.out_tile * 128 + ln;
+          const int u = ((ti.x >> 8) & 0xff) * 128 + ln;
           const bool uvalid = u < dl;
-          const bool use_y = is_out && uvalid && (u >= nd.mask_start) && nd.top >= MCPC_TOP_GAUSS;
-          // operands of THIS tile were prefetched one tile ago; issue the loads of the next tile now so their
-          // L2 latency hides behind this tile's work
-          const float bias = bias_n;
           float yv[RPT];
+          if (!p.y_tmem && is_out) {
+            // targets do not fit TMEM (32-chain CTAs): they were fetched one tile ago; fetch the next tile's now
 #pragma unroll
-          for (int i = 0; i < RPT; ++i) yv[i] = yv_n[i];
-          {
+            for (int i = 0; i < RPT; ++i) yv[i] = yv_n[i];
             int tn = t + 1;
-            if (tn >= n_tiles_all) {
+            if (tn >= p.n_out_tiles) {
               const int ts1 = ts + 1;
               const bool traj1 = (p.traj_every > 0) && (ts1 % p.traj_every == 0);
               tn = (nd.top_has_grad || (traj1 && p.traj_out != nullptr)) ? 0 : p.n_out_tiles;
             }
-            if (tn < n_tiles_all) prefetch_tile(tn);
+            if (tn < p.n_out_tiles) target_of(tn, yv_n);
           }
-          if (!is_out && !((x_waited >> T.lin) & 1u)) {       // x_lin of THIS step was written by group U last step
-            mbar_wait(&bars.acts_ready[T.lin], ts & 1);
-            x_waited |= 1u << T.lin;
+          TC_STAMP(gtid == 0 && k == 3, ts, 60);
+          if (!is_out && !((x_waited >> lin) & 1u)) {         // x_lin of THIS step was written by group U last step
+            mbar_wait(&bars.acts_ready[lin], ts & 1);
+            x_waited |= 1u << lin;
           }
           mbar_wait(&bars.dA_full[db], (ph_dAf >> db) & 1u);
           ph_dAf ^= 1u << db;
+          TC_STAMP(gtid == 0 && k == 3, ts, 61);
           if (has_b) {
             mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
             ph_ge ^= 1u << gb;
@@ -583,15 +612,22 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
           fence_after_sync();
           TC_STAMP(gtid == 0 && k == 3, ts, 55);
           uint8_t* gptr = smem + p.gbuf_off[gb] + g_thread_off;
-          float d[RPT];
-          tmem_ld<RPT>(lane_addr + col_dA + db * NR, d);
-          TC_STAMP(gtid == 0 && k == 3, ts, 56);
+          float d[RPT], bias1[1];
+          __nv_bfloat16 g16[RPT];
+          __nv_bfloat16* sg_ptr = nullptr;
+          tmem_ld_nw<RPT>(lane_addr + col_dA + db * NR, d);
+          tmem_ld_nw<1>(lane_base + col_bias + (uint32_t)t, bias1);
           if (!is_out) {
-            const int h = T.h_out;
-            const float ce = 0.5f * nd.c[T.lin], gc = nd.gc[T.lin];
+            const float ce = 0.5f * nd.c[lin], gc = nd.gc[lin];
             float xv[RPT], gv[RPT];
-            tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
-            __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[T.lin] + u : nullptr;
+            tmem_ld_nw<RPT>(lane_addr + col_x + h * NR, xv);
+            tmem_ld_wait();
+            tmem_ld_tie(d);
+            tmem_ld_tie(bias1);
+            tmem_ld_tie(xv);
+            TC_STAMP(gtid == 0 && k == 3, ts, 56);
+            const float bias = bias1[0];
+            __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[lin] + u : nullptr;
             // straight-line math for all RPT chains (independent chains interleave); only the stores are predicated
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
@@ -601,13 +637,20 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
             }
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
-              const __nv_bfloat16 gb16 = __float2bfloat16(gv[i]);
-              *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = gb16;
-              if (sg != nullptr && i < nrow) sg[(size_t)i * p.sg_pitch] = gb16;
+              g16[i] = __float2bfloat16(gv[i]);
+              *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = g16[i];
             }
+            sg_ptr = sg;
             tmem_st<RPT>(lane_addr + col_g + h * NR, gv);
             tmem_st_wait();
           } else {
+            if (p.y_tmem) tmem_ld_nw<RPT>(lane_addr + col_y + (uint32_t)t * NR, yv);
+            tmem_ld_wait();
+            tmem_ld_tie(d);
+            tmem_ld_tie(bias1);
+            tmem_ld_tie(yv);
+            TC_STAMP(gtid == 0 && k == 3, ts, 56);
+            const float bias = bias1[0];
             __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[L] + u : nullptr;
             float* to = (do_traj && p.traj_out != nullptr && uvalid) ? p.traj_out + ((size_t)rec * p.B + rb) * nd.d_out + u : nullptr;
             const bool bern = nd.top == MCPC_TOP_BERNOULLI;
@@ -616,10 +659,11 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
 #pragma unroll
               for (int i = 0; i < RPT; ++i) {
                 const float o = d[i] + bias;
+                const float y = yv[i];
+                const bool on = (y == y);                      // NaN marks "no loss on this element"
                 const float z = __expf(-fabsf(o));
-                const float lv = fmaxf(o, 0.0f) - o * yv[i] + __logf(1.0f + z);
-                const float e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[i];
-                const bool on = use_y && i < nrow;
+                const float lv = fmaxf(o, 0.0f) - o * y + __logf(1.0f + z);
+                const float e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - y;
                 l_part += on ? lv : 0.0f;
                 ev[i] = on ? e : 0.0f;
                 ov[i] = o;
@@ -628,19 +672,24 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
 #pragma unroll
               for (int i = 0; i < RPT; ++i) {
                 const float o = d[i] + bias;
-                const float dd = o - yv[i];
-                const bool on = use_y && i < nrow;
-                l_part = fmaf(on ? 0.5f * nd.inv_var * dd : 0.0f, dd, l_part);
-                ev[i] = on ? dd * nd.inv_var : 0.0f;
+                const float y = yv[i];
+                const bool on = (y == y);
+                const float dd = on ? o - y : 0.0f;            // (0 * NaN would poison the sum)
+                l_part = fmaf(0.5f * nd.inv_var * dd, dd, l_part);
+                ev[i] = dd * nd.inv_var;
                 ov[i] = o;
               }
             }
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
-              const __nv_bfloat16 eb16 = __float2bfloat16(ev[i]);
-              if (has_b) *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = eb16;
-              if (to != nullptr && i < nrow) to[(size_t)i * nd.d_out] = ov[i];
-              if (sg != nullptr && i < nrow) sg[(size_t)i * p.sg_pitch] = eb16;
+              g16[i] = __float2bfloat16(ev[i]);
+              if (has_b) *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = g16[i];
+            }
+            sg_ptr = sg;
+            if (to != nullptr) {
+#pragma unroll
+              for (int i = 0; i < RPT; ++i)
+                if (i < nrow) to[(size_t)i * nd.d_out] = ov[i];
             }
           }
           TC_STAMP(gtid == 0 && k == 3, ts, 57);
@@ -651,9 +700,16 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
             fence_async_smem();
             mbar_arrive(&bars.g_full[gb]);
           }
+          // the saved dW operand goes out AFTER the hand-over: the proxy fence above waits for every earlier memory
+          // operation of the thread, global stores included, so they must not sit in front of it
+          if (sg_ptr != nullptr) {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+              if (i < nrow) sg_ptr[(size_t)i * p.sg_pitch] = g16[i];
+          }
           TC_STAMP(gtid == 0 && k == 3, ts, 59);
           // own-layer errors of layer `lin` are complete after the last tile of Linear lin
-          if (!is_out && (t + 1 == n_tiles_all || p.tiles[t + 1].lin != T.lin)) mbar_arrive(&bars.g_ready[T.lin]);
+          if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) mbar_arrive(&bars.g_ready[lin]);
           TC_STAMP(gtid == 0, ts, 22 + k);
         }
         e_part = warp_sum_tc(e_part);
@@ -698,7 +754,7 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
   }
   p->h_off[nd.L] = HT;
   p->HT = HT;
-  if ((2 + 3 * HT) * NR > 512) {
+  if ((2 + 3 * HT) * NR + 32 > 512) {
     set_error("bf16 path: %d hidden unit tiles x %d chains per CTA do not fit the 512 TMEM columns", HT, NR);
     return MCPC_ERR_UNSUPPORTED;
   }
@@ -749,6 +805,7 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
     if (lin == nd.L) p->n_out_tiles = nt;
   }
   p->n_hid_tiles = nt - p->n_out_tiles;
+  p->y_tmem = ((2 + 3 * HT) * NR + 32 + p->n_out_tiles * NR <= 512) ? 1 : 0;
   *packed_bytes = gsrc;
   // residency: everything if it fits, else as many leading tiles as fit beside a 2-slot ring
   const uint32_t slack = 4096;             // MN-major reads of narrow tiles overrun their 128 x Kp footprint
@@ -786,12 +843,19 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
   return MCPC_OK;
 }
 
-int choose_nr(int B) {
+// Chains per CTA (RV) and MMA N extent (NR).  One wave of 8-chain CTAs while the batch allows it (the epilogues,
+// not the MMAs, bound the step: more SMs beat fuller MMAs), 32-chain CTAs once 16-chain ones exceed two waves.
+struct RowsChoice { int nr, rv; };
+RowsChoice choose_rows(int B) {
   if (const char* env = getenv("MCPC_TC_ROWS")) {
     const int v = atoi(env);
-    if (v == 16 || v == 32) return v;
+    if (v == 8) return {16, 8};
+    if (v == 16) return {16, 16};
+    if (v == 32) return {32, 32};
   }
-  return (B + 15) / 16 >= 2 * 148 ? 32 : 16;
+  if ((B + 7) / 8 <= 148) return {16, 8};
+  if ((B + 15) / 16 >= 2 * 148) return {32, 32};
+  return {16, 16};
 }
 
 }  // namespace
@@ -806,14 +870,14 @@ bool infer_tc_fits(const NetDev& nd, int B) {
 int infer_tc_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes) {
   TcParams p{};
   size_t smem = 0, packed = 0;
-  int NR = choose_nr(B);
-  int rc = plan_tc(nd, NR, &p, &smem, &packed);
-  if (rc != MCPC_OK && NR == 32) {
-    NR = 16;
-    rc = plan_tc(nd, NR, &p, &smem, &packed);
+  RowsChoice rc_ = choose_rows(B);
+  int rc = plan_tc(nd, rc_.nr, &p, &smem, &packed);
+  if (rc != MCPC_OK && rc_.nr == 32) {
+    rc_ = {16, 16};
+    rc = plan_tc(nd, rc_.nr, &p, &smem, &packed);
   }
   if (rc != MCPC_OK) return rc;
-  const int n_ctas = (B + NR - 1) / NR;
+  const int n_ctas = (B + rc_.rv - 1) / rc_.rv;
   *bytes = ((packed + 255) & ~(size_t)255) + (size_t)n_steps * n_ctas * 4 * sizeof(float) + 512;
   return MCPC_OK;
 }
@@ -826,17 +890,17 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   }
   TcParams p{};
   size_t smem = 0, packed = 0;
-  int NR = choose_nr(B);
-  int rc = plan_tc(nd, NR, &p, &smem, &packed);
-  if (rc != MCPC_OK && NR == 32) {
-    NR = 16;
+  RowsChoice rows = choose_rows(B);
+  int rc = plan_tc(nd, rows.nr, &p, &smem, &packed);
+  if (rc != MCPC_OK && rows.nr == 32) {
+    rows = {16, 16};
     p = TcParams{};
-    rc = plan_tc(nd, NR, &p, &smem, &packed);
+    rc = plan_tc(nd, rows.nr, &p, &smem, &packed);
   }
   if (rc != MCPC_OK) return rc;
   p.net = nd;
   p.B = B;
-  p.n_ctas = (B + NR - 1) / NR;
+  p.n_ctas = (B + rows.rv - 1) / rows.rv;
   size_t need = 0;
   infer_tc_workspace(nd, B, o->n_steps, &need);
   if (ws == nullptr || ws_bytes < need) {
@@ -902,12 +966,15 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     cudaMalloc(&p.dbg, 8 * 64 * sizeof(long long));
     cudaMemsetAsync(p.dbg, 0, 8 * 64 * sizeof(long long), stream);
   }
-  if (NR == 32) {
-    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    infer_tc_kernel<32><<<p.n_ctas, 576, smem, stream>>>(p);
+  if (rows.rv == 32) {
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infer_tc_kernel<32, 32><<<p.n_ctas, 576, smem, stream>>>(p);
+  } else if (rows.rv == 16) {
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infer_tc_kernel<16, 16><<<p.n_ctas, 576, smem, stream>>>(p);
   } else {
-    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    infer_tc_kernel<16><<<p.n_ctas, 576, smem, stream>>>(p);
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infer_tc_kernel<16, 8><<<p.n_ctas, 576, smem, stream>>>(p);
   }
   MCPC_CUDA_CHECK(cudaGetLastError());
   count_launch();

@@ -119,6 +119,46 @@ template <int X> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (
 template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
 template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) { tmem_ld8(taddr, v); }
 template <> __device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) { tmem_ld4(taddr, v); }
+
+// Batched loads: issue several tmem_ld_nw<X>() back to back, then ONE tmem_ld_wait() and a tmem_ld_tie() per
+// destination array.  The tie is an empty volatile asm with read-write constraints on the registers: it cannot move
+// above the wait (volatile asms keep their order) and every consumer depends on it, so no use is scheduled early.
+template <int X> __device__ __forceinline__ void tmem_ld_nw(uint32_t taddr, float (&v)[X]);
+template <> __device__ __forceinline__ void tmem_ld_nw<1>(uint32_t taddr, float (&v)[1]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(v[0]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld_nw<4>(uint32_t taddr, float (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld_nw<8>(uint32_t taddr, float (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld_nw<16>(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_tie(float (&v)[1]) { asm volatile("" : "+f"(v[0]) :: "memory"); }
+__device__ __forceinline__ void tmem_ld_tie(float (&v)[4]) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_tie(float (&v)[8]) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_tie(float (&v)[16]) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                    "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(taddr), "r"(__float_as_uint(v)) : "memory");
+}
 template <int X> __device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[X]);
 template <> __device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const float (&v)[16]) { tmem_st16(taddr, v); }
 template <> __device__ __forceinline__ void tmem_st<8>(uint32_t taddr, const float (&v)[8]) { tmem_st8(taddr, v); }

@@ -113,7 +113,8 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 }
 
 // variant: 0 = issued inside `if (lane == 0)`, 1 = converged warp + elect.sync, 2 = as 1 with SWIZZLE_128B
-// descriptors, 3 = as 1 with the A operand in TMEM
+// descriptors, 3 = as 1 with the A operand in TMEM, 4 = as 1 with an MN-major A operand in the no-swizzle canonical
+// layout (the resident kernel's back-projection), 5 = MN-major A with SWIZZLE_128B, 6 = as 1, unrolled by 8
 __global__ void __launch_bounds__(160) umma_timing_kernel(int M, int N, int n_mma, int n_acc, int variant, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -128,8 +129,11 @@ __global__ void __launch_bounds__(160) umma_timing_kernel(int M, int N, int n_mm
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   if (warp == 4) {
-    const uint32_t id = idesc_bf16(M, N, false, false);
+    const uint32_t id = idesc_bf16(M, N, variant >= 4, false);
     uint64_t ad = smem_desc(smem_u32(smem), 128u, 2048u);
+    uint32_t a_step = (variant == 2) ? 2u : 16u;
+    if (variant == 4) { ad = smem_desc(smem_u32(smem), 2048u, 128u); a_step = 256u; }
+    if (variant == 5) { ad = smem_desc(smem_u32(smem), 8192u, 1024u) | ((uint64_t)2 << 61); a_step = 128u; }
     uint64_t bd = smem_desc(smem_u32(smem) + 32768, 128u, 256u);
     if (variant == 2) {
       ad = smem_desc(smem_u32(smem), 16u, 1024u) | ((uint64_t)2 << 61);
@@ -148,12 +152,19 @@ __global__ void __launch_bounds__(160) umma_timing_kernel(int M, int N, int n_mm
       } else {
         t0 = clock64();
         if (elect_one()) {
-          if (variant == 3) {
+          if (variant == 6) {
+            // descriptors precomputed: fully unrolled groups of 8 so that every MMA reads its own uniform registers
+            for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                mma_bf16_ss(tmem, ad + (uint64_t)(j * 16), bd + (uint64_t)(j * 16), id, (i + j) > 0);
+            }
+          } else if (variant == 3) {
             for (int i = 0; i < n_mma; ++i)
               mma_bf16_ts(tmem + (uint32_t)((i % n_acc) * N), tmem + 256 + (uint32_t)((i & 7) * 8), bd, id, i >= n_acc);
           } else {
             for (int i = 0; i < n_mma; ++i)
-              mma_bf16_ss(tmem + (uint32_t)((i % n_acc) * N), ad + (uint64_t)((i & 7) * (variant == 2 ? 2 : 16)), bd, id, i >= n_acc);
+              mma_bf16_ss(tmem + (uint32_t)((i % n_acc) * N), ad + (uint64_t)((i & 7) * a_step), bd, id, i >= n_acc);
           }
           mma_commit(&bar);
         }
@@ -178,12 +189,12 @@ int launch_umma_timing(cudaStream_t stream) {
   cudaFuncSetAttribute(umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int Ms[2] = {128, 64};
   const int Ns[5] = {16, 32, 64, 128, 256};
-  for (int variant = 0; variant < 4; ++variant)
+  for (int variant = 0; variant < 7; ++variant)
     for (int mi = 0; mi < 2; ++mi)
       for (int ni = 0; ni < 5; ni += 2)
         for (int n_acc = 1; n_acc <= 2; ++n_acc) {
           const int M = Ms[mi], N = Ns[ni];
-          if (n_acc * N > 256 || (variant == 3 && M == 64)) continue;
+          if (n_acc * N > 256 || (variant >= 3 && M == 64)) continue;
           umma_timing_kernel<<<1, 160, 64 * 1024, stream>>>(M, N, 32, n_acc, variant, d);
           long long h[2];
           cudaStreamSynchronize(stream);
