@@ -11,9 +11,8 @@
 // own-layer error and all accumulators live in TMEM (lane = unit, column = chain), the bf16 operand
 // copies in shared memory.
 //
-// Warp roles (192 threads): warps 0-3 = epilogue (thread <-> TMEM lane <-> unit), warp 4 = MMA issuer
-// (one elected lane, tcgen05.mma) + TMEM allocator, warp 5 = weight-tile loader.  Per step and per weight
-// tile t:  MMA_A(t) -> epilogue(t): eps, energy / loss, G (bf16 -> smem)  -> MMA_B(t); then the update
+// Warp roles are listed at the kernel (8 tile-epilogue warps, 8 update warps, 2 MMA issuers, 1 loader).  Per step and
+// per weight tile t:  MMA_A(t) -> tile epilogue(t): eps, energy / loss, G (bf16 -> smem)  -> MMA_B(t); then the update
 // epilogue applies  x <- x - lr*grad (SGD | Adam)  and  x <- x - lr*noise (Philox)  and re-emits act(x).
 // All hand-offs are mbarriers; the tensor pipe never waits on a __syncthreads.
 //
@@ -83,13 +82,14 @@ struct TcParams {
   float noise_scale;
   uint64_t seed, chain_offset;
   int traj_every, save_begin, save_end;
-  long long* dbg;               // optional timing trace of CTA 0 (MCPC_TC_TIMING=1), 64 slots per step
+  long long* dbg;               // optional timing trace of CTA 0 (MCPC_TC_TIMING=<first step>), 8 steps x 64 slots
+  int dbg_t0;
 };
 
 struct Barriers {
   uint64_t w_res;            // resident tiles landed
   uint64_t w_full[2], w_empty[2];
-  uint64_t dA_full[2], dA_empty[2];
+  uint64_t dA_full[4], dA_empty[4];   // prediction accumulators: 4 in flight with 16-column MMAs, 2 with 32
   uint64_t g_full[2], g_empty[2];
   uint64_t acts_ready[kMaxL];   // act(x_l) / x_l of the coming step are in place (group U -> MMA warp, group T)
   uint64_t bp_ready[kMaxL];     // back-projection into layer l complete (MMA warp -> group U)
@@ -102,7 +102,9 @@ __device__ __forceinline__ float warp_sum_tc(float v) {
   return v;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-#define TC_STAMP(cond, ts, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (cond) && (ts) < 8) p.dbg[(ts) * 64 + (idx)] = clock64(); } while (0)
+// compiled in only for the TRACE instantiation (MCPC_TC_TIMING): the stamps cost ~60 instructions per tile, and the
+// epilogue warps are bound by instruction fetch / issue
+#define TC_STAMP(cond, ts, idx) do { if constexpr (TRACE) { if (blockIdx.x == 0 && (cond) && (unsigned)((ts) - p.dbg_t0) < 8u) p.dbg[((ts) - p.dbg_t0) * 64 + (idx)] = clock64(); } } while (0)
 
 // fp32 W [rows x cols] (nn.Linear layout) -> bf16 tiles of 128 output units in canonical K-major order
 __global__ void pack_weights_kernel(const float* __restrict__ W, int rows, int cols, int Kp, int n_tiles,
@@ -139,11 +141,11 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
   return k == 0 ? n[0] : (k == 1 ? n[1] : (k == 2 ? n[2] : n[3]));
 }
 
-// NR chains per CTA.  Warp roles (18 warps):
+// NR chains per CTA.  Warp roles (19 warps):
 //   warps 8-15  group T: per-tile epilogue (errors of the units a weight tile predicts, G operand for phase B)
 //   warps 0-7   group U: latent update of one layer as soon as its back-projection is complete
-//   warp 16     MMA issuer (converged warp, one elected lane issues tcgen05.mma / commit)
-//   warp 17     weight-tile loader (bulk async copies for tiles that are not resident)
+//   warp 16/17  MMA issuers (converged warps, one elected lane issues tcgen05.mma / commit): predictions / back-projections
+//   warp 18     weight-tile loader (bulk async copies for tiles that are not resident)
 // Every epilogue thread owns one unit (TMEM lane) and RPT = RV/2 of the chains (two warps per 32-lane quarter).
 // RV <= NR is the number of chains the CTA really holds: the epilogues are issue-bound (not the tensor pipe), so a
 // batch that would leave SMs idle at RV = NR = 16 runs with RV = 8 on twice as many SMs; the MMA stays N = 16 (the
@@ -151,11 +153,17 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
 // Tiles are visited top-down (output tiles first, then Linear L-1 ... 1): the update of layer l only needs the
 // tiles of Linear l+1 (back-projection) and Linear l (own error), so group U works on layer l while the tensor
 // pipe and group T are already busy with the NEXT step's output tiles -- the step is pipelined across layers.
-template <int NR, int RV>
-__global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
+template <int NR, int RV, bool TRACE>
+__global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int RPT = RV / 2;
+  constexpr bool ALT = (RV <= 8);            // group T works on alternate tiles (see there)
   constexpr int kGrp = 256;                  // threads per epilogue group
-  constexpr int kMmaWarp = 16, kLoadWarp = 17;
+  constexpr int kTileArr = ALT ? 128 : 256;  // group-T threads that hand one tile over
+  constexpr int kDA = (NR == 16) ? 4 : 2;    // prediction accumulators in flight (TMEM columns permitting)
+  constexpr int CH = RPT < 8 ? RPT : 8;      // chains a thread of group U processes at a time
+  constexpr bool kNoiseEarly = (RV <= 8);    // draw the Langevin noise before waiting for the back-projection
+                                             // (wider chain tiles have no registers to hold it across the wait)
+  constexpr int kMmaWarp = 16, kMmaWarpB = 17, kLoadWarp = 18;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Barriers bars;
   __shared__ uint32_t tmem_base_s;
@@ -176,10 +184,12 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.w_full[i], 1);
       mbar_init(&bars.w_empty[i], 1);
-      mbar_init(&bars.dA_full[i], 1);
-      mbar_init(&bars.dA_empty[i], kGrp);
-      mbar_init(&bars.g_full[i], kGrp);
+      mbar_init(&bars.g_full[i], kTileArr);
       mbar_init(&bars.g_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bars.dA_full[i], 1);
+      mbar_init(&bars.dA_empty[i], kTileArr);
     }
     for (int l = 0; l < kMaxL; ++l) {
       mbar_init(&bars.acts_ready[l], kGrp);
@@ -193,11 +203,11 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  // TMEM column map (fp32 columns): [dA0 | dA1 | bp_h ... | x_h ... | gown_h ...], NR columns each
+  // TMEM column map (fp32 columns): [dA0 .. dA(kDA-1) | bp_h ... | x_h ... | gown_h ...], NR columns each
   // then one bias column per weight tile (32 reserved) and, if p.y_tmem, NR target columns per output tile
-  const uint32_t col_dA = 0, col_bp = 2 * NR, col_x = (2 + HT) * NR, col_g = (2 + 2 * HT) * NR;
-  const uint32_t col_bias = (2 + 3 * HT) * NR, col_y = col_bias + 32;
-  const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;      // table order: output tiles, then Linear L-1 ... 1
+  const uint32_t col_dA = 0, col_bp = kDA * NR, col_x = (kDA + HT) * NR, col_g = (kDA + 2 * HT) * NR;
+  const uint32_t col_bias = (kDA + 3 * HT) * NR, col_y = col_bias + 32;
+  const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;      // table order: Linear 1 ... L-1, then the output tiles
 
   // =====================================================================================================
   if (warp == kLoadWarp) {
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
         const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
-        for (int t = need_out ? 0 : p.n_out_tiles; t < n_tiles_all; ++t) {
+        for (int t = 0; t < (need_out ? n_tiles_all : p.n_hid_tiles); ++t) {
           const Tile& T = p.tiles[t];
           if (T.slot < 0) continue;
           mbar_wait(&bars.w_empty[T.slot], (empty_phase >> T.slot) & 1u);
@@ -228,60 +238,23 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
       }
     }
   } else if (warp == kMmaWarp) {
-    // ---------------- MMA issuer (converged warp; descriptors stay in uniform registers) ----------------
+    // ---------------- MMA issuer A: predictions (converged warp; one elected lane issues) ----------------
+    // Two issuer warps: this one runs ahead with the prediction GEMMs (phase A), warp kMmaWarpB issues the
+    // back-projections (phase B) as soon as group T hands a G operand over.  Neither waits for the other's barriers,
+    // so a late hand-over does not hold back the next tile's prediction.
     const uint32_t id_a = idesc_bf16(128, NR, false, false);
-    const uint32_t id_b = idesc_bf16(128, NR, true, false);
     const uint32_t smem_base = smem_u32(smem);
-    uint32_t ph_wfull = 0, ph_dAe = 3, ph_gfull = 0;
-    uint32_t bp_started = 0;
+    uint32_t ph_wfull = 0, ph_dAe = (1u << kDA) - 1u;
     mbar_wait(&bars.w_res, 0);
-
-    auto phaseB = [&](int t, int k, bool last_of_lin) {
-      const Tile& T = p.tiles[t];
-      const int gb = k & 1;
-      const bool has_b = (T.lin < L) || nd.top_has_grad;
-      if (has_b) {
-        mbar_wait(&bars.g_full[gb], (ph_gfull >> gb) & 1u);
-        ph_gfull ^= 1u << gb;
-        fence_after_sync();
-        const int in_layer = T.lin - 1;
-        const uint64_t bd0 = smem_desc(smem_base + p.gbuf_off[gb], 128u, 2048u);
-        const uint32_t a_step = (uint32_t)(2 * T.sbo) >> 4;
-        for (int u = 0; u < p.ut[in_layer]; ++u) {
-          const int h = p.h_off[in_layer] + u;
-          const uint64_t ad0 = smem_desc(smem_base + T.smem_off + u * 2048, (uint32_t)T.sbo, 128u);
-          const uint32_t dcol = tmem + col_bp + h * NR;
-          const bool acc0 = (bp_started >> h) & 1u;
-          if (elect_one()) {
-            mma_bf16_ss(dcol, ad0, bd0, id_b, acc0);
-#pragma unroll
-            for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * 16), id_b, true);
-          }
-          __syncwarp();
-          bp_started |= 1u << h;
-        }
-        if (elect_one()) {
-          mma_commit(&bars.g_empty[gb]);
-          if (last_of_lin) mma_commit(&bars.bp_ready[in_layer]);     // back-projection into layer lin-1 is complete
-        }
-        __syncwarp();
-      }
-      if (T.slot >= 0) {
-        if (elect_one()) mma_commit(&bars.w_empty[T.slot]);
-        __syncwarp();
-      }
-    };
-
     for (int ts = 0; ts < p.n_steps; ++ts) {
       const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
       const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
-      const int t_first = need_out ? 0 : p.n_out_tiles;
-      bp_started = 0;
+      const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
       uint32_t acts_waited = 0;
       TC_STAMP(lane == 0, ts, 0);
-      for (int t = t_first; t < n_tiles_all; ++t) {
+      for (int t = 0; t < t_end; ++t) {
         const Tile& T = p.tiles[t];
-        const int k = t - t_first;
+        const int k = t;
         const int in_layer = T.lin - 1;
         if (!((acts_waited >> in_layer) & 1u)) {                    // act(x_{lin-1}) of THIS step: written by group U
           mbar_wait(&bars.acts_ready[in_layer], ts & 1);
@@ -291,7 +264,7 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
           mbar_wait(&bars.w_full[T.slot], (ph_wfull >> T.slot) & 1u);
           ph_wfull ^= 1u << T.slot;
         }
-        const int db = k & 1;
+        const int db = k & (kDA - 1);
         mbar_wait(&bars.dA_empty[db], (ph_dAe >> db) & 1u);
         ph_dAe ^= 1u << db;
         fence_after_sync();
@@ -300,6 +273,7 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
         const uint64_t bd0 = smem_desc(smem_base + p.act_off[in_layer], 128u, act_sbo);
         const uint32_t dcol = tmem + col_dA + db * NR;
         const int nk = T.Kp / 16;
+        const bool has_b = (T.lin < L) || nd.top_has_grad;
         if (elect_one()) {
           // groups of 8 K-steps fully unrolled: every MMA then reads its own pre-computed uniform registers and the
           // instructions issue back to back (46 instead of 91 cycles each, scripts/umma_timing.py variants 6 / 1)
@@ -312,13 +286,64 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
           }
           for (; ks < nk; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), id_a, ks > 0);
           mma_commit(&bars.dA_full[db]);
+          // a streamed tile without back-projection is free again once this prediction has read it
+          if (T.slot >= 0 && !has_b) mma_commit(&bars.w_empty[T.slot]);
         }
         __syncwarp();
         TC_STAMP(lane == 0, ts, 1 + k);
-        if (t > t_first) phaseB(t - 1, k - 1, p.tiles[t - 1].lin != T.lin);
       }
-      if (n_tiles_all > t_first) phaseB(n_tiles_all - 1, n_tiles_all - 1 - t_first, true);
       TC_STAMP(lane == 0, ts, 21);
+    }
+  } else if (warp == kMmaWarpB) {
+    // ---------------- MMA issuer B: back-projections through the MN-major view of the same weight tiles ----------------
+    const uint32_t id_b = idesc_bf16(128, NR, true, false);
+    const uint32_t smem_base = smem_u32(smem);
+    uint32_t ph_gfull = 0;
+    mbar_wait(&bars.w_res, 0);
+    for (int ts = 0; ts < p.n_steps; ++ts) {
+      const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+      const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+      const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
+      uint32_t bp_started = 0;
+      for (int t = 0; t < t_end; ++t) {
+        const Tile& T = p.tiles[t];
+        const int gb = t & 1;
+        const bool has_b = (T.lin < L) || nd.top_has_grad;
+        if (!has_b) continue;                                         // read-out only: nothing flows back
+        const bool last_of_lin = (t + 1 == n_tiles_all) || (p.tiles[t + 1].lin != T.lin);   // (output tiles come last)
+        mbar_wait(&bars.g_full[gb], (ph_gfull >> gb) & 1u);            // group T consumed the prediction of this tile,
+        ph_gfull ^= 1u << gb;                                         // so phase A has finished reading it as well
+        fence_after_sync();
+        const int in_layer = T.lin - 1;
+        const uint64_t bd0 = smem_desc(smem_base + p.gbuf_off[gb], 128u, 2048u);
+        const uint32_t a_step = (uint32_t)(2 * T.sbo) >> 4;
+        // K extent = the tile's valid output units in groups of 16 (rows of G beyond them are never written)
+        const int n_units = ((T.lin == L) ? nd.d_out : nd.dims[T.lin]) - T.out_tile * 128;
+        const int nkb = n_units >= 128 ? 8 : (n_units + 15) / 16;
+        for (int u = 0; u < p.ut[in_layer]; ++u) {
+          const int h = p.h_off[in_layer] + u;
+          const uint64_t ad0 = smem_desc(smem_base + T.smem_off + u * 2048, (uint32_t)T.sbo, 128u);
+          const uint32_t dcol = tmem + col_bp + h * NR;
+          const bool acc0 = (bp_started >> h) & 1u;
+          if (elect_one()) {
+            mma_bf16_ss(dcol, ad0, bd0, id_b, acc0);
+            if (nkb == 8) {
+#pragma unroll
+              for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * 16), id_b, true);
+            } else {
+              for (int ks = 1; ks < nkb; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * 16), id_b, true);
+            }
+          }
+          __syncwarp();
+          bp_started |= 1u << h;
+        }
+        if (elect_one()) {
+          mma_commit(&bars.g_empty[gb]);
+          if (last_of_lin) mma_commit(&bars.bp_ready[in_layer]);       // back-projection into layer lin-1 is complete
+          if (T.slot >= 0) mma_commit(&bars.w_empty[T.slot]);
+        }
+        __syncwarp();
+      }
     }
   } else {
     // ---------------- epilogue groups ----------------
@@ -382,130 +407,189 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
           step_size = (float)(p.lr_d / (1.0 - b1p));
           inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
         }
-        for (int l = L - 1; l >= 0; --l) {
+        for (int l = 0; l < L; ++l) {                        // bottom-up, the order the tiles complete in
           const bool has_above = (l + 1 < L) || nd.top_has_grad;
-          if (has_above) mbar_wait(&bars.bp_ready[l], ts & 1);          // all tiles of Linear l+1 back-projected
-          if (l > 0) mbar_wait(&bars.g_ready[l], ts & 1);               // group T stored the own-layer error of layer l
-          fence_after_sync();
-          TC_STAMP(gtid == 0, ts, 40 + l);
           const int kind = nd.act[l];
           const int dl = nd.dims[l];
           const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
-          for (int hi = 0; hi < p.ut[l]; ++hi) {
+          const int n_ut = p.ut[l];
+          const bool defer = (RV <= 8) && (n_ut == 1);       // one unit tile: global stores go out after the hand-over
+                                                             // (wider chain tiles have no registers to spare for it)
+          // the deferred stores only need the pre-update latents (single-tile layers keep them in registers across the
+          // hand-over); f(x) and the layer-0 error are recomputed from them
+          float xold[CH], b0 = 0.0f;
+          bool uvalid = false;
+          int u = 0;
+          auto global_stores = [&](int c0) {
+            if (!uvalid) return;
+            if (do_traj && p.traj_x[l] != nullptr) {
+              float* tx = p.traj_x[l] + ((size_t)rec * p.B + rb) * dl + u;
+#pragma unroll
+              for (int i = 0; i < CH; ++i)
+                if (c0 + i < nrow) tx[(size_t)(c0 + i) * dl] = xold[i];
+            }
+            if (do_save) {
+              __nv_bfloat16* sf = sf_row + p.sg_off[l] + u;
+#pragma unroll
+              for (int i = 0; i < CH; ++i)
+                if (c0 + i < nrow) sf[(size_t)(c0 + i) * p.sf_pitch] = __float2bfloat16(act_tc(kind, xold[i]));
+              if (l == 0) {                                  // layer 0 has no weight tile: its G operand is saved here
+                __nv_bfloat16* sg = sg_row + u;
+#pragma unroll
+                for (int i = 0; i < CH; ++i)
+                  if (c0 + i < nrow) sg[(size_t)(c0 + i) * p.sg_pitch] = __float2bfloat16(-nd.gc[0] * (xold[i] - b0));
+              }
+            }
+          };
+          for (int hi = 0; hi < n_ut; ++hi) {
             const int h = p.h_off[l] + hi;
-            const int u = hi * 128 + ln;
-            const bool uvalid = u < dl;
+            u = hi * 128 + ln;
+            uvalid = u < dl;
             const int gu = nd.off[l] + u;
-            float xv[RPT], bp[RPT], gown[RPT];
-            tmem_ld<RPT>(lane_addr + col_x + h * NR, xv);
-            if (has_above) {
-              tmem_ld<RPT>(lane_addr + col_bp + h * NR, bp);
-            } else {
-#pragma unroll
-              for (int i = 0; i < RPT; ++i) bp[i] = 0.0f;
-            }
-            if (l > 0) {
-              tmem_ld<RPT>(lane_addr + col_g + h * NR, gown);
-            } else {
-              // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
-              const float b0 = (uvalid && p.b[0] != nullptr) ? __ldg(p.b[0] + u) : 0.0f;
-              const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
-              __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + u : nullptr;
-#pragma unroll
-              for (int i = 0; i < RPT; ++i) {
-                const float eps = xv[i] - b0;
-                gown[i] = -gc * eps;
-                if (uvalid && i < nrow) {
-                  e_part = fmaf(ce * eps, eps, e_part);
-                  if (sg != nullptr) sg[(size_t)i * p.sg_pitch] = __float2bfloat16(gown[i]);
-                }
+            // a warp whose 32 units are all padding (e.g. 3 of 4 warps on a 20-unit layer) has nothing to update: its
+            // TMEM lanes keep the zeros written at start-up; it only takes part in the waits and the hand-over
+            const bool warp_idle = (hi * 128 + q * 32) >= dl;
+            if (warp_idle) {
+              if (hi == 0) {
+                if (has_above) mbar_wait(&bars.bp_ready[l], ts & 1);
+                if (l > 0) mbar_wait(&bars.g_ready[l], ts & 1);
               }
+              continue;
             }
-            if (uvalid) {
-              float mv[RPT], vv[RPT], nz[RPT];
+            // the chains of the thread go through in chunks of CH <= 8: bounded register pressure and code size
+#pragma unroll 1
+            for (int c0 = 0; c0 < RPT; c0 += CH) {
+              const int rbc = rb + c0, cbc = cbase + c0;
+              const int nrc = nrow - c0;
+              const uint32_t lac = lane_addr + (uint32_t)c0;
+              const size_t xoffc = (size_t)rbc * dl + u;
+              // ---- 1. everything that does not depend on this step's MMAs: noise, Adam state, the layer-0 bias ----
+              float mv[CH], vv[CH], nz[CH];
 #pragma unroll
-              for (int i = 0; i < RPT; ++i) { mv[i] = 0.0f; vv[i] = 0.0f; nz[i] = 0.0f; }
-              const size_t xoff = (size_t)rb * dl + u;
-              if (adam && p.update_x) {
+              for (int i = 0; i < CH; ++i) { mv[i] = 0.0f; vv[i] = 0.0f; nz[i] = 0.0f; }
+              b0 = 0.0f;
+              if (uvalid) {
+                if (l == 0 && p.b[0] != nullptr) b0 = __ldg(p.b[0] + u);
+                if (adam && p.update_x) {
 #pragma unroll
-                for (int i = 0; i < RPT; ++i) {
-                  mv[i] = (i < nrow) ? p.m[l][xoff + (size_t)i * dl] : 0.0f;
-                  vv[i] = (i < nrow) ? p.v[l][xoff + (size_t)i * dl] : 0.0f;
-                }
-              }
-              if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
-                const float* np_ = p.noise + ((size_t)ts * p.B + rb) * nd.SD + gu;
-#pragma unroll
-                for (int i = 0; i < RPT; ++i) nz[i] = (i < nrow) ? __ldg(np_ + (size_t)i * nd.SD) : 0.0f;
-              } else if (p.noise_mode == MCPC_NOISE_PHILOX) {
-                float nrm[4];
-                uint64_t cur_q = ~0ull;
-#pragma unroll
-                for (int i = 0; i < RPT; ++i) {
-                  const uint64_t chain = p.chain_offset + (uint64_t)(rb + i);
-                  if ((chain >> 2) != cur_q) {
-                    cur_q = chain >> 2;
-                    langevin_normals4(p.seed, (uint32_t)gu, (uint32_t)t_abs, cur_q, nrm);
+                  for (int i = 0; i < CH; ++i) {
+                    mv[i] = (i < nrc) ? p.m[l][xoffc + (size_t)i * dl] : 0.0f;
+                    vv[i] = (i < nrc) ? p.v[l][xoffc + (size_t)i * dl] : 0.0f;
                   }
-                  nz[i] = p.noise_scale * sel4(nrm, (uint32_t)(chain & 3));
                 }
               }
-              uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
-                              (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
-              float* tx = (do_traj && p.traj_x[l] != nullptr) ? p.traj_x[l] + ((size_t)rec * p.B + rb) * dl + u : nullptr;
-              __nv_bfloat16* sf = do_save ? sf_row + p.sg_off[l] + u : nullptr;
-              float* xg = (last && p.xgrad[l] != nullptr) ? p.xgrad[l] + xoff : nullptr;
-              float av[RPT], gradv[RPT], m1v[RPT], v1v[RPT];
+              auto draw_noise = [&]() {
+                if (!uvalid) return;
+                if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
+                  const float* np_ = p.noise + ((size_t)ts * p.B + rbc) * nd.SD + gu;
 #pragma unroll
-              for (int i = 0; i < RPT; ++i) {                 // straight-line: RPT independent chains interleave
+                  for (int i = 0; i < CH; ++i) nz[i] = (i < nrc) ? __ldg(np_ + (size_t)i * nd.SD) : 0.0f;
+                } else if (p.noise_mode == MCPC_NOISE_PHILOX) {
+                  float nrm[4];
+                  uint64_t cur_q = ~0ull;
+#pragma unroll
+                  for (int i = 0; i < CH; ++i) {
+                    const uint64_t chain = p.chain_offset + (uint64_t)(rbc + i);
+                    if ((chain >> 2) != cur_q) {
+                      cur_q = chain >> 2;
+                      langevin_normals4(p.seed, (uint32_t)gu, (uint32_t)t_abs, cur_q, nrm);
+                    }
+                    nz[i] = p.noise_scale * sel4(nrm, (uint32_t)(chain & 3));
+                  }
+                }
+              };
+              if (kNoiseEarly) draw_noise();                    // before the wait: off the critical hand-over chain
+              // ---- 2. wait for this layer's back-projection and own error, then ONE batch of TMEM loads ----
+              if (hi == 0 && c0 == 0) {
+                if (has_above) mbar_wait(&bars.bp_ready[l], ts & 1);      // all tiles of Linear l+1 back-projected
+                if (l > 0) mbar_wait(&bars.g_ready[l], ts & 1);           // group T stored the own-layer error of layer l
+                fence_after_sync();
+                TC_STAMP(gtid == 0, ts, 40 + l);
+              }
+              __syncwarp();
+              float xv[CH], bp[CH], gown[CH], gradv[CH];
+              tmem_ld_nw<CH>(lac + col_x + h * NR, xv);
+              if (has_above) tmem_ld_nw<CH>(lac + col_bp + h * NR, bp);
+              if (l > 0) tmem_ld_nw<CH>(lac + col_g + h * NR, gown);
+              tmem_ld_wait();
+              tmem_ld_tie(xv);
+              if (has_above) {
+                tmem_ld_tie(bp);
+              } else {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) bp[i] = 0.0f;
+              }
+              if (l > 0) {
+                tmem_ld_tie(gown);
+              } else {
+                // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
+                const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                  const float eps = xv[i] - b0;
+                  gown[i] = -gc * eps;
+                  if (uvalid && i < nrc) e_part = fmaf(ce * eps, eps, e_part);
+                }
+              }
+              if (!kNoiseEarly) draw_noise();
+              // ---- 3. update (straight-line: CH independent chains interleave) ----
+#pragma unroll
+              for (int i = 0; i < CH; ++i) {
                 const float x = xv[i];
                 const float a = act_tc(kind, x);
-                av[i] = a;
+                xold[i] = x;
                 gradv[i] = fmaf(dact_tc(kind, x, a), bp[i], -gown[i]);
               }
-              if (tx != nullptr) {
+              if (uvalid && last && p.xgrad[l] != nullptr) {
 #pragma unroll
-                for (int i = 0; i < RPT; ++i)
-                  if (i < nrow) tx[(size_t)i * dl] = xv[i];
+                for (int i = 0; i < CH; ++i)
+                  if (i < nrc) p.xgrad[l][xoffc + (size_t)i * dl] = gradv[i];
               }
               if (p.update_x) {
                 if (!adam) {
 #pragma unroll
-                  for (int i = 0; i < RPT; ++i) xv[i] = fmaf(-p.lr, gradv[i], xv[i]);
+                  for (int i = 0; i < CH; ++i) xv[i] = fmaf(-p.lr, gradv[i], xv[i]);
                 } else {
 #pragma unroll
-                  for (int i = 0; i < RPT; ++i) {
-                    m1v[i] = fmaf(p.one_minus_b1, gradv[i] - mv[i], mv[i]);
-                    v1v[i] = fmaf(p.one_minus_b2 * gradv[i], gradv[i], vv[i] * p.beta2f);
-                    xv[i] = fmaf(-step_size, __fdividef(m1v[i], fmaf(sqrtf(v1v[i]), inv_bc2_sqrt, p.adam_eps)), xv[i]);
+                  for (int i = 0; i < CH; ++i) {
+                    mv[i] = fmaf(p.one_minus_b1, gradv[i] - mv[i], mv[i]);
+                    vv[i] = fmaf(p.one_minus_b2 * gradv[i], gradv[i], vv[i] * p.beta2f);
+                    xv[i] = fmaf(-step_size, __fdividef(mv[i], fmaf(sqrtf(vv[i]), inv_bc2_sqrt, p.adam_eps)), xv[i]);
                   }
+                  if (uvalid) {
 #pragma unroll
-                  for (int i = 0; i < RPT; ++i)
-                    if (i < nrow) {
-                      p.m[l][xoff + (size_t)i * dl] = m1v[i];
-                      p.v[l][xoff + (size_t)i * dl] = v1v[i];
-                    }
+                    for (int i = 0; i < CH; ++i)
+                      if (i < nrc) {
+                        p.m[l][xoffc + (size_t)i * dl] = mv[i];
+                        p.v[l][xoffc + (size_t)i * dl] = vv[i];
+                      }
+                  }
                 }
               }
               if (p.noise_mode != MCPC_NOISE_NONE) {
 #pragma unroll
-                for (int i = 0; i < RPT; ++i) xv[i] = fmaf(-p.lr, nz[i], xv[i]);
+                for (int i = 0; i < CH; ++i) xv[i] = fmaf(-p.lr, nz[i], xv[i]);
               }
+              // ---- 4. next step's operands: bf16 act(x) to shared memory, fp32 x back to TMEM ----
+              uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbc >> 3) * asbo + (uint32_t)(cbc & 7) * 16u +
+                              (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
 #pragma unroll
-              for (int i = 0; i < RPT; ++i) {
-                if (i >= nrow) xv[i] = 0.0f;                  // chains past the batch keep their zeros
-                *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(kind, xv[i]));
-                if (sf != nullptr && i < nrow) sf[(size_t)i * p.sf_pitch] = __float2bfloat16(av[i]);
-                if (xg != nullptr && i < nrow) xg[(size_t)i * dl] = gradv[i];
+              for (int i = 0; i < CH; ++i) {
+                if (i >= nrc || !uvalid) xv[i] = uvalid ? 0.0f : xold[i];   // chains past the batch keep their zeros
+                if (uvalid) *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(kind, xv[i]));
               }
+              __syncwarp();                                    // .sync.aligned store: every lane executes it
+              tmem_st<CH>(lac + col_x + h * NR, xv);
+              if (!defer) global_stores(c0);
             }
-            __syncwarp();                                    // .sync.aligned store: every lane executes it
-            tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
           }
           tmem_st_wait();
           fence_async_smem();
           fence_before_sync();
           mbar_arrive(&bars.acts_ready[l]);                  // act(x_l) / x_l of step ts+1 are in place
+          // the proxy fence above waits for every earlier memory operation of the thread: the global stores of a
+          // single-tile layer are issued after the hand-over so that they do not delay it
+          if (defer) global_stores(0);
         }
         TC_STAMP(gtid == 0, ts, 54);
         // layer-0 energy of this step
@@ -531,18 +615,31 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
       }
     } else {
       // ======================= group T: per-tile epilogues =======================
+      // ALT (8-chain CTAs): the two halves of the group (one warp per lane quarter each) take ALTERNATE tiles with all
+      // RV chains per thread -- the per-tile chain (wait, TMEM load, MUFU, store, fence, arrive) is latency-bound, so two
+      // tiles in flight nearly double the tile rate.  Half h owns accumulator / G buffer h.  Otherwise the two warps of a
+      // lane quarter split the chains of every tile.
+      constexpr int RT = ALT ? RV : RPT;
+      const int half = gw >> 2;
+      const int cbT = ALT ? 0 : cbase;
+      const int rbT = row0 + cbT;
+      const int nrT = max(0, min(RT, p.B - rbT));
+      const uint32_t laT = lane_base + (uint32_t)cbT;
+      const uint32_t gtoT = (uint32_t)(cbT >> 3) * 2048u + (uint32_t)(cbT & 7) * 16u + (uint32_t)(ln >> 3) * 128u +
+                            (uint32_t)(ln & 7) * 2u;
+      const bool stamp_thr = ALT ? ((gtid & 127) == 0) : (gtid == 0);
       uint32_t ph_dAf = 0, ph_ge = 3;
       const float qnan = __int_as_float(0x7fc00000);
       // Per-tile constants live in TMEM, not in global memory: one bias column per tile and, when they fit, the
       // targets of every output tile (NaN = "this element carries no loss": masked, past the batch, padding).
       // The tile loop then needs no global load and no per-element mask logic.
-      auto target_of = [&](int t, float (&yv)[RPT]) {
+      auto target_of = [&](int t, float (&yv)[RT]) {
         const int2 ti = s_tile[t];
         const int un = ((ti.x >> 8) & 0xff) * 128 + ln;
         const bool uy = ((ti.x & 0xff) == L) && un < ti.y && un >= nd.mask_start && nd.top >= MCPC_TOP_GAUSS;
-        const float* yp = p.target + (size_t)rb * nd.d_out + un;
+        const float* yp = p.target + (size_t)rbT * nd.d_out + un;
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) yv[i] = (uy && i < nrow) ? __ldg(yp + (size_t)i * nd.d_out) : qnan;
+        for (int i = 0; i < RT; ++i) yv[i] = (uy && i < nrT) ? __ldg(yp + (size_t)i * nd.d_out) : qnan;
       };
       for (int t = 0; t < n_tiles_all; ++t) {
         const int2 ti = s_tile[t];
@@ -550,114 +647,119 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
         const float bv = (un < ti.y && p.b[lin] != nullptr) ? __ldg(p.b[lin] + un) : 0.0f;
         __syncwarp();
         tmem_st1(lane_base + col_bias + (uint32_t)t, bv);           // both warps of a lane quarter write the same value
-        if (p.y_tmem && lin == L) {
-          float yv[RPT];
+        if (p.y_tmem && lin == L && (!ALT || (t & 1) == half)) {
+          float yv[RT];
           target_of(t, yv);
           __syncwarp();
-          tmem_st<RPT>(lane_addr + col_y + (uint32_t)t * NR, yv);
+          tmem_st<RT>(laT + col_y + (uint32_t)(t - p.n_hid_tiles) * NR, yv);
         }
       }
       tmem_st_wait();
-      float yv_n[RPT];
-      if (!p.y_tmem) {
-        const bool traj0 = (p.traj_every > 0);
-        const int t0 = (nd.top_has_grad || (traj0 && p.traj_out != nullptr)) ? 0 : p.n_out_tiles;
-        if (t0 < p.n_out_tiles) target_of(t0, yv_n);
-      }
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
         const int slot = ts - p.save_begin;
         const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
         const int rec = do_traj ? ts / p.traj_every : 0;
         const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
-        const int t_first = need_out ? 0 : p.n_out_tiles;
+        const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
         float e_part = 0.0f, l_part = 0.0f;
-        __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * p.sg_pitch : nullptr;
+        __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rbT) * p.sg_pitch : nullptr;
         uint32_t x_waited = 0;
         TC_STAMP(gtid == 0, ts, 32);
-        for (int t = t_first; t < n_tiles_all; ++t) {
+        for (int t = 0; t < t_end; ++t) {
           const int2 ti = s_tile[t];
           const int lin = ti.x & 0xff, h = ((ti.x >> 16) & 0xff) - 1, dl = ti.y;
-          const int k = t - t_first;
-          const int db = k & 1, gb = k & 1;
+          const int k = t;
+          const int db = k & (kDA - 1), gb = k & 1;
           const bool is_out = (lin == L);
           const bool has_b = !is_out || nd.top_has_grad;
           const int u = ((ti.x >> 8) & 0xff) * 128 + ln;
           const bool uvalid = u < dl;
-          float yv[RPT];
-          if (!p.y_tmem && is_out) {
-            // targets do not fit TMEM (32-chain CTAs): they were fetched one tile ago; fetch the next tile's now
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) yv[i] = yv_n[i];
-            int tn = t + 1;
-            if (tn >= p.n_out_tiles) {
-              const int ts1 = ts + 1;
-              const bool traj1 = (p.traj_every > 0) && (ts1 % p.traj_every == 0);
-              tn = (nd.top_has_grad || (traj1 && p.traj_out != nullptr)) ? 0 : p.n_out_tiles;
-            }
-            if (tn < p.n_out_tiles) target_of(tn, yv_n);
+          if (ALT && (k & 1) != half) {                       // the other half's tile
+            if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) mbar_arrive(&bars.g_ready[lin]);
+            continue;
           }
-          TC_STAMP(gtid == 0 && k == 3, ts, 60);
+          float yv[RT];
+          if (!p.y_tmem && is_out) target_of(t, yv);          // targets do not fit TMEM: plain loads
+          TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 60);
           if (!is_out && !((x_waited >> lin) & 1u)) {         // x_lin of THIS step was written by group U last step
             mbar_wait(&bars.acts_ready[lin], ts & 1);
             x_waited |= 1u << lin;
           }
           mbar_wait(&bars.dA_full[db], (ph_dAf >> db) & 1u);
           ph_dAf ^= 1u << db;
-          TC_STAMP(gtid == 0 && k == 3, ts, 61);
-          if (has_b) {
-            mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
-            ph_ge ^= 1u << gb;
-          }
+          TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 61);
           fence_after_sync();
-          TC_STAMP(gtid == 0 && k == 3, ts, 55);
-          uint8_t* gptr = smem + p.gbuf_off[gb] + g_thread_off;
-          float d[RPT], bias1[1];
-          __nv_bfloat16 g16[RPT];
+          TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 55);
+          // a warp whose 32 units are all padding (partial last tile of a Linear) only hands the buffers over: the
+          // back-projection of a partial tile reads the valid 16-unit groups of G only
+          if (((ti.x >> 8) & 0xff) * 128 + q * 32 >= dl) {
+            if (has_b) {
+              mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
+              ph_ge ^= 1u << gb;
+            }
+            fence_before_sync();
+            mbar_arrive(&bars.dA_empty[db]);
+            if (has_b) mbar_arrive(&bars.g_full[gb]);
+            if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) mbar_arrive(&bars.g_ready[lin]);
+            continue;
+          }
+          uint8_t* gptr = smem + p.gbuf_off[gb] + gtoT;
+          // the G buffer is only needed for the stores at the end: by then the back-projection that read its previous
+          // content (two tiles ago) has long completed
+          auto wait_g_buffer = [&]() {
+            if (has_b) {
+              mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
+              ph_ge ^= 1u << gb;
+            }
+          };
+          float d[RT], bias1[1];
+          __nv_bfloat16 g16[RT];
           __nv_bfloat16* sg_ptr = nullptr;
-          tmem_ld_nw<RPT>(lane_addr + col_dA + db * NR, d);
+          tmem_ld_nw<RT>(laT + col_dA + db * NR, d);
           tmem_ld_nw<1>(lane_base + col_bias + (uint32_t)t, bias1);
           if (!is_out) {
             const float ce = 0.5f * nd.c[lin], gc = nd.gc[lin];
-            float xv[RPT], gv[RPT];
-            tmem_ld_nw<RPT>(lane_addr + col_x + h * NR, xv);
+            float xv[RT], gv[RT];
+            tmem_ld_nw<RT>(laT + col_x + h * NR, xv);
             tmem_ld_wait();
             tmem_ld_tie(d);
             tmem_ld_tie(bias1);
             tmem_ld_tie(xv);
-            TC_STAMP(gtid == 0 && k == 3, ts, 56);
+            TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 56);
             const float bias = bias1[0];
             __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[lin] + u : nullptr;
-            // straight-line math for all RPT chains (independent chains interleave); only the stores are predicated
+            // straight-line math for all RT chains (independent chains interleave); only the stores are predicated
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
+            for (int i = 0; i < RT; ++i) {
               const float eps = xv[i] - (d[i] + bias);
               gv[i] = uvalid ? -gc * eps : 0.0f;
-              e_part = fmaf((uvalid && i < nrow) ? ce * eps : 0.0f, eps, e_part);
+              e_part = fmaf((uvalid && i < nrT) ? ce * eps : 0.0f, eps, e_part);
             }
+            wait_g_buffer();
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
+            for (int i = 0; i < RT; ++i) {
               g16[i] = __float2bfloat16(gv[i]);
               *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = g16[i];
             }
             sg_ptr = sg;
-            tmem_st<RPT>(lane_addr + col_g + h * NR, gv);
+            tmem_st<RT>(laT + col_g + h * NR, gv);
             tmem_st_wait();
           } else {
-            if (p.y_tmem) tmem_ld_nw<RPT>(lane_addr + col_y + (uint32_t)t * NR, yv);
+            if (p.y_tmem) tmem_ld_nw<RT>(laT + col_y + (uint32_t)(t - p.n_hid_tiles) * NR, yv);
             tmem_ld_wait();
             tmem_ld_tie(d);
             tmem_ld_tie(bias1);
             tmem_ld_tie(yv);
-            TC_STAMP(gtid == 0 && k == 3, ts, 56);
+            TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 56);
             const float bias = bias1[0];
             __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[L] + u : nullptr;
-            float* to = (do_traj && p.traj_out != nullptr && uvalid) ? p.traj_out + ((size_t)rec * p.B + rb) * nd.d_out + u : nullptr;
+            float* to = (do_traj && p.traj_out != nullptr && uvalid) ? p.traj_out + ((size_t)rec * p.B + rbT) * nd.d_out + u : nullptr;
             const bool bern = nd.top == MCPC_TOP_BERNOULLI;
-            float ov[RPT], ev[RPT];
+            float ov[RT], ev[RT];
             if (bern) {
 #pragma unroll
-              for (int i = 0; i < RPT; ++i) {
+              for (int i = 0; i < RT; ++i) {
                 const float o = d[i] + bias;
                 const float y = yv[i];
                 const bool on = (y == y);                      // NaN marks "no loss on this element"
@@ -670,7 +772,7 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < RPT; ++i) {
+              for (int i = 0; i < RT; ++i) {
                 const float o = d[i] + bias;
                 const float y = yv[i];
                 const bool on = (y == y);
@@ -680,22 +782,23 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
                 ov[i] = o;
               }
             }
+            wait_g_buffer();
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
+            for (int i = 0; i < RT; ++i) {
               g16[i] = __float2bfloat16(ev[i]);
               if (has_b) *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = g16[i];
             }
             sg_ptr = sg;
             if (to != nullptr) {
 #pragma unroll
-              for (int i = 0; i < RPT; ++i)
-                if (i < nrow) to[(size_t)i * nd.d_out] = ov[i];
+              for (int i = 0; i < RT; ++i)
+                if (i < nrT) to[(size_t)i * nd.d_out] = ov[i];
             }
           }
-          TC_STAMP(gtid == 0 && k == 3, ts, 57);
+          TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 57);
           fence_before_sync();
           mbar_arrive(&bars.dA_empty[db]);
-          TC_STAMP(gtid == 0 && k == 3, ts, 58);
+          TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 58);
           if (has_b) {
             fence_async_smem();
             mbar_arrive(&bars.g_full[gb]);
@@ -704,13 +807,13 @@ __global__ void __launch_bounds__(576, 1) infer_tc_kernel(const __grid_constant_
           // operation of the thread, global stores included, so they must not sit in front of it
           if (sg_ptr != nullptr) {
 #pragma unroll
-            for (int i = 0; i < RPT; ++i)
-              if (i < nrow) sg_ptr[(size_t)i * p.sg_pitch] = g16[i];
+            for (int i = 0; i < RT; ++i)
+              if (i < nrT) sg_ptr[(size_t)i * p.sg_pitch] = g16[i];
           }
-          TC_STAMP(gtid == 0 && k == 3, ts, 59);
+          TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 59);
           // own-layer errors of layer `lin` are complete after the last tile of Linear lin
           if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) mbar_arrive(&bars.g_ready[lin]);
-          TC_STAMP(gtid == 0, ts, 22 + k);
+          TC_STAMP(stamp_thr, ts, 22 + k);
         }
         e_part = warp_sum_tc(e_part);
         l_part = warp_sum_tc(l_part);
@@ -754,7 +857,8 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
   }
   p->h_off[nd.L] = HT;
   p->HT = HT;
-  if ((2 + 3 * HT) * NR + 32 > 512) {
+  const int nda = (NR == 16) ? 4 : 2;
+  if ((nda + 3 * HT) * NR + 32 > 512) {
     set_error("bf16 path: %d hidden unit tiles x %d chains per CTA do not fit the 512 TMEM columns", HT, NR);
     return MCPC_ERR_UNSUPPORTED;
   }
@@ -770,15 +874,15 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
     off += (uint32_t)NR * 128 * 2;
   }
   off = (off + 1023u) & ~1023u;
-  // tile table, in the order a step visits them: output tiles first, then Linear L-1 ... 1 (top-down)
+  // tile table, in the order a step visits them: Linear 1 ... L-1, then the output tiles (bottom-up).  The update of
+  // the top hidden layer closes the step (it needs every output tile); the tiles of the lower Linears of the NEXT step
+  // only need the lower layers' updates, which finished long before, so they overlap with it.
   int nt = 0;
   size_t gsrc = 0;
   uint32_t max_tile = 0;
-  p->n_out_tiles = 0;
-  for (int pass = 0; pass < nd.L; ++pass) {
-    const int lin = nd.L - pass;
+  p->n_hid_tiles = 0;
+  for (int lin = 1; lin <= nd.L; ++lin) {
     if (lin == nd.L && nd.d_out == 0) continue;
-    if (lin < 1) break;
     const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
     const int Kp = pad16(nd.dims[lin - 1]);
     if (Kp > 1024) {
@@ -802,10 +906,10 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
       gsrc += (size_t)T.bytes;
       if ((uint32_t)T.bytes > max_tile) max_tile = (uint32_t)T.bytes;
     }
-    if (lin == nd.L) p->n_out_tiles = nt;
+    if (lin < nd.L) p->n_hid_tiles = nt;
   }
-  p->n_hid_tiles = nt - p->n_out_tiles;
-  p->y_tmem = ((2 + 3 * HT) * NR + 32 + p->n_out_tiles * NR <= 512) ? 1 : 0;
+  p->n_out_tiles = nt - p->n_hid_tiles;
+  p->y_tmem = ((nda + 3 * HT) * NR + 32 + p->n_out_tiles * NR <= 512) ? 1 : 0;
   *packed_bytes = gsrc;
   // residency: everything if it fits, else as many leading tiles as fit beside a 2-slot ring
   const uint32_t slack = 4096;             // MN-major reads of narrow tiles overrun their 128 x Kp footprint
@@ -963,19 +1067,25 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   p.save_end = o->save_end;
   const bool timing = getenv("MCPC_TC_TIMING") != nullptr;     // debug only: allocates + synchronises
   if (timing) {
+    p.dbg_t0 = atoi(getenv("MCPC_TC_TIMING"));
     cudaMalloc(&p.dbg, 8 * 64 * sizeof(long long));
     cudaMemsetAsync(p.dbg, 0, 8 * 64 * sizeof(long long), stream);
   }
+  auto launch = [&](auto kernel) -> int {
+    MCPC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<p.n_ctas, 608, smem, stream>>>(p);
+    return MCPC_OK;
+  };
   if (rows.rv == 32) {
-    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    infer_tc_kernel<32, 32><<<p.n_ctas, 576, smem, stream>>>(p);
+    rc = launch(infer_tc_kernel<32, 32, false>);
   } else if (rows.rv == 16) {
-    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    infer_tc_kernel<16, 16><<<p.n_ctas, 576, smem, stream>>>(p);
+    rc = launch(infer_tc_kernel<16, 16, false>);
+  } else if (timing) {
+    rc = launch(infer_tc_kernel<16, 8, true>);       // the cycle trace exists for the 8-chain variant only
   } else {
-    MCPC_CUDA_CHECK(cudaFuncSetAttribute(infer_tc_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    infer_tc_kernel<16, 8><<<p.n_ctas, 576, smem, stream>>>(p);
+    rc = launch(infer_tc_kernel<16, 8, false>);
   }
+  if (rc != MCPC_OK) return rc;
   MCPC_CUDA_CHECK(cudaGetLastError());
   count_launch();
   if (timing) {
@@ -983,9 +1093,9 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(p.dbg);
-    for (int ts = 0; ts < 8 && ts < o->n_steps; ++ts) {
+    for (int ts = 0; ts < 8 && ts + p.dbg_t0 < o->n_steps; ++ts) {
       const long long base = h[ts * 64 + 32];
-      fprintf(stderr, "[tc timing] step %d (cycles rel. to epilogue step start):", ts);
+      fprintf(stderr, "[tc timing] step %d (abs %lld; cycles rel. to epilogue step start):", ts + p.dbg_t0, base);
       for (int i = 0; i < 64; ++i)
         if (h[ts * 64 + i] != 0) fprintf(stderr, " %d:%lld", i, h[ts * 64 + i] - base);
       fprintf(stderr, "\n");

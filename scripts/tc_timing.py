@@ -1,11 +1,13 @@
-import sys, os, warnings
-sys.path.insert(0, '/root/repo'); warnings.simplefilter('ignore')
+"""Cycle trace of CTA 0 of the resident bf16 kernel on the C2 workload (MCPC_TC_TIMING=<first step> prints 8 steps)."""
+import os, sys, warnings
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); warnings.simplefilter('ignore')
 import torch, torch.optim as optim
 from montecarlopredictivecoding_b200 import mcpc_utils as mu
 dev = torch.device('cuda:0'); torch.manual_seed(0)
 CFG = dict(input_size=20, hidden_size=128, hidden2_size=128, output_size=784, activation_fn="relu")
 model = mu.get_model(CFG, use_cuda=False).to(dev)
-config = {"mixing": 5, "sampling": 10, "optimizer_x_kwargs_mcpc": {"lr": 0.03}, "optimizer_p_fn_mcpc": optim.Adam, "optimizer_p_kwargs_mcpc": {"lr": 0.01}}
+MIX, SAMP = int(os.environ.get("MIX", 5)), int(os.environ.get("SAMP", 10))
+config = {"mixing": MIX, "sampling": SAMP, "optimizer_x_kwargs_mcpc": {"lr": 0.03}, "optimizer_p_fn_mcpc": optim.Adam, "optimizer_p_kwargs_mcpc": {"lr": 0.01}}
 tr = mu.get_mcpc_trainer(model, config, training=True); tr.set_precision('bf16')
 B = 1024; y = (torch.rand(B, 784, device=dev) < 0.5).float(); z = torch.zeros(B, 20, device=dev)
 for i in range(2):
