@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         for (int t = 0; t < (need_out ? n_tiles_all : p.n_hid_tiles); ++t) {
           const Tile& T = p.tiles[t];
           if (T.slot < 0) continue;
-          mbar_wait(&bars.w_empty[T.slot], (empty_phase >> T.slot) & 1u);
+          mbar_wait_parked(&bars.w_empty[T.slot], (empty_phase >> T.slot) & 1u);
           empty_phase ^= 1u << T.slot;
           mbar_expect_tx(&bars.w_full[T.slot], (uint32_t)T.bytes);
           bulk_g2s(smem + T.smem_off, p.packed + T.gsrc, (uint32_t)T.bytes, &bars.w_full[T.slot]);
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
     const uint32_t id_a = idesc_bf16(128, NR, false, false);
     const uint32_t smem_base = smem_u32(smem);
     uint32_t ph_wfull = 0, ph_dAe = (1u << kDA) - 1u;
-    mbar_wait(&bars.w_res, 0);
+    mbar_wait_parked(&bars.w_res, 0);
     for (int ts = 0; ts < p.n_steps; ++ts) {
       const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
       const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
@@ -257,15 +257,15 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         const int k = t;
         const int in_layer = T.lin - 1;
         if (!((acts_waited >> in_layer) & 1u)) {                    // act(x_{lin-1}) of THIS step: written by group U
-          mbar_wait(&bars.acts_ready[in_layer], ts & 1);
+          mbar_wait_parked(&bars.acts_ready[in_layer], ts & 1);
           acts_waited |= 1u << in_layer;
         }
         if (T.slot >= 0) {
-          mbar_wait(&bars.w_full[T.slot], (ph_wfull >> T.slot) & 1u);
+          mbar_wait_parked(&bars.w_full[T.slot], (ph_wfull >> T.slot) & 1u);
           ph_wfull ^= 1u << T.slot;
         }
         const int db = k & (kDA - 1);
-        mbar_wait(&bars.dA_empty[db], (ph_dAe >> db) & 1u);
+        mbar_wait_parked(&bars.dA_empty[db], (ph_dAe >> db) & 1u);
         ph_dAe ^= 1u << db;
         fence_after_sync();
         const uint32_t act_sbo = (uint32_t)(p.act_kp[in_layer] / 8) * 128u;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
     const uint32_t id_b = idesc_bf16(128, NR, true, false);
     const uint32_t smem_base = smem_u32(smem);
     uint32_t ph_gfull = 0;
-    mbar_wait(&bars.w_res, 0);
+    mbar_wait_parked(&bars.w_res, 0);
     for (int ts = 0; ts < p.n_steps; ++ts) {
       const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
       const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         const bool has_b = (T.lin < L) || nd.top_has_grad;
         if (!has_b) continue;                                         // read-out only: nothing flows back
         const bool last_of_lin = (t + 1 == n_tiles_all) || (p.tiles[t + 1].lin != T.lin);   // (output tiles come last)
-        mbar_wait(&bars.g_full[gb], (ph_gfull >> gb) & 1u);            // group T consumed the prediction of this tile,
+        mbar_wait_parked(&bars.g_full[gb], (ph_gfull >> gb) & 1u);            // group T consumed the prediction of this tile,
         ph_gfull ^= 1u << gb;                                         // so phase A has finished reading it as well
         fence_after_sync();
         const int in_layer = T.lin - 1;
@@ -451,8 +451,8 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
             const bool warp_idle = (hi * 128 + q * 32) >= dl;
             if (warp_idle) {
               if (hi == 0) {
-                if (has_above) mbar_wait(&bars.bp_ready[l], ts & 1);
-                if (l > 0) mbar_wait(&bars.g_ready[l], ts & 1);
+                if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);
+                if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);
               }
               continue;
             }
@@ -501,8 +501,8 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               if (kNoiseEarly) draw_noise();                    // before the wait: off the critical hand-over chain
               // ---- 2. wait for this layer's back-projection and own error, then ONE batch of TMEM loads ----
               if (hi == 0 && c0 == 0) {
-                if (has_above) mbar_wait(&bars.bp_ready[l], ts & 1);      // all tiles of Linear l+1 back-projected
-                if (l > 0) mbar_wait(&bars.g_ready[l], ts & 1);           // group T stored the own-layer error of layer l
+                if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);      // all tiles of Linear l+1 back-projected
+                if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);           // group T stored the own-layer error of layer l
                 fence_after_sync();
                 TC_STAMP(gtid == 0, ts, 40 + l);
               }
@@ -683,10 +683,10 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
           if (!p.y_tmem && is_out) target_of(t, yv);          // targets do not fit TMEM: plain loads
           TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 60);
           if (!is_out && !((x_waited >> lin) & 1u)) {         // x_lin of THIS step was written by group U last step
-            mbar_wait(&bars.acts_ready[lin], ts & 1);
+            mbar_wait_parked(&bars.acts_ready[lin], ts & 1);
             x_waited |= 1u << lin;
           }
-          mbar_wait(&bars.dA_full[db], (ph_dAf >> db) & 1u);
+          mbar_wait_parked(&bars.dA_full[db], (ph_dAf >> db) & 1u);
           ph_dAf ^= 1u << db;
           TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 61);
           fence_after_sync();
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
           // back-projection of a partial tile reads the valid 16-unit groups of G only
           if (((ti.x >> 8) & 0xff) * 128 + q * 32 >= dl) {
             if (has_b) {
-              mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
+              mbar_wait_parked(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
               ph_ge ^= 1u << gb;
             }
             fence_before_sync();
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
           // content (two tiles ago) has long completed
           auto wait_g_buffer = [&]() {
             if (has_b) {
-              mbar_wait(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
+              mbar_wait_parked(&bars.g_empty[gb], (ph_ge >> gb) & 1u);
               ph_ge ^= 1u << gb;
             }
           };

@@ -185,6 +185,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n\t}\n"
       :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same wait with a long suspend-time hint: the hint bounds how long the hardware may park the thread before
+// try_wait returns false, the thread still resumes as soon as the phase completes.  For warps that wait long and
+// often (MMA issuers, loader, the update group) it keeps their spinning out of the issue slots the working warps
+// need (22 % of all issued instructions of the resident kernel before).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}\n"
+      :: "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 
 // ---- async (bulk) copies and proxy fences --------------------------------------------------------------
 // global -> shared, `bytes` a multiple of 16, completion counted on `bar` (SASS: UBLKCP)
