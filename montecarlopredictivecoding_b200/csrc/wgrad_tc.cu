@@ -4,15 +4,17 @@
 //
 // G (d overall / d mu) and F (act(x)) were saved by infer_tc_kernel as bf16 row-major [n_save*B, width] with
 // every layer's block padded to 8 columns.  The reduction index (rows = saved steps x chains, ~1e5 for the
-// mcpc_ml call) is the MMA K dimension and BOTH operands are "MN-major": rows of 8 units (16 B) are the
-// core-matrix rows, so a row-major slab is scattered into the canonical no-swizzle layout with plain 16-byte
-// cp.async (LDGSTS) -- no register staging, no tensor map.
+// mcpc_ml call) is the MMA K dimension, so BOTH operands are "MN-major": a 3-D tensor map (64 columns, rows,
+// column block) over the row-major slab lets ONE TMA box land as consecutive SWIZZLE_128B MN-major operand
+// blocks of 64 units x 64 rows (tma.cuh).  (The first version scattered the slab with 16-byte cp.async: ~2,200
+// LDGSTS per stage, producer-bound at 0.27 ms per mcpc_ml call.)
 //
-// Grid = (output tile, K slab).  Output tile = 128 output units x <=128 input units (+ a constant block of
-// ones appended to the B operand, which makes column N of the accumulator the bias gradient for free).
-// Warps 0-3: cp.async producers (4-stage ring, 64 rows per stage), later the epilogue; warp 4: MMA issuer.
-// Partial tiles are added to global memory with coalesced fp32 reductions (via a shared-memory transpose).
+// Grid = (output tile, K slab).  Output tile = 128 output units x <=128 input units; a constant block whose first
+// column is ones follows the B operand's two blocks, which makes column 128 of the accumulator the bias gradient
+// for free.  Warp 0: TMA producer (one elected lane, 4-stage mbarrier ring, 64 rows per stage); warp 4: MMA issuer;
+// warps 0-3: epilogue.  Partial tiles are added to global memory with fp32 atomics from a shared-memory transpose.
 #include "mcpc_common.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 
 namespace mcpc {
@@ -23,22 +25,21 @@ using namespace umma;
 constexpr int kStages = 4;
 constexpr int kStageRows = 64;
 constexpr int kMaxWTiles = 64;
+constexpr uint32_t kBlk = 8192;       // one MN-major operand block: 64 rows (K) x 64 units, SWIZZLE_128B
 
 struct WTile {
   int lin;        // Linear index (0..L)
   int m0;         // first output unit
   int n0;         // first input unit
   int n_real;     // input units in this tile (multiple of 16, 0 for a bias-only tile)
-  int with_bias;  // column n_real of the accumulator is the bias gradient
-  int g_col;      // first column of the A slab in save_g
-  int f_col;      // first column of the B slab in save_f
+  int with_bias;  // the column after the F blocks of the accumulator is the bias gradient
+  int nblk;       // 64-unit blocks of F the tile loads (0, 1 or 2)
 };
 
 struct WgradParams {
   WTile tiles[kMaxWTiles];
-  const __nv_bfloat16* G;
-  const __nv_bfloat16* F;
-  int g_pitch, f_pitch;           // row pitches in elements
+  CUtensorMap mapG[kMaxL + 1];    // G block of Linear l:   (64 cols, rows, column blocks) from its first column
+  CUtensorMap mapF[kMaxL + 1];    // F block of layer l-1 (input of Linear l), same view
   float* gW[kMaxL + 1];
   float* gb[kMaxL + 1];
   int d_out_units[kMaxL + 1];     // rows of gW_l
@@ -46,12 +47,6 @@ struct WgradParams {
   int rows, rows_per_slab;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ bool elect_one_w() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
@@ -65,29 +60,34 @@ __global__ void __launch_bounds__(160, 1) wgrad_tc_kernel(const __grid_constant_
 
   const WTile& T = p.tiles[blockIdx.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tot = T.n_real + 16;                       // + the ones block
-  const uint32_t lbo_a = 16 * 128, lbo_b = (uint32_t)(n_tot / 8) * 128u;     // k-group strides; mn-group stride is 128
-  const uint32_t a_bytes = (kStageRows / 8) * lbo_a, b_bytes = (kStageRows / 8) * lbo_b;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  // the F box always carries two 64-unit blocks (a second block the tile does not need is junk or zero fill and is
+  // never written back), so the ones block sits at a fixed place and the accumulator is 144 columns wide
+  const int f_blocks = (T.nblk > 0) ? 2 : 0;
+  const int n_tot = f_blocks * 64 + 16;                  // F blocks + the first 16 columns of the ones block
+  const uint32_t a_bytes = 2 * kBlk, b_bytes = (uint32_t)f_blocks * kBlk;
+  const uint32_t stage_bytes = a_bytes + 2 * kBlk + kBlk;          // fixed stride: A | up to 2 F blocks | ones block
   const int r_begin = blockIdx.y * p.rows_per_slab;
   const int r_end = min(p.rows, r_begin + p.rows_per_slab);
   const int n_stage = (r_end > r_begin) ? (r_end - r_begin + kStageRows - 1) / kStageRows : 0;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 128);
+      mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(&done, 1);
     fence_mbar_init();
+    tma_prefetch_desc(&p.mapG[T.lin]);
+    if (T.nblk > 0) tma_prefetch_desc(&p.mapF[T.lin]);
   }
   if (warp == 4) tmem_alloc(&tmem_base_s, 256);
-  // the ones block of every stage's B operand: element (k, unit n_real) = 1, the other 15 columns 0
-  for (int i = tid; i < kStages * kStageRows * 2; i += blockDim.x) {
-    const int s = i / (kStageRows * 2), r = (i / 2) % kStageRows, g = i & 1;
+  // the ones block right after the F blocks of every stage: element (k, column 0) = 1, everything else 0.  In the
+  // SWIZZLE_128B layout row k keeps its 16-byte chunk c at position c ^ (k % 8).
+  for (int i = tid; i < kStages * kStageRows * 8; i += blockDim.x) {
+    const int s = i / (kStageRows * 8), k = (i / 8) % kStageRows, c = i & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (g == 0) v.x = 0x00003F80u;                         // bf16 1.0 in the first of the 8 units
-    *reinterpret_cast<uint4*>(smem + s * stage_bytes + a_bytes + (r >> 3) * lbo_b + (T.n_real / 8 + g) * 128 + (r & 7) * 16) = v;
+    if (c == (k & 7)) v.x = 0x00003F80u;                   // chunk 0 of row k: bf16 1.0 in its first element
+    *reinterpret_cast<uint4*>(smem + s * stage_bytes + a_bytes + b_bytes + k * 128 + c * 16) = v;
   }
   fence_async_smem();
   fence_before_sync();
@@ -99,35 +99,21 @@ __global__ void __launch_bounds__(160, 1) wgrad_tc_kernel(const __grid_constant_
     return;
   }
 
-  if (warp < 4) {
-    // ---------------- producers: 64 rows x (128 + n_real) units per stage ----------------
-    const int r_in = tid >> 1, half = tid & 1;
-    const uint32_t smem_base = smem_u32(smem);
-    const int nb = T.n_real / 8;
-    constexpr int D = kStages - 1;                          // stages in flight
-    for (int s = 0; s < n_stage + D; ++s) {
-      if (s < n_stage) {
+  if (warp == 0) {
+    // ---------------- TMA producer: 64 rows x (128 + 64*nblk) units per stage, two instructions ----------------
+    if (elect_one_w()) {
+      for (int s = 0; s < n_stage; ++s) {
         const int slot = s % kStages;
         mbar_wait(&empty[slot], ((s / kStages) & 1) ^ 1);
-        const int row = r_begin + s * kStageRows + r_in;
-        const uint32_t ok = (row < r_end) ? 16u : 0u;       // rows past the slab are zero-filled
-        const size_t rr = (size_t)min(row, p.rows - 1);
-        const uint32_t dst_row = smem_base + slot * stage_bytes + (r_in >> 3) * lbo_a + (r_in & 7) * 16;
-        const __nv_bfloat16* ga = p.G + rr * p.g_pitch + T.g_col + half * 64;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) cp_async16(dst_row + (half * 8 + c) * 128, ga + c * 8, ok);
-        const uint32_t dst_rowb = smem_base + slot * stage_bytes + a_bytes + (r_in >> 3) * lbo_b + (r_in & 7) * 16;
-        const __nv_bfloat16* fb = p.F + rr * p.f_pitch + T.f_col;
-        for (int c = half; c < nb; c += 2) cp_async16(dst_rowb + c * 128, fb + c * 8, ok);
-      }
-      cp_async_commit();
-      if (s >= D) {
-        cp_async_wait<D>();                                 // the group of stage s-D has landed
-        fence_async_smem();
-        mbar_arrive(&full[(s - D) % kStages]);
+        uint8_t* st = smem + slot * stage_bytes;
+        const int row = r_begin + s * kStageRows;          // rows past the end of the buffer are zero-filled by TMA
+        mbar_expect_tx(&full[slot], a_bytes + b_bytes);
+        tma_load_3d(st, &p.mapG[T.lin], 0, row, T.m0 / 64, &full[slot]);
+        if (f_blocks > 0) tma_load_3d(st + a_bytes, &p.mapF[T.lin], 0, row, T.n0 / 64, &full[slot]);
       }
     }
-  } else {
+    __syncwarp();
+  } else if (warp == 4) {
     // ---------------- MMA issuer ----------------
     const uint32_t id = idesc_bf16(128, n_tot, true, true);
     const uint32_t smem_base = smem_u32(smem);
@@ -135,12 +121,12 @@ __global__ void __launch_bounds__(160, 1) wgrad_tc_kernel(const __grid_constant_
       const int slot = s % kStages;
       mbar_wait(&full[slot], (s / kStages) & 1);
       fence_after_sync();
-      const uint64_t ad0 = smem_desc(smem_base + slot * stage_bytes, lbo_a, 128u);
-      const uint64_t bd0 = smem_desc(smem_base + slot * stage_bytes + a_bytes, lbo_b, 128u);
+      const uint64_t ad0 = smem_desc_sw128(smem_base + slot * stage_bytes, kBlk, 1024u);
+      const uint64_t bd0 = smem_desc_sw128(smem_base + slot * stage_bytes + a_bytes, kBlk, 1024u);
       if (elect_one_w()) {
 #pragma unroll
-        for (int ks = 0; ks < kStageRows / 16; ++ks)
-          mma_bf16_ss(tmem, ad0 + (uint64_t)(ks * ((2 * lbo_a) >> 4)), bd0 + (uint64_t)(ks * ((2 * lbo_b) >> 4)), id, s > 0 || ks > 0);
+        for (int ks = 0; ks < kStageRows / 16; ++ks)      // 16 rows (K) = 2048 bytes further into every block
+          mma_bf16_ss(tmem, ad0 + (uint64_t)(ks * 128), bd0 + (uint64_t)(ks * 128), id, s > 0 || ks > 0);
         mma_commit(&empty[slot]);
         if (s == n_stage - 1) mma_commit(&done);
       }
@@ -148,7 +134,7 @@ __global__ void __launch_bounds__(160, 1) wgrad_tc_kernel(const __grid_constant_
     }
   }
 
-  // ---------------- epilogue: TMEM -> smem transpose -> coalesced global reductions ----------------
+  // ---------------- epilogue: TMEM -> smem transpose -> global reductions ----------------
   if (warp < 4) {
     mbar_wait(&done, 0);
     fence_after_sync();
@@ -166,13 +152,14 @@ __global__ void __launch_bounds__(160, 1) wgrad_tc_kernel(const __grid_constant_
     const int d_out_l = p.d_out_units[T.lin], d_in_l = p.d_in_units[T.lin];
     float* gW = p.gW[T.lin];
     float* gb = p.gb[T.lin];
+    const int bias_col = f_blocks * 64;
     for (int r = warp; r < 128; r += 4) {
       const int mo = T.m0 + r;
       if (mo >= d_out_l) break;
       if (gW != nullptr)
         for (int n = lane; n < T.n_real; n += 32)
           if (T.n0 + n < d_in_l) atomicAdd(gW + (size_t)mo * d_in_l + T.n0 + n, tr[r * pitch + n]);
-      if (T.with_bias && gb != nullptr && lane == 0) atomicAdd(gb + mo, tr[r * pitch + T.n_real]);
+      if (T.with_bias && gb != nullptr && lane == 0) atomicAdd(gb + mo, tr[r * pitch + bias_col]);
     }
   }
   fence_before_sync();
@@ -206,10 +193,8 @@ int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_s
   WgradParams p{};
   int g_off[kMaxL + 1], f_off[kMaxL + 1], gw = 0, fw = 0;
   save_layout_bf16(nd, g_off, &gw, f_off, &fw);
-  p.G = reinterpret_cast<const __nv_bfloat16*>(io->save_g);
-  p.F = reinterpret_cast<const __nv_bfloat16*>(io->save_f);
-  p.g_pitch = gw;
-  p.f_pitch = fw;
+  const __nv_bfloat16* G = reinterpret_cast<const __nv_bfloat16*>(io->save_g);
+  const __nv_bfloat16* F = reinterpret_cast<const __nv_bfloat16*>(io->save_f);
   p.rows = n_save * B;
   int nt = 0;
   const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
@@ -236,9 +221,19 @@ int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_s
         T.n0 = j * 128;
         T.n_real = (d_i == 0 || p.gW[l] == nullptr) ? 0 : pad16i(d_i - j * 128 < 128 ? d_i - j * 128 : 128);
         T.with_bias = (j == 0) ? 1 : 0;
-        T.g_col = g_off[l] + m0;
-        T.f_col = (l == 0) ? 0 : f_off[l - 1] + j * 128;
+        T.nblk = (T.n_real + 63) / 64;
       }
+    // tensor maps from the first column of the layer's block; the last 64-column block may run past the block
+    // (neighbouring columns, or the start of the next row / the buffer's slack after the last row): those
+    // accumulator rows / columns are never written back
+    int rc = make_tmap_bf16_mn3(&p.mapG[l], G + g_off[l], (uint64_t)((gw - g_off[l] + 63) / 64) * 64, (uint64_t)p.rows,
+                                (uint64_t)gw, kStageRows, 2);
+    if (rc != MCPC_OK) return rc;
+    if (l > 0 && p.gW[l] != nullptr) {
+      rc = make_tmap_bf16_mn3(&p.mapF[l], F + f_off[l - 1], (uint64_t)((fw - f_off[l - 1] + 63) / 64) * 64, (uint64_t)p.rows,
+                              (uint64_t)fw, kStageRows, 2);
+      if (rc != MCPC_OK) return rc;
+    }
   }
   if (nt == 0) return MCPC_OK;
   int slabs = (148 + nt - 1) / nt;
@@ -246,8 +241,8 @@ int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_s
   rps = ((rps + kStageRows - 1) / kStageRows) * kStageRows;
   slabs = (p.rows + rps - 1) / rps;
   p.rows_per_slab = rps;
-  // widest stage: A 16 KB + B (128+16)/8 * 128 * 8 = 18 KB
-  const size_t smem = (size_t)kStages * ((kStageRows / 8) * 16 * 128 + (kStageRows / 8) * (144 / 8) * 128) + 1024;
+  // stage: A 16 KB + up to 2 F blocks + the ones block = 40 KB; the epilogue's transpose reuses the ring
+  const size_t smem = (size_t)kStages * 5 * kBlk + 1024;
   const size_t tr_bytes = (size_t)128 * 145 * 4 + 1024;
   const size_t dyn = smem > tr_bytes ? smem : tr_bytes;
   MCPC_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
