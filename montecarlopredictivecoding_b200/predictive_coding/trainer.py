@@ -647,8 +647,8 @@ class PCTrainer(object):
         if target is not None:
             target = target.detach().to(torch.float32).contiguous()
         xs = [layer.get_x().data for layer in netp.pc_layers]
-        energy = torch.zeros(T, dtype=torch.float64, device=device)
-        loss = torch.zeros(T, dtype=torch.float64, device=device)
+        scalars = torch.zeros(2, T, dtype=torch.float64, device=device)     # one allocation, one D2H at the end
+        energy, loss = scalars[0], scalars[1]
 
         want_traj = ctx["want_outputs"] or ctx["want_reps"] or ctx["want_xs"]
         every_t = ctx["every_t"]
@@ -697,10 +697,16 @@ class PCTrainer(object):
             ends_with_p = (t1 - 1) in self._update_p_set
             need_grads = self._keep_unused_param_grads or any(u >= t0 for u in later_p_updates)
             win_begin = None
+            flat_ready = False
+            zero_steps = []
             if need_grads:
                 zero_steps = [t for t in range(t0, t1) if self._is_zero_grad_step(t)]
                 win_begin = zero_steps[-1] if zero_steps else t0
-                flat, gW, gb = self._ensure_flat_grads(netp, zero=bool(zero_steps))
+                if streaming:           # the streaming kernels accumulate dW themselves: buffers must exist up front
+                    flat, gW, gb = self._ensure_flat_grads(netp, zero=bool(zero_steps))
+                    flat_ready = True
+                else:
+                    gW = gb = None      # resident modes: (re)zeroed after the inference launch, off the launch path
             # the window may be cut further so the saved operands fit the scratch budget
             g_w, f_w, s_dtype = self._save_layout(netp, top)
             row_bytes = (4 if s_dtype == torch.float32 else 2) * B * (g_w + f_w)
@@ -741,6 +747,9 @@ class PCTrainer(object):
                 if x_opt["kind"] == N.OPT_ADAM and (c0 in self._update_x_set):
                     adam_step0 += n
                     self._adam["step"] = adam_step0
+                if need_grads and not flat_ready:
+                    flat, gW, gb = self._ensure_flat_grads(netp, zero=bool(zero_steps))
+                    flat_ready = True
                 if save_g is not None:
                     eng.weight_grad(netp, top, self._energy_coefficient, B, se - sb, save_g, save_f, inputs_dev,
                                     gW, gb, self._precision)
@@ -749,7 +758,7 @@ class PCTrainer(object):
                 self._p_step(flat, B)
         self.last_call_info = {"mode": "fused", "launches": n_launch, "segments": len(segs),
                                "noise": noise_mode, "precision": self._precision}
-        return {"energy": energy, "loss": loss, "traj_x": traj_x, "traj_out": traj_out, "n_rec": n_rec}
+        return {"energy": energy, "loss": loss, "scalars": scalars, "traj_x": traj_x, "traj_out": traj_out, "n_rec": n_rec}
 
     # --------------------------------------------------------------------------------------
     def _run_stepwise(self, ctx, loss_fn, cb_bwd, cb_bwd_kwargs, cb_t, cb_t_kwargs, check_after_cb):
@@ -876,7 +885,8 @@ class PCTrainer(object):
     def _build_results(self, ctx, rec, has_loss):
         every_t = ctx["every_t"]
         netp = ctx["netp"]
-        stacked = self._reduce_scalars(torch.stack([rec["energy"], rec["loss"]]))
+        both = rec.get("scalars")
+        stacked = self._reduce_scalars(both if both is not None else torch.stack([rec["energy"], rec["loss"]]))
         host = stacked.to("cpu", torch.float64).numpy()       # the ONE device->host sync of the call
         e, l = host[0], host[1]
         sel = slice(None) if every_t else slice(len(e) - 1, len(e))
