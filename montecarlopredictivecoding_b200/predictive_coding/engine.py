@@ -3,6 +3,7 @@ libmcpc_b200.so on torch's current CUDA stream.  This is the only engine the pro
 it refuses anything that is not a contiguous fp32 CUDA tensor (no CPU fallback).
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -54,7 +55,36 @@ class InferCall:
     gb: Optional[List[Optional[torch.Tensor]]] = None
 
 
+_net_cache = {}
+_ENV_KNOBS = ("MCPC_FORCE_STREAMING", "MCPC_TC_ROWS", "MCPC_ROWS", "MCPC_WIDE_CTAS")
+
+
+def _env_key():
+    """Debug / test knobs the library reads with getenv(): part of every cache key that depends on them."""
+    return tuple(os.environ.get(k) for k in _ENV_KNOBS)
+
+
+
+def _net_key(plan: NetPlan, top: TopPlan, energy_coefficient: float):
+    return (plan.d_in, tuple(plan.dims), plan.d_out, tuple(plan.act), tuple(plan.energy_scale), float(energy_coefficient),
+            top.kind, float(top.inv_var), top.mask_start)
+
+
 def net_struct(plan: NetPlan, top: TopPlan, energy_coefficient: float) -> N.McpcNet:
+    """The McpcNet of a (plan, top, coefficient); built once per distinct network description (the structs are
+    read-only for the library)."""
+    key = _net_key(plan, top, energy_coefficient)
+    hit = _net_cache.get(key)
+    if hit is not None:
+        return hit
+    net = _build_net_struct(plan, top, energy_coefficient)
+    if len(_net_cache) > 256:
+        _net_cache.clear()
+    _net_cache[key] = net
+    return net
+
+
+def _build_net_struct(plan: NetPlan, top: TopPlan, energy_coefficient: float) -> N.McpcNet:
     net = N.McpcNet()
     net.n_layers = plan.L
     net.d_in = plan.d_in
@@ -88,11 +118,22 @@ class NativeEngine:
     def __init__(self):
         self._lib = N.load()
         self._ws = {}
+        self._ws_need = {}
+        self._layout_cache = {}
+        self._mode_cache = {}
 
     def _workspace(self, net, B, n_steps, precision, device):
-        need = C.c_size_t(0)
-        N.check(self._lib.mcpc_workspace_bytes(C.byref(net), B, n_steps, precision, C.byref(need)),
-                "mcpc_workspace_bytes")
+        nkey = (C.addressof(net), B, n_steps, precision, _env_key())   # net structs are cached objects (net_struct)
+        need_v = self._ws_need.get(nkey)
+        if need_v is None:
+            need = C.c_size_t(0)
+            N.check(self._lib.mcpc_workspace_bytes(C.byref(net), B, n_steps, precision, C.byref(need)),
+                    "mcpc_workspace_bytes")
+            need_v = need.value
+            if len(self._ws_need) > 1024:
+                self._ws_need.clear()
+            self._ws_need[nkey] = need_v
+        need = C.c_size_t(need_v)
         key = (device.index, )
         buf = self._ws.get(key)
         if buf is None or buf.numel() < need.value:
@@ -102,17 +143,28 @@ class NativeEngine:
 
     def save_layout(self, plan: NetPlan, top: TopPlan, precision: int):
         """(g_width, f_width, torch dtype) of the operands saved for the weight update."""
+        key = (_net_key(plan, top, 1.0), precision)
+        hit = self._layout_cache.get(key)
+        if hit is not None:
+            return hit
         net = net_struct(plan, top, 1.0)
         gw, fw, eb = C.c_int32(0), C.c_int32(0), C.c_int32(0)
         N.check(self._lib.mcpc_save_layout(C.byref(net), precision, C.byref(gw), C.byref(fw), C.byref(eb)),
                 "mcpc_save_layout")
-        return gw.value, fw.value, (torch.float32 if eb.value == 4 else torch.bfloat16)
+        out = (gw.value, fw.value, (torch.float32 if eb.value == 4 else torch.bfloat16))
+        self._layout_cache[key] = out
+        return out
 
     def infer_mode(self, plan: NetPlan, top: TopPlan, B: int, precision: int) -> int:
         """N.MODE_*: how mcpc_infer will execute this network (resident one-launch vs streaming per-step GEMMs)."""
+        key = (_net_key(plan, top, 1.0), B, precision, _env_key())
+        hit = self._mode_cache.get(key)
+        if hit is not None:
+            return hit
         net = net_struct(plan, top, 1.0)
         mode = C.c_int32(0)
         N.check(self._lib.mcpc_infer_mode(C.byref(net), B, precision, C.byref(mode)), "mcpc_infer_mode")
+        self._mode_cache[key] = mode.value
         return mode.value
 
     def infer(self, c: InferCall) -> None:

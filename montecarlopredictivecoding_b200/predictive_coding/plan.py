@@ -87,9 +87,35 @@ def classify_energy_fn(fn) -> float:
     return c
 
 
+_plan_cache = {}
+
+
 def compile_net(model: nn.Module) -> NetPlan:
-    """Walk the module list and recognise ``[Linear, PCLayer, act?]* [Linear]?``."""
+    """Walk the module list and recognise ``[Linear, PCLayer, act?]* [Linear]?``.
+
+    The result is cached per module list (identity of the children); what a user can flip on a live PCLayer
+    (masks, per-datapoint energies, held errors, the energy function) and the Linear shapes are re-checked on a hit."""
     mods = list(model.children()) if not isinstance(model, (nn.Linear, PCLayer)) else [model]
+    key = tuple(id(m) for m in mods)
+    hit = _plan_cache.get(key)
+    if hit is not None:
+        plan, efns, shapes = hit
+        ok = all(m._S is None and m._M is None and not m.is_keep_energy_per_datapoint and not m.is_holding_error
+                 for m in plan.pc_layers)
+        ok = ok and all(pcl._energy_fn is f for pcl, f in zip(plan.pc_layers, efns))
+        ok = ok and all((lin.in_features, lin.out_features, lin.bias is None) == sh for lin, sh in zip(plan.linears, shapes))
+        if ok:
+            return plan
+        del _plan_cache[key]
+    plan = _compile_net(model, mods)
+    if len(_plan_cache) > 64:
+        _plan_cache.clear()
+    _plan_cache[key] = (plan, [pcl._energy_fn for pcl in plan.pc_layers],
+                        [(lin.in_features, lin.out_features, lin.bias is None) for lin in plan.linears])
+    return plan
+
+
+def _compile_net(model: nn.Module, mods) -> NetPlan:
     if any(len(list(m.children())) > 0 for m in mods):
         raise UnsupportedModel("nested containers are not supported by the fused kernel; use a flat nn.Sequential of "
                                "Linear / PCLayer / activation modules")
@@ -213,6 +239,9 @@ class LangevinPlan:
     var: float
 
 
+_cb_default_var = {}
+
+
 def classify_callback_after_t(cb, kwargs: dict, trainer) -> Optional[LangevinPlan]:
     """Recognise the Langevin ``random_step`` callback (utils/model.py:35-44).
 
@@ -232,10 +261,15 @@ def classify_callback_after_t(cb, kwargs: dict, trainer) -> Optional[LangevinPla
         return None
     var = kwargs.get("var", None)
     if var is None:
-        try:
-            var = inspect.signature(cb).parameters["var"].default
-        except (KeyError, TypeError, ValueError):
-            return None
+        hit = _cb_default_var.get(id(cb))
+        if hit is not None and hit[0] is cb:
+            var = hit[1]
+        else:
+            try:
+                var = inspect.signature(cb).parameters["var"].default
+            except (KeyError, TypeError, ValueError):
+                return None
+            _cb_default_var[id(cb)] = (cb, var)
     try:
         var = float(var)
     except (TypeError, ValueError):

@@ -556,6 +556,26 @@ class PCTrainer(object):
         acc = self._accumulate_p_at
         return (t in self._update_p_set and t not in self._acc_set) or (len(acc) > 0 and t == acc[0])
 
+    def _refresh_schedule_sets(self):
+        """Set views of the three step lists, rebuilt only when a list object was replaced or resized."""
+        key = (id(self._update_p_at), len(self._update_p_at), id(self._update_x_at), len(self._update_x_at),
+               id(self._accumulate_p_at), len(self._accumulate_p_at))
+        if getattr(self, "_sched_key", None) != key:
+            self._sched_key = key
+            self._update_p_set = set(self._update_p_at)
+            self._update_x_set = set(self._update_x_at)
+            self._acc_set = set(self._accumulate_p_at)
+            self._seg_cache = {}
+
+    def _segments_cached(self, T, split_last):
+        """(segments, zero_grad steps inside each segment) for the current schedule."""
+        hit = self._seg_cache.get((T, split_last))
+        if hit is None:
+            segs = self._segments(T, split_last)
+            hit = (segs, [[t for t in range(t0, t1) if self._is_zero_grad_step(t)] for (t0, t1) in segs])
+            self._seg_cache[(T, split_last)] = hit
+        return hit
+
     def _segments(self, T, split_last):
         """Cut [0, T) where the kernel arguments change: after every p-update step, where the
         ``update_x_at`` membership flips, and (optionally) before the last step."""
@@ -639,9 +659,7 @@ class PCTrainer(object):
     def _run_fused(self, ctx, x_opt, langevin):
         netp, top, B, T, device = ctx["netp"], ctx["top"], ctx["B"], ctx["T"], ctx["device"]
         eng = self._get_engine()
-        self._update_p_set = set(self._update_p_at)
-        self._update_x_set = set(self._update_x_at)
-        self._acc_set = set(self._accumulate_p_at)
+        self._refresh_schedule_sets()
         inputs_dev = self._inputs_or_none(ctx["inputs"])
         target = ctx["target"]
         if target is not None:
@@ -690,17 +708,17 @@ class PCTrainer(object):
         streaming = hasattr(eng, "infer_mode") and \
             eng.infer_mode(netp, top, B, self._precision) == N.MODE_STREAMING_BF16
         later_p_updates = sorted(self._update_p_set)
-        segs = self._segments(T, split_last=(want_traj and not every_t))
+        segs, seg_zero_steps = self._segments_cached(T, split_last=(want_traj and not every_t))
         flat = None
         n_launch = 0
-        for (t0, t1) in segs:
+        for si, (t0, t1) in enumerate(segs):
             ends_with_p = (t1 - 1) in self._update_p_set
             need_grads = self._keep_unused_param_grads or any(u >= t0 for u in later_p_updates)
             win_begin = None
             flat_ready = False
             zero_steps = []
             if need_grads:
-                zero_steps = [t for t in range(t0, t1) if self._is_zero_grad_step(t)]
+                zero_steps = seg_zero_steps[si]
                 win_begin = zero_steps[-1] if zero_steps else t0
                 if streaming:           # the streaming kernels accumulate dW themselves: buffers must exist up front
                     flat, gW, gb = self._ensure_flat_grads(netp, zero=bool(zero_steps))
