@@ -1020,7 +1020,8 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     const int lin = T.lin;
     const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
     const int n_lin_tiles = (rows + 127) / 128;
-    pack_weights_kernel<<<2 * n_lin_tiles > 64 ? 64 : 2 * n_lin_tiles + 2, 256, 0, stream>>>(
+    const int n_elems = n_lin_tiles * 128 * T.Kp;                     // 2 elements per thread: the call is latency-bound
+    pack_weights_kernel<<<(n_elems + 511) / 512, 256, 0, stream>>>(
         io->W[lin], rows, nd.dims[lin - 1], T.Kp, n_lin_tiles, wsb + T.gsrc);
     count_launch();
     t += n_lin_tiles;
