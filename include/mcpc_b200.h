@@ -154,6 +154,19 @@ int mcpc_weight_grad(const McpcNet* net, const McpcGradIO* io, int32_t B, int32_
 int mcpc_fill_noise(uint64_t seed, int32_t t_begin, int32_t n_steps, uint64_t chain_offset, int32_t B,
                     int32_t n_units, float noise_scale, float* out, void* stream);
 
+/* SURVEY 8(f) N1 -- importance-sampling estimate of the marginal log-likelihood of a Bernoulli generative model
+ * (utils/training_evaluation.py:177-206, get_marginal_likelihood):
+ *   losses[i][s] = sum_j BCEWithLogits(clamp(logits[s][j], +-clamp_abs), data[i][j])
+ *   row_ll[i]    = log(mean_s exp(-(losses[i][s] - m_i))) - m_i,  m_i = min_s losses[i][s]      (:203-205)
+ *   *ml_out      = mean_i row_ll[i]
+ * logits [S, D] are the pre-sigmoid outputs of S prior samples (sample_pc(..., is_return_hidden=True), :72-100),
+ * data [N, D] targets in [0, 1]; both fp32 row-major device pointers.  ml_out: one device double; row_ll: optional
+ * device [N] fp32.  One tcgen05 GEMM (bf16 hi/lo split operands, fp32 accumulation) with a streaming min / sum-exp
+ * epilogue; clamp_abs <= 0 disables the clamp. */
+int mcpc_marginal_ll_workspace_bytes(int32_t N, int32_t S, int32_t D, size_t* bytes);
+int mcpc_marginal_ll_bernoulli(const float* logits, int32_t S, const float* data, int32_t N, int32_t D, float clamp_abs,
+                               void* workspace, size_t workspace_bytes, double* ml_out, float* row_ll, void* stream);
+
 /* Validation only: known-answer test of the tcgen05/TMEM/bulk-copy primitives of the bf16 path.
  * Wt [128, Kin], Bx [N, Kin], G [N, 128] -> D1 [128, N] = Wt Bx^T,  D2 [128, N]: D2[m][n] = sum_j Wt[j][m] G[n][j]
  * (rows m >= Kin undefined).  ws: >= 128*Kin*2 bytes of device scratch. */

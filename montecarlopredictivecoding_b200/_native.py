@@ -96,7 +96,8 @@ _lib = None
 _lock = threading.Lock()
 LIB_NAME = "libmcpc_b200.so"
 EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer_mode", "mcpc_infer", "mcpc_weight_grad",
-           "mcpc_fill_noise", "mcpc_debug_umma", "mcpc_debug_tma")
+           "mcpc_fill_noise", "mcpc_marginal_ll_workspace_bytes", "mcpc_marginal_ll_bernoulli", "mcpc_debug_umma",
+           "mcpc_debug_tma")
 
 
 def lib_path():
@@ -136,6 +137,11 @@ def load():
         lib.mcpc_fill_noise.restype = C.c_int
         lib.mcpc_fill_noise.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                         C.c_float, C.c_void_p, C.c_void_p]
+        lib.mcpc_marginal_ll_workspace_bytes.restype = C.c_int
+        lib.mcpc_marginal_ll_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+        lib.mcpc_marginal_ll_bernoulli.restype = C.c_int
+        lib.mcpc_marginal_ll_bernoulli.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mcpc_debug_umma.restype = C.c_int
         lib.mcpc_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]

@@ -241,6 +241,20 @@ int mcpc_fill_noise(uint64_t seed, int32_t t_begin, int32_t n_steps, uint64_t ch
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mcpc_marginal_ll_workspace_bytes(int32_t N, int32_t S, int32_t D, size_t* bytes) {
+  if (bytes == nullptr) {
+    set_error("mcpc_marginal_ll_workspace_bytes: NULL argument");
+    return MCPC_ERR_INVALID;
+  }
+  return marginal_ll_workspace(N, S, D, bytes);
+}
+
+int mcpc_marginal_ll_bernoulli(const float* logits, int32_t S, const float* data, int32_t N, int32_t D, float clamp_abs,
+                               void* workspace, size_t workspace_bytes, double* ml_out, float* row_ll, void* stream) {
+  return launch_marginal_ll(logits, S, data, N, D, clamp_abs, workspace, workspace_bytes, ml_out, row_ll,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
 int mcpc_debug_umma(const float* Wt, const float* Bx, const float* G, int32_t Kin, int32_t N, float* D1, float* D2,
                     void* ws, void* stream) {
   if (Wt == nullptr || Bx == nullptr || G == nullptr || D1 == nullptr || D2 == nullptr || ws == nullptr) {

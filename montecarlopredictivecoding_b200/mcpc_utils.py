@@ -120,3 +120,74 @@ def get_mcpc_trainer_one_sample(gen_pc, config, training=True):
         gen_pc, T=config["K"], update_x_at="all", optimizer_x_fn=optim.SGD,
         optimizer_x_kwargs=config["optimizer_x_kwargs_mcpc"], update_p_at="last" if training else "never",
         plot_progress_at=[], **_mcpc_p_kwargs(config, training))
+
+
+# ---- prior sampling and the marginal-likelihood estimate of table_1 --------------------------
+def sample_pc(num_samples, model, config, use_cuda=False, is_return_hidden=False):
+    """Ancestral samples of the generative model (utils/training_evaluation.py:72-100): every PCLayer adds unit
+    Gaussian noise to its prediction; ``is_return_hidden`` returns the pre-sigmoid / pre-noise sensory prediction.
+    Same arguments and return value; the noise is drawn on the model's device instead of on the CPU."""
+    device = next(model.parameters()).device
+    temp = torch.zeros((num_samples, config["input_size"]), device=device)
+    with torch.no_grad():
+        for layer in model:
+            if isinstance(layer, PCLayer):
+                temp = temp + torch.randn_like(temp)           # N(mu, I): cholesky(eye) of the reference is the identity
+            else:
+                temp = layer(temp)
+    if is_return_hidden:
+        return temp.detach()
+    loss_fn = config["loss_fn"]
+    if getattr(loss_fn, "__name__", "") == "fe_fn":
+        temp = temp + float(config["input_var"]) ** 0.5 * torch.randn_like(temp)
+    elif getattr(loss_fn, "__name__", "") == "bernoulli_fn":
+        temp = (torch.rand_like(temp) <= temp.sigmoid()).double()
+    return temp.detach()
+
+
+_mll_ws = {}
+
+
+def bernoulli_marginal_ll(logits, data, clamp_abs=20.0, return_rows=False):
+    """``mean_i log mean_s exp(-sum_j BCEWithLogits(clamp(logits[s]), data[i]))`` on the GPU through
+    ``mcpc_marginal_ll_bernoulli`` (one tcgen05 GEMM with a streaming min / sum-exp epilogue).
+    logits [S, D], data [N, D]: CUDA tensors; returns a 0-d float32 CPU tensor like the reference's ``ml``."""
+    import ctypes as C
+
+    from . import _native as N
+    if not (logits.is_cuda and data.is_cuda):
+        raise RuntimeError("bernoulli_marginal_ll needs CUDA tensors: the B200 build has no CPU path")
+    logits = logits.detach().to(torch.float32).contiguous()
+    data = data.detach().to(device=logits.device, dtype=torch.float32).contiguous()
+    if logits.dim() != 2 or data.dim() != 2 or logits.shape[1] != data.shape[1]:
+        raise RuntimeError(f"logits {tuple(logits.shape)} and data {tuple(data.shape)} must be [S, D] and [N, D]")
+    S, D = logits.shape
+    n = data.shape[0]
+    lib = N.load()
+    need = C.c_size_t(0)
+    N.check(lib.mcpc_marginal_ll_workspace_bytes(n, S, D, C.byref(need)), "mcpc_marginal_ll_workspace_bytes")
+    ws = _mll_ws.get(logits.device.index)
+    if ws is None or ws.numel() < need.value:
+        ws = torch.empty(need.value, dtype=torch.uint8, device=logits.device)
+        _mll_ws[logits.device.index] = ws
+    ml = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    rows = torch.empty(n, dtype=torch.float32, device=logits.device) if return_rows else None
+    stream = torch.cuda.current_stream(logits.device).cuda_stream
+    with torch.cuda.device(logits.device):
+        N.check(lib.mcpc_marginal_ll_bernoulli(logits.data_ptr(), S, data.data_ptr(), n, D, float(clamp_abs), ws.data_ptr(),
+                                               ws.numel(), ml.data_ptr(), None if rows is None else rows.data_ptr(),
+                                               C.c_void_p(stream)), "mcpc_marginal_ll_bernoulli")
+    out = ml.to("cpu", torch.float32).reshape(())
+    return (out, rows) if return_rows else out
+
+
+def get_marginal_likelihood(gen_pc, config, dataloader, use_cuda, n_samples=5000):
+    """utils/training_evaluation.py:177-206 for Bernoulli models: S prior samples, every data row scored against all
+    of them.  Same arguments and return value; the 4000 x 5000 x 784 elementwise BCE of the reference is one GEMM."""
+    if getattr(config["loss_fn"], "__name__", "") != "bernoulli_fn":
+        raise NotImplementedError("only the Bernoulli likelihood is implemented (the reference raises for fe_fn too)")
+    logits = sample_pc(n_samples, gen_pc, config, use_cuda=use_cuda, is_return_hidden=True)
+    dataset = dataloader.dataset
+    loader = torch.utils.data.DataLoader(dataset, batch_size=4096)
+    data = torch.cat([d.reshape(d.shape[0], -1) for d, _ in loader], dim=0)
+    return bernoulli_marginal_ll(logits, data.to(logits.device), clamp_abs=20.0)
