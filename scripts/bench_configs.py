@@ -149,14 +149,41 @@ def c5(prec, B=2048, T=20, width=4096, L=4):
             "algorithmic_tflops": flops / s / 1e12, "frac_of_bf16_peak": flops / s / 1e12 / PEAK_TF}
 
 
+def n1(prec, N=10000, S=5000, D=784):
+    """get_marginal_likelihood of table_1.py (10,000 test images x 5,000 prior samples x 784 pixels)."""
+    import time
+
+    import numpy as np
+
+    from oracle import mcpc_oracle as orc
+    g = torch.Generator(device="cpu").manual_seed(0)
+    logits = (torch.randn(S, D, generator=g) * 4.0).to(DEV)
+    data = (torch.rand(N, D, generator=g) < 0.2).float().to(DEV)
+    out = {}
+
+    def run():
+        out["ml"] = mu.bernoulli_marginal_ll(logits, data)
+    s = timed(run, reps=5, warm=2)
+    flops = 2.0 * N * S * D
+    rows = 40                                              # bounded CPU sample of the same workload, scaled in N
+    t0 = time.perf_counter()
+    orc.marginal_ll_bernoulli(logits.cpu().numpy(), data[:rows].cpu().numpy(), dtype=np.float32)
+    cpu_s = (time.perf_counter() - t0) * N / rows
+    return {"workload": f"N1 marginal likelihood, {N} rows x {S} samples x {D} pixels (table_1.py:253)", "precision": "bf16 hi/lo split x3, fp32 accumulate",
+            "ms": s * 1e3, "rows_per_s": N / s, "algorithmic_tflops": flops / s / 1e12,
+            "tensor_tflops_issued": 3 * flops * (832.0 / 784.0) / s / 1e12,
+            "frac_of_bf16_peak_issued": 3 * flops * (832.0 / 784.0) / s / 1e12 / PEAK_TF, "ml": float(out["ml"]),
+            "cpu_port_s_scaled": cpu_s, "cpu_sample": f"{rows} rows of the numpy oracle, scaled to {N}"}
+
+
 if __name__ == "__main__":
     prec = "bf16"
     if "--precision" in sys.argv:
         prec = sys.argv[sys.argv.index("--precision") + 1]
-    which = [a for a in sys.argv[1:] if a in ("c1", "c3", "c4", "c5")] or ["c1", "c3", "c4", "c5"]
+    which = [a for a in sys.argv[1:] if a in ("c1", "c3", "c4", "c5", "n1")] or ["c1", "c3", "c4", "c5"]
     for w in which:
         try:
-            out = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[w](prec)
+            out = {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "n1": n1}[w](prec)
             if int(os.environ.get("RANK", "0")) == 0:
                 print(json.dumps(out))
         except Exception as exc:  # noqa: BLE001
