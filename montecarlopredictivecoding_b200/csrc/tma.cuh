@@ -99,6 +99,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* t
                :: "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// the same boxes, fetched into L2 only (no shared-memory destination, no mbarrier): hides the DRAM latency of
+// first-touch operands behind stages that are still far away
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
