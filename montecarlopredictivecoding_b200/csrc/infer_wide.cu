@@ -66,6 +66,7 @@ struct WideParams {
   uint64_t seed, chain_offset;
   int mn3;                                // MN-major operands come in through 3-D tensor maps (all widths % 64 == 0)
   int l2_prefetch;                        // stages ahead of the ring whose boxes are prefetched into L2 (0 = off)
+  int skip_epilogue;                      // debug: MCPC_WIDE_SKIP_EPI=1
   long long* dbg;                         // MCPC_WIDE_TIMING=1: per-role cycle counters of CTA 0 (debug)
 };
 
@@ -110,6 +111,12 @@ struct Pipe {
 };
 
 enum { KIND_PREDICT = 0, KIND_UPDATE = 1, KIND_WGRAD = 2 };
+
+// Epilogue warps per CTA (8 = two per sub-partition).  Measured on C5: 16 warps for the update kernel made it slower
+// (500k vs 437k cycles per CTA: its epilogue is bound by the 32-lines-per-instruction global access pattern and by
+// Philox latency chains, and a lane = unit version of it executed 2x the instructions); the predict and wgrad
+// epilogues are memory-shaped and, transposed through shared memory, hide behind the mainloop.
+__host__ __device__ constexpr int epi_warps(int kind) { return kind >= 0 ? 8 : 8; }
 
 struct TileDesc {
   int idx;          // Linear index (predict / wgrad) or layer index (update)
@@ -353,6 +360,124 @@ __device__ __forceinline__ void epilogue_update(const WideParams& p, const StepA
   }
 }
 
+// ---- coalesced epilogues -------------------------------------------------------------------------------------
+// tcgen05.ld hands every lane one ROW of the accumulator; reading / writing global memory in that shape touches 32
+// cache lines per instruction (the L1 wavefront rate, not HBM, bounded the first epilogues: the three kernels ran at
+// 0.98 ms per C5 step against 0.57 ms with the epilogues switched off).  Each epilogue warp therefore transposes its
+// 32 x 32 sub-blocks through a private padded shared-memory tile: afterwards lane = COLUMN, registers = rows, and
+// every global access of a warp is one contiguous 128-byte row segment.
+constexpr int kTP = 33;                                   // padded pitch of the transpose tile (floats)
+constexpr uint32_t kTransBytes = 8 * 32 * kTP * 4;        // 8 epilogue warps
+
+__device__ __forceinline__ void acc_block_to_columns(uint32_t acc_addr, bool has_acc, float* tb, int lane, float (&col)[32]) {
+  if (!has_acc) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) col[r] = 0.0f;
+    return;
+  }
+  float v[16];
+  tmem_ld16(acc_addr, v);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tb[lane * kTP + i] = v[i];
+  tmem_ld16(acc_addr + 16, v);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tb[lane * kTP + 16 + i] = v[i];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 32; ++r) col[r] = tb[r * kTP + lane];
+  __syncwarp();                                           // the tile is rewritten by the next sub-block
+}
+
+// errors of the units a tile predicts, lane = unit: eps / energy / own-layer G (hidden Linears) or loss / dLoss (output)
+__device__ __forceinline__ void epilogue_predict_t(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_q,
+                                                   int q, int c_begin, float* tb, int lane, float& e_part, float& l_part) {
+  const NetDev& nd = p.net;
+  const int lin = t.idx;
+  const bool is_out = (lin == nd.L);
+  const int d_o = is_out ? nd.d_out : nd.dims[lin];
+  const int row0 = t.m0 + q * 32;
+  const int n_rows = min(32, p.B - row0);
+  const float ce = is_out ? 0.0f : 0.5f * nd.c[lin], gc = is_out ? 0.0f : nd.gc[lin];
+  const bool bern = nd.top == MCPC_TOP_BERNOULLI;
+  for (int sb = 0; sb < 4; ++sb) {
+    const int n0 = t.n0 + c_begin + sb * 32;
+    if (n0 >= d_o) break;                                               // uniform over the warp
+    float d[32];
+    acc_block_to_columns(acc_q + c_begin + sb * 32, t.k_ext > 0, tb, lane, d);
+    const int n = n0 + lane;
+    if (n >= d_o || n_rows <= 0) continue;
+    const float bias = (p.b[lin] != nullptr) ? __ldg(p.b[lin] + n) : 0.0f;
+    __nv_bfloat16* gbp = p.Gb + (size_t)row0 * p.g_pitch + p.poff[lin] + n;
+    if (!is_out) {
+      const float* xp = p.x[lin] + (size_t)row0 * d_o + n;
+      float xv[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) xv[r] = (r < n_rows) ? xp[(size_t)r * d_o] : 0.0f;
+      float* g32 = p.G32 + (size_t)row0 * nd.SD + nd.off[lin] + n;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (r < n_rows) {
+          const float eps = xv[r] - (d[r] + bias);
+          e_part = fmaf(ce * eps, eps, e_part);
+          const float g = -gc * eps;
+          g32[(size_t)r * nd.SD] = g;
+          gbp[(size_t)r * p.g_pitch] = __float2bfloat16(g);
+        }
+    } else {
+      const bool use_y = nd.top >= MCPC_TOP_GAUSS;
+      const bool on = use_y && (n >= nd.mask_start);
+      const float* yp = p.target + (size_t)row0 * d_o + n;
+      float yv[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) yv[r] = (use_y && r < n_rows) ? yp[(size_t)r * d_o] : 0.0f;
+      float* to = (st.do_traj && p.traj_out != nullptr) ? p.traj_out + ((size_t)st.rec * p.B + row0) * d_o + n : nullptr;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (r < n_rows) {
+          const float o = d[r] + bias;
+          float lv, e;
+          if (bern) {
+            const float z = __expf(-fabsf(o));
+            lv = fmaxf(o, 0.0f) - o * yv[r] + __logf(1.0f + z);
+            e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[r];
+          } else {
+            const float dd = o - yv[r];
+            lv = 0.5f * nd.inv_var * dd * dd;
+            e = dd * nd.inv_var;
+          }
+          l_part += on ? lv : 0.0f;
+          gbp[(size_t)r * p.g_pitch] = __float2bfloat16(on ? e : 0.0f);
+          if (to != nullptr) to[(size_t)r * d_o] = o;
+        }
+    }
+  }
+}
+
+// gW tile += accumulator (exactly one CTA owns each tile: plain read-modify-write), lane = input unit
+__device__ __forceinline__ void epilogue_wgrad_t(const WideParams& p, const TileDesc& t, uint32_t acc_q, int q, int c_begin,
+                                                 float* tb, int lane) {
+  const NetDev& nd = p.net;
+  const int lin = t.idx;
+  const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = nd.dims[lin - 1];
+  float* gW = p.gW[lin];
+  const int mo0 = t.m0 + q * 32;
+  for (int sb = 0; sb < 4; ++sb) {
+    const int n0 = t.n0 + c_begin + sb * 32;
+    if (n0 >= d_i) break;                                 // uniform over the warp
+    float col[32];
+    acc_block_to_columns(acc_q + c_begin + sb * 32, true, tb, lane, col);
+    const int n = n0 + lane;
+    if (gW == nullptr || n >= d_i) continue;
+    float* dst = gW + (size_t)mo0 * d_i + n;
+    float cur[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) cur[r] = (mo0 + r < d_o) ? dst[(size_t)r * d_i] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+      if (mo0 + r < d_o) dst[(size_t)r * d_i] = cur[r] + col[r];
+  }
+}
+
 __device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDesc& t, uint32_t acc_addr, int row_in_tile,
                                                int c_begin, int c_end) {
   const NetDev& nd = p.net;
@@ -379,7 +504,7 @@ __device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDe
 // warp 4 MMA issuer, warps 5-8 epilogue; two 256-column accumulators in TMEM so the epilogue of tile i overlaps the
 // mainloop of tile i+1.
 template <int KIND>
-__global__ void __launch_bounds__(320, 1) wide_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st,
+__global__ void __launch_bounds__(64 + 32 * epi_warps(KIND), 1) wide_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st,
                                                       const __grid_constant__ WideMaps mp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Pipe pipe;
@@ -397,7 +522,7 @@ __global__ void __launch_bounds__(320, 1) wide_kernel(const __grid_constant__ Wi
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&pipe.acc_full[b], 1);
-      mbar_init(&pipe.acc_empty[b], 256);
+      mbar_init(&pipe.acc_empty[b], 32 * epi_warps(KIND));
     }
     fence_mbar_init();
   }
@@ -494,9 +619,11 @@ __global__ void __launch_bounds__(320, 1) wide_kernel(const __grid_constant__ Wi
   } else {
     // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----------------
     const int q = warp & 3;
-    const int ew = warp - 2;                               // 0..7
-    const int c_begin = (ew >> 2) * (kBN / 2), c_end = c_begin + kBN / 2;
+    const int ew = warp - 2;                               // 0 .. epi_warps-1
+    constexpr int kColsPerWarp = kBN / (epi_warps(KIND) / 4);
+    const int c_begin = (ew >> 2) * kColsPerWarp, c_end = c_begin + kColsPerWarp;
     const int row_in_tile = q * 32 + lane;
+    float* trans = reinterpret_cast<float*>(smem + kWS * stage_bytes);     // 8 private transpose tiles after the ring
     uint32_t gi = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const TileDesc t = decode_tile<KIND>(p, mp, tile);
@@ -507,9 +634,11 @@ __global__ void __launch_bounds__(320, 1) wide_kernel(const __grid_constant__ Wi
         fence_after_sync();
       }
       const uint32_t acc_addr = tmem + ((uint32_t)(q * 32) << 16) + ab * kBN;
-      if (KIND == KIND_PREDICT) {
+      if (p.skip_epilogue) {
+        // debug (MCPC_WIDE_SKIP_EPI=1, results are garbage): mainloop-only rate of the three kernels
+      } else if (KIND == KIND_PREDICT) {
         float e_part = 0.0f, l_part = 0.0f;
-        epilogue_predict(p, st, t, acc_addr, row_in_tile, c_begin, c_end, e_part, l_part);
+        epilogue_predict_t(p, st, t, acc_addr, q, c_begin, trans + ew * 32 * kTP, lane, e_part, l_part);
         e_part = warp_sum_w(e_part);
         l_part = warp_sum_w(l_part);
         if (lane == 0) { s_red[ew][0] = e_part; s_red[ew][1] = l_part; }
@@ -524,7 +653,7 @@ __global__ void __launch_bounds__(320, 1) wide_kernel(const __grid_constant__ Wi
       } else if (KIND == KIND_UPDATE) {
         epilogue_update(p, st, t, acc_addr, row_in_tile, c_begin, c_end, lane);
       } else {
-        epilogue_wgrad(p, t, acc_addr, row_in_tile, c_begin, c_end);
+        epilogue_wgrad_t(p, t, acc_addr, q, c_begin, trans + ew * 32 * kTP, lane);
       }
       if (has_gemm) {
         fence_before_sync();
@@ -739,6 +868,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.mn3 = mn3 ? 1 : 0;
   p.l2_prefetch = 0;     // measured on C5: 0.98 ms/step without, 1.09-1.14 with 4/8/16 stages of L2 prefetch (extra TMA work, no gain)
   if (const char* env = getenv("MCPC_WIDE_L2PF")) p.l2_prefetch = atoi(env);
+  p.skip_epilogue = getenv("MCPC_WIDE_SKIP_EPI") != nullptr ? 1 : 0;
   for (int l = 0; l < nd.L; ++l) {
     rc = make_tmap_bf16(&mp.act_k[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, 128);
     if (rc == MCPC_OK)
@@ -758,7 +888,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
                : make_tmap_bf16(&mp.w_mn[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, 64);
     if (rc != MCPC_OK) return rc;
   }
-  const size_t smem_g = (size_t)kWS * (kABytes + kBBytes) + 1024;
+  const size_t smem_g = (size_t)kWS * (kABytes + kBBytes) + kTransBytes + 1024;
   MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
@@ -808,7 +938,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
       wide_bias_kernel<<<(p.g_pitch + 31) / 32, 256, 0, stream>>>(p);
       count_launch();
     }
-    wide_kernel<KIND_UPDATE><<<n_update < n_sm ? n_update : n_sm, 320, smem_g, stream>>>(p, st, mp);
+    wide_kernel<KIND_UPDATE><<<n_update < n_sm ? n_update : n_sm, 64 + 32 * epi_warps(KIND_UPDATE), smem_g, stream>>>(p, st, mp);
     count_launch();
   }
   MCPC_CUDA_CHECK(cudaGetLastError());
