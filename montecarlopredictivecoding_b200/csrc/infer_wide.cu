@@ -453,6 +453,159 @@ __device__ __forceinline__ void epilogue_predict_t(const WideParams& p, const St
   }
 }
 
+// Second shape, for the ALU-heavy update epilogue: lane = (row quad rq2 = lane / 8, column quad cq = lane % 8) and the
+// lane owns rows 4*(rq2 + 4i) + j (i < 2, j < 4) x columns 4*cq .. 4*cq+3 of the 32 x 32 sub-block.  One warp
+// instruction then covers 4 rows x 128 contiguous bytes with 16-byte accesses (4 cache lines instead of 32, a quarter
+// of the instructions of the lane = column shape) and the 4 rows of a quad are 4 consecutive chains of one unit:
+// exactly one Philox counter, no shuffles.
+constexpr int kTQ = 32;                                   // unpadded 32 x 32 tile; the 16-byte chunk q of row r sits at q ^ (r % 8)
+__device__ __forceinline__ void acc_block_to_quads(uint32_t acc_addr, bool has_acc, float* tb, int lane, float (&v)[2][4][4]) {
+  if (!has_acc) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[i][j][c] = 0.0f;
+    return;
+  }
+  float a[16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    tmem_ld16(acc_addr + h * 16, a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<float4*>(tb + lane * kTQ + 4 * ((h * 4 + k) ^ (lane & 7))) = make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
+  }
+  __syncwarp();
+  const int rq2 = lane >> 3, cq = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int R = 4 * (rq2 + 4 * i) + j;
+      const float4 t4 = *reinterpret_cast<const float4*>(tb + R * kTQ + 4 * (cq ^ (R & 7)));
+      v[i][j][0] = t4.x; v[i][j][1] = t4.y; v[i][j][2] = t4.z; v[i][j][3] = t4.w;
+    }
+  __syncwarp();
+}
+
+// latent update of layer t.idx: x <- x - lr*grad (SGD | Adam), x <- x - lr*noise, act(x) re-emitted in bf16
+__device__ __forceinline__ void epilogue_update_q(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_q,
+                                                  int q, int c_begin, float* tb, int lane) {
+  const NetDev& nd = p.net;
+  const int l = t.idx;
+  const int dl = nd.dims[l];
+  const int row0 = t.m0 + q * 32;
+  const int kind = nd.act[l];
+  const bool adam = p.optimizer == MCPC_OPT_ADAM;
+  const bool quad_rng = ((p.chain_offset + (uint64_t)row0) & 3) == 0;   // a row quad = one Philox counter
+  const int rq2 = lane >> 3, cq = lane & 7;
+  for (int sb = 0; sb < 4; ++sb) {
+    const int n0 = t.n0 + c_begin + sb * 32;
+    if (n0 >= dl) break;                                                // uniform over the warp (widths % 16 == 0)
+    float bp[2][4][4];
+    acc_block_to_quads(acc_q + c_begin + sb * 32, t.k_ext > 0, tb, lane, bp);
+    const int n = n0 + 4 * cq;
+    if (n >= dl) continue;
+    const int gu = nd.off[l] + n;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int rbase = row0 + 4 * (rq2 + 4 * i);                       // first of the 4 consecutive chains
+      if (rbase >= p.B) continue;
+      float xv[4][4], g[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = rbase + j < p.B;
+        const float4 x4 = ok ? *reinterpret_cast<const float4*>(p.x[l] + (size_t)(rbase + j) * dl + n) : make_float4(0, 0, 0, 0);
+        const float4 g4 = ok ? *reinterpret_cast<const float4*>(p.G32 + (size_t)(rbase + j) * nd.SD + gu) : make_float4(0, 0, 0, 0);
+        xv[j][0] = x4.x; xv[j][1] = x4.y; xv[j][2] = x4.z; xv[j][3] = x4.w;
+        g[j][0] = g4.x; g[j][1] = g4.y; g[j][2] = g4.z; g[j][3] = g4.w;
+      }
+      if (st.do_traj && p.traj_x[l] != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (rbase + j < p.B)
+            *reinterpret_cast<float4*>(p.traj_x[l] + ((size_t)st.rec * p.B + rbase + j) * dl + n) =
+                make_float4(xv[j][0], xv[j][1], xv[j][2], xv[j][3]);
+      }
+      float nz[4][4];                                                   // [chain j][unit c]
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) nz[j][c] = 0.0f;
+      if (p.noise_mode == MCPC_NOISE_PHILOX) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (quad_rng) {
+            float q4[4];
+            langevin_normals4(p.seed, (uint32_t)(gu + c), (uint32_t)st.t_abs, (p.chain_offset + (uint64_t)rbase) >> 2, q4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nz[j][c] = p.noise_scale * q4[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t chain = p.chain_offset + (uint64_t)(rbase + j);
+              float q4[4];
+              langevin_normals4(p.seed, (uint32_t)(gu + c), (uint32_t)st.t_abs, chain >> 2, q4);
+              const int kc = (int)(chain & 3);
+              nz[j][c] = p.noise_scale * (kc == 0 ? q4[0] : (kc == 1 ? q4[1] : (kc == 2 ? q4[2] : q4[3])));
+            }
+          }
+        }
+      } else if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (rbase + j < p.B) {
+            const float4 z4 = *reinterpret_cast<const float4*>(p.noise + ((size_t)st.ts * p.B + rbase + j) * nd.SD + gu);
+            nz[j][0] = z4.x; nz[j][1] = z4.y; nz[j][2] = z4.z; nz[j][3] = z4.w;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (rbase + j >= p.B) continue;
+        const size_t xo = (size_t)(rbase + j) * dl + n;
+        float mv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
+        if (adam && p.update_x) {
+          const float4 m4 = *reinterpret_cast<const float4*>(p.m[l] + xo), v4 = *reinterpret_cast<const float4*>(p.v[l] + xo);
+          mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
+          vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
+        }
+        float gradv[4], a_new[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float x = xv[j][c];
+          const float a = act_w(kind, x);
+          const float grad = fmaf(dact_w(kind, x, a), bp[i][j][c], -g[j][c]);
+          gradv[c] = grad;
+          if (p.update_x) {
+            if (!adam) {
+              x = fmaf(-p.lr, grad, x);
+            } else {
+              mv[c] = fmaf(p.one_minus_b1, grad - mv[c], mv[c]);
+              vv[c] = fmaf(p.one_minus_b2 * grad, grad, vv[c] * p.beta2f);
+              x = fmaf(-st.step_size, __fdividef(mv[c], fmaf(sqrtf(vv[c]), st.inv_bc2_sqrt, p.adam_eps)), x);
+            }
+          }
+          x = fmaf(-p.lr, nz[j][c], x);
+          xv[j][c] = x;
+          a_new[c] = act_w(kind, x);
+        }
+        if (st.last && p.xgrad[l] != nullptr)
+          *reinterpret_cast<float4*>(p.xgrad[l] + xo) = make_float4(gradv[0], gradv[1], gradv[2], gradv[3]);
+        if (adam && p.update_x) {
+          *reinterpret_cast<float4*>(p.m[l] + xo) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+          *reinterpret_cast<float4*>(p.v[l] + xo) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        }
+        *reinterpret_cast<float4*>(p.x[l] + xo) = make_float4(xv[j][0], xv[j][1], xv[j][2], xv[j][3]);
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a_new[0], a_new[1]), h1 = __floats2bfloat162_rn(a_new[2], a_new[3]);
+        *reinterpret_cast<uint2*>(p.act + (size_t)(rbase + j) * p.a_pitch + p.poff[l] + n) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+    }
+  }
+}
+
 // gW tile += accumulator (exactly one CTA owns each tile: plain read-modify-write), lane = input unit
 __device__ __forceinline__ void epilogue_wgrad_t(const WideParams& p, const TileDesc& t, uint32_t acc_q, int q, int c_begin,
                                                  float* tb, int lane) {
@@ -651,7 +804,7 @@ __global__ void __launch_bounds__(64 + 32 * epi_warps(KIND), 1) wide_kernel(cons
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       } else if (KIND == KIND_UPDATE) {
-        epilogue_update(p, st, t, acc_addr, row_in_tile, c_begin, c_end, lane);
+        epilogue_update_q(p, st, t, acc_addr, q, c_begin, trans + ew * 32 * kTQ, lane);
       } else {
         epilogue_wgrad_t(p, t, acc_addr, q, c_begin, trans + ew * 32 * kTP, lane);
       }
