@@ -12,7 +12,8 @@
 // (cp.async.bulk.tensor with SWIZZLE_128B tensor maps over the row-major global matrices; K-major or MN-major
 // as the operand's storage order dictates -- no transposed copies of anything), 4-stage mbarrier ring, two
 // 256-column accumulators in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.  Warp roles:
-// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (thread = TMEM lane = chain, or output unit for wgrad).
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (TMEM lane quarter = warp % 4, column half = (warp-2)/4;
+// sub-blocks are transposed through shared memory so that global accesses are contiguous, see "coalesced epilogues").
 // (A first version scattered operands with 16-byte cp.async: it was bound by the L1TEX wavefront rate -- 8 cache
 // lines per instruction, ~2000 cycles to issue one stage -- see DESIGN.md.)
 // Reference semantics: predictive_coding/pc_trainer.py:733-918 + utils/model.py:35-44.
@@ -168,196 +169,6 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const WideM
     t.mapB = &mp.act_mn[lin - 1];                                 // act(x_{l-1}) as B[k=chain][n]: MN-major
   }
   return t;
-}
-
-__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float (&v)[16]) {
-  uint32_t w[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    w[i] = *reinterpret_cast<const uint32_t*>(&h);
-  }
-  reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
-__device__ __forceinline__ void load_f32x16(const float* src, float (&v)[16]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 t = reinterpret_cast<const float4*>(src)[i];
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-}
-__device__ __forceinline__ void store_f32x16(float* dst, const float (&v)[16]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-
-// ---- epilogues: thread = TMEM lane = chain (predict / update) or output unit (wgrad); 16 columns at a time ----
-__device__ __forceinline__ void epilogue_predict(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_addr,
-                                                 int row_in_tile, int c_begin, int c_end, float& e_part, float& l_part) {
-  const NetDev& nd = p.net;
-  const int lin = t.idx;
-  const bool is_out = (lin == nd.L);
-  const int d_o = is_out ? nd.d_out : nd.dims[lin];
-  const int row = t.m0 + row_in_tile;
-  const bool rvalid = row < p.B;
-  const float ce = is_out ? 0.0f : 0.5f * nd.c[lin], gc = is_out ? 0.0f : nd.gc[lin];
-  const bool bern = nd.top == MCPC_TOP_BERNOULLI;
-  for (int c = c_begin; c < c_end; c += 16) {
-    const int n = t.n0 + c;
-    if (n >= d_o) break;                                  // uniform over the warp
-    float d[16];
-    if (t.k_ext > 0) tmem_ld16(acc_addr + c, d);         // .sync.aligned: every lane executes it
-    else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) d[i] = 0.0f;
-    }
-    if (!rvalid) continue;
-    float bias[16];
-    if (p.b[lin] != nullptr) load_f32x16(p.b[lin] + n, bias);
-    else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) bias[i] = 0.0f;
-    }
-    float g[16];
-    if (!is_out) {
-      float xv[16];
-      load_f32x16(p.x[lin] + (size_t)row * d_o + n, xv);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float eps = xv[i] - (d[i] + bias[i]);
-        e_part = fmaf(ce * eps, eps, e_part);
-        g[i] = -gc * eps;
-      }
-      store_f32x16(p.G32 + (size_t)row * nd.SD + nd.off[lin] + n, g);
-    } else {
-      float yv[16];
-      const bool use_y = nd.top >= MCPC_TOP_GAUSS;
-      if (use_y) load_f32x16(p.target + (size_t)row * d_o + n, yv);
-      else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) yv[i] = 0.0f;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float o = d[i] + bias[i];
-        const bool on = use_y && (n + i >= nd.mask_start);
-        float lv, e;
-        if (bern) {
-          const float z = __expf(-fabsf(o));
-          lv = fmaxf(o, 0.0f) - o * yv[i] + __logf(1.0f + z);
-          e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[i];
-        } else {
-          const float dd = o - yv[i];
-          lv = 0.5f * nd.inv_var * dd * dd;
-          e = dd * nd.inv_var;
-        }
-        l_part += on ? lv : 0.0f;
-        g[i] = on ? e : 0.0f;
-        d[i] = o;
-      }
-      if (st.do_traj && p.traj_out != nullptr) store_f32x16(p.traj_out + ((size_t)st.rec * p.B + row) * d_o + n, d);
-    }
-    store_bf16x16(p.Gb + (size_t)row * p.g_pitch + p.poff[lin] + n, g);
-  }
-}
-
-__device__ __forceinline__ void epilogue_update(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_addr,
-                                                int row_in_tile, int c_begin, int c_end, int lane) {
-  const NetDev& nd = p.net;
-  const int l = t.idx;
-  const int dl = nd.dims[l];
-  const int row = t.m0 + row_in_tile;
-  const bool rvalid = row < p.B;
-  const int kind = nd.act[l];
-  const bool adam = p.optimizer == MCPC_OPT_ADAM;
-  const uint64_t chain = p.chain_offset + (uint64_t)row;
-  const bool grouped_rng = (p.chain_offset & 3) == 0;             // lanes 4q..4q+3 share one Philox counter
-  for (int c = c_begin; c < c_end; c += 16) {
-    const int n = t.n0 + c;
-    if (n >= dl) break;                                           // uniform over the warp
-    float bp[16];
-    if (t.k_ext > 0) tmem_ld16(acc_addr + c, bp);
-    else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) bp[i] = 0.0f;
-    }
-    float nz[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) nz[i] = 0.0f;
-    if (p.noise_mode == MCPC_NOISE_PHILOX) {
-      if (grouped_rng) {
-        float mine[4][4];                                         // my 4 counters (units n + (lane&3) + 4j) x 4 chains
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          langevin_normals4(p.seed, (uint32_t)(nd.off[l] + n + (lane & 3) + 4 * j), (uint32_t)st.t_abs, chain >> 2, mine[j]);
-        // 4x4 transpose across the 4 lanes of a group: afterwards mine[j][a] = normal of MY chain for unit n + 4j + a
-        const int a = lane & 3;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int sft = 1; sft <= 2; sft <<= 1) {
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              if ((c4 & sft) == 0) {
-                const float send = (a & sft) ? mine[j][c4] : mine[j][c4 | sft];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, sft);
-                if (a & sft) mine[j][c4] = recv; else mine[j][c4 | sft] = recv;
-              }
-            }
-          }
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) nz[4 * j + c4] = p.noise_scale * mine[j][c4];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float q4[4];
-          langevin_normals4(p.seed, (uint32_t)(nd.off[l] + n + i), (uint32_t)st.t_abs, chain >> 2, q4);
-          const int kc = (int)(chain & 3);
-          nz[i] = p.noise_scale * (kc == 0 ? q4[0] : (kc == 1 ? q4[1] : (kc == 2 ? q4[2] : q4[3])));
-        }
-      }
-    }
-    if (!rvalid) continue;
-    if (p.noise_mode == MCPC_NOISE_SUPPLIED) load_f32x16(p.noise + ((size_t)st.ts * p.B + row) * nd.SD + nd.off[l] + n, nz);
-    float xv[16], g[16], a_new[16], gradv[16];
-    float* xp = p.x[l] + (size_t)row * dl + n;
-    load_f32x16(xp, xv);
-    load_f32x16(p.G32 + (size_t)row * nd.SD + nd.off[l] + n, g);
-    float mv[16], vv[16];
-    if (adam && p.update_x) {
-      load_f32x16(p.m[l] + (size_t)row * dl + n, mv);
-      load_f32x16(p.v[l] + (size_t)row * dl + n, vv);
-    }
-    if (st.do_traj && p.traj_x[l] != nullptr) store_f32x16(p.traj_x[l] + ((size_t)st.rec * p.B + row) * dl + n, xv);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float x = xv[i];
-      const float a = act_w(kind, x);
-      const float grad = fmaf(dact_w(kind, x, a), bp[i], -g[i]);
-      gradv[i] = grad;
-      if (p.update_x) {
-        if (!adam) {
-          x = fmaf(-p.lr, grad, x);
-        } else {
-          mv[i] = fmaf(p.one_minus_b1, grad - mv[i], mv[i]);
-          vv[i] = fmaf(p.one_minus_b2 * grad, grad, vv[i] * p.beta2f);
-          x = fmaf(-st.step_size, __fdividef(mv[i], fmaf(sqrtf(vv[i]), st.inv_bc2_sqrt, p.adam_eps)), x);
-        }
-      }
-      x = fmaf(-p.lr, nz[i], x);
-      xv[i] = x;
-      a_new[i] = act_w(kind, x);
-    }
-    if (st.last && p.xgrad[l] != nullptr) store_f32x16(p.xgrad[l] + (size_t)row * dl + n, gradv);
-    if (adam && p.update_x) {
-      store_f32x16(p.m[l] + (size_t)row * dl + n, mv);
-      store_f32x16(p.v[l] + (size_t)row * dl + n, vv);
-    }
-    store_f32x16(xp, xv);
-    store_bf16x16(p.act + (size_t)row * p.a_pitch + p.poff[l] + n, a_new);
-  }
 }
 
 // ---- coalesced epilogues -------------------------------------------------------------------------------------
@@ -631,28 +442,6 @@ __device__ __forceinline__ void epilogue_wgrad_t(const WideParams& p, const Tile
   }
 }
 
-__device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDesc& t, uint32_t acc_addr, int row_in_tile,
-                                               int c_begin, int c_end) {
-  const NetDev& nd = p.net;
-  const int lin = t.idx;
-  const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = nd.dims[lin - 1];
-  const int mo = t.m0 + row_in_tile;
-  float* gW = p.gW[lin];
-  for (int c = c_begin; c < c_end; c += 16) {
-    const int n = t.n0 + c;
-    if (n >= d_i) break;
-    float d[16];
-    tmem_ld16(acc_addr + c, d);
-    if (mo >= d_o || gW == nullptr) continue;
-    float* dst = gW + (size_t)mo * d_i + n;                // exactly one CTA owns each tile: plain read-modify-write
-    float cur[16];
-    load_f32x16(dst, cur);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) cur[i] += d[i];
-    store_f32x16(dst, cur);
-  }
-}
-
 // Persistent grouped GEMM: each CTA walks tiles blockIdx.x, +gridDim.x, ...  Warps 0-3 cp.async producers (4-stage ring),
 // warp 4 MMA issuer, warps 5-8 epilogue; two 256-column accumulators in TMEM so the epilogue of tile i overlaps the
 // mainloop of tile i+1.
@@ -774,8 +563,7 @@ __global__ void __launch_bounds__(64 + 32 * epi_warps(KIND), 1) wide_kernel(cons
     const int q = warp & 3;
     const int ew = warp - 2;                               // 0 .. epi_warps-1
     constexpr int kColsPerWarp = kBN / (epi_warps(KIND) / 4);
-    const int c_begin = (ew >> 2) * kColsPerWarp, c_end = c_begin + kColsPerWarp;
-    const int row_in_tile = q * 32 + lane;
+    const int c_begin = (ew >> 2) * kColsPerWarp;
     float* trans = reinterpret_cast<float*>(smem + kWS * stage_bytes);     // 8 private transpose tiles after the ring
     uint32_t gi = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
