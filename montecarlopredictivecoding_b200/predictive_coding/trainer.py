@@ -711,6 +711,7 @@ class PCTrainer(object):
         segs, seg_zero_steps = self._segments_cached(T, split_last=(want_traj and not every_t))
         flat = None
         n_launch = 0
+        host_scalars = None
         for si, (t0, t1) in enumerate(segs):
             ends_with_p = (t1 - 1) in self._update_p_set
             need_grads = self._keep_unused_param_grads or any(u >= t0 for u in later_p_updates)
@@ -762,6 +763,10 @@ class PCTrainer(object):
                     gb=gb if (streaming and need_grads and se > sb) else None)
                 eng.infer(call)
                 n_launch += 1
+                if c1 == T:
+                    # the per-step scalars are final here: start their read-back on a side stream now, so that the
+                    # host gets them while the weight-gradient / optimizer_p kernels of this call are still running
+                    host_scalars = self._start_scalar_readback(scalars)
                 if x_opt["kind"] == N.OPT_ADAM and (c0 in self._update_x_set):
                     adam_step0 += n
                     self._adam["step"] = adam_step0
@@ -776,7 +781,8 @@ class PCTrainer(object):
                 self._p_step(flat, B)
         self.last_call_info = {"mode": "fused", "launches": n_launch, "segments": len(segs),
                                "noise": noise_mode, "precision": self._precision}
-        return {"energy": energy, "loss": loss, "scalars": scalars, "traj_x": traj_x, "traj_out": traj_out, "n_rec": n_rec}
+        return {"energy": energy, "loss": loss, "scalars": scalars, "host_scalars": host_scalars, "traj_x": traj_x,
+                "traj_out": traj_out, "n_rec": n_rec}
 
     # --------------------------------------------------------------------------------------
     def _run_stepwise(self, ctx, loss_fn, cb_bwd, cb_bwd_kwargs, cb_t, cb_t_kwargs, check_after_cb):
@@ -893,6 +899,29 @@ class PCTrainer(object):
             layer._energy = None
             layer._lazy_energy = recompute
 
+    def _start_scalar_readback(self, scalars):
+        """Asynchronous device->host copy of the [2, T] energy / loss scalars on a side stream (CUDA tensors only).
+        Returns (pinned host tensor, completion event) or None; ``_build_results`` waits for the event only."""
+        if not scalars.is_cuda:
+            return None
+        vec = self._reduce_scalars(scalars)                  # data-parallel: all-reduce on the main stream first
+        dev = vec.device
+        side = getattr(self, "_copy_stream", None)
+        if side is None or side.device != dev:
+            side = self._copy_stream = torch.cuda.Stream(device=dev)
+        host = getattr(self, "_host_scalars", None)
+        if host is None or host.shape != vec.shape:
+            host = self._host_scalars = torch.empty(vec.shape, dtype=torch.float64).pin_memory()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            host.copy_(vec, non_blocking=True)
+            vec.record_stream(side)
+            done = torch.cuda.Event()
+            done.record(side)
+        return host, done
+
     def _reduce_scalars(self, vec):
         if self._dp_group is not None:
             import torch.distributed as dist
@@ -903,9 +932,14 @@ class PCTrainer(object):
     def _build_results(self, ctx, rec, has_loss):
         every_t = ctx["every_t"]
         netp = ctx["netp"]
-        both = rec.get("scalars")
-        stacked = self._reduce_scalars(both if both is not None else torch.stack([rec["energy"], rec["loss"]]))
-        host = stacked.to("cpu", torch.float64).numpy()       # the ONE device->host sync of the call
+        pending = rec.get("host_scalars")
+        if pending is not None:
+            pending[1].synchronize()                          # the ONE host wait of the call: the scalars only
+            host = pending[0].numpy().copy()
+        else:
+            both = rec.get("scalars")
+            stacked = self._reduce_scalars(both if both is not None else torch.stack([rec["energy"], rec["loss"]]))
+            host = stacked.to("cpu", torch.float64).numpy()   # the ONE device->host sync of the call
         e, l = host[0], host[1]
         sel = slice(None) if every_t else slice(len(e) - 1, len(e))
         # round to fp32 like `.item()` of the reference's fp32 scalars (pc_trainer.py:780,794,836)
