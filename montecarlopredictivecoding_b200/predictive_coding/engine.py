@@ -110,6 +110,22 @@ def _ptr(t: Optional[torch.Tensor], what: str, dtype=torch.float32):
     return t.data_ptr()
 
 
+class _OnDevice:
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already current (the context manager costs ~10 us)."""
+
+    def __init__(self, dev):
+        self._ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            return self._ctx.__exit__(*exc)
+        return False
+
+
 class NativeEngine:
     """Calls the sm_100a kernels through the C ABI."""
 
@@ -215,7 +231,7 @@ class NativeEngine:
         o.precision = int(c.precision)
         ws = self._workspace(net, c.B, c.n_steps, c.precision, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             N.check(self._lib.mcpc_infer(C.byref(net), C.byref(io), C.byref(o), c.B, ws.data_ptr(), ws.numel(),
                                          C.c_void_p(stream)), "mcpc_infer")
 
@@ -232,7 +248,7 @@ class NativeEngine:
             io.gW[i] = _ptr(gW[i], "gW")
             io.gb[i] = _ptr(gb[i], "gb")
         stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             N.check(self._lib.mcpc_weight_grad(C.byref(net), C.byref(io), B, n_save, precision, C.c_void_p(stream)),
                     "mcpc_weight_grad")
 

@@ -325,6 +325,22 @@ class PCTrainer(object):
         else:
             self._optimizer_x = self._manual_optimizer_x_fn()
 
+    def _reset_optimizer_x(self) -> None:
+        """``recreate_optimize_x`` without building a new torch object when nothing but its state has to go: the
+        latents are the same Parameters as before (no re-sampling), so clearing the state and restoring the
+        hyper-parameter defaults leaves the optimizer exactly as a freshly constructed one (pc_trainer.py:749-752)."""
+        opt = self._optimizer_x
+        if self._manual_optimizer_x_fn is not None or opt is None or len(opt.param_groups) != 1:
+            return self.recreate_optimize_x()
+        held = opt.param_groups[0]["params"]
+        xs = list(self.get_model_xs())
+        if len(held) != len(xs) or any(a is not b for a, b in zip(held, xs)):
+            return self.recreate_optimize_x()
+        opt.state.clear()
+        group = opt.param_groups[0]
+        for k, v in opt.defaults.items():
+            group[k] = v
+
     def recreate_optimize_p(self) -> None:
         if self._manual_optimizer_p_fn is None:
             self._optimizer_p = self._optimizer_p_fn(self.get_model_parameters(), **self._optimizer_p_kwargs)
@@ -494,8 +510,11 @@ class PCTrainer(object):
                 raise RuntimeError(f"latent of PCLayer {l} has shape {tuple(x.shape)}, expected [B, {netp.dims[l]}]")
             if x.dtype != torch.float32 or not x.is_contiguous():
                 layer._x = nn.Parameter(x.detach().to(torch.float32).contiguous(), True)
-        if sample_x or reset_x or self._optimizer_x is None:
+        if sample_x or self._optimizer_x is None:
             self.recreate_optimize_x()
+            self._adam = None
+        elif reset_x:
+            self._reset_optimizer_x()
             self._adam = None
         if reset_p:
             self.recreate_optimize_p()
@@ -947,9 +966,9 @@ class PCTrainer(object):
         l32 = l.astype(np.float32)
         o32 = ((l32 if has_loss else 0.0) + e32 * np.float32(self._energy_coefficient)).astype(np.float32)
         results = {
-            "loss": [float(v) for v in l32[sel]] if has_loss else [],
-            "energy": [float(v) for v in e32[sel]],
-            "overall": [float(v) for v in o32[sel]],
+            "loss": l32[sel].astype(np.float64).tolist() if has_loss else [],      # Python floats, like .item()
+            "energy": e32[sel].astype(np.float64).tolist(),
+            "overall": o32[sel].astype(np.float64).tolist(),
         }
         n_rec = rec["n_rec"]
         if ctx["want_outputs"]:
