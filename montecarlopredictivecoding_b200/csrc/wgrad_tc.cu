@@ -236,7 +236,13 @@ int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_s
     }
   }
   if (nt == 0) return MCPC_OK;
-  int slabs = (148 + nt - 1) / nt;
+  // K slabs: as many as keep the whole grid in ONE wave (nt * slabs <= SMs; one CTA per SM by shared memory) --
+  // rounding up instead put 153 CTAs on 148 SMs and doubled the kernel time
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int slabs = n_sm / nt;
+  if (slabs < 1) slabs = 1;
   int rps = (p.rows + slabs - 1) / slabs;
   rps = ((rps + kStageRows - 1) / kStageRows) * kStageRows;
   slabs = (p.rows + rps - 1) / rps;
