@@ -50,6 +50,7 @@ struct TcParams {
   int n_hid_tiles, n_out_tiles;
   Tile tiles[kMaxTiles];
   int y_tmem;                   // targets of the output tiles are kept in TMEM (they fit beside the accumulators)
+  int adam_tmem;                // Adam's m and v of the latents live in TMEM for the whole call (they fit as well)
   int HT;                       // hidden unit tiles in total
   int h_layer[kMaxHT];          // layer of hidden unit tile h
   int h_index[kMaxHT];          // its index inside the layer
@@ -74,6 +75,7 @@ struct TcParams {
   const float* target;
   const float* noise;
   float* partials;
+  const float* adam_tab;        // [n_steps][2]: lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t) (adam_table_kernel)
   int B, n_ctas, n_steps, t_begin;
   int optimizer, update_x;
   float lr, adam_eps, one_minus_b1, one_minus_b2, beta2f;
@@ -118,6 +120,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, int rows, int c
     const float val = (row < rows && k < cols) ? W[(size_t)row * cols + k] : 0.0f;
     *reinterpret_cast<__nv_bfloat16*>(out + (size_t)t * per_tile * 2 + kmajor_off(r, k, 128u, sbo)) = __float2bfloat16(val);
   }
+}
+
+// Adam bias corrections of steps step0+1 .. step0+n (torch.optim.Adam: step_size = lr / (1 - beta1^t), the second
+// moment is divided by sqrt(1 - beta2^t)), in double like the host code of torch
+__global__ void adam_table_kernel(double beta1, double beta2, double lr, int step0, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double t = (double)(step0 + i + 1);
+  out[2 * i] = (float)(lr / (1.0 - pow(beta1, t)));
+  out[2 * i + 1] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
 }
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -207,6 +219,8 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
   // then one bias column per weight tile (32 reserved) and, if p.y_tmem, NR target columns per output tile
   const uint32_t col_dA = 0, col_bp = kDA * NR, col_x = (kDA + HT) * NR, col_g = (kDA + 2 * HT) * NR;
   const uint32_t col_bias = (kDA + 3 * HT) * NR, col_y = col_bias + 32;
+  // Adam on the latents (deterministic PC / MAP): m and v behind the targets, HT * NR columns each
+  const uint32_t col_m = col_y + (p.y_tmem ? (uint32_t)p.n_out_tiles * NR : 0u), col_v = col_m + HT * NR;
   const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;      // table order: Linear 1 ... L-1, then the output tiles
 
   // =====================================================================================================
@@ -382,13 +396,24 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         }
         __syncwarp();
         tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
+        if (p.adam_tmem) {
+          float mv[RPT], vv[RPT];
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const bool ok = (u < dl && i < nrow);
+            mv[i] = ok ? p.m[l][(size_t)(rb + i) * dl + u] : 0.0f;
+            vv[i] = ok ? p.v[l][(size_t)(rb + i) * dl + u] : 0.0f;
+          }
+          __syncwarp();
+          tmem_st<RPT>(lane_addr + col_m + h * NR, mv);
+          tmem_st<RPT>(lane_addr + col_v + h * NR, vv);
+        }
       }
       tmem_st_wait();
       fence_async_smem();
       fence_before_sync();
       for (int l = 0; l < L; ++l) mbar_arrive(&bars.acts_ready[l]);
 
-      double b1p = p.b1_pow0, b2p = p.b2_pow0;
       const bool adam = (p.optimizer == MCPC_OPT_ADAM);
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const int t_abs = p.t_begin + ts;
@@ -402,10 +427,10 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         __nv_bfloat16* sf_row = do_save ? p.save_f + ((size_t)slot * p.B + rb) * p.sf_pitch : nullptr;
         float step_size = 0.0f, inv_bc2_sqrt = 1.0f;
         if (adam && p.update_x) {
-          b1p *= p.beta1;
-          b2p *= p.beta2;
-          step_size = (float)(p.lr_d / (1.0 - b1p));
-          inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
+          // bias corrections come from a table built in fp64 by adam_table_kernel: two divisions and a square root in
+          // double per thread and step cost ~6k cycles of the (1/64-rate) FP64 pipe on the step's critical path
+          step_size = __ldg(p.adam_tab + 2 * ts);
+          inv_bc2_sqrt = __ldg(p.adam_tab + 2 * ts + 1);
         }
         for (int l = 0; l < L; ++l) {                        // bottom-up, the order the tiles complete in
           const bool has_above = (l + 1 < L) || nd.top_has_grad;
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               b0 = 0.0f;
               if (uvalid) {
                 if (l == 0 && p.b[0] != nullptr) b0 = __ldg(p.b[0] + u);
-                if (adam && p.update_x) {
+                if (adam && p.update_x && !p.adam_tmem) {
 #pragma unroll
                   for (int i = 0; i < CH; ++i) {
                     mv[i] = (i < nrc) ? p.m[l][xoffc + (size_t)i * dl] : 0.0f;
@@ -511,8 +536,17 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               tmem_ld_nw<CH>(lac + col_x + h * NR, xv);
               if (has_above) tmem_ld_nw<CH>(lac + col_bp + h * NR, bp);
               if (l > 0) tmem_ld_nw<CH>(lac + col_g + h * NR, gown);
+              const bool adam_t = adam && p.update_x && p.adam_tmem;
+              if (adam_t) {
+                tmem_ld_nw<CH>(lac + col_m + h * NR, mv);
+                tmem_ld_nw<CH>(lac + col_v + h * NR, vv);
+              }
               tmem_ld_wait();
               tmem_ld_tie(xv);
+              if (adam_t) {
+                tmem_ld_tie(mv);
+                tmem_ld_tie(vv);
+              }
               if (has_above) {
                 tmem_ld_tie(bp);
               } else {
@@ -556,7 +590,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
                     vv[i] = fmaf(p.one_minus_b2 * gradv[i], gradv[i], vv[i] * p.beta2f);
                     xv[i] = fmaf(-step_size, __fdividef(mv[i], fmaf(sqrtf(vv[i]), inv_bc2_sqrt, p.adam_eps)), xv[i]);
                   }
-                  if (uvalid) {
+                  if (uvalid && !p.adam_tmem) {
 #pragma unroll
                     for (int i = 0; i < CH; ++i)
                       if (i < nrc) {
@@ -580,6 +614,10 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               }
               __syncwarp();                                    // .sync.aligned store: every lane executes it
               tmem_st<CH>(lac + col_x + h * NR, xv);
+              if (adam_t) {
+                tmem_st<CH>(lac + col_m + h * NR, mv);
+                tmem_st<CH>(lac + col_v + h * NR, vv);
+              }
               if (!defer) global_stores(c0);
             }
           }
@@ -612,6 +650,17 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < RPT; ++i)
           if (u < dl && i < nrow) p.x[l][(size_t)(rb + i) * dl + u] = xv[i];
+        if (p.adam_tmem) {
+          float mv[RPT], vv[RPT];
+          tmem_ld<RPT>(lane_addr + col_m + h * NR, mv);
+          tmem_ld<RPT>(lane_addr + col_v + h * NR, vv);
+#pragma unroll
+          for (int i = 0; i < RPT; ++i)
+            if (u < dl && i < nrow) {
+              p.m[l][(size_t)(rb + i) * dl + u] = mv[i];
+              p.v[l][(size_t)(rb + i) * dl + u] = vv[i];
+            }
+        }
       }
     } else {
       // ======================= group T: per-tile epilogues =======================
@@ -982,7 +1031,8 @@ int infer_tc_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes) {
   }
   if (rc != MCPC_OK) return rc;
   const int n_ctas = (B + rc_.rv - 1) / rc_.rv;
-  *bytes = ((packed + 255) & ~(size_t)255) + (size_t)n_steps * n_ctas * 4 * sizeof(float) + 512;
+  *bytes = ((packed + 255) & ~(size_t)255) + (((size_t)n_steps * n_ctas * 4 * sizeof(float) + 255) & ~(size_t)255) +
+           (size_t)n_steps * 2 * sizeof(float) + 512;
   return MCPC_OK;
 }
 
@@ -1014,6 +1064,14 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   uint8_t* wsb = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   p.packed = wsb;
   p.partials = reinterpret_cast<float*>(wsb + ((packed + 255) & ~(size_t)255));
+  float* adam_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.partials) +
+                                             (((size_t)o->n_steps * p.n_ctas * 4 * sizeof(float) + 255) & ~(size_t)255));
+  p.adam_tab = adam_tab;
+  if (o->optimizer == MCPC_OPT_ADAM && o->update_x) {
+    adam_table_kernel<<<(o->n_steps + 127) / 128, 128, 0, stream>>>(o->adam_beta1, o->adam_beta2, o->lr, o->adam_step0, o->n_steps,
+                                                                     adam_tab);
+    count_launch();
+  }
   // pack the weights (fp32 nn.Linear layout -> bf16 canonical tiles); they change once per learning step
   for (int t = 0; t < p.n_hid_tiles + p.n_out_tiles;) {
     const Tile& T = p.tiles[t];
@@ -1047,6 +1105,12 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   p.t_begin = o->t_begin;
   p.optimizer = o->optimizer;
   p.update_x = o->update_x;
+  {
+    const int nda = (rows.nr == 16) ? 4 : 2;
+    const int used = (nda + 3 * p.HT) * rows.nr + 32 + (p.y_tmem ? p.n_out_tiles * rows.nr : 0);
+    p.adam_tmem = (o->optimizer == MCPC_OPT_ADAM && o->update_x && io->adam_m[0] != nullptr &&
+                   used + 2 * p.HT * rows.nr <= 512) ? 1 : 0;
+  }
   p.lr = (float)o->lr;
   p.lr_d = o->lr;
   p.beta1 = o->adam_beta1;

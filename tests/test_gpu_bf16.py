@@ -24,7 +24,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 BF16_CASES = ["mcpc_relu_bce_learn", "mcpc_ml_checkpoint", "pc_tanh_adam_mask", "fig2_linear", "free_output_layer",
-              "gauss_mask_one_sample", "zero_fn_sampling", "update_p_all"]
+              "gauss_mask_one_sample", "zero_fn_sampling", "update_p_all", "adam_carryover_batch_resize",
+              "last_half_schedules"]
 
 
 @pytest.mark.parametrize("name", BF16_CASES)

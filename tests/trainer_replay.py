@@ -84,7 +84,8 @@ def replay(name, device, engine_factory=None, precision="fp32", tol_x=1e-5, tol_
             # measures ONE call, not the drift accumulated over the preceding (chaotic, Adam) calls
             with torch.no_grad():
                 for l, layer in enumerate(pcs):
-                    layer.get_x().copy_(torch.from_numpy(gc.x0(ci)[l]).to(device))
+                    if not call.get("sample_x", True):      # (a sampling call installs its own start state below)
+                        layer.get_x().copy_(torch.from_numpy(gc.x0(ci)[l]).to(device))
                 Wb, bb = gc.weights(ci, "before")
                 for lin, w, b_ in zip(lins, Wb, bb):
                     lin.weight.copy_(torch.from_numpy(w).to(device))
