@@ -32,6 +32,10 @@ def sample_x_fn_cte(inputs):
     return 3 * torch.ones_like(inputs["mu"])
 
 
+for _fn in (sample_x_fn, sample_x_fn_normal, sample_x_fn_cte):
+    _fn.__mcpc_shape_only__ = True      # lets the trainer draw the t=0 latents without a model forward
+
+
 # ---- sensory-layer losses ------------------------------------------------------------------------
 def fe_fn(output, _target, _var):
     return (1 / _var) * 0.5 * (output - _target).pow(2).sum()

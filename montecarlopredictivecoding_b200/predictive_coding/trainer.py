@@ -43,6 +43,15 @@ def _slow_down_warning(base, prop, solution):
         base, prop, solution), category=RuntimeWarning)
 
 
+def _is_shape_only_sampler(fn) -> bool:
+    """True for the t=0 initialisers that use nothing but the shape of ``mu``: the ones of ``mcpc_utils`` (tagged) and
+    the reference's own ``utils/model.py`` functions (recognised by name and module, like ``random_step``)."""
+    if getattr(fn, "__mcpc_shape_only__", False):
+        return True
+    return getattr(fn, "__name__", "") in ("sample_x_fn", "sample_x_fn_normal", "sample_x_fn_cte") and \
+        (getattr(fn, "__module__", "") or "").split(".")[-1] == "model"
+
+
 class PCTrainer(object):
     """Trainer for predictive-coding models built from :class:`PCLayer`."""
 
@@ -498,7 +507,19 @@ class PCTrainer(object):
             x = layer.get_x()
             if x is None or x.shape[0] != inputs.shape[0] or x.device != inputs.device:
                 need_forward = True      # the layer will warn and sample on its own (pc_layer.py:185-218)
-        if sample_x:
+        if sample_x and all(_is_shape_only_sampler(layer._sample_x_fn) for layer in netp.pc_layers):
+            # the library samplers (utils/model.py:8-15) only look at the SHAPE of mu: draw the latents layer by layer in
+            # module order (same generator calls as the t=0 forward of pc_trainer.py:717-733) without running the model
+            lin0 = netp.linears[0].weight
+            B = inputs.shape[0]
+            with torch.no_grad():
+                for l, layer in enumerate(netp.pc_layers):
+                    mu_like = torch.empty(B, netp.dims[l], device=lin0.device, dtype=lin0.dtype)
+                    fresh = layer._sample_x_fn({"mu": mu_like, "x": layer._x})
+                    layer._x = nn.Parameter(fresh.to(lin0.device), True)
+                    layer._is_sample_x = False
+            need_forward = False
+        elif sample_x:
             for layer in netp.pc_layers:
                 layer.set_is_sample_x(True)
         if need_forward:

@@ -126,3 +126,33 @@ def test_product_refuses_cpu_tensors():
     tr = pc.PCTrainer(model, T=3, update_p_at="never", plot_progress_at=[])
     with pytest.raises((RuntimeError, OSError)):
         tr.train_on_batch(torch.zeros(2, 3), is_log_progress=False)
+
+
+def test_fast_t0_sampling_draws_the_same_latents_as_the_forward():
+    """pc_trainer.py:717-733: the t=0 forward samples every PCLayer in module order.  For the library samplers (they
+    only use the shape of mu) the trainer draws the latents directly; the generator must be consumed identically."""
+    import torch
+    import torch.optim as optim
+
+    from montecarlopredictivecoding_b200 import mcpc_utils as mu
+    from montecarlopredictivecoding_b200 import predictive_coding as pc
+    from montecarlopredictivecoding_b200.predictive_coding import plan as P
+    cfg = {"input_size": 5, "hidden_size": 7, "hidden2_size": 6, "output_size": 9, "activation_fn": "relu"}
+    for sampler in (mu.sample_x_fn, mu.sample_x_fn_normal, mu.sample_x_fn_cte):
+        torch.manual_seed(3)
+        model = mu.get_model(cfg, use_cuda=False, sample_x_fn=sampler)
+        pcs = [m for m in model if isinstance(m, pc.PCLayer)]
+        inputs = torch.zeros(4, 5)
+        torch.manual_seed(11)
+        for layer in pcs:
+            layer.set_is_sample_x(True)
+        with torch.no_grad():
+            model(inputs)
+        want = [layer.get_x().detach().clone() for layer in pcs]
+        trainer = pc.PCTrainer(model, T=2, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.1}, update_p_at="never",
+                               plot_progress_at=[])
+        torch.manual_seed(11)
+        trainer._start_of_batch(P.compile_net(model), inputs, True, True, False)
+        for layer, w in zip(pcs, want):
+            assert torch.equal(layer.get_x().detach(), w)
+            assert layer.get_x().requires_grad
