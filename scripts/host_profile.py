@@ -26,7 +26,22 @@ for o, n in [(P, "compile_net"), (P, "classify_loss"), (P, "classify_callback_af
              (tr, "_install_lazy_energies"), (tr, "_segments"), (tr, "_param_tensors"), (tr, "_save_layout")]:
     if hasattr(o, n):
         wrap(o, n)
+if os.environ.get("MODE") == "map":
+    CFG2 = dict(input_size=25, hidden_size=128, hidden2_size=128, output_size=784, activation_fn="tanh")
+    model = mu.get_model(CFG2, use_cuda=False).to(dev)
+    tr = mu.get_pc_trainer(model, {"T_pc": 250, "optimizer_x_fn_pc": optim.Adam, "optimizer_x_kwargs_pc": {"lr": 0.3}}, is_mcpc=True)
+    tr.set_precision('bf16')
+    z = torch.zeros(B, 25, device=dev)
+    eng = tr._get_engine()
+    for o, n in [(tr, "_start_of_batch"), (tr, "_run_fused"), (eng, "infer"), (eng, "weight_grad"), (tr, "_build_results"),
+                 (tr, "_ensure_flat_grads"), (tr, "recreate_optimize_x")]:
+        wrap(o, n)
+
+
 def call():
+    if os.environ.get("MODE") == "map":
+        return tr.train_on_batch(inputs=z, loss_fn=mu.bernoulli_fn_mask, loss_fn_kwargs={"_target": y, "_var": 1.0}, is_log_progress=False,
+                                 is_return_results_every_t=False, is_checking_after_callback_after_t=False)
     return tr.train_on_batch(inputs=z, loss_fn=mu.bernoulli_fn, loss_fn_kwargs={"_target": y, "_var": 1.0}, callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": tr}, is_sample_x_at_batch_start=False, is_log_progress=False, is_checking_after_callback_after_t=False)
 for _ in range(5): call()
 torch.cuda.synchronize(); acc.clear()
