@@ -25,6 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv[1:] or any(a.startswith("--impl=reference") for a in sys.argv[1:]):
+    # the CPU arm uses every host thread it can get; torchrun exports OMP_NUM_THREADS=1 before Python starts
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np  # noqa: E402
 
 CFG = dict(input_size=20, hidden_size=128, hidden2_size=128, output_size=784, activation_fn="relu")
