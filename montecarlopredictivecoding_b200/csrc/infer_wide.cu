@@ -73,6 +73,7 @@ struct WideParams {
 
 struct StepArgs {
   int ts, t_abs, rec, do_traj, last;
+  int acc;                                // this step is inside the weight-gradient window: bias gradients accumulate
   float step_size, inv_bc2_sqrt;          // Adam bias corrections of this step
 };
 
@@ -201,7 +202,8 @@ __device__ __forceinline__ void acc_block_to_columns(uint32_t acc_addr, bool has
 
 // errors of the units a tile predicts, lane = unit: eps / energy / own-layer G (hidden Linears) or loss / dLoss (output)
 __device__ __forceinline__ void epilogue_predict_t(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_q,
-                                                   int q, int c_begin, float* tb, int lane, float& e_part, float& l_part) {
+                                                   int q, int c_begin, float* tb, int lane, float& e_part, float& l_part,
+                                                   float (&gsum)[4]) {
   const NetDev& nd = p.net;
   const int lin = t.idx;
   const bool is_out = (lin == nd.L);
@@ -210,6 +212,9 @@ __device__ __forceinline__ void epilogue_predict_t(const WideParams& p, const St
   const int n_rows = min(32, p.B - row0);
   const float ce = is_out ? 0.0f : 0.5f * nd.c[lin], gc = is_out ? 0.0f : nd.gc[lin];
   const bool bern = nd.top == MCPC_TOP_BERNOULLI;
+#pragma unroll
+  for (int sb = 0; sb < 4; ++sb) gsum[sb] = 0.0f;
+#pragma unroll
   for (int sb = 0; sb < 4; ++sb) {
     const int n0 = t.n0 + c_begin + sb * 32;
     if (n0 >= d_o) break;                                               // uniform over the warp
@@ -232,7 +237,9 @@ __device__ __forceinline__ void epilogue_predict_t(const WideParams& p, const St
           e_part = fmaf(ce * eps, eps, e_part);
           const float g = -gc * eps;
           g32[(size_t)r * nd.SD] = g;
-          gbp[(size_t)r * p.g_pitch] = __float2bfloat16(g);
+          const __nv_bfloat16 gb16 = __float2bfloat16(g);
+          gbp[(size_t)r * p.g_pitch] = gb16;
+          gsum[sb] += __bfloat162float(gb16);                           // the bias gradient sums the operand the dW GEMM sees
         }
     } else {
       const bool use_y = nd.top >= MCPC_TOP_GAUSS;
@@ -257,7 +264,9 @@ __device__ __forceinline__ void epilogue_predict_t(const WideParams& p, const St
             e = dd * nd.inv_var;
           }
           l_part += on ? lv : 0.0f;
-          gbp[(size_t)r * p.g_pitch] = __float2bfloat16(on ? e : 0.0f);
+          const __nv_bfloat16 eb16 = __float2bfloat16(on ? e : 0.0f);
+          gbp[(size_t)r * p.g_pitch] = eb16;
+          gsum[sb] += __bfloat162float(eb16);
           if (to != nullptr) to[(size_t)r * d_o] = o;
         }
     }
@@ -578,17 +587,40 @@ __global__ void __launch_bounds__(64 + 32 * epi_warps(KIND), 1) wide_kernel(cons
       if (p.skip_epilogue) {
         // debug (MCPC_WIDE_SKIP_EPI=1, results are garbage): mainloop-only rate of the three kernels
       } else if (KIND == KIND_PREDICT) {
-        float e_part = 0.0f, l_part = 0.0f;
-        epilogue_predict_t(p, st, t, acc_addr, q, c_begin, trans + ew * 32 * kTP, lane, e_part, l_part);
+        float e_part = 0.0f, l_part = 0.0f, gsum[4];
+        float* my_tile = trans + ew * 32 * kTP;
+        epilogue_predict_t(p, st, t, acc_addr, q, c_begin, my_tile, lane, e_part, l_part, gsum);
         e_part = warp_sum_w(e_part);
         l_part = warp_sum_w(l_part);
         if (lane == 0) { s_red[ew][0] = e_part; s_red[ew][1] = l_part; }
+        // gb_l += column sums of G: every warp leaves its 128 partial sums (rows of its lane quarter) in its private
+        // tile, the quarter-0 warp of each column half adds the four up and issues ONE atomic per column and tile
+        if (st.acc) {
+#pragma unroll
+          for (int sb = 0; sb < 4; ++sb) my_tile[sb * 32 + lane] = gsum[sb];
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (ew == 0 && lane < 2) {
           float sum = 0.0f;
 #pragma unroll
           for (int w = 0; w < 8; ++w) sum += s_red[w][lane];
           p.partials[((size_t)st.ts * p.n_part + tile) * 2 + lane] = sum;
+        }
+        if (st.acc && q == 0) {
+          const NetDev& nd = p.net;
+          const int lin = t.idx;
+          const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
+          const bool live = (lin < nd.L) || nd.top_has_grad;
+          if (live && p.gb[lin] != nullptr) {
+#pragma unroll
+            for (int sb = 0; sb < 4; ++sb) {
+              const int n = t.n0 + c_begin + sb * 32 + lane;
+              float tot = 0.0f;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) tot += trans[((ew & 4) + w) * 32 * kTP + sb * 32 + lane];
+              if (n < d_o) atomicAdd(p.gb[lin] + n, tot);
+            }
+          }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       } else if (KIND == KIND_UPDATE) {
@@ -606,30 +638,6 @@ __global__ void __launch_bounds__(64 + 32 * epi_warps(KIND), 1) wide_kernel(cons
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
-}
-
-// gb_l[m] += sum over chains of G_l[chain][m]   (all Linears at once: the columns of Gb)
-__global__ void __launch_bounds__(256) wide_bias_kernel(const __grid_constant__ WideParams p) {
-  __shared__ float red[8][33];
-  const NetDev& nd = p.net;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int rg = threadIdx.x >> 5;
-  float s = 0.0f;
-  if (c < p.g_pitch)
-    for (int r = rg; r < p.B; r += 8) s += __bfloat162float(p.Gb[(size_t)r * p.g_pitch + c]);
-  red[rg][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (rg == 0 && c < p.g_pitch) {
-    float tot = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x & 31];
-    int lin = 0;
-    while (lin < nd.L && c >= p.poff[lin + 1]) ++lin;
-    const int m = c - p.poff[lin];
-    const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
-    const bool live = (lin < nd.L) || nd.top_has_grad;
-    if (m < d_o && live && p.gb[lin] != nullptr) p.gb[lin][m] += tot;
-  }
 }
 
 __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
@@ -865,19 +873,18 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
       st.step_size = (float)(o->lr / (1.0 - b1p));
       st.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
     }
+    const bool acc = any_grad && ts >= o->save_begin && ts < o->save_end;
+    st.acc = acc ? 1 : 0;                  // the predict epilogue adds the bias gradients (column sums of G) on these steps
     if (n_predict > 0) {
       wide_kernel<KIND_PREDICT><<<n_predict < n_sm ? n_predict : n_sm, 320, smem_g, stream>>>(p, st, mp);
       count_launch();
     }
     // the weight update reads G (this step's errors) and act(x) of the state BEFORE the update: it runs between the two
-    const bool acc = any_grad && ts >= o->save_begin && ts < o->save_end;
     if (acc) {
       if (n_wgrad > 0) {
         wide_kernel<KIND_WGRAD><<<n_wgrad < n_sm ? n_wgrad : n_sm, 320, smem_g, stream>>>(p, st, mp);
         count_launch();
       }
-      wide_bias_kernel<<<(p.g_pitch + 31) / 32, 256, 0, stream>>>(p);
-      count_launch();
     }
     wide_kernel<KIND_UPDATE><<<n_update < n_sm ? n_update : n_sm, 64 + 32 * epi_warps(KIND_UPDATE), smem_g, stream>>>(p, st, mp);
     count_launch();
