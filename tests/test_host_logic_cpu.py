@@ -156,3 +156,61 @@ def test_fast_t0_sampling_draws_the_same_latents_as_the_forward():
         for layer, w in zip(pcs, want):
             assert torch.equal(layer.get_x().detach(), w)
             assert layer.get_x().requires_grad
+
+
+def test_optimizer_x_reset_in_place_equals_a_fresh_optimizer():
+    """pc_trainer.py:749-752 re-creates optimizer_x at every batch start; when the latents are the same Parameters the
+    drop-in clears the state and restores the defaults instead.  A changed lr must not survive, state must be empty,
+    and re-sampled latents (new Parameters) must lead to a really new optimizer."""
+    import torch
+    import torch.optim as optim
+
+    from montecarlopredictivecoding_b200 import mcpc_utils as mu
+    from montecarlopredictivecoding_b200 import predictive_coding as pc
+    cfg = {"input_size": 4, "hidden_size": 6, "hidden2_size": 5, "output_size": 7, "activation_fn": "tanh"}
+    torch.manual_seed(0)
+    model = mu.get_model(cfg, use_cuda=False)
+    trainer = pc.PCTrainer(model, T=2, optimizer_x_fn=optim.Adam, optimizer_x_kwargs={"lr": 0.1}, update_p_at="never",
+                           plot_progress_at=[])
+    for layer in (m for m in model if isinstance(m, pc.PCLayer)):
+        layer.set_is_sample_x(True)
+    with torch.no_grad():
+        model(torch.zeros(3, 4))
+    trainer.recreate_optimize_x()
+    opt = trainer.get_optimizer_x()
+    for x in trainer.get_model_xs():
+        x.grad = torch.ones_like(x)
+    opt.step()
+    opt.param_groups[0]["lr"] = 7.0
+    assert len(opt.state) > 0
+    trainer._reset_optimizer_x()
+    assert trainer.get_optimizer_x() is opt and len(opt.state) == 0 and opt.param_groups[0]["lr"] == 0.1
+    for layer in (m for m in model if isinstance(m, pc.PCLayer)):
+        layer.set_is_sample_x(True)
+    with torch.no_grad():
+        model(torch.zeros(3, 4))                     # new Parameters
+    trainer._reset_optimizer_x()
+    assert trainer.get_optimizer_x() is not opt
+
+
+def test_compiled_plan_cache_rechecks_live_layer_flags():
+    import torch
+
+    from montecarlopredictivecoding_b200 import mcpc_utils as mu
+    from montecarlopredictivecoding_b200 import predictive_coding as pc
+    from montecarlopredictivecoding_b200.predictive_coding import plan as P
+    cfg = {"input_size": 4, "hidden_size": 6, "hidden2_size": 5, "output_size": 7, "activation_fn": "relu"}
+    model = mu.get_model(cfg, use_cuda=False)
+    a = P.compile_net(model)
+    assert P.compile_net(model) is a                 # cached
+    layer = [m for m in model if isinstance(m, pc.PCLayer)][0]
+    layer.is_holding_error = True
+    try:
+        P.compile_net(model)
+        raise AssertionError("held errors must be refused even on a cache hit")
+    except NotImplementedError:
+        pass
+    layer.is_holding_error = False
+    b = P.compile_net(model)
+    assert b.dims == a.dims
+    _ = torch
