@@ -165,7 +165,11 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
 // Tiles are visited top-down (output tiles first, then Linear L-1 ... 1): the update of layer l only needs the
 // tiles of Linear l+1 (back-projection) and Linear l (own error), so group U works on layer l while the tensor
 // pipe and group T are already busy with the NEXT step's output tiles -- the step is pipelined across layers.
-template <int NR, int RV, bool TRACE>
+// SPEC folds the modes of the two calls that matter most into compile-time constants (the epilogue warps are bound by
+// instruction fetch / issue, and every dead branch costs code footprint): 1 = MCPC learning / sampling (SGD + in-kernel
+// Philox noise, Bernoulli top, update_x), 2 = deterministic PC / MAP (Adam, no noise, Bernoulli top, update_x),
+// 0 = everything read from the parameters.
+template <int NR, int RV, bool TRACE, int SPEC>
 __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int RPT = RV / 2;
   constexpr bool ALT = (RV <= 8);            // group T works on alternate tiles (see there)
@@ -185,6 +189,11 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
   const NetDev& nd = p.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = nd.L, HT = p.HT;
+  const int opt_kind = (SPEC == 1) ? (int)MCPC_OPT_SGD : (SPEC == 2 ? (int)MCPC_OPT_ADAM : p.optimizer);
+  const int noise_kind = (SPEC == 1) ? (int)MCPC_NOISE_PHILOX : (SPEC == 2 ? (int)MCPC_NOISE_NONE : p.noise_mode);
+  const int top_kind = (SPEC != 0) ? (int)MCPC_TOP_BERNOULLI : nd.top;
+  const bool top_has_grad = (SPEC != 0) ? true : (bool)nd.top_has_grad;
+  const bool do_update_x = (SPEC != 0) ? true : (p.update_x != 0);
   const int row0 = blockIdx.x * RV;
 
   if (tid < p.n_hid_tiles + p.n_out_tiles) {
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
       uint32_t empty_phase = 3;
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
-        const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+        const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
         for (int t = 0; t < (need_out ? n_tiles_all : p.n_hid_tiles); ++t) {
           const Tile& T = p.tiles[t];
           if (T.slot < 0) continue;
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
     mbar_wait_parked(&bars.w_res, 0);
     for (int ts = 0; ts < p.n_steps; ++ts) {
       const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
-      const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+      const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
       const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
       uint32_t acts_waited = 0;
       TC_STAMP(lane == 0, ts, 0);
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         const uint64_t bd0 = smem_desc(smem_base + p.act_off[in_layer], 128u, act_sbo);
         const uint32_t dcol = tmem + col_dA + db * NR;
         const int nk = T.Kp / 16;
-        const bool has_b = (T.lin < L) || nd.top_has_grad;
+        const bool has_b = (T.lin < L) || top_has_grad;
         if (elect_one()) {
           // groups of 8 K-steps fully unrolled: every MMA then reads its own pre-computed uniform registers and the
           // instructions issue back to back (46 instead of 91 cycles each, scripts/umma_timing.py variants 6 / 1)
@@ -316,13 +325,13 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
     mbar_wait_parked(&bars.w_res, 0);
     for (int ts = 0; ts < p.n_steps; ++ts) {
       const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
-      const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+      const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
       const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
       uint32_t bp_started = 0;
       for (int t = 0; t < t_end; ++t) {
         const Tile& T = p.tiles[t];
         const int gb = t & 1;
-        const bool has_b = (T.lin < L) || nd.top_has_grad;
+        const bool has_b = (T.lin < L) || top_has_grad;
         if (!has_b) continue;                                         // read-out only: nothing flows back
         const bool last_of_lin = (t + 1 == n_tiles_all) || (p.tiles[t + 1].lin != T.lin);   // (output tiles come last)
         mbar_wait_parked(&bars.g_full[gb], (ph_gfull >> gb) & 1u);            // group T consumed the prediction of this tile,
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
       fence_before_sync();
       for (int l = 0; l < L; ++l) mbar_arrive(&bars.acts_ready[l]);
 
-      const bool adam = (p.optimizer == MCPC_OPT_ADAM);
+      const bool adam = (opt_kind == MCPC_OPT_ADAM);
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const int t_abs = p.t_begin + ts;
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
@@ -426,14 +435,14 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * p.sg_pitch : nullptr;
         __nv_bfloat16* sf_row = do_save ? p.save_f + ((size_t)slot * p.B + rb) * p.sf_pitch : nullptr;
         float step_size = 0.0f, inv_bc2_sqrt = 1.0f;
-        if (adam && p.update_x) {
+        if (adam && do_update_x) {
           // bias corrections come from a table built in fp64 by adam_table_kernel: two divisions and a square root in
           // double per thread and step cost ~6k cycles of the (1/64-rate) FP64 pipe on the step's critical path
           step_size = __ldg(p.adam_tab + 2 * ts);
           inv_bc2_sqrt = __ldg(p.adam_tab + 2 * ts + 1);
         }
         for (int l = 0; l < L; ++l) {                        // bottom-up, the order the tiles complete in
-          const bool has_above = (l + 1 < L) || nd.top_has_grad;
+          const bool has_above = (l + 1 < L) || top_has_grad;
           const int kind = nd.act[l];
           const int dl = nd.dims[l];
           const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
@@ -495,7 +504,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               b0 = 0.0f;
               if (uvalid) {
                 if (l == 0 && p.b[0] != nullptr) b0 = __ldg(p.b[0] + u);
-                if (adam && p.update_x && !p.adam_tmem) {
+                if (adam && do_update_x && !p.adam_tmem) {
 #pragma unroll
                   for (int i = 0; i < CH; ++i) {
                     mv[i] = (i < nrc) ? p.m[l][xoffc + (size_t)i * dl] : 0.0f;
@@ -505,11 +514,11 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               }
               auto draw_noise = [&]() {
                 if (!uvalid) return;
-                if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
+                if (noise_kind == MCPC_NOISE_SUPPLIED) {
                   const float* np_ = p.noise + ((size_t)ts * p.B + rbc) * nd.SD + gu;
 #pragma unroll
                   for (int i = 0; i < CH; ++i) nz[i] = (i < nrc) ? __ldg(np_ + (size_t)i * nd.SD) : 0.0f;
-                } else if (p.noise_mode == MCPC_NOISE_PHILOX) {
+                } else if (noise_kind == MCPC_NOISE_PHILOX) {
                   float nrm[4];
                   uint64_t cur_q = ~0ull;
 #pragma unroll
@@ -536,7 +545,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               tmem_ld_nw<CH>(lac + col_x + h * NR, xv);
               if (has_above) tmem_ld_nw<CH>(lac + col_bp + h * NR, bp);
               if (l > 0) tmem_ld_nw<CH>(lac + col_g + h * NR, gown);
-              const bool adam_t = adam && p.update_x && p.adam_tmem;
+              const bool adam_t = adam && do_update_x && p.adam_tmem;
               if (adam_t) {
                 tmem_ld_nw<CH>(lac + col_m + h * NR, mv);
                 tmem_ld_nw<CH>(lac + col_v + h * NR, vv);
@@ -579,7 +588,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
                 for (int i = 0; i < CH; ++i)
                   if (i < nrc) p.xgrad[l][xoffc + (size_t)i * dl] = gradv[i];
               }
-              if (p.update_x) {
+              if (do_update_x) {
                 if (!adam) {
 #pragma unroll
                   for (int i = 0; i < CH; ++i) xv[i] = fmaf(-p.lr, gradv[i], xv[i]);
@@ -600,7 +609,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
                   }
                 }
               }
-              if (p.noise_mode != MCPC_NOISE_NONE) {
+              if (noise_kind != MCPC_NOISE_NONE) {
 #pragma unroll
                 for (int i = 0; i < CH; ++i) xv[i] = fmaf(-p.lr, nz[i], xv[i]);
               }
@@ -685,7 +694,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
       auto target_of = [&](int t, float (&yv)[RT]) {
         const int2 ti = s_tile[t];
         const int un = ((ti.x >> 8) & 0xff) * 128 + ln;
-        const bool uy = ((ti.x & 0xff) == L) && un < ti.y && un >= nd.mask_start && nd.top >= MCPC_TOP_GAUSS;
+        const bool uy = ((ti.x & 0xff) == L) && un < ti.y && un >= nd.mask_start && top_kind >= MCPC_TOP_GAUSS;
         const float* yp = p.target + (size_t)rbT * nd.d_out + un;
 #pragma unroll
         for (int i = 0; i < RT; ++i) yv[i] = (uy && i < nrT) ? __ldg(yp + (size_t)i * nd.d_out) : qnan;
@@ -709,7 +718,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         const int slot = ts - p.save_begin;
         const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
         const int rec = do_traj ? ts / p.traj_every : 0;
-        const bool need_out = nd.top_has_grad || (do_traj && p.traj_out != nullptr);
+        const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
         const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
         float e_part = 0.0f, l_part = 0.0f;
         __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rbT) * p.sg_pitch : nullptr;
@@ -721,7 +730,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
           const int k = t;
           const int db = k & (kDA - 1), gb = k & 1;
           const bool is_out = (lin == L);
-          const bool has_b = !is_out || nd.top_has_grad;
+          const bool has_b = !is_out || top_has_grad;
           const int u = ((ti.x >> 8) & 0xff) * 128 + ln;
           const bool uvalid = u < dl;
           if (ALT && (k & 1) != half) {                       // the other half's tile
@@ -804,7 +813,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
             const float bias = bias1[0];
             __nv_bfloat16* sg = (do_save && uvalid) ? sg_row + p.sg_off[L] + u : nullptr;
             float* to = (do_traj && p.traj_out != nullptr && uvalid) ? p.traj_out + ((size_t)rec * p.B + rbT) * nd.d_out + u : nullptr;
-            const bool bern = nd.top == MCPC_TOP_BERNOULLI;
+            const bool bern = top_kind == MCPC_TOP_BERNOULLI;
             float ov[RT], ev[RT];
             if (bern) {
 #pragma unroll
@@ -1141,14 +1150,21 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     kernel<<<p.n_ctas, 608, smem, stream>>>(p);
     return MCPC_OK;
   };
+  const bool bern_grad = nd.top == MCPC_TOP_BERNOULLI && nd.top_has_grad;
+  const bool spec_mcpc = bern_grad && o->update_x && o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX;
+  const bool spec_map = bern_grad && o->update_x && o->optimizer == MCPC_OPT_ADAM && o->noise_mode == MCPC_NOISE_NONE;
   if (rows.rv == 32) {
-    rc = launch(infer_tc_kernel<32, 32, false>);
+    rc = launch(infer_tc_kernel<32, 32, false, 0>);
   } else if (rows.rv == 16) {
-    rc = launch(infer_tc_kernel<16, 16, false>);
+    rc = launch(infer_tc_kernel<16, 16, false, 0>);
   } else if (timing) {
-    rc = launch(infer_tc_kernel<16, 8, true>);       // the cycle trace exists for the 8-chain variant only
+    rc = launch(infer_tc_kernel<16, 8, true, 0>);    // the cycle trace exists for the 8-chain variant only
+  } else if (spec_mcpc) {
+    rc = launch(infer_tc_kernel<16, 8, false, 1>);
+  } else if (spec_map) {
+    rc = launch(infer_tc_kernel<16, 8, false, 2>);
   } else {
-    rc = launch(infer_tc_kernel<16, 8, false>);
+    rc = launch(infer_tc_kernel<16, 8, false, 0>);
   }
   if (rc != MCPC_OK) return rc;
   MCPC_CUDA_CHECK(cudaGetLastError());
