@@ -168,7 +168,8 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
 // SPEC folds the modes of the two calls that matter most into compile-time constants (the epilogue warps are bound by
 // instruction fetch / issue, and every dead branch costs code footprint): 1 = MCPC learning / sampling (SGD + in-kernel
 // Philox noise, Bernoulli top, update_x), 2 = deterministic PC / MAP (Adam, no noise, Bernoulli top, update_x),
-// 0 = everything read from the parameters.
+// 3 = sampling without a sensory gradient (SGD + Philox, zero_fn / no loss: no output tile is ever visited),
+// 0 = everything read from the parameters.  SPEC != 0 also means: no trajectories, no x.grad read-out.
 template <int NR, int RV, bool TRACE, int SPEC>
 __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int RPT = RV / 2;
@@ -189,10 +190,10 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
   const NetDev& nd = p.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = nd.L, HT = p.HT;
-  const int opt_kind = (SPEC == 1) ? (int)MCPC_OPT_SGD : (SPEC == 2 ? (int)MCPC_OPT_ADAM : p.optimizer);
-  const int noise_kind = (SPEC == 1) ? (int)MCPC_NOISE_PHILOX : (SPEC == 2 ? (int)MCPC_NOISE_NONE : p.noise_mode);
-  const int top_kind = (SPEC != 0) ? (int)MCPC_TOP_BERNOULLI : nd.top;
-  const bool top_has_grad = (SPEC != 0) ? true : (bool)nd.top_has_grad;
+  const int opt_kind = (SPEC == 1 || SPEC == 3) ? (int)MCPC_OPT_SGD : (SPEC == 2 ? (int)MCPC_OPT_ADAM : p.optimizer);
+  const int noise_kind = (SPEC == 1 || SPEC == 3) ? (int)MCPC_NOISE_PHILOX : (SPEC == 2 ? (int)MCPC_NOISE_NONE : p.noise_mode);
+  const int top_kind = (SPEC == 1 || SPEC == 2) ? (int)MCPC_TOP_BERNOULLI : nd.top;
+  const bool top_has_grad = (SPEC == 1 || SPEC == 2) ? true : (SPEC == 3 ? false : (bool)nd.top_has_grad);
   const bool do_update_x = (SPEC != 0) ? true : (p.update_x != 0);
   const int row0 = blockIdx.x * RV;
 
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
       }
       uint32_t empty_phase = 3;
       for (int ts = 0; ts < p.n_steps; ++ts) {
-        const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
         const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
         for (int t = 0; t < (need_out ? n_tiles_all : p.n_hid_tiles); ++t) {
           const Tile& T = p.tiles[t];
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
     uint32_t ph_wfull = 0, ph_dAe = (1u << kDA) - 1u;
     mbar_wait_parked(&bars.w_res, 0);
     for (int ts = 0; ts < p.n_steps; ++ts) {
-      const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+      const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
       const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
       const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
       uint32_t acts_waited = 0;
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
     uint32_t ph_gfull = 0;
     mbar_wait_parked(&bars.w_res, 0);
     for (int ts = 0; ts < p.n_steps; ++ts) {
-      const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+      const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
       const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
       const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
       uint32_t bp_started = 0;
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         const int t_abs = p.t_begin + ts;
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
         const int slot = ts - p.save_begin;
-        const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
         const int rec = do_traj ? ts / p.traj_every : 0;
         const bool last = (ts == p.n_steps - 1);
         float e_part = 0.0f;
@@ -583,7 +584,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
                 xold[i] = x;
                 gradv[i] = fmaf(dact_tc(kind, x, a), bp[i], -gown[i]);
               }
-              if (uvalid && last && p.xgrad[l] != nullptr) {
+              if (SPEC == 0 && uvalid && last && p.xgrad[l] != nullptr) {
 #pragma unroll
                 for (int i = 0; i < CH; ++i)
                   if (i < nrc) p.xgrad[l][xoffc + (size_t)i * dl] = gradv[i];
@@ -716,7 +717,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
         const int slot = ts - p.save_begin;
-        const bool do_traj = (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
         const int rec = do_traj ? ts / p.traj_every : 0;
         const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
         const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
@@ -1150,19 +1151,26 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     kernel<<<p.n_ctas, 608, smem, stream>>>(p);
     return MCPC_OK;
   };
+  bool plain = (p.traj_every == 0) && o->update_x;           // what every specialisation assumes
+  for (int l = 0; l < nd.L; ++l) plain = plain && io->x_grad[l] == nullptr;
   const bool bern_grad = nd.top == MCPC_TOP_BERNOULLI && nd.top_has_grad;
-  const bool spec_mcpc = bern_grad && o->update_x && o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX;
-  const bool spec_map = bern_grad && o->update_x && o->optimizer == MCPC_OPT_ADAM && o->noise_mode == MCPC_NOISE_NONE;
+  const bool sgd_philox = o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX;
+  int spec = 0;
+  if (plain && bern_grad && sgd_philox) spec = 1;
+  else if (plain && bern_grad && o->optimizer == MCPC_OPT_ADAM && o->noise_mode == MCPC_NOISE_NONE) spec = 2;
+  else if (plain && !nd.top_has_grad && sgd_philox) spec = 3;
   if (rows.rv == 32) {
-    rc = launch(infer_tc_kernel<32, 32, false, 0>);
+    rc = spec == 3 ? launch(infer_tc_kernel<32, 32, false, 3>) : launch(infer_tc_kernel<32, 32, false, 0>);
   } else if (rows.rv == 16) {
-    rc = launch(infer_tc_kernel<16, 16, false, 0>);
+    rc = spec == 1 ? launch(infer_tc_kernel<16, 16, false, 1>) : launch(infer_tc_kernel<16, 16, false, 0>);
   } else if (timing) {
-    rc = launch(infer_tc_kernel<16, 8, true, 0>);    // the cycle trace exists for the 8-chain variant only
-  } else if (spec_mcpc) {
+    rc = launch(infer_tc_kernel<16, 8, true, 0>);    // the cycle trace exists for the generic 8-chain variant only
+  } else if (spec == 1) {
     rc = launch(infer_tc_kernel<16, 8, false, 1>);
-  } else if (spec_map) {
+  } else if (spec == 2) {
     rc = launch(infer_tc_kernel<16, 8, false, 2>);
+  } else if (spec == 3) {
+    rc = launch(infer_tc_kernel<16, 8, false, 3>);
   } else {
     rc = launch(infer_tc_kernel<16, 8, false, 0>);
   }
