@@ -195,6 +195,9 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
   const int top_kind = (SPEC == 1 || SPEC == 2) ? (int)MCPC_TOP_BERNOULLI : nd.top;
   const bool top_has_grad = (SPEC == 1 || SPEC == 2) ? true : (SPEC == 3 ? false : (bool)nd.top_has_grad);
   const bool do_update_x = (SPEC != 0) ? true : (p.update_x != 0);
+  // the specialisations also require (the host checks): targets and Adam state resident in TMEM, one unit tile per layer
+  const bool y_in_tmem = (SPEC == 1 || SPEC == 2) ? true : (SPEC == 3 ? false : (p.y_tmem != 0));   // 3: no output tile is visited
+  const bool adam_in_tmem = (SPEC == 2) ? true : (SPEC != 0 ? false : (p.adam_tmem != 0));
   const int row0 = blockIdx.x * RV;
 
   if (tid < p.n_hid_tiles + p.n_out_tiles) {
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
   const uint32_t col_dA = 0, col_bp = kDA * NR, col_x = (kDA + HT) * NR, col_g = (kDA + 2 * HT) * NR;
   const uint32_t col_bias = (kDA + 3 * HT) * NR, col_y = col_bias + 32;
   // Adam on the latents (deterministic PC / MAP): m and v behind the targets, HT * NR columns each
-  const uint32_t col_m = col_y + (p.y_tmem ? (uint32_t)p.n_out_tiles * NR : 0u), col_v = col_m + HT * NR;
+  const uint32_t col_m = col_y + (y_in_tmem ? (uint32_t)p.n_out_tiles * NR : 0u), col_v = col_m + HT * NR;
   const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;      // table order: Linear 1 ... L-1, then the output tiles
 
   // =====================================================================================================
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         }
         __syncwarp();
         tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
-        if (p.adam_tmem) {
+        if (adam_in_tmem) {
           float mv[RPT], vv[RPT];
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
@@ -448,7 +451,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
           const int dl = nd.dims[l];
           const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
           const int n_ut = p.ut[l];
-          const bool defer = (RV <= 8) && (n_ut == 1);       // one unit tile: global stores go out after the hand-over
+          const bool defer = (RV <= 8) && (SPEC != 0 || n_ut == 1);   // one unit tile: global stores go out after the hand-over
                                                              // (wider chain tiles have no registers to spare for it)
           // the deferred stores only need the pre-update latents (single-tile layers keep them in registers across the
           // hand-over); f(x) and the layer-0 error are recomputed from them
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               b0 = 0.0f;
               if (uvalid) {
                 if (l == 0 && p.b[0] != nullptr) b0 = __ldg(p.b[0] + u);
-                if (adam && do_update_x && !p.adam_tmem) {
+                if (adam && do_update_x && !adam_in_tmem) {
 #pragma unroll
                   for (int i = 0; i < CH; ++i) {
                     mv[i] = (i < nrc) ? p.m[l][xoffc + (size_t)i * dl] : 0.0f;
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               tmem_ld_nw<CH>(lac + col_x + h * NR, xv);
               if (has_above) tmem_ld_nw<CH>(lac + col_bp + h * NR, bp);
               if (l > 0) tmem_ld_nw<CH>(lac + col_g + h * NR, gown);
-              const bool adam_t = adam && do_update_x && p.adam_tmem;
+              const bool adam_t = adam && do_update_x && adam_in_tmem;
               if (adam_t) {
                 tmem_ld_nw<CH>(lac + col_m + h * NR, mv);
                 tmem_ld_nw<CH>(lac + col_v + h * NR, vv);
@@ -600,7 +603,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
                     vv[i] = fmaf(p.one_minus_b2 * gradv[i], gradv[i], vv[i] * p.beta2f);
                     xv[i] = fmaf(-step_size, __fdividef(mv[i], fmaf(sqrtf(vv[i]), inv_bc2_sqrt, p.adam_eps)), xv[i]);
                   }
-                  if (uvalid && !p.adam_tmem) {
+                  if (uvalid && !adam_in_tmem) {
 #pragma unroll
                     for (int i = 0; i < CH; ++i)
                       if (i < nrc) {
@@ -660,7 +663,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < RPT; ++i)
           if (u < dl && i < nrow) p.x[l][(size_t)(rb + i) * dl + u] = xv[i];
-        if (p.adam_tmem) {
+        if (adam_in_tmem) {
           float mv[RPT], vv[RPT];
           tmem_ld<RPT>(lane_addr + col_m + h * NR, mv);
           tmem_ld<RPT>(lane_addr + col_v + h * NR, vv);
@@ -706,7 +709,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
         const float bv = (un < ti.y && p.b[lin] != nullptr) ? __ldg(p.b[lin] + un) : 0.0f;
         __syncwarp();
         tmem_st1(lane_base + col_bias + (uint32_t)t, bv);           // both warps of a lane quarter write the same value
-        if (p.y_tmem && lin == L && (!ALT || (t & 1) == half)) {
+        if (y_in_tmem && lin == L && (!ALT || (t & 1) == half)) {
           float yv[RT];
           target_of(t, yv);
           __syncwarp();
@@ -739,7 +742,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
             continue;
           }
           float yv[RT];
-          if (!p.y_tmem && is_out) target_of(t, yv);          // targets do not fit TMEM: plain loads
+          if (!y_in_tmem && is_out) target_of(t, yv);          // targets do not fit TMEM: plain loads
           TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 60);
           if (!is_out && !((x_waited >> lin) & 1u)) {         // x_lin of THIS step was written by group U last step
             mbar_wait_parked(&bars.acts_ready[lin], ts & 1);
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
             tmem_st<RT>(laT + col_g + h * NR, gv);
             tmem_st_wait();
           } else {
-            if (p.y_tmem) tmem_ld_nw<RT>(laT + col_y + (uint32_t)(t - p.n_hid_tiles) * NR, yv);
+            if (y_in_tmem) tmem_ld_nw<RT>(laT + col_y + (uint32_t)(t - p.n_hid_tiles) * NR, yv);
             tmem_ld_wait();
             tmem_ld_tie(d);
             tmem_ld_tie(bias1);
@@ -1152,10 +1155,12 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     return MCPC_OK;
   };
   bool plain = (p.traj_every == 0) && o->update_x;           // what every specialisation assumes
-  for (int l = 0; l < nd.L; ++l) plain = plain && io->x_grad[l] == nullptr;
+  for (int l = 0; l < nd.L; ++l) plain = plain && io->x_grad[l] == nullptr && p.ut[l] == 1;
+  plain = plain && (p.y_tmem || !nd.top_has_grad) && (p.adam_tmem || o->optimizer != MCPC_OPT_ADAM);
   const bool bern_grad = nd.top == MCPC_TOP_BERNOULLI && nd.top_has_grad;
   const bool sgd_philox = o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX;
   int spec = 0;
+  if (getenv("MCPC_TC_NOSPEC") != nullptr) plain = false;      // testing hook: the generic instantiation
   if (plain && bern_grad && sgd_philox) spec = 1;
   else if (plain && bern_grad && o->optimizer == MCPC_OPT_ADAM && o->noise_mode == MCPC_NOISE_NONE) spec = 2;
   else if (plain && !nd.top_has_grad && sgd_philox) spec = 3;

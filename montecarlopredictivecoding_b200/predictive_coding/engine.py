@@ -56,7 +56,7 @@ class InferCall:
 
 
 _net_cache = {}
-_ENV_KNOBS = ("MCPC_FORCE_STREAMING", "MCPC_TC_ROWS", "MCPC_ROWS", "MCPC_WIDE_CTAS")
+_ENV_KNOBS = ("MCPC_FORCE_STREAMING", "MCPC_TC_ROWS", "MCPC_ROWS", "MCPC_WIDE_CTAS", "MCPC_TC_NOSPEC")
 
 
 def _env_key():

@@ -91,3 +91,56 @@ def test_bf16_kernel_vs_bf16_oracle(act, top, B):
     print(act, top, B, {k: f"{v:.2e}" for k, v in errs.items()})
     for k, v in errs.items():
         assert v < 2e-3, (k, v)
+
+
+def _run_plain_call(kind, B, nospec):
+    """One call without trajectories (the shape the specialised kernel instantiations serve); returns final latents,
+    energies and parameter gradients."""
+    import os
+    if nospec:
+        os.environ["MCPC_TC_NOSPEC"] = "1"
+    else:
+        os.environ.pop("MCPC_TC_NOSPEC", None)
+    try:
+        torch.manual_seed(0)
+        act = "tanh" if kind == "map" else "relu"
+        cfg = {"input_size": 20, "hidden_size": 128, "hidden2_size": 128, "output_size": 784, "activation_fn": act}
+        model = mu.get_model(cfg, use_cuda=False, sample_x_fn=mu.sample_x_fn_normal).to(DEV)
+        y = (torch.rand(B, 784, device=DEV) < 0.5).float()
+        z = torch.zeros(B, 20, device=DEV)
+        if kind == "map":
+            tr = pc.PCTrainer(model, T=40, optimizer_x_fn=optim.Adam, optimizer_x_kwargs={"lr": 0.1}, update_p_at="never",
+                              plot_progress_at=[])
+            kw = dict(loss_fn=mu.bernoulli_fn, loss_fn_kwargs={"_target": y, "_var": None})
+        else:
+            tr = pc.PCTrainer(model, T=30, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.03}, update_p_at="last",
+                              accumulate_p_at=list(range(10, 30)), optimizer_p_fn=optim.SGD, optimizer_p_kwargs={"lr": 0.0},
+                              plot_progress_at=[])
+            kw = dict(callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": tr})
+            if kind == "mcpc":
+                kw.update(loss_fn=mu.bernoulli_fn, loss_fn_kwargs={"_target": y, "_var": None})
+            else:
+                kw.update(loss_fn=mu.zero_fn)
+        tr.set_precision("bf16")
+        tr.set_noise_seed(77)
+        torch.manual_seed(5)
+        res = tr.train_on_batch(inputs=z, is_log_progress=False, is_checking_after_callback_after_t=False, **kw)
+        xs = [layer.get_x().detach().clone() for layer in model if isinstance(layer, pc.PCLayer)]
+        grads = [p.grad.detach().clone() for p in model.parameters() if p.grad is not None]
+        return xs, torch.tensor(res["energy"]), grads
+    finally:
+        os.environ.pop("MCPC_TC_NOSPEC", None)
+
+
+@pytest.mark.parametrize("kind,B", [("mcpc", 1024), ("map", 512), ("sample", 1024), ("sample", 8192), ("mcpc", 2048)])
+def test_specialised_instantiations_equal_the_generic_kernel(kind, B):
+    """The mode-specialised instantiations (SGD+Philox+Bernoulli, Adam+Bernoulli, sampling without top gradient) only
+    fold runtime flags into constants: same arithmetic, same results as the generic instantiation."""
+    a = _run_plain_call(kind, B, nospec=False)
+    b = _run_plain_call(kind, B, nospec=True)
+    for xa, xb in zip(a[0], b[0]):
+        assert torch.allclose(xa, xb, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(a[1], b[1], rtol=1e-5)
+    assert len(a[2]) == len(b[2])
+    for ga, gb in zip(a[2], b[2]):
+        assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-6)
