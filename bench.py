@@ -376,7 +376,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "mcpc_infer (all T steps, one launch)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "traffic": (228774400 if (args.precision == "bf16" and B == 1024) else (499053568 if B == 1024 else None)),
+                         "traffic": (226595328 if (args.precision == "bf16" and B == 1024) else (499053568 if B == 1024 else None)),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
                                            "kernel (profiles/r01_*_ncu_summary.csv): the bf16 / fp32 saved dW operands",
                          "peak_source": peak_src, "kernel_ms": infer_ms,
