@@ -311,6 +311,9 @@ __device__ __forceinline__ void acc_block_to_quads(uint32_t acc_addr, bool has_a
 }
 
 // latent update of layer t.idx: x <- x - lr*grad (SGD | Adam), x <- x - lr*noise, act(x) re-emitted in bf16
+// SPEC = 1 folds the Langevin call's modes into constants (SGD, in-kernel Philox with aligned chain quads, no
+// trajectories, no x.grad read-out): the epilogue is bound by instruction issue / fetch, dead branches cost.
+template <int SPEC>
 __device__ __forceinline__ void epilogue_update_q(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_q,
                                                   int q, int c_begin, float* tb, int lane) {
   const NetDev& nd = p.net;
@@ -318,8 +321,12 @@ __device__ __forceinline__ void epilogue_update_q(const WideParams& p, const Ste
   const int dl = nd.dims[l];
   const int row0 = t.m0 + q * 32;
   const int kind = nd.act[l];
-  const bool adam = p.optimizer == MCPC_OPT_ADAM;
-  const bool quad_rng = ((p.chain_offset + (uint64_t)row0) & 3) == 0;   // a row quad = one Philox counter
+  const bool adam = (SPEC == 1) ? false : (p.optimizer == MCPC_OPT_ADAM);
+  const bool quad_rng = (SPEC == 1) ? true : (((p.chain_offset + (uint64_t)row0) & 3) == 0);   // a row quad = one Philox counter
+  const int noise_kind = (SPEC == 1) ? (int)MCPC_NOISE_PHILOX : p.noise_mode;
+  const bool do_traj = (SPEC == 1) ? false : (st.do_traj != 0);
+  const bool want_xgrad = (SPEC == 1) ? false : (st.last != 0);
+  const bool upd_x = (SPEC == 1) ? true : (p.update_x != 0);
   const int rq2 = lane >> 3, cq = lane & 7;
   for (int sb = 0; sb < 4; ++sb) {
     const int n0 = t.n0 + c_begin + sb * 32;
@@ -342,7 +349,7 @@ __device__ __forceinline__ void epilogue_update_q(const WideParams& p, const Ste
         xv[j][0] = x4.x; xv[j][1] = x4.y; xv[j][2] = x4.z; xv[j][3] = x4.w;
         g[j][0] = g4.x; g[j][1] = g4.y; g[j][2] = g4.z; g[j][3] = g4.w;
       }
-      if (st.do_traj && p.traj_x[l] != nullptr) {
+      if (do_traj && p.traj_x[l] != nullptr) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (rbase + j < p.B)
@@ -354,7 +361,7 @@ __device__ __forceinline__ void epilogue_update_q(const WideParams& p, const Ste
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int c = 0; c < 4; ++c) nz[j][c] = 0.0f;
-      if (p.noise_mode == MCPC_NOISE_PHILOX) {
+      if (noise_kind == MCPC_NOISE_PHILOX) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (quad_rng) {
@@ -373,7 +380,7 @@ __device__ __forceinline__ void epilogue_update_q(const WideParams& p, const Ste
             }
           }
         }
-      } else if (p.noise_mode == MCPC_NOISE_SUPPLIED) {
+      } else if (noise_kind == MCPC_NOISE_SUPPLIED) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (rbase + j < p.B) {
@@ -386,7 +393,7 @@ __device__ __forceinline__ void epilogue_update_q(const WideParams& p, const Ste
         if (rbase + j >= p.B) continue;
         const size_t xo = (size_t)(rbase + j) * dl + n;
         float mv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
-        if (adam && p.update_x) {
+        if (adam && upd_x) {
           const float4 m4 = *reinterpret_cast<const float4*>(p.m[l] + xo), v4 = *reinterpret_cast<const float4*>(p.v[l] + xo);
           mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
           vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
@@ -398,7 +405,7 @@ __device__ __forceinline__ void epilogue_update_q(const WideParams& p, const Ste
           const float a = act_w(kind, x);
           const float grad = fmaf(dact_w(kind, x, a), bp[i][j][c], -g[j][c]);
           gradv[c] = grad;
-          if (p.update_x) {
+          if (upd_x) {
             if (!adam) {
               x = fmaf(-p.lr, grad, x);
             } else {
@@ -411,9 +418,9 @@ __device__ __forceinline__ void epilogue_update_q(const WideParams& p, const Ste
           xv[j][c] = x;
           a_new[c] = act_w(kind, x);
         }
-        if (st.last && p.xgrad[l] != nullptr)
+        if (want_xgrad && p.xgrad[l] != nullptr)
           *reinterpret_cast<float4*>(p.xgrad[l] + xo) = make_float4(gradv[0], gradv[1], gradv[2], gradv[3]);
-        if (adam && p.update_x) {
+        if (adam && upd_x) {
           *reinterpret_cast<float4*>(p.m[l] + xo) = make_float4(mv[0], mv[1], mv[2], mv[3]);
           *reinterpret_cast<float4*>(p.v[l] + xo) = make_float4(vv[0], vv[1], vv[2], vv[3]);
         }
@@ -454,7 +461,7 @@ __device__ __forceinline__ void epilogue_wgrad_t(const WideParams& p, const Tile
 // Persistent grouped GEMM: each CTA walks tiles blockIdx.x, +gridDim.x, ...  Warps 0-3 cp.async producers (4-stage ring),
 // warp 4 MMA issuer, warps 5-8 epilogue; two 256-column accumulators in TMEM so the epilogue of tile i overlaps the
 // mainloop of tile i+1.
-template <int KIND>
+template <int KIND, int SPEC>
 __global__ void __launch_bounds__(64 + 32 * epi_warps(KIND), 1) wide_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st,
                                                       const __grid_constant__ WideMaps mp) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -624,7 +631,7 @@ __global__ void __launch_bounds__(64 + 32 * epi_warps(KIND), 1) wide_kernel(cons
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       } else if (KIND == KIND_UPDATE) {
-        epilogue_update_q(p, st, t, acc_addr, q, c_begin, trans + ew * 32 * kTQ, lane);
+        epilogue_update_q<SPEC>(p, st, t, acc_addr, q, c_begin, trans + ew * 32 * kTQ, lane);
       } else {
         epilogue_wgrad_t(p, t, acc_addr, q, c_begin, trans + ew * 32 * kTP, lane);
       }
@@ -838,9 +845,10 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
     if (rc != MCPC_OK) return rc;
   }
   const size_t smem_g = (size_t)kWS * (kABytes + kBBytes) + kTransBytes + 1024;
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_WGRAD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
   int n_sm = 148;
   {
     int dev = 0;
@@ -860,6 +868,9 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   init_act_kernel<<<1184, 256, 0, stream>>>(p);
   count_launch();
   double b1p = pow(o->adam_beta1, (double)o->adam_step0), b2p = pow(o->adam_beta2, (double)o->adam_step0);
+  bool spec_update = !any_traj && o->update_x && o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX &&
+                     (o->chain_offset & 3) == 0;                       // what wide_kernel<KIND_UPDATE, 1> assumes
+  for (int l = 0; l < nd.L; ++l) spec_update = spec_update && io->x_grad[l] == nullptr;
   for (int ts = 0; ts < o->n_steps; ++ts) {
     StepArgs st{};
     st.ts = ts;
@@ -876,17 +887,20 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
     const bool acc = any_grad && ts >= o->save_begin && ts < o->save_end;
     st.acc = acc ? 1 : 0;                  // the predict epilogue adds the bias gradients (column sums of G) on these steps
     if (n_predict > 0) {
-      wide_kernel<KIND_PREDICT><<<n_predict < n_sm ? n_predict : n_sm, 320, smem_g, stream>>>(p, st, mp);
+      wide_kernel<KIND_PREDICT, 0><<<n_predict < n_sm ? n_predict : n_sm, 320, smem_g, stream>>>(p, st, mp);
       count_launch();
     }
     // the weight update reads G (this step's errors) and act(x) of the state BEFORE the update: it runs between the two
     if (acc) {
       if (n_wgrad > 0) {
-        wide_kernel<KIND_WGRAD><<<n_wgrad < n_sm ? n_wgrad : n_sm, 320, smem_g, stream>>>(p, st, mp);
+        wide_kernel<KIND_WGRAD, 0><<<n_wgrad < n_sm ? n_wgrad : n_sm, 320, smem_g, stream>>>(p, st, mp);
         count_launch();
       }
     }
-    wide_kernel<KIND_UPDATE><<<n_update < n_sm ? n_update : n_sm, 64 + 32 * epi_warps(KIND_UPDATE), smem_g, stream>>>(p, st, mp);
+    if (spec_update)
+      wide_kernel<KIND_UPDATE, 1><<<n_update < n_sm ? n_update : n_sm, 64 + 32 * epi_warps(KIND_UPDATE), smem_g, stream>>>(p, st, mp);
+    else
+      wide_kernel<KIND_UPDATE, 0><<<n_update < n_sm ? n_update : n_sm, 64 + 32 * epi_warps(KIND_UPDATE), smem_g, stream>>>(p, st, mp);
     count_launch();
   }
   MCPC_CUDA_CHECK(cudaGetLastError());
