@@ -871,6 +871,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   bool spec_update = !any_traj && o->update_x && o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX &&
                      (o->chain_offset & 3) == 0;                       // what wide_kernel<KIND_UPDATE, 1> assumes
   for (int l = 0; l < nd.L; ++l) spec_update = spec_update && io->x_grad[l] == nullptr;
+  if (getenv("MCPC_TC_NOSPEC") != nullptr) spec_update = false;       // testing hook: the generic instantiation
   for (int ts = 0; ts < o->n_steps; ++ts) {
     StepArgs st{};
     st.ts = ts;

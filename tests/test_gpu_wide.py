@@ -107,3 +107,43 @@ def tr_plan(tr):
 def tr_top(tr, loss_fn, y, B, d_out):
     from montecarlopredictivecoding_b200.predictive_coding import plan as P
     return P.classify_loss(loss_fn, {"_target": y, "_var": 1.0}, B, d_out, None)
+
+
+@pytest.mark.parametrize("B", [256, 1000])
+def test_specialised_update_kernel_equals_the_generic_one(B):
+    """wide_kernel<UPDATE, 1> (SGD + in-kernel Philox, no trajectories) only folds runtime flags into constants: the call
+    must give the same latents, energies and weight gradients as the generic instantiation (MCPC_TC_NOSPEC)."""
+    dev = torch.device(DEV)
+
+    def run(nospec):
+        if nospec:
+            os.environ["MCPC_TC_NOSPEC"] = "1"
+        else:
+            os.environ.pop("MCPC_TC_NOSPEC", None)
+        try:
+            model = _model([128, 256, 192], 320, "tanh", dev, seed=3)
+            T = 8
+            tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.02}, update_p_at="last",
+                              accumulate_p_at=list(range(2, T)), optimizer_p_fn=optim.SGD, optimizer_p_kwargs={"lr": 0.0},
+                              plot_progress_at=[])
+            tr.set_precision("bf16")
+            tr.set_noise_seed(11)
+            for layer in (m for m in model if isinstance(m, pc.PCLayer)):
+                layer._sample_x_fn = mu.sample_x_fn_normal
+            torch.manual_seed(9)
+            y = torch.randn(B, 320, device=dev)
+            res = tr.train_on_batch(torch.zeros(B, 128, device=dev), loss_fn=mu.fe_fn, loss_fn_kwargs={"_target": y, "_var": 1.0},
+                                    callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": tr},
+                                    is_log_progress=False, is_checking_after_callback_after_t=False)
+            assert tr.last_call_info["mode"] == "fused"
+            xs = [layer.get_x().detach().clone() for layer in model if isinstance(layer, pc.PCLayer)]
+            grads = [p.grad.detach().clone() for p in model.parameters() if p.grad is not None]
+            return xs, torch.tensor(res["energy"]), grads
+        finally:
+            os.environ.pop("MCPC_TC_NOSPEC", None)
+    a, b = run(False), run(True)
+    for xa, xb in zip(a[0], b[0]):
+        assert torch.allclose(xa, xb, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(a[1], b[1], rtol=1e-5)
+    for ga, gb in zip(a[2], b[2]):
+        assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-5)
