@@ -1,21 +1,29 @@
 // mcpc_infer, MCPC_PREC_BF16, networks too wide to stay on chip (SURVEY config C5: 4 x 4096): the
 // "streaming" path.  Latents x (fp32), their activations (bf16) and the error signals live in HBM / L2;
-// every Langevin step is three grouped tcgen05 GEMM kernels with fused epilogues:
+// every Langevin step is two grouped tcgen05 GEMM kernels with fused epilogues, plus a third one every few steps:
 //
-//   wide_predict_kernel   for every Linear l:  mu = act(x_{l-1}) W_l^T + b  ->  eps = x_l - mu, energy, loss,
-//                         G_l = d overall / d mu_l (bf16 operand copy + fp32 own-layer term), e_out
-//   wide_wgrad_kernel     (steps of the accumulate window)  gW_l += G_l^T act(x_{l-1}),  gb_l += colsum G_l
-//   wide_update_kernel    for every PCLayer l: bp = G_{l+1} W_{l+1};  grad = -G_l + act'(x_l) * bp;
-//                         x <- SGD | Adam step; x <- x - lr * noise (Philox);  act(x) re-emitted as bf16
+//   PREDICT   for every Linear l:  mu = act(x_{l-1}) W_l^T + b  ->  eps = x_l - mu, energy, loss,
+//             G_l = d overall / d mu_l (bf16 operand copy + fp32 own-layer term), e_out, bias gradients
+//   UPDATE    for every PCLayer l: bp = G_{l+1} W_{l+1};  grad = -G_l + act'(x_l) * bp;
+//             x <- SGD | Adam step; x <- x - lr * noise (Philox);  act(x) re-emitted as bf16
+//   WGRAD     gW_l += sum over the last s accumulate steps of G_l^T act(x_{l-1}): the bf16 operands of s steps stay
+//             in a ring of s slots, so that the contraction index is (step, chain) and the fp32 gW tiles are read and
+//             written once per s steps instead of once per step (537 MB of HBM traffic per C5 step otherwise).
 //
-// All three share one persistent mainloop: 128 x 256 output tile, K in stages of 64, operands brought in by TMA
-// (cp.async.bulk.tensor with SWIZZLE_128B tensor maps over the row-major global matrices; K-major or MN-major
-// as the operand's storage order dictates -- no transposed copies of anything), 4-stage mbarrier ring, two
-// 256-column accumulators in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.  Warp roles:
-// warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (TMEM lane quarter = warp % 4, column half = (warp-2)/4;
-// sub-blocks are transposed through shared memory so that global accesses are contiguous, see "coalesced epilogues").
-// (A first version scattered operands with 16-byte cp.async: it was bound by the L1TEX wavefront rate -- 8 cache
-// lines per instruction, ~2000 cycles to issue one stage -- see DESIGN.md.)
+// Orientation: UNITS on the M axis (TMEM lanes), CHAINS on the N axis (TMEM columns).  tcgen05.ld hands every thread
+// one accumulator row, i.e. one unit and a run of chains: the 32 lanes of a warp then touch 32 CONSECUTIVE units of
+// one chain -- every global access of the epilogues is a contiguous 128-byte row segment without any transpose
+// (the first version had chains on M and needed a shared-memory transpose per 32 x 32 block), and the four chains of
+// a Philox counter are four registers of one thread.
+//
+// All three kinds share one persistent mainloop: (128*CG) x 256 output tile, K in stages of 64, operands brought in
+// by TMA (cp.async.bulk.tensor with SWIZZLE_128B tensor maps over the row-major global matrices; K-major or MN-major
+// as the operand's storage order dictates -- no transposed copies of anything), mbarrier ring, two 256-column
+// accumulators in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.  CG = 2 runs the tile on a CTA
+// PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256): each CTA stages its 128 units of A and HALF of the chains of
+// B, so a stage is 32 KB per CTA instead of 48 KB (6 stages instead of 4) and every byte of B is fetched into shared
+// memory once per pair instead of once per CTA.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only),
+// warps 2-9 epilogue (TMEM lane quarter = warp % 4, chain half = (warp - 2) / 4).
 // Reference semantics: predictive_coding/pc_trainer.py:733-918 + utils/model.py:35-44.
 #include <cstdlib>
 
@@ -29,11 +37,16 @@ namespace {
 
 using namespace umma;
 
-constexpr int kWS = 4;                      // pipeline stages
-constexpr int kBK = 64;                     // K per stage
-constexpr int kBN = 256;                    // output-tile width (N of the MMA)
-constexpr uint32_t kABytes = 128 * kBK * 2;             // A operand stage: 128 (M) x 64 (K) bf16
-constexpr uint32_t kBBytes = kBN * kBK * 2;             // B operand stage: 256 (N) x 64 (K) bf16
+constexpr int kBK = 64;                     // K per stage (128 bytes: one SWIZZLE_128B row)
+constexpr int kTM = 128;                    // units per CTA tile (M of one CTA)
+constexpr int kTN = 256;                    // chains (PREDICT / UPDATE) or output units (WGRAD) per tile (N of the MMA)
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kMaxStages = 6;
+__host__ __device__ constexpr int n_stages(int cg) { return cg == 2 ? 6 : 4; }
+__host__ __device__ constexpr uint32_t a_bytes() { return kTM * kBK * 2; }
+__host__ __device__ constexpr uint32_t b_bytes(int cg) { return (kTN / cg) * kBK * 2; }
+__host__ __device__ constexpr uint32_t stage_bytes(int cg) { return a_bytes() + b_bytes(cg); }
 
 struct WideParams {
   NetDev net;
@@ -44,9 +57,8 @@ struct WideParams {
   float* traj_x[kMaxL];
   float* traj_out;
   const float* b[kMaxL + 1];
-  const __nv_bfloat16* Wb[kMaxL + 1];     // bf16 copies of the weights, row-major [d_l][d_{l-1}]
-  __nv_bfloat16* act;                     // [B][a_pitch]: act(x_l) at column poff[l]
-  __nv_bfloat16* Gb;                      // [B][g_pitch]: G_l at column poff[l], e_out at poff[L]
+  __nv_bfloat16* act;                     // [S][Bpad][a_pitch]: act(x_l) at column poff[l]
+  __nv_bfloat16* Gb;                      // [S][Bpad][g_pitch]: G_l at column poff[l], e_out at poff[L]
   float* G32;                             // [B][SD]: fp32 G_l (own-layer gradient term) at column off[l]
   const float* target;
   const float* noise;
@@ -55,27 +67,42 @@ struct WideParams {
   float* partials;                        // [n_steps][n_part][2]
   int poff[kMaxL + 1];
   int a_pitch, g_pitch;
-  int B, mt;                              // chains, chain tiles of 128
-  int tP_first[kMaxL + 2];                // predict tiles: prefix over Linear 1..L (index lin)
+  int B, Bpad;                            // chains; rows of one ring slot (B rounded up to 64)
+  int tP_first[kMaxL + 2];                // predict tiles: prefix over Linear 0..L (index lin)
   int tU_first[kMaxL + 1];                // update tiles: prefix over layers 0..L-1
   int tW_first[kMaxL + 2];                // wgrad tiles: prefix over Linear 0..L
-  int n_part;                             // partial slots per step (predict tiles + update tiles of layer 0)
+  int n_part;                             // partial slots per step (8 per predict CTA tile)
   int optimizer, update_x;
   float lr, adam_eps, one_minus_b1, one_minus_b2, beta2f;
   int noise_mode;
   float noise_scale;
   uint64_t seed, chain_offset;
   int mn3;                                // MN-major operands come in through 3-D tensor maps (all widths % 64 == 0)
-  int l2_prefetch;                        // stages ahead of the ring whose boxes are prefetched into L2 (0 = off)
-  int skip_epilogue;                      // debug: MCPC_WIDE_SKIP_EPI=1
-  long long* dbg;                         // MCPC_WIDE_TIMING=1: per-role cycle counters of CTA 0 (debug)
+  int skip_epilogue;                      // debug build only
 };
 
 struct StepArgs {
   int ts, t_abs, rec, do_traj, last;
   int acc;                                // this step is inside the weight-gradient window: bias gradients accumulate
+  int slot, slot_next;                    // ring slot this step's act / G live in; slot the update writes act(x) to
+  int k_rows;                             // WGRAD: contraction extent = (slots in use) * Bpad
   float step_size, inv_bc2_sqrt;          // Adam bias corrections of this step
 };
+
+// Tensor maps over the row-major bf16 matrices, one per layer block so that out-of-range K / M / N are zero-filled:
+//   *_k : box 64 (inner = contraction index) x rows           -> K-major operand stage
+//   *_mn: box 64 (inner = M/N index) x 64 rows (contraction)  -> MN-major operand stage, one 8 KB block per 64 units
+struct WideMaps {
+  CUtensorMap act_k[kMaxL], act_mn[kMaxL];
+  CUtensorMap gb_k[kMaxL + 1], gb_mn[kMaxL + 1];
+  CUtensorMap w_k[kMaxL + 1], w_mn[kMaxL + 1];
+};
+
+struct Pipe {
+  uint64_t full[kMaxStages], empty[kMaxStages], acc_full[2], acc_empty[2];
+};
+
+enum { KIND_PREDICT = 0, KIND_UPDATE = 1, KIND_WGRAD = 2 };
 
 __device__ __forceinline__ bool elect1() {
   uint32_t pred;
@@ -90,40 +117,99 @@ __device__ __forceinline__ float tanh_fast_w(float x) {
 __device__ __forceinline__ float act_w(int kind, float x) {
   return kind == MCPC_ACT_RELU ? fmaxf(x, 0.0f) : (kind == MCPC_ACT_TANH ? tanh_fast_w(x) : x);
 }
-__device__ __forceinline__ float dact_w(int kind, float x, float a) {
-  return kind == MCPC_ACT_RELU ? (x > 0.0f ? 1.0f : 0.0f) : (kind == MCPC_ACT_TANH ? fmaf(-a, a, 1.0f) : 1.0f);
-}
 __device__ __forceinline__ float warp_sum_w(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// Tensor maps over the row-major bf16 matrices, one per layer block so that out-of-range K / M / N are zero-filled:
-//   *_k : box 64 (inner = contraction index) x 128|256 rows  -> K-major operand stage
-//   *_mn: box 64 (inner = M/N index) x 64 rows (contraction) -> MN-major operand stage, one box per 64 units
-struct WideMaps {
-  CUtensorMap act_k[kMaxL], act_mn[kMaxL];
-  CUtensorMap gb_k[kMaxL + 1], gb_mn[kMaxL + 1];
-  CUtensorMap w_k[kMaxL + 1], w_mn[kMaxL + 1];
-};
+// ---- CTA-pair (cta_group::2) primitives ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* dst_smem, uint32_t ncols) {      // one full warp (of each CTA)
+  if (CG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    tmem_alloc(dst_smem, ncols);
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+  if (CG == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+  else
+    tmem_dealloc(taddr, ncols);
+}
+template <int CG>
+__device__ __forceinline__ void mma_bf16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  if (CG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+  } else {
+    mma_bf16_ss(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
+// arrive on the barrier at this shared-memory offset (of BOTH CTAs of the pair for CG = 2) once every MMA issued so far
+// has completed
+template <int CG>
+__device__ __forceinline__ void mma_commit_cg(uint64_t* mbar) {
+  if (CG == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(mbar)), "h"((uint16_t)3) : "memory");
+  } else {
+    mma_commit(mbar);
+  }
+}
+// TMA box loads; `bar` is a shared::cluster address (for CG = 2: the LEADER's full barrier, which counts the bytes of
+// both CTAs)
+template <int CG>
+__device__ __forceinline__ void tma2d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  if (CG == 2) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma3d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  if (CG == 2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  }
+}
 
-struct Pipe {
-  uint64_t full[kWS], empty[kWS], acc_full[2], acc_empty[2];
-};
-
-enum { KIND_PREDICT = 0, KIND_UPDATE = 1, KIND_WGRAD = 2 };
-
-// Epilogue warps per CTA (8 = two per sub-partition).  Measured on C5: 16 warps for the update kernel made it slower
-// (500k vs 437k cycles per CTA: its epilogue is bound by the 32-lines-per-instruction global access pattern and by
-// Philox latency chains, and a lane = unit version of it executed 2x the instructions); the predict and wgrad
-// epilogues are memory-shaped and, transposed through shared memory, hide behind the mainloop.
-__host__ __device__ constexpr int epi_warps(int kind) { return kind >= 0 ? 8 : 8; }
-
+// ---- tiles ---------------------------------------------------------------------------------------------------
 struct TileDesc {
   int idx;          // Linear index (predict / wgrad) or layer index (update)
-  int m0, n0;
-  int k_ext;        // 0: no contraction for this tile
+  int m0;           // first unit (M) of THIS CTA's 128 rows of the tile
+  int n0;           // first chain / output unit (N) of the tile (all 256 columns)
+  int nb0;          // first N index this CTA stages into shared memory (its 256 / CG columns of B)
+  int k_ext;        // contraction extent; 0: no GEMM for this tile
+  int k_base;       // first row (chain axis) of the K-major B operand: ring slot * Bpad (PREDICT / UPDATE), 0 for WGRAD
   const CUtensorMap* mapA;
   const CUtensorMap* mapB;
 };
@@ -133,525 +219,510 @@ __device__ __forceinline__ int n_tiles_of(const WideParams& p) {
   return KIND == KIND_PREDICT ? p.tP_first[p.net.L + 1] : (KIND == KIND_UPDATE ? p.tU_first[p.net.L] : p.tW_first[p.net.L + 1]);
 }
 
-template <int KIND>
-__device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const WideMaps& mp, int tile) {
+// Tiles are numbered per CTA pair (CG = 2) / CTA (CG = 1); inside a group the chain (N) tile index runs fastest so that
+// the CTAs working at the same time share the weight rows of a few unit tiles and all the chains.
+template <int KIND, int CG>
+__device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const StepArgs& st, const WideMaps& mp, int tile, int rank) {
   const NetDev& nd = p.net;
   TileDesc t{};
   if (KIND == KIND_PREDICT) {
     int lin = 0;
     while (tile >= p.tP_first[lin + 1]) ++lin;
-    const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
     const int d_i = (lin == 0) ? 0 : nd.dims[lin - 1];            // Linear_0 sees zero inputs: mu_0 = b_0
-    const int ntn = (d_o + kBN - 1) / kBN, local = tile - p.tP_first[lin];
-    t.idx = lin; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = d_i;
+    const int ntn = (p.B + kTN - 1) / kTN, local = tile - p.tP_first[lin];
+    t.idx = lin; t.m0 = (local / ntn) * (kTM * CG) + rank * kTM; t.n0 = (local % ntn) * kTN; t.k_ext = d_i;
+    t.k_base = st.slot * p.Bpad;
     if (d_i > 0) {
-      t.mapA = &mp.act_k[lin - 1];                                // act(x_{l-1}) [B x d_i], K-major
-      t.mapB = &mp.w_k[lin];                                      // W_l [d_o x d_i], K-major
+      t.mapA = &mp.w_k[lin];                                      // W_l [d_o x d_i], K-major
+      t.mapB = &mp.act_k[lin - 1];                                // act(x_{l-1}) [chains x d_i], K-major
     }
   } else if (KIND == KIND_UPDATE) {
     int l = 0;
     while (tile >= p.tU_first[l + 1]) ++l;
-    const int dl = nd.dims[l];
-    const int ntn = (dl + kBN - 1) / kBN, local = tile - p.tU_first[l];
+    const int ntn = (p.B + kTN - 1) / kTN, local = tile - p.tU_first[l];
     const bool has_above = (l + 1 < nd.L) || nd.top_has_grad;
     const int d_up = (l + 1 < nd.L) ? nd.dims[l + 1] : nd.d_out;
-    t.idx = l; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = has_above ? d_up : 0;
+    t.idx = l; t.m0 = (local / ntn) * (kTM * CG) + rank * kTM; t.n0 = (local % ntn) * kTN; t.k_ext = has_above ? d_up : 0;
+    t.k_base = st.slot * p.Bpad;
     if (has_above) {
-      t.mapA = &mp.gb_k[l + 1];                                   // G_{l+1} [B x d_up], K-major
-      t.mapB = &mp.w_mn[l + 1];                                   // W_{l+1} [d_up x d_l] as B[k][n]: MN-major
+      t.mapA = &mp.w_mn[l + 1];                                   // W_{l+1} [d_up x d_l] as A[m][k]: MN-major
+      t.mapB = &mp.gb_k[l + 1];                                   // G_{l+1} [chains x d_up], K-major
     }
   } else {
     int lin = 1;
     while (tile >= p.tW_first[lin + 1]) ++lin;
-    const int d_i = nd.dims[lin - 1];
-    const int ntn = (d_i + kBN - 1) / kBN, local = tile - p.tW_first[lin];
-    t.idx = lin; t.m0 = (local / ntn) * 128; t.n0 = (local % ntn) * kBN; t.k_ext = p.B;
-    t.mapA = &mp.gb_mn[lin];                                      // G_l as A[k=chain][m]: MN-major
-    t.mapB = &mp.act_mn[lin - 1];                                 // act(x_{l-1}) as B[k=chain][n]: MN-major
+    const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
+    const int ntn = (d_o + kTN - 1) / kTN, local = tile - p.tW_first[lin];
+    t.idx = lin; t.m0 = (local / ntn) * (kTM * CG) + rank * kTM; t.n0 = (local % ntn) * kTN; t.k_ext = st.k_rows;
+    t.k_base = 0;
+    t.mapA = &mp.act_mn[lin - 1];                                 // act(x_{l-1}) as A[m = input unit][k = chain]: MN-major
+    t.mapB = &mp.gb_mn[lin];                                      // G_l as B[n = output unit][k = chain]: MN-major
   }
+  t.nb0 = t.n0 + rank * (kTN / CG);
   return t;
 }
 
-// ---- coalesced epilogues -------------------------------------------------------------------------------------
-// tcgen05.ld hands every lane one ROW of the accumulator; reading / writing global memory in that shape touches 32
-// cache lines per instruction (the L1 wavefront rate, not HBM, bounded the first epilogues: the three kernels ran at
-// 0.98 ms per C5 step against 0.57 ms with the epilogues switched off).  Each epilogue warp therefore transposes its
-// 32 x 32 sub-blocks through a private padded shared-memory tile: afterwards lane = COLUMN, registers = rows, and
-// every global access of a warp is one contiguous 128-byte row segment.
-constexpr int kTP = 33;                                   // padded pitch of the transpose tile (floats)
-constexpr uint32_t kTransBytes = 8 * 32 * kTP * 4;        // 8 epilogue warps
+// ---- epilogues: lane = unit (accumulator row), registers = chains ---------------------------------------------
+struct EpiPos {
+  int q, h, lane, ew;     // TMEM lane quarter, column half, lane, epilogue warp index
+};
 
-__device__ __forceinline__ void acc_block_to_columns(uint32_t acc_addr, bool has_acc, float* tb, int lane, float (&col)[32]) {
-  if (!has_acc) {
-#pragma unroll
-    for (int r = 0; r < 32; ++r) col[r] = 0.0f;
-    return;
-  }
-  float v[16];
-  tmem_ld16(acc_addr, v);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) tb[lane * kTP + i] = v[i];
-  tmem_ld16(acc_addr + 16, v);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) tb[lane * kTP + 16 + i] = v[i];
-  __syncwarp();
-#pragma unroll
-  for (int r = 0; r < 32; ++r) col[r] = tb[r * kTP + lane];
-  __syncwarp();                                           // the tile is rewritten by the next sub-block
-}
-
-// errors of the units a tile predicts, lane = unit: eps / energy / own-layer G (hidden Linears) or loss / dLoss (output)
-__device__ __forceinline__ void epilogue_predict_t(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_q,
-                                                   int q, int c_begin, float* tb, int lane, float& e_part, float& l_part,
-                                                   float (&gsum)[4]) {
+// errors of the units a tile predicts: eps / energy / own-layer G (hidden Linears) or loss / dLoss (output)
+template <bool HAS_ACC>
+__device__ __forceinline__ void epilogue_predict(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc,
+                                                 const EpiPos& ep, int slot_id) {
   const NetDev& nd = p.net;
   const int lin = t.idx;
   const bool is_out = (lin == nd.L);
   const int d_o = is_out ? nd.d_out : nd.dims[lin];
-  const int row0 = t.m0 + q * 32;
-  const int n_rows = min(32, p.B - row0);
+  const int u = t.m0 + ep.q * 32 + ep.lane;
+  const bool u_ok = u < d_o;
+  const int c_base = t.n0 + ep.h * (kTN / 2);
+  const float bias = (u_ok && p.b[lin] != nullptr) ? __ldg(p.b[lin] + u) : 0.0f;
   const float ce = is_out ? 0.0f : 0.5f * nd.c[lin], gc = is_out ? 0.0f : nd.gc[lin];
-  const bool bern = nd.top == MCPC_TOP_BERNOULLI;
+  float e_part = 0.0f, l_part = 0.0f, gsum = 0.0f;
+  __nv_bfloat16* gbp = p.Gb + ((size_t)st.slot * p.Bpad) * p.g_pitch + p.poff[lin] + u;
+  if (!is_out) {
+    const float* xp = p.x[lin] + u;
+    float* g32 = p.G32 + nd.off[lin] + u;
+#pragma unroll 1
+    for (int ch = 0; ch < kTN / 32; ++ch) {
+      const int c0 = c_base + ch * 16;
+      if (c0 >= p.B) break;                                             // uniform over the warp
+      float xv[16];
 #pragma unroll
-  for (int sb = 0; sb < 4; ++sb) gsum[sb] = 0.0f;
+      for (int j = 0; j < 16; ++j) xv[j] = (u_ok && c0 + j < p.B) ? xp[(size_t)(c0 + j) * d_o] : 0.0f;
+      float d[16];
+      if (HAS_ACC) {
+        tmem_ld16(acc + ch * 16, d);
+      } else {
 #pragma unroll
-  for (int sb = 0; sb < 4; ++sb) {
-    const int n0 = t.n0 + c_begin + sb * 32;
-    if (n0 >= d_o) break;                                               // uniform over the warp
-    float d[32];
-    acc_block_to_columns(acc_q + c_begin + sb * 32, t.k_ext > 0, tb, lane, d);
-    const int n = n0 + lane;
-    if (n >= d_o || n_rows <= 0) continue;
-    const float bias = (p.b[lin] != nullptr) ? __ldg(p.b[lin] + n) : 0.0f;
-    __nv_bfloat16* gbp = p.Gb + (size_t)row0 * p.g_pitch + p.poff[lin] + n;
-    if (!is_out) {
-      const float* xp = p.x[lin] + (size_t)row0 * d_o + n;
-      float xv[32];
+        for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+      }
 #pragma unroll
-      for (int r = 0; r < 32; ++r) xv[r] = (r < n_rows) ? xp[(size_t)r * d_o] : 0.0f;
-      float* g32 = p.G32 + (size_t)row0 * nd.SD + nd.off[lin] + n;
-#pragma unroll
-      for (int r = 0; r < 32; ++r)
-        if (r < n_rows) {
-          const float eps = xv[r] - (d[r] + bias);
+      for (int j = 0; j < 16; ++j)
+        if (u_ok && c0 + j < p.B) {
+          const float eps = xv[j] - (d[j] + bias);
           e_part = fmaf(ce * eps, eps, e_part);
           const float g = -gc * eps;
-          g32[(size_t)r * nd.SD] = g;
+          g32[(size_t)(c0 + j) * nd.SD] = g;
           const __nv_bfloat16 gb16 = __float2bfloat16(g);
-          gbp[(size_t)r * p.g_pitch] = gb16;
-          gsum[sb] += __bfloat162float(gb16);                           // the bias gradient sums the operand the dW GEMM sees
+          gbp[(size_t)(c0 + j) * p.g_pitch] = gb16;
+          gsum += __bfloat162float(gb16);                               // the bias gradient sums the operand the dW GEMM sees
         }
-    } else {
-      const bool use_y = nd.top >= MCPC_TOP_GAUSS;
-      const bool on = use_y && (n >= nd.mask_start);
-      const float* yp = p.target + (size_t)row0 * d_o + n;
-      float yv[32];
+    }
+  } else {
+    const bool use_y = nd.top >= MCPC_TOP_GAUSS;
+    const bool bern = nd.top == MCPC_TOP_BERNOULLI;
+    const bool on = use_y && (u >= nd.mask_start);
+    const float* yp = p.target + u;
+    float* to = (st.do_traj && p.traj_out != nullptr) ? p.traj_out + (size_t)st.rec * p.B * d_o + u : nullptr;
+#pragma unroll 1
+    for (int ch = 0; ch < kTN / 32; ++ch) {
+      const int c0 = c_base + ch * 16;
+      if (c0 >= p.B) break;
+      float yv[16];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) yv[r] = (use_y && r < n_rows) ? yp[(size_t)r * d_o] : 0.0f;
-      float* to = (st.do_traj && p.traj_out != nullptr) ? p.traj_out + ((size_t)st.rec * p.B + row0) * d_o + n : nullptr;
+      for (int j = 0; j < 16; ++j) yv[j] = (use_y && u_ok && c0 + j < p.B) ? yp[(size_t)(c0 + j) * d_o] : 0.0f;
+      float d[16];
+      if (HAS_ACC) {
+        tmem_ld16(acc + ch * 16, d);
+      } else {
 #pragma unroll
-      for (int r = 0; r < 32; ++r)
-        if (r < n_rows) {
-          const float o = d[r] + bias;
+        for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (u_ok && c0 + j < p.B) {
+          const float o = d[j] + bias;
           float lv, e;
           if (bern) {
             const float z = __expf(-fabsf(o));
-            lv = fmaxf(o, 0.0f) - o * yv[r] + __logf(1.0f + z);
-            e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[r];
+            lv = fmaxf(o, 0.0f) - o * yv[j] + __logf(1.0f + z);
+            e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[j];
           } else {
-            const float dd = o - yv[r];
+            const float dd = o - yv[j];
             lv = 0.5f * nd.inv_var * dd * dd;
             e = dd * nd.inv_var;
           }
           l_part += on ? lv : 0.0f;
           const __nv_bfloat16 eb16 = __float2bfloat16(on ? e : 0.0f);
-          gbp[(size_t)r * p.g_pitch] = eb16;
-          gsum[sb] += __bfloat162float(eb16);
-          if (to != nullptr) to[(size_t)r * d_o] = o;
+          gbp[(size_t)(c0 + j) * p.g_pitch] = eb16;
+          gsum += __bfloat162float(eb16);
+          if (to != nullptr) to[(size_t)(c0 + j) * d_o] = o;
         }
     }
   }
+  e_part = warp_sum_w(e_part);
+  l_part = warp_sum_w(l_part);
+  if (ep.lane == 0) {
+    float* dst = p.partials + ((size_t)st.ts * p.n_part + slot_id) * 2;
+    dst[0] = e_part;
+    dst[1] = l_part;
+  }
+  // gb_l += column sums of G over this warp's chains (lane = unit: the sum is already in a register)
+  if (st.acc && u_ok && p.gb[lin] != nullptr && ((lin < nd.L) || nd.top_has_grad)) atomicAdd(p.gb[lin] + u, gsum);
 }
 
-// Second shape, for the ALU-heavy update epilogue: lane = (row quad rq2 = lane / 8, column quad cq = lane % 8) and the
-// lane owns rows 4*(rq2 + 4i) + j (i < 2, j < 4) x columns 4*cq .. 4*cq+3 of the 32 x 32 sub-block.  One warp
-// instruction then covers 4 rows x 128 contiguous bytes with 16-byte accesses (4 cache lines instead of 32, a quarter
-// of the instructions of the lane = column shape) and the 4 rows of a quad are 4 consecutive chains of one unit:
-// exactly one Philox counter, no shuffles.
-constexpr int kTQ = 32;                                   // unpadded 32 x 32 tile; the 16-byte chunk q of row r sits at q ^ (r % 8)
-__device__ __forceinline__ void acc_block_to_quads(uint32_t acc_addr, bool has_acc, float* tb, int lane, float (&v)[2][4][4]) {
-  if (!has_acc) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[i][j][c] = 0.0f;
-    return;
-  }
-  float a[16];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    tmem_ld16(acc_addr + h * 16, a);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      *reinterpret_cast<float4*>(tb + lane * kTQ + 4 * ((h * 4 + k) ^ (lane & 7))) = make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
-  }
-  __syncwarp();
-  const int rq2 = lane >> 3, cq = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int R = 4 * (rq2 + 4 * i) + j;
-      const float4 t4 = *reinterpret_cast<const float4*>(tb + R * kTQ + 4 * (cq ^ (R & 7)));
-      v[i][j][0] = t4.x; v[i][j][1] = t4.y; v[i][j][2] = t4.z; v[i][j][3] = t4.w;
-    }
-  __syncwarp();
-}
-
-// latent update of layer t.idx: x <- x - lr*grad (SGD | Adam), x <- x - lr*noise, act(x) re-emitted in bf16
+// latent update of layer t.idx: x <- x - lr*grad (SGD | Adam), x <- x - lr*noise, act(x) re-emitted in bf16.
 // SPEC = 1 folds the Langevin call's modes into constants (SGD, in-kernel Philox with aligned chain quads, no
-// trajectories, no x.grad read-out): the epilogue is bound by instruction issue / fetch, dead branches cost.
-template <int SPEC>
-__device__ __forceinline__ void epilogue_update_q(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc_q,
-                                                  int q, int c_begin, float* tb, int lane) {
+// trajectories, no x.grad read-out) and ACT is the layer's activation as a compile-time constant (ACT < 0: read from
+// the net at run time).  Only loads and stores are predicated: the arithmetic runs unconditionally on every lane.
+template <int ACT>
+__device__ __forceinline__ float act_t(int kind, float x) {
+  if (ACT == MCPC_ACT_RELU) return fmaxf(x, 0.0f);
+  if (ACT == MCPC_ACT_TANH) return tanh_fast_w(x);
+  if (ACT == MCPC_ACT_IDENTITY) return x;
+  const float th = tanh_fast_w(x), rl = fmaxf(x, 0.0f);                  // run-time kind: branch-free selects
+  return kind == MCPC_ACT_TANH ? th : (kind == MCPC_ACT_RELU ? rl : x);
+}
+template <int ACT>
+__device__ __forceinline__ float dact_t(int kind, float x, float a) {
+  if (ACT == MCPC_ACT_RELU) return x > 0.0f ? 1.0f : 0.0f;
+  if (ACT == MCPC_ACT_TANH) return fmaf(-a, a, 1.0f);
+  if (ACT == MCPC_ACT_IDENTITY) return 1.0f;
+  return kind == MCPC_ACT_TANH ? fmaf(-a, a, 1.0f) : (kind == MCPC_ACT_RELU ? (x > 0.0f ? 1.0f : 0.0f) : 1.0f);
+}
+
+// One chunk = 16 chains of one unit per lane.  GUARD = false: every (lane, chain) of the chunk exists (the steady state:
+// no predicates at all); GUARD = true: edge chunks, loads and stores predicated by `n_ok` (chains c < n_ok are valid).
+// All global offsets are 32-bit element indices from warp-uniform base pointers (wide_layout checks the ranges).
+struct UpdCtx {
+  float* x;                    // p.x[l]
+  const float* g32;            // p.G32
+  __nv_bfloat16* act;          // act ring slot the update writes
+  uint32_t dl, SD, a_pitch;
+  uint32_t xo, go, ao;         // element offsets of (chain 0 of the tile half, this lane's unit)
+  uint32_t gu;                 // global unit index (Philox counter word 0)
+  float nlr, nscale;
+};
+
+template <bool GUARD>
+__device__ __forceinline__ void upd_load(const UpdCtx& c, int cc, int n_ok, float (&xv)[16], float (&gv)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool ok = !GUARD || (cc + j < n_ok);
+    xv[j] = ok ? c.x[c.xo + (uint32_t)(cc + j) * c.dl] : 0.0f;
+    gv[j] = ok ? c.g32[c.go + (uint32_t)(cc + j) * c.SD] : 0.0f;
+  }
+}
+
+template <int SPEC, int ACT, bool GUARD>
+__device__ __forceinline__ void upd_chunk(const WideParams& p, const StepArgs& st, const UpdCtx& c, int l, int kind, int c_abs, int cc,
+                                          int n_ok, uint32_t acc_addr, bool has_acc, const float (&xv)[16], const float (&gv)[16]) {
+  const bool adam = (SPEC == 1) ? false : (p.optimizer == MCPC_OPT_ADAM);
+  const bool quad_rng = (SPEC == 1) ? true : ((p.chain_offset & 3) == 0);       // 4 aligned chains = one Philox counter
+  const int noise_kind = (SPEC == 1) ? (int)MCPC_NOISE_PHILOX : p.noise_mode;
+  const bool do_traj = (SPEC == 1) ? false : (st.do_traj != 0 && p.traj_x[l] != nullptr);
+  const bool want_xgrad = (SPEC == 1) ? false : (st.last != 0 && p.xgrad[l] != nullptr);
+  const bool upd_x = (SPEC == 1) ? true : (p.update_x != 0);
+  float nz[16];
+  if (noise_kind == MCPC_NOISE_PHILOX) {
+    if (quad_rng) {
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd)
+        langevin_normals4(p.seed, c.gu, (uint32_t)st.t_abs, (p.chain_offset + (uint64_t)(c_abs + 4 * qd)) >> 2, &nz[4 * qd]);
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 16; ++j) {
+        const uint64_t chain = p.chain_offset + (uint64_t)(c_abs + j);
+        float q4[4];
+        langevin_normals4(p.seed, c.gu, (uint32_t)st.t_abs, chain >> 2, q4);
+        const int kc = (int)(chain & 3);
+        nz[j] = kc == 0 ? q4[0] : (kc == 1 ? q4[1] : (kc == 2 ? q4[2] : q4[3]));
+      }
+    }
+  } else if (noise_kind == MCPC_NOISE_SUPPLIED) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      nz[j] = (!GUARD || cc + j < n_ok) ? __ldg(p.noise + ((size_t)st.ts * p.B + c_abs + j) * c.SD + c.gu) : 0.0f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) nz[j] = 0.0f;
+  }
+  float bp[16];
+  if (has_acc) {
+    tmem_ld16(acc_addr, bp);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) bp[j] = 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool ok = !GUARD || (cc + j < n_ok);
+    const uint32_t xo = c.xo + (uint32_t)(cc + j) * c.dl;
+    float x = xv[j];
+    if (SPEC == 0 && do_traj && ok) p.traj_x[l][((size_t)st.rec * p.B + c_abs + j) * c.dl + (c.gu - (uint32_t)p.net.off[l])] = x;
+    const float a = act_t<ACT>(kind, x);
+    const float grad = fmaf(dact_t<ACT>(kind, x, a), bp[j], -gv[j]);
+    if (SPEC == 0 && want_xgrad && ok) p.xgrad[l][xo] = grad;
+    if (SPEC == 1) {
+      x = fmaf(c.nlr, grad, x);
+    } else if (upd_x) {
+      if (!adam) {
+        x = fmaf(c.nlr, grad, x);
+      } else if (ok) {
+        float mv = p.m[l][xo], vv = p.v[l][xo];
+        mv = fmaf(p.one_minus_b1, grad - mv, mv);
+        vv = fmaf(p.one_minus_b2 * grad, grad, vv * p.beta2f);
+        x = fmaf(-st.step_size, __fdividef(mv, fmaf(sqrtf(vv), st.inv_bc2_sqrt, p.adam_eps)), x);
+        p.m[l][xo] = mv;
+        p.v[l][xo] = vv;
+      }
+    }
+    x = fmaf(c.nscale, nz[j], x);
+    const __nv_bfloat16 a16 = __float2bfloat16(act_t<ACT>(kind, x));
+    if (ok) {
+      c.x[xo] = x;
+      c.act[c.ao + (uint32_t)(cc + j) * c.a_pitch] = a16;
+    }
+  }
+}
+
+template <int SPEC, int ACT>
+__device__ __forceinline__ void epilogue_update(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc,
+                                                bool has_acc, const EpiPos& ep) {
   const NetDev& nd = p.net;
   const int l = t.idx;
   const int dl = nd.dims[l];
-  const int row0 = t.m0 + q * 32;
   const int kind = nd.act[l];
-  const bool adam = (SPEC == 1) ? false : (p.optimizer == MCPC_OPT_ADAM);
-  const bool quad_rng = (SPEC == 1) ? true : (((p.chain_offset + (uint64_t)row0) & 3) == 0);   // a row quad = one Philox counter
-  const int noise_kind = (SPEC == 1) ? (int)MCPC_NOISE_PHILOX : p.noise_mode;
-  const bool do_traj = (SPEC == 1) ? false : (st.do_traj != 0);
-  const bool want_xgrad = (SPEC == 1) ? false : (st.last != 0);
-  const bool upd_x = (SPEC == 1) ? true : (p.update_x != 0);
-  const int rq2 = lane >> 3, cq = lane & 7;
-  for (int sb = 0; sb < 4; ++sb) {
-    const int n0 = t.n0 + c_begin + sb * 32;
-    if (n0 >= dl) break;                                                // uniform over the warp (widths % 16 == 0)
-    float bp[2][4][4];
-    acc_block_to_quads(acc_q + c_begin + sb * 32, t.k_ext > 0, tb, lane, bp);
-    const int n = n0 + 4 * cq;
-    if (n >= dl) continue;
-    const int gu = nd.off[l] + n;
+  const int u = t.m0 + ep.q * 32 + ep.lane;
+  const bool u_ok = u < dl;
+  const int c_base = t.n0 + ep.h * (kTN / 2);
+  UpdCtx c;
+  c.x = p.x[l];
+  c.g32 = p.G32;
+  c.act = p.act + ((size_t)st.slot_next * p.Bpad) * p.a_pitch;
+  c.dl = (uint32_t)dl; c.SD = (uint32_t)nd.SD; c.a_pitch = (uint32_t)p.a_pitch;
+  c.xo = (uint32_t)c_base * c.dl + (uint32_t)u;
+  c.go = (uint32_t)c_base * c.SD + (uint32_t)(nd.off[l] + u);
+  c.ao = (uint32_t)c_base * c.a_pitch + (uint32_t)(p.poff[l] + u);
+  c.gu = (uint32_t)(nd.off[l] + u);
+  c.nlr = -p.lr;
+  c.nscale = c.nlr * p.noise_scale;                                      // x <- x - lr * (noise_scale * xi)
+  const int n_ok = u_ok ? (p.B - c_base) : 0;                            // chunk-relative chains cc < n_ok are this lane's
+  const int n_warp = min(kTN / 2, p.B - c_base);                         // chains of this tile half that exist (uniform)
+  const bool lanes_full = (t.m0 + ep.q * 32 + 32 <= dl);                 // uniform: every lane of the warp has a unit
+  if (n_warp <= 0) return;
+  float xv[16], gv[16];
+  if (lanes_full && n_warp >= 16) upd_load<false>(c, 0, n_ok, xv, gv);
+  else upd_load<true>(c, 0, n_ok, xv, gv);
+#pragma unroll 1
+  for (int cc = 0; cc < n_warp; cc += 16) {
+    // operands of the NEXT chunk: in flight while this one is computed
+    float xn[16], gn[16];
+    const int cn = cc + 16;
+    if (lanes_full && cn + 16 <= n_warp) upd_load<false>(c, cn, n_ok, xn, gn);
+    else upd_load<true>(c, cn, cn < n_warp ? n_ok : 0, xn, gn);
+    if (lanes_full && cc + 16 <= n_warp)
+      upd_chunk<SPEC, ACT, false>(p, st, c, l, kind, c_base + cc, cc, n_ok, acc + cc, has_acc, xv, gv);
+    else
+      upd_chunk<SPEC, ACT, true>(p, st, c, l, kind, c_base + cc, cc, n_ok, acc + cc, has_acc, xv, gv);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int rbase = row0 + 4 * (rq2 + 4 * i);                       // first of the 4 consecutive chains
-      if (rbase >= p.B) continue;
-      float xv[4][4], g[4][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = rbase + j < p.B;
-        const float4 x4 = ok ? *reinterpret_cast<const float4*>(p.x[l] + (size_t)(rbase + j) * dl + n) : make_float4(0, 0, 0, 0);
-        const float4 g4 = ok ? *reinterpret_cast<const float4*>(p.G32 + (size_t)(rbase + j) * nd.SD + gu) : make_float4(0, 0, 0, 0);
-        xv[j][0] = x4.x; xv[j][1] = x4.y; xv[j][2] = x4.z; xv[j][3] = x4.w;
-        g[j][0] = g4.x; g[j][1] = g4.y; g[j][2] = g4.z; g[j][3] = g4.w;
-      }
-      if (do_traj && p.traj_x[l] != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (rbase + j < p.B)
-            *reinterpret_cast<float4*>(p.traj_x[l] + ((size_t)st.rec * p.B + rbase + j) * dl + n) =
-                make_float4(xv[j][0], xv[j][1], xv[j][2], xv[j][3]);
-      }
-      float nz[4][4];                                                   // [chain j][unit c]
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) nz[j][c] = 0.0f;
-      if (noise_kind == MCPC_NOISE_PHILOX) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (quad_rng) {
-            float q4[4];
-            langevin_normals4(p.seed, (uint32_t)(gu + c), (uint32_t)st.t_abs, (p.chain_offset + (uint64_t)rbase) >> 2, q4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) nz[j][c] = p.noise_scale * q4[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t chain = p.chain_offset + (uint64_t)(rbase + j);
-              float q4[4];
-              langevin_normals4(p.seed, (uint32_t)(gu + c), (uint32_t)st.t_abs, chain >> 2, q4);
-              const int kc = (int)(chain & 3);
-              nz[j][c] = p.noise_scale * (kc == 0 ? q4[0] : (kc == 1 ? q4[1] : (kc == 2 ? q4[2] : q4[3])));
-            }
-          }
-        }
-      } else if (noise_kind == MCPC_NOISE_SUPPLIED) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (rbase + j < p.B) {
-            const float4 z4 = *reinterpret_cast<const float4*>(p.noise + ((size_t)st.ts * p.B + rbase + j) * nd.SD + gu);
-            nz[j][0] = z4.x; nz[j][1] = z4.y; nz[j][2] = z4.z; nz[j][3] = z4.w;
-          }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (rbase + j >= p.B) continue;
-        const size_t xo = (size_t)(rbase + j) * dl + n;
-        float mv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
-        if (adam && upd_x) {
-          const float4 m4 = *reinterpret_cast<const float4*>(p.m[l] + xo), v4 = *reinterpret_cast<const float4*>(p.v[l] + xo);
-          mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
-          vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
-        }
-        float gradv[4], a_new[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float x = xv[j][c];
-          const float a = act_w(kind, x);
-          const float grad = fmaf(dact_w(kind, x, a), bp[i][j][c], -g[j][c]);
-          gradv[c] = grad;
-          if (upd_x) {
-            if (!adam) {
-              x = fmaf(-p.lr, grad, x);
-            } else {
-              mv[c] = fmaf(p.one_minus_b1, grad - mv[c], mv[c]);
-              vv[c] = fmaf(p.one_minus_b2 * grad, grad, vv[c] * p.beta2f);
-              x = fmaf(-st.step_size, __fdividef(mv[c], fmaf(sqrtf(vv[c]), st.inv_bc2_sqrt, p.adam_eps)), x);
-            }
-          }
-          x = fmaf(-p.lr, nz[j][c], x);
-          xv[j][c] = x;
-          a_new[c] = act_w(kind, x);
-        }
-        if (want_xgrad && p.xgrad[l] != nullptr)
-          *reinterpret_cast<float4*>(p.xgrad[l] + xo) = make_float4(gradv[0], gradv[1], gradv[2], gradv[3]);
-        if (adam && upd_x) {
-          *reinterpret_cast<float4*>(p.m[l] + xo) = make_float4(mv[0], mv[1], mv[2], mv[3]);
-          *reinterpret_cast<float4*>(p.v[l] + xo) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        }
-        *reinterpret_cast<float4*>(p.x[l] + xo) = make_float4(xv[j][0], xv[j][1], xv[j][2], xv[j][3]);
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a_new[0], a_new[1]), h1 = __floats2bfloat162_rn(a_new[2], a_new[3]);
-        *reinterpret_cast<uint2*>(p.act + (size_t)(rbase + j) * p.a_pitch + p.poff[l] + n) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-      }
+    for (int j = 0; j < 16; ++j) {
+      xv[j] = xn[j];
+      gv[j] = gn[j];
     }
   }
 }
 
-// gW tile += accumulator (exactly one CTA owns each tile: plain read-modify-write), lane = input unit
-__device__ __forceinline__ void epilogue_wgrad_t(const WideParams& p, const TileDesc& t, uint32_t acc_q, int q, int c_begin,
-                                                 float* tb, int lane) {
+// gW tile += accumulator (exactly one CTA owns each tile: plain read-modify-write); lane = INPUT unit, so for a fixed
+// output unit the 32 lanes touch 32 consecutive floats of one gW row
+__device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDesc& t, uint32_t acc, const EpiPos& ep) {
   const NetDev& nd = p.net;
   const int lin = t.idx;
   const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = nd.dims[lin - 1];
-  float* gW = p.gW[lin];
-  const int mo0 = t.m0 + q * 32;
-  for (int sb = 0; sb < 4; ++sb) {
-    const int n0 = t.n0 + c_begin + sb * 32;
-    if (n0 >= d_i) break;                                 // uniform over the warp
-    float col[32];
-    acc_block_to_columns(acc_q + c_begin + sb * 32, true, tb, lane, col);
-    const int n = n0 + lane;
-    if (gW == nullptr || n >= d_i) continue;
-    float* dst = gW + (size_t)mo0 * d_i + n;
-    float cur[32];
+  const int mi = t.m0 + ep.q * 32 + ep.lane;
+  const bool m_ok = mi < d_i && p.gW[lin] != nullptr;
+  float* gW = p.gW[lin] + mi;
+  const int n_base = t.n0 + ep.h * (kTN / 2);
+#pragma unroll 1
+  for (int ch = 0; ch < kTN / 32; ++ch) {
+    const int n0 = n_base + ch * 16;
+    if (n0 >= d_o) break;                                 // uniform over the warp
+    float cur[16];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) cur[r] = (mo0 + r < d_o) ? dst[(size_t)r * d_i] : 0.0f;
+    for (int j = 0; j < 16; ++j) cur[j] = (m_ok && n0 + j < d_o) ? gW[(size_t)(n0 + j) * d_i] : 0.0f;
+    float col[16];
+    tmem_ld16(acc + ch * 16, col);
 #pragma unroll
-    for (int r = 0; r < 32; ++r)
-      if (mo0 + r < d_o) dst[(size_t)r * d_i] = cur[r] + col[r];
+    for (int j = 0; j < 16; ++j)
+      if (m_ok && n0 + j < d_o) gW[(size_t)(n0 + j) * d_i] = cur[j] + col[j];
   }
 }
 
-// Persistent grouped GEMM: each CTA walks tiles blockIdx.x, +gridDim.x, ...  Warps 0-3 cp.async producers (4-stage ring),
-// warp 4 MMA issuer, warps 5-8 epilogue; two 256-column accumulators in TMEM so the epilogue of tile i overlaps the
-// mainloop of tile i+1.
-template <int KIND, int SPEC>
-__global__ void __launch_bounds__(64 + 32 * epi_warps(KIND), 1) wide_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st,
-                                                      const __grid_constant__ WideMaps mp) {
+// Persistent grouped GEMM: each CTA (pair) walks tiles first, +stride, ...
+template <int KIND, int SPEC, int CG>
+__global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant__ WideParams p, const __grid_constant__ StepArgs st,
+                                                           const __grid_constant__ WideMaps mp) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Pipe pipe;
   __shared__ uint32_t tmem_s;
-  __shared__ float s_red[8][2];
-  constexpr bool A_MN = (KIND == KIND_WGRAD), B_MN = (KIND != KIND_PREDICT);
-  constexpr uint32_t stage_bytes = kABytes + kBBytes;
+  constexpr bool A_MN = (KIND != KIND_PREDICT), B_MN = (KIND == KIND_WGRAD);
+  constexpr int NS = n_stages(CG);
+  constexpr uint32_t kA = a_bytes(), kB = b_bytes(CG), kStage = stage_bytes(CG);
+  constexpr int kBRows = kTN / CG;                       // N indices of B this CTA stages
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = n_tiles_of<KIND>(p);
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const int first_tile = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (tid == 0) {
-    for (int s = 0; s < kWS; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&pipe.full[s], 1);
       mbar_init(&pipe.empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&pipe.acc_full[b], 1);
-      mbar_init(&pipe.acc_empty[b], 32 * epi_warps(KIND));
+      mbar_init(&pipe.acc_empty[b], CG * kEpiWarps);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_s, 512);
+  if (warp == 1) tmem_alloc_cg<CG>(&tmem_s, 512);
   fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_s;
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
-    // ---------------- TMA producer: one elected lane, one mbarrier transaction per 48 KB stage ----------------
+    // ---------------- TMA producer: one elected lane, one mbarrier transaction per stage ----------------
     if (lane == 0) {
       uint32_t issued = 0;
-      long long c_empty = 0, c_issue = 0;
-      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileDesc t = decode_tile<KIND>(p, mp, tile);
+      for (int tile = first_tile; tile < n_tiles; tile += tile_stride) {
+        const TileDesc t = decode_tile<KIND, CG>(p, st, mp, tile, rank);
         const int n_stage = (t.k_ext + kBK - 1) / kBK;
         for (int s = 0; s < n_stage; ++s, ++issued) {
-          const uint32_t slot = issued % kWS;
-          const long long t0 = prof ? clock64() : 0;
-          if (p.l2_prefetch > 0 && s + p.l2_prefetch < n_stage) {
-            // operands of a stage far beyond the shared-memory ring: into L2 now (first touches come from DRAM)
-            const int kp = (s + p.l2_prefetch) * kBK;
-            if (!A_MN) tma_prefetch_l2_2d(t.mapA, kp, t.m0);
-            else if (p.mn3) tma_prefetch_l2_3d(t.mapA, 0, kp, t.m0 / 64);
-            if (!B_MN) tma_prefetch_l2_2d(t.mapB, kp, t.n0);
-            else if (p.mn3) tma_prefetch_l2_3d(t.mapB, 0, kp, t.n0 / 64);
+          const uint32_t slot = issued % NS;
+          mbar_wait(&pipe.empty[slot], ((issued / NS) & 1u) ^ 1u);
+          uint8_t* sa = smem + slot * kStage;
+          uint8_t* sb = sa + kA;
+          uint32_t bar = smem_u32(&pipe.full[slot]);
+          if (CG == 2) {
+            if (rank == 0) mbar_expect_tx(&pipe.full[slot], 2 * kStage);
+            bar = mapa_rank(bar, 0);
+          } else {
+            mbar_expect_tx(&pipe.full[slot], kStage);
           }
-          mbar_wait(&pipe.empty[slot], ((issued / kWS) & 1u) ^ 1u);
-          const long long t1 = prof ? clock64() : 0;
-          uint8_t* sa = smem + slot * stage_bytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&pipe.full[slot], stage_bytes);
           const int k0 = s * kBK;
-          if (!A_MN) tma_load_2d(sa, t.mapA, k0, t.m0, &pipe.full[slot]);
-          else if (p.mn3) tma_load_3d(sa, t.mapA, 0, k0, t.m0 / 64, &pipe.full[slot]);
+          if (!A_MN) tma2d<CG>(sa, t.mapA, k0, t.m0, bar);
+          else if (p.mn3) tma3d<CG>(sa, t.mapA, 0, k0, t.m0 / 64, bar);
           else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tma_load_2d(sa + j * 8192, t.mapA, t.m0 + j * 64, k0, &pipe.full[slot]);
+            for (int j = 0; j < kTM / 64; ++j) tma2d<CG>(sa + j * 8192, t.mapA, t.m0 + j * 64, k0, bar);
           }
-          if (!B_MN) tma_load_2d(sb, t.mapB, k0, t.n0, &pipe.full[slot]);
-          else if (p.mn3) tma_load_3d(sb, t.mapB, 0, k0, t.n0 / 64, &pipe.full[slot]);
+          if (!B_MN) tma2d<CG>(sb, t.mapB, k0, t.k_base + t.nb0, bar);
+          else if (p.mn3) tma3d<CG>(sb, t.mapB, 0, k0, t.nb0 / 64, bar);
           else {
 #pragma unroll
-            for (int j = 0; j < kBN / 64; ++j) tma_load_2d(sb + j * 8192, t.mapB, t.n0 + j * 64, k0, &pipe.full[slot]);
+            for (int j = 0; j < kBRows / 64; ++j) tma2d<CG>(sb + j * 8192, t.mapB, t.nb0 + j * 64, k0, bar);
           }
-          if (prof) { c_empty += t1 - t0; c_issue += clock64() - t1; }
         }
       }
-      if (prof) { p.dbg[KIND * 8 + 0] = c_empty; p.dbg[KIND * 8 + 1] = c_issue; p.dbg[KIND * 8 + 2] = 0; p.dbg[KIND * 8 + 3] = issued; }
+      // tail: every commit that releases one of this CTA's slots has landed before the CTA may exit (for CG = 2 they are
+      // remote arrivals from the leader's tensor core)
+      for (uint32_t k = issued; k < issued + NS; ++k) mbar_wait(&pipe.empty[k % NS], ((k / NS) & 1u) ^ 1u);
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    const uint32_t id = idesc_bf16(128, kBN, A_MN, B_MN);
-    // SWIZZLE_128B operand descriptors (tma.cuh): K-major LBO field 1 / SBO 1024, 32 B per K step;
-    // MN-major LBO 8192 (next 64 units) / SBO 1024 (next 8 k-rows), 2048 B per K step
-    constexpr uint32_t lbo_a = A_MN ? 8192u : 16u, lbo_b = B_MN ? 8192u : 16u;
-    constexpr uint32_t adv_a = A_MN ? (2048u >> 4) : (32u >> 4), adv_b = B_MN ? (2048u >> 4) : (32u >> 4);
-    uint32_t sc = 0, gi = 0;
-    long long c_acc = 0, c_full = 0;
-    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
-    const long long k0 = clock64();
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileDesc t = decode_tile<KIND>(p, mp, tile);
-      const int n_stage = (t.k_ext + kBK - 1) / kBK;
-      if (n_stage == 0) continue;
-      const uint32_t ab = gi & 1u;
-      const long long a0 = clock64();
-      mbar_wait(&pipe.acc_empty[ab], ((gi >> 1) & 1u) ^ 1u);
-      c_acc += clock64() - a0;
-      fence_after_sync();
-      for (int s = 0; s < n_stage; ++s, ++sc) {
-        const uint32_t slot = sc % kWS;
-        const long long f0 = clock64();
-        mbar_wait(&pipe.full[slot], (sc / kWS) & 1u);
-        c_full += clock64() - f0;
+    // ---------------- MMA issuer (leader CTA of a pair only) ----------------
+    if (rank == 0) {
+      const uint32_t id = idesc_bf16(kTM * CG, kTN, A_MN, B_MN);
+      // SWIZZLE_128B operand descriptors (tma.cuh): K-major LBO field 1 / SBO 1024, 32 B per K step;
+      // MN-major LBO 8192 (next 64 units) / SBO 1024 (next 8 k-rows), 2048 B per K step
+      constexpr uint32_t lbo_a = A_MN ? 8192u : 16u, lbo_b = B_MN ? 8192u : 16u;
+      constexpr uint32_t adv_a = A_MN ? (2048u >> 4) : (32u >> 4), adv_b = B_MN ? (2048u >> 4) : (32u >> 4);
+      uint32_t sc = 0, gi = 0;
+      for (int tile = first_tile; tile < n_tiles; tile += tile_stride) {
+        const TileDesc t = decode_tile<KIND, CG>(p, st, mp, tile, rank);
+        const int n_stage = (t.k_ext + kBK - 1) / kBK;
+        if (n_stage == 0) continue;
+        const uint32_t ab = gi & 1u;
+        mbar_wait(&pipe.acc_empty[ab], ((gi >> 1) & 1u) ^ 1u);
         fence_after_sync();
-        const uint64_t ad0 = smem_desc_sw128(smem_base + slot * stage_bytes, lbo_a, 1024u);
-        const uint64_t bd0 = smem_desc_sw128(smem_base + slot * stage_bytes + kABytes, lbo_b, 1024u);
-        if (elect1()) {
+        for (int s = 0; s < n_stage; ++s, ++sc) {
+          const uint32_t slot = sc % NS;
+          mbar_wait(&pipe.full[slot], (sc / NS) & 1u);
+          fence_after_sync();
+          const uint64_t ad0 = smem_desc_sw128(smem_base + slot * kStage, lbo_a, 1024u);
+          const uint64_t bd0 = smem_desc_sw128(smem_base + slot * kStage + kA, lbo_b, 1024u);
+          if (elect1()) {
 #pragma unroll
-          for (int ks = 0; ks < kBK / 16; ++ks)
-            mma_bf16_ss(tmem + ab * kBN, ad0 + (uint64_t)(ks * adv_a), bd0 + (uint64_t)(ks * adv_b), id, s > 0 || ks > 0);
-          mma_commit(&pipe.empty[slot]);
-          if (s == n_stage - 1) mma_commit(&pipe.acc_full[ab]);
+            for (int ks = 0; ks < kBK / 16; ++ks)
+              mma_bf16_cg<CG>(tmem + ab * kTN, ad0 + (uint64_t)(ks * adv_a), bd0 + (uint64_t)(ks * adv_b), id, s > 0 || ks > 0);
+            mma_commit_cg<CG>(&pipe.empty[slot]);
+            if (s == n_stage - 1) mma_commit_cg<CG>(&pipe.acc_full[ab]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        ++gi;
       }
-      ++gi;
     }
-    if (prof) { p.dbg[KIND * 8 + 4] = c_acc; p.dbg[KIND * 8 + 5] = c_full; p.dbg[KIND * 8 + 6] = clock64() - k0; }
   } else {
-    // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----------------
-    const int q = warp & 3;
-    const int ew = warp - 2;                               // 0 .. epi_warps-1
-    constexpr int kColsPerWarp = kBN / (epi_warps(KIND) / 4);
-    const int c_begin = (ew >> 2) * kColsPerWarp;
-    float* trans = reinterpret_cast<float*>(smem + kWS * stage_bytes);     // 8 private transpose tiles after the ring
+    // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, chain half = (warp - 2) / 4 ----------------
+    EpiPos ep;
+    ep.q = warp & 3;
+    ep.ew = warp - 2;
+    ep.h = ep.ew >> 2;
+    ep.lane = lane;
+    const uint32_t acc_empty_addr = (CG == 2) ? mapa_rank(smem_u32(&pipe.acc_empty[0]), 0) : smem_u32(&pipe.acc_empty[0]);
     uint32_t gi = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileDesc t = decode_tile<KIND>(p, mp, tile);
+    for (int tile = first_tile; tile < n_tiles; tile += tile_stride) {
+      const TileDesc t = decode_tile<KIND, CG>(p, st, mp, tile, rank);
       const bool has_gemm = t.k_ext > 0;
       const uint32_t ab = gi & 1u;
       if (has_gemm) {
         mbar_wait(&pipe.acc_full[ab], (gi >> 1) & 1u);
         fence_after_sync();
       }
-      const uint32_t acc_addr = tmem + ((uint32_t)(q * 32) << 16) + ab * kBN;
+      const uint32_t acc = tmem + ((uint32_t)(ep.q * 32) << 16) + ab * kTN + ep.h * (kTN / 2);
+#ifdef MCPC_DEBUG_BUILD
       if (p.skip_epilogue) {
         // debug (MCPC_WIDE_SKIP_EPI=1, results are garbage): mainloop-only rate of the three kernels
-      } else if (KIND == KIND_PREDICT) {
-        float e_part = 0.0f, l_part = 0.0f, gsum[4];
-        float* my_tile = trans + ew * 32 * kTP;
-        epilogue_predict_t(p, st, t, acc_addr, q, c_begin, my_tile, lane, e_part, l_part, gsum);
-        e_part = warp_sum_w(e_part);
-        l_part = warp_sum_w(l_part);
-        if (lane == 0) { s_red[ew][0] = e_part; s_red[ew][1] = l_part; }
-        // gb_l += column sums of G: every warp leaves its 128 partial sums (rows of its lane quarter) in its private
-        // tile, the quarter-0 warp of each column half adds the four up and issues ONE atomic per column and tile
-        if (st.acc) {
-#pragma unroll
-          for (int sb = 0; sb < 4; ++sb) my_tile[sb * 32 + lane] = gsum[sb];
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (ew == 0 && lane < 2) {
-          float sum = 0.0f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) sum += s_red[w][lane];
-          p.partials[((size_t)st.ts * p.n_part + tile) * 2 + lane] = sum;
-        }
-        if (st.acc && q == 0) {
-          const NetDev& nd = p.net;
-          const int lin = t.idx;
-          const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
-          const bool live = (lin < nd.L) || nd.top_has_grad;
-          if (live && p.gb[lin] != nullptr) {
-#pragma unroll
-            for (int sb = 0; sb < 4; ++sb) {
-              const int n = t.n0 + c_begin + sb * 32 + lane;
-              float tot = 0.0f;
-#pragma unroll
-              for (int w = 0; w < 4; ++w) tot += trans[((ew & 4) + w) * 32 * kTP + sb * 32 + lane];
-              if (n < d_o) atomicAdd(p.gb[lin] + n, tot);
-            }
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+      } else
+#endif
+      if (KIND == KIND_PREDICT) {
+        const int slot_id = (tile * CG + rank) * kEpiWarps + ep.ew;
+        if (has_gemm) epilogue_predict<true>(p, st, t, acc, ep, slot_id);
+        else epilogue_predict<false>(p, st, t, acc, ep, slot_id);
       } else if (KIND == KIND_UPDATE) {
-        epilogue_update_q<SPEC>(p, st, t, acc_addr, q, c_begin, trans + ew * 32 * kTQ, lane);
+        if (SPEC == 1) {
+          const int kind = p.net.act[t.idx];
+          if (kind == MCPC_ACT_TANH) epilogue_update<1, MCPC_ACT_TANH>(p, st, t, acc, has_gemm, ep);
+          else if (kind == MCPC_ACT_RELU) epilogue_update<1, MCPC_ACT_RELU>(p, st, t, acc, has_gemm, ep);
+          else epilogue_update<1, MCPC_ACT_IDENTITY>(p, st, t, acc, has_gemm, ep);
+        } else {
+          epilogue_update<0, -1>(p, st, t, acc, has_gemm, ep);
+        }
       } else {
-        epilogue_wgrad_t(p, t, acc_addr, q, c_begin, trans + ew * 32 * kTP, lane);
+        epilogue_wgrad(p, t, acc, ep);
       }
       if (has_gemm) {
         fence_before_sync();
-        mbar_arrive(&pipe.acc_empty[ab]);
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(acc_empty_addr + ab * 8);
+          else mbar_arrive(&pipe.acc_empty[ab]);
+        }
         ++gi;
       }
     }
   }
   fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) tmem_dealloc_cg<CG>(tmem, 512);
 }
 
-__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = __float2bfloat16(src[i]);
+// fp32 [rows][cols] -> bf16 [rows][pitch] (pitch = cols rounded up to 8: TMA needs 16-byte row strides); pad columns zero
+__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols, int pitch) {
+  const size_t total = (size_t)rows * pitch;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / pitch), c = (int)(i % pitch);
+    dst[i] = __float2bfloat16(c < cols ? src[(size_t)r * cols + c] : 0.0f);
+  }
 }
 
+// act(x) of the initial latents into ring slot 0
 __global__ void init_act_kernel(WideParams p) {
   const NetDev& nd = p.net;
   const size_t total = (size_t)p.B * nd.SD;
@@ -665,43 +736,272 @@ __global__ void init_act_kernel(WideParams p) {
 }
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+inline int pad8w(int v) { return (v + 7) & ~7; }
 
 struct WideLayout {
   size_t wb_off[kMaxL + 1], act_off, gb_off, g32_off, part_off, total;
-  int poff[kMaxL + 1], a_pitch, g_pitch, n_part;
+  int poff[kMaxL + 1], a_pitch, g_pitch, n_part, Bpad, S, cg;
+  size_t act_slot, gb_slot;                  // bytes of one ring slot
 };
 
+struct WideKnobs {
+  int cg, slots, ctas, nospec;
+#ifdef MCPC_DEBUG_BUILD
+  int skip_epi;
+#endif
+};
+
+// Test hooks (documented in DESIGN.md): MCPC_WIDE_CG = 1 | 2 (CTA pairs off / on), MCPC_WIDE_SLOTS (steps per weight-gradient
+// launch), MCPC_WIDE_CTAS (few persistent CTAs => many tiles per CTA), MCPC_TC_NOSPEC (generic update instantiation).
+WideKnobs wide_knobs() {
+  WideKnobs k{};
+  k.cg = 2;
+  if (const char* env = getenv("MCPC_WIDE_CG")) k.cg = (atoi(env) == 1) ? 1 : 2;
+  k.slots = 0;
+  if (const char* env = getenv("MCPC_WIDE_SLOTS")) k.slots = atoi(env);
+  k.ctas = 0;
+  if (const char* env = getenv("MCPC_WIDE_CTAS")) k.ctas = atoi(env);
+  k.nospec = getenv("MCPC_TC_NOSPEC") != nullptr ? 1 : 0;
+#ifdef MCPC_DEBUG_BUILD
+  k.skip_epi = getenv("MCPC_WIDE_SKIP_EPI") != nullptr ? 1 : 0;
+#endif
+  return k;
+}
+
 int wide_layout(const NetDev& nd, int B, int n_steps, WideLayout* lay) {
-  for (int l = 0; l < nd.L; ++l)
-    if (nd.dims[l] % 16 != 0) {
-      set_error("bf16 streaming path: layer widths must be multiples of 16 (got %d)", nd.dims[l]);
-      return MCPC_ERR_UNSUPPORTED;
-    }
-  if (nd.d_out % 16 != 0) {
-    set_error("bf16 streaming path: output width must be a multiple of 16 (got %d)", nd.d_out);
-    return MCPC_ERR_UNSUPPORTED;
-  }
+  const WideKnobs kn = wide_knobs();
   int f_off[kMaxL + 1];
   save_layout_bf16(nd, lay->poff, &lay->g_pitch, f_off, &lay->a_pitch);
+  lay->cg = kn.cg;
+  lay->Bpad = (B + 63) & ~63;
+  {
+    // the epilogues index global memory with 32-bit element offsets
+    const size_t widest = (size_t)(lay->g_pitch > nd.SD ? lay->g_pitch : nd.SD);
+    if ((size_t)(lay->Bpad + kTN) * widest >= ((size_t)1 << 31)) {
+      set_error("bf16 streaming path: B * row width = %zu elements exceeds the 2^31 the kernels index; shard the batch",
+                (size_t)B * widest);
+      return MCPC_ERR_UNSUPPORTED;
+    }
+  }
   size_t o = 0;
   const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
   for (int l = 1; l < n_lin; ++l) {
     lay->wb_off[l] = o;
-    o += align256((size_t)(l == nd.L ? nd.d_out : nd.dims[l]) * nd.dims[l - 1] * 2);
+    o += align256((size_t)(l == nd.L ? nd.d_out : nd.dims[l]) * pad8w(nd.dims[l - 1]) * 2);
   }
+  // ring of S slots of the bf16 operands: S steps of the accumulate window are contracted by ONE weight-gradient launch.
+  // Default 4: with C5's 2048 chains both operands of a layer (134 MB) stay L2-resident during the launch.
+  lay->act_slot = (size_t)lay->Bpad * lay->a_pitch * 2;
+  lay->gb_slot = (size_t)lay->Bpad * lay->g_pitch * 2;
+  int S = 4;
+  const size_t budget = (size_t)4 << 30;
+  while (S > 1 && (size_t)S * (lay->act_slot + lay->gb_slot) > budget) --S;
+  if (kn.slots >= 1 && kn.slots <= 64) S = kn.slots;
+  if (S > n_steps) S = n_steps;
+  lay->S = S;
   lay->act_off = o;
-  o += align256((size_t)B * lay->a_pitch * 2 + 4096);
+  o += align256((size_t)S * lay->act_slot + 65536);
   lay->gb_off = o;
-  o += align256((size_t)B * lay->g_pitch * 2 + 4096);
+  o += align256((size_t)S * lay->gb_slot + 65536);
   lay->g32_off = o;
   o += align256((size_t)B * nd.SD * 4);
-  const int mt = (B + 127) / 128;
+  const int ntn = (B + kTN - 1) / kTN;
   int n_part = 0;
-  for (int l = 0; l < n_lin; ++l) n_part += mt * (((l == nd.L ? nd.d_out : nd.dims[l]) + kBN - 1) / kBN);
+  for (int l = 0; l < n_lin; ++l) {
+    const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
+    n_part += ((d_o + kTM * lay->cg - 1) / (kTM * lay->cg)) * ntn * lay->cg * kEpiWarps;
+  }
   lay->n_part = n_part;
   lay->part_off = o;
   o += align256((size_t)n_steps * n_part * 2 * sizeof(float));
   lay->total = o + 512;
+  return MCPC_OK;
+}
+
+template <int KIND, int SPEC, int CG>
+int launch_wide(const WideParams& p, const StepArgs& st, const WideMaps& mp, int n_tiles, int max_ctas, size_t smem_bytes,
+                cudaStream_t stream) {
+  if (n_tiles <= 0) return MCPC_OK;
+  cudaLaunchConfig_t cfg{};
+  int grid = n_tiles * CG < max_ctas ? n_tiles * CG : max_ctas;
+  if (CG == 2) grid &= ~1;
+  if (grid < CG) grid = CG;
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MCPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, wide_kernel<KIND, SPEC, CG>, p, st, mp));
+  count_launch();
+  return MCPC_OK;
+}
+
+template <int CG>
+int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& p, const WideLayout& lay, const WideKnobs& kn,
+             const __nv_bfloat16* const* Wb, cudaStream_t stream) {
+  const int B = p.B;
+  const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
+  // tile tables: (128 * CG) units x 256 chains per (pair) tile
+  const int ntn = (B + kTN - 1) / kTN;
+  int t = 0;
+  for (int l = 0; l <= nd.L; ++l) {
+    p.tP_first[l] = t;
+    if (l < nd.L || nd.d_out > 0) t += (((l == nd.L ? nd.d_out : nd.dims[l]) + kTM * CG - 1) / (kTM * CG)) * ntn;
+  }
+  p.tP_first[nd.L + 1] = t;
+  const int n_predict = t;
+  t = 0;
+  for (int l = 0; l < nd.L; ++l) {
+    p.tU_first[l] = t;
+    t += ((nd.dims[l] + kTM * CG - 1) / (kTM * CG)) * ntn;
+  }
+  p.tU_first[nd.L] = t;
+  const int n_update = t;
+  t = 0;
+  bool any_grad = false;
+  p.tW_first[0] = p.tW_first[1] = 0;
+  for (int l = 1; l <= nd.L; ++l) {
+    p.tW_first[l] = t;
+    const bool is_out = (l == nd.L);
+    if (is_out && (nd.d_out == 0 || !nd.top_has_grad)) continue;
+    if (p.gW[l] == nullptr) continue;
+    const int d_o = is_out ? nd.d_out : nd.dims[l];
+    t += ((nd.dims[l - 1] + kTM * CG - 1) / (kTM * CG)) * ((d_o + kTN - 1) / kTN);     // M = input units, N = output units
+  }
+  p.tW_first[nd.L + 1] = t;
+  const int n_wgrad = t;
+  for (int l = 0; l <= nd.L; ++l) any_grad = any_grad || p.gW[l] != nullptr || p.gb[l] != nullptr;
+  if (p.n_part != n_predict * CG * kEpiWarps) {
+    set_error("internal: partial-slot count mismatch (%d vs %d)", p.n_part, n_predict * CG * kEpiWarps);
+    return MCPC_ERR_INVALID;
+  }
+
+  bool any_traj = io->traj_out != nullptr;
+  for (int l = 0; l < nd.L; ++l) any_traj = any_traj || io->traj_x[l] != nullptr;
+  const int traj_every = any_traj ? (o->traj_every > 0 ? o->traj_every : 1) : 0;
+
+  // tensor maps: one per layer block (base offset = the block's first column) so TMA zero-fills past its extent;
+  // the row (chain) axis spans all S ring slots
+  WideMaps mp;
+  bool mn3 = (nd.d_out % 64 == 0);
+  for (int l = 0; l < nd.L; ++l) mn3 = mn3 && (nd.dims[l] % 64 == 0);
+  p.mn3 = mn3 ? 1 : 0;
+  const uint64_t rows = (uint64_t)lay.S * lay.Bpad;
+  constexpr int kBRows = kTN / CG;
+  int rc = MCPC_OK;
+  for (int l = 0; l < nd.L; ++l) {
+    rc = make_tmap_bf16(&mp.act_k[l], p.act + p.poff[l], nd.dims[l], rows, p.a_pitch, 64, kBRows);             // predict B
+    if (rc == MCPC_OK)
+      rc = mn3 ? make_tmap_bf16_mn3(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], rows, p.a_pitch, 64, kTM / 64)  // wgrad A
+               : make_tmap_bf16(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], rows, p.a_pitch, 64, 64);
+    if (rc != MCPC_OK) return rc;
+  }
+  for (int l = 0; l < n_lin; ++l) {
+    const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
+    rc = make_tmap_bf16(&mp.gb_k[l], p.Gb + p.poff[l], d_o, rows, p.g_pitch, 64, kBRows);                       // update B
+    if (rc == MCPC_OK)
+      rc = mn3 ? make_tmap_bf16_mn3(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, rows, p.g_pitch, 64, kBRows / 64)        // wgrad B
+               : make_tmap_bf16(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, rows, p.g_pitch, 64, 64);
+    if (rc == MCPC_OK && l >= 1) {
+      const int d_i = nd.dims[l - 1], wp = pad8w(d_i);
+      rc = make_tmap_bf16(&mp.w_k[l], Wb[l], d_i, d_o, wp, 64, kTM);                                             // predict A
+      if (rc == MCPC_OK)
+        rc = mn3 ? make_tmap_bf16_mn3(&mp.w_mn[l], Wb[l], d_i, d_o, wp, 64, kTM / 64)                            // update A
+                 : make_tmap_bf16(&mp.w_mn[l], Wb[l], d_i, d_o, wp, 64, 64);
+    }
+    if (rc != MCPC_OK) return rc;
+  }
+  const size_t smem_g = (size_t)n_stages(CG) * stage_bytes(CG) + 1024;
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 1, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_WGRAD, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  int n_sm = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (CG == 2) {
+      // persistent pairs: never more CTAs than clusters that can be resident at once (a GPC with an odd number of free
+      // SMs leaves one unpaired)
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(n_sm & ~1));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem_g;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, wide_kernel<KIND_UPDATE, 0, CG>, &cfg) == cudaSuccess && n_clusters > 0 &&
+          2 * n_clusters < n_sm)
+        n_sm = 2 * n_clusters;
+    }
+    if (kn.ctas >= 1 && kn.ctas <= n_sm) n_sm = kn.ctas;          // testing hook: few persistent CTAs => many tiles per CTA
+    if (CG == 2 && n_sm < 2) n_sm = 2;
+  }
+
+  // rows B..Bpad of every ring slot enter the weight-gradient contraction: they must be zero in both operands
+  if (lay.Bpad > B) {
+    for (int s = 0; s < lay.S; ++s) {
+      MCPC_CUDA_CHECK(cudaMemsetAsync(p.act + ((size_t)s * lay.Bpad + B) * p.a_pitch, 0, (size_t)(lay.Bpad - B) * p.a_pitch * 2, stream));
+      MCPC_CUDA_CHECK(cudaMemsetAsync(p.Gb + ((size_t)s * lay.Bpad + B) * p.g_pitch, 0, (size_t)(lay.Bpad - B) * p.g_pitch * 2, stream));
+    }
+  }
+  init_act_kernel<<<1184, 256, 0, stream>>>(p);
+  count_launch();
+  double b1p = pow(o->adam_beta1, (double)o->adam_step0), b2p = pow(o->adam_beta2, (double)o->adam_step0);
+  bool spec_update = !any_traj && o->update_x && o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX &&
+                     (o->chain_offset & 3) == 0;                       // what wide_kernel<KIND_UPDATE, 1> assumes
+  for (int l = 0; l < nd.L; ++l) spec_update = spec_update && io->x_grad[l] == nullptr;
+  if (kn.nospec) spec_update = false;                                 // testing hook: the generic instantiation
+  int used = 0;                                                       // accumulate steps waiting in ring slots [0, used)
+  for (int ts = 0; ts < o->n_steps; ++ts) {
+    StepArgs st{};
+    st.ts = ts;
+    st.t_abs = o->t_begin + ts;
+    st.do_traj = (traj_every > 0 && ts % traj_every == 0) ? 1 : 0;
+    st.rec = st.do_traj ? ts / traj_every : 0;
+    st.last = (ts == o->n_steps - 1) ? 1 : 0;
+    if (o->optimizer == MCPC_OPT_ADAM && o->update_x) {
+      b1p *= o->adam_beta1;
+      b2p *= o->adam_beta2;
+      st.step_size = (float)(o->lr / (1.0 - b1p));
+      st.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
+    }
+    const bool acc = any_grad && ts >= o->save_begin && ts < o->save_end;
+    st.acc = acc ? 1 : 0;                  // the predict epilogue adds the bias gradients (column sums of G) on these steps
+    st.slot = used;
+    rc = launch_wide<KIND_PREDICT, 0, CG>(p, st, mp, n_predict, n_sm, smem_g, stream);
+    if (rc != MCPC_OK) return rc;
+    // the weight update reads G (this step's errors) and act(x) of the state BEFORE the update: it runs between the two,
+    // once the ring is full or the window ends
+    if (acc) {
+      ++used;
+      const bool window_ends = (ts + 1 >= o->save_end) || (ts + 1 >= o->n_steps);
+      if (used == lay.S || window_ends) {
+        st.k_rows = used * lay.Bpad;
+        rc = launch_wide<KIND_WGRAD, 0, CG>(p, st, mp, n_wgrad, n_sm, smem_g, stream);
+        if (rc != MCPC_OK) return rc;
+        used = 0;
+      }
+    }
+    st.slot_next = used;
+    if (spec_update) rc = launch_wide<KIND_UPDATE, 1, CG>(p, st, mp, n_update, n_sm, smem_g, stream);
+    else rc = launch_wide<KIND_UPDATE, 0, CG>(p, st, mp, n_update, n_sm, smem_g, stream);
+    if (rc != MCPC_OK) return rc;
+  }
+  MCPC_CUDA_CHECK(cudaGetLastError());
+  if (io->energy != nullptr || io->loss != nullptr) return launch_reduce_partials(p.partials, o->n_steps, p.n_part, io->energy, io->loss, stream);
   return MCPC_OK;
 }
 
@@ -725,6 +1025,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
     set_error("bf16 streaming path accumulates the weight update itself (McpcIO.gW/gb); save_g/save_f are not used");
     return MCPC_ERR_INVALID;
   }
+  const WideKnobs kn = wide_knobs();
   WideLayout lay;
   int rc = wide_layout(nd, B, o->n_steps, &lay);
   if (rc != MCPC_OK) return rc;
@@ -736,7 +1037,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   WideParams p{};
   p.net = nd;
   p.B = B;
-  p.mt = (B + 127) / 128;
+  p.Bpad = lay.Bpad;
   const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
   for (int l = 0; l <= nd.L; ++l) {
     p.poff[l] = lay.poff[l];
@@ -751,12 +1052,14 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.G32 = reinterpret_cast<float*>(wsb + lay.g32_off);
   p.partials = reinterpret_cast<float*>(wsb + lay.part_off);
   p.n_part = lay.n_part;
+  const __nv_bfloat16* Wb[kMaxL + 1] = {};
   for (int l = 1; l < n_lin; ++l) {
     __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(wsb + lay.wb_off[l]);
-    const size_t n = (size_t)(l == nd.L ? nd.d_out : nd.dims[l]) * nd.dims[l - 1];
-    to_bf16_kernel<<<(int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184), 256, 0, stream>>>(io->W[l], wb, n);
+    const int rows = (l == nd.L) ? nd.d_out : nd.dims[l], cols = nd.dims[l - 1];
+    const size_t n = (size_t)rows * pad8w(cols);
+    to_bf16_kernel<<<(int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184), 256, 0, stream>>>(io->W[l], wb, rows, cols, pad8w(cols));
     count_launch();
-    p.Wb[l] = wb;
+    Wb[l] = wb;
   }
   for (int l = 0; l < nd.L; ++l) {
     p.x[l] = io->x[l];
@@ -779,145 +1082,10 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.noise_scale = (float)o->noise_scale;
   p.seed = o->seed;
   p.chain_offset = o->chain_offset;
-  // tile tables (128 chains / output units x kBN columns per tile)
-  int t = 0;
-  for (int l = 0; l <= nd.L; ++l) {
-    p.tP_first[l] = t;
-    if (l < nd.L || nd.d_out > 0) t += p.mt * (((l == nd.L ? nd.d_out : nd.dims[l]) + kBN - 1) / kBN);
-  }
-  p.tP_first[nd.L + 1] = t;
-  const int n_predict = t;
-  t = 0;
-  for (int l = 0; l < nd.L; ++l) {
-    p.tU_first[l] = t;
-    t += p.mt * ((nd.dims[l] + kBN - 1) / kBN);
-  }
-  p.tU_first[nd.L] = t;
-  const int n_update = t;
-  t = 0;
-  bool any_grad = false;
-  p.tW_first[0] = p.tW_first[1] = 0;
-  for (int l = 1; l <= nd.L; ++l) {
-    p.tW_first[l] = t;
-    const bool is_out = (l == nd.L);
-    if (is_out && (nd.d_out == 0 || !nd.top_has_grad)) continue;
-    if (p.gW[l] == nullptr) continue;
-    const int d_o = is_out ? nd.d_out : nd.dims[l];
-    t += ((d_o + 127) / 128) * ((nd.dims[l - 1] + kBN - 1) / kBN);
-  }
-  p.tW_first[nd.L + 1] = t;
-  const int n_wgrad = t;
-  for (int l = 0; l <= nd.L; ++l) any_grad = any_grad || p.gW[l] != nullptr || p.gb[l] != nullptr;
-  if (p.n_part != n_predict) {
-    set_error("internal: partial-slot count mismatch (%d vs %d)", p.n_part, n_predict);
-    return MCPC_ERR_INVALID;
-  }
-
-  bool any_traj = io->traj_out != nullptr;
-  for (int l = 0; l < nd.L; ++l) any_traj = any_traj || io->traj_x[l] != nullptr;
-  const int traj_every = any_traj ? (o->traj_every > 0 ? o->traj_every : 1) : 0;
-
-  // tensor maps: one per layer block (base offset = the block's first column) so TMA zero-fills past its extent
-  WideMaps mp;
-  bool mn3 = (nd.d_out % 64 == 0);
-  for (int l = 0; l < nd.L; ++l) mn3 = mn3 && (nd.dims[l] % 64 == 0);
-  p.mn3 = mn3 ? 1 : 0;
-  p.l2_prefetch = 0;     // measured on C5: 0.98 ms/step without, 1.09-1.14 with 4/8/16 stages of L2 prefetch (extra TMA work, no gain)
-  if (const char* env = getenv("MCPC_WIDE_L2PF")) p.l2_prefetch = atoi(env);
-  p.skip_epilogue = getenv("MCPC_WIDE_SKIP_EPI") != nullptr ? 1 : 0;
-  for (int l = 0; l < nd.L; ++l) {
-    rc = make_tmap_bf16(&mp.act_k[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, 128);
-    if (rc == MCPC_OK)
-      rc = mn3 ? make_tmap_bf16_mn3(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, kBN / 64)   // wgrad B operand
-               : make_tmap_bf16(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], B, p.a_pitch, 64, 64);
-    if (rc != MCPC_OK) return rc;
-  }
-  for (int l = 0; l < n_lin; ++l) {
-    const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
-    rc = make_tmap_bf16(&mp.gb_k[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 128);
-    if (rc == MCPC_OK)
-      rc = mn3 ? make_tmap_bf16_mn3(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 2)                   // wgrad A operand
-               : make_tmap_bf16(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, B, p.g_pitch, 64, 64);
-    if (rc == MCPC_OK && l >= 1) rc = make_tmap_bf16(&mp.w_k[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, 256);
-    if (rc == MCPC_OK && l >= 1)
-      rc = mn3 ? make_tmap_bf16_mn3(&mp.w_mn[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, kBN / 64)       // update B operand
-               : make_tmap_bf16(&mp.w_mn[l], p.Wb[l], nd.dims[l - 1], d_o, nd.dims[l - 1], 64, 64);
-    if (rc != MCPC_OK) return rc;
-  }
-  const size_t smem_g = (size_t)kWS * (kABytes + kBBytes) + kTransBytes + 1024;
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_WGRAD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  int n_sm = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (const char* env = getenv("MCPC_WIDE_CTAS")) {        // testing hook: few persistent CTAs => many tiles per CTA
-      const int v = atoi(env);
-      if (v >= 1 && v <= n_sm) n_sm = v;
-    }
-  }
-
-  const bool timing = getenv("MCPC_WIDE_TIMING") != nullptr;      // debug only: allocates + synchronises
-  if (timing) {
-    cudaMalloc(&p.dbg, 32 * sizeof(long long));
-    cudaMemsetAsync(p.dbg, 0, 32 * sizeof(long long), stream);
-  }
-  init_act_kernel<<<1184, 256, 0, stream>>>(p);
-  count_launch();
-  double b1p = pow(o->adam_beta1, (double)o->adam_step0), b2p = pow(o->adam_beta2, (double)o->adam_step0);
-  bool spec_update = !any_traj && o->update_x && o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX &&
-                     (o->chain_offset & 3) == 0;                       // what wide_kernel<KIND_UPDATE, 1> assumes
-  for (int l = 0; l < nd.L; ++l) spec_update = spec_update && io->x_grad[l] == nullptr;
-  if (getenv("MCPC_TC_NOSPEC") != nullptr) spec_update = false;       // testing hook: the generic instantiation
-  for (int ts = 0; ts < o->n_steps; ++ts) {
-    StepArgs st{};
-    st.ts = ts;
-    st.t_abs = o->t_begin + ts;
-    st.do_traj = (traj_every > 0 && ts % traj_every == 0) ? 1 : 0;
-    st.rec = st.do_traj ? ts / traj_every : 0;
-    st.last = (ts == o->n_steps - 1) ? 1 : 0;
-    if (o->optimizer == MCPC_OPT_ADAM && o->update_x) {
-      b1p *= o->adam_beta1;
-      b2p *= o->adam_beta2;
-      st.step_size = (float)(o->lr / (1.0 - b1p));
-      st.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2p));
-    }
-    const bool acc = any_grad && ts >= o->save_begin && ts < o->save_end;
-    st.acc = acc ? 1 : 0;                  // the predict epilogue adds the bias gradients (column sums of G) on these steps
-    if (n_predict > 0) {
-      wide_kernel<KIND_PREDICT, 0><<<n_predict < n_sm ? n_predict : n_sm, 320, smem_g, stream>>>(p, st, mp);
-      count_launch();
-    }
-    // the weight update reads G (this step's errors) and act(x) of the state BEFORE the update: it runs between the two
-    if (acc) {
-      if (n_wgrad > 0) {
-        wide_kernel<KIND_WGRAD, 0><<<n_wgrad < n_sm ? n_wgrad : n_sm, 320, smem_g, stream>>>(p, st, mp);
-        count_launch();
-      }
-    }
-    if (spec_update)
-      wide_kernel<KIND_UPDATE, 1><<<n_update < n_sm ? n_update : n_sm, 64 + 32 * epi_warps(KIND_UPDATE), smem_g, stream>>>(p, st, mp);
-    else
-      wide_kernel<KIND_UPDATE, 0><<<n_update < n_sm ? n_update : n_sm, 64 + 32 * epi_warps(KIND_UPDATE), smem_g, stream>>>(p, st, mp);
-    count_launch();
-  }
-  MCPC_CUDA_CHECK(cudaGetLastError());
-  if (timing) {
-    long long h[32];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    cudaFree(p.dbg);
-    const char* names[3] = {"predict", "update", "wgrad"};
-    for (int k = 0; k < 3; ++k)
-      fprintf(stderr, "[wide timing] %s (CTA 0, last launch): producer wait-empty %lld, issue %lld, (%lld) cyc over %lld stages; "
-                      "mma wait-acc %lld, wait-full %lld, total %lld cyc\n", names[k], h[k * 8], h[k * 8 + 1], h[k * 8 + 2], h[k * 8 + 3],
-              h[k * 8 + 4], h[k * 8 + 5], h[k * 8 + 6]);
-  }
-  if (io->energy != nullptr || io->loss != nullptr) return launch_reduce_partials(p.partials, o->n_steps, p.n_part, io->energy, io->loss, stream);
-  return MCPC_OK;
+#ifdef MCPC_DEBUG_BUILD
+  p.skip_epilogue = kn.skip_epi;
+#endif
+  return lay.cg == 2 ? run_wide<2>(nd, io, o, p, lay, kn, Wb, stream) : run_wide<1>(nd, io, o, p, lay, kn, Wb, stream);
 }
 
 }  // namespace mcpc

@@ -56,7 +56,8 @@ class InferCall:
 
 
 _net_cache = {}
-_ENV_KNOBS = ("MCPC_FORCE_STREAMING", "MCPC_TC_ROWS", "MCPC_ROWS", "MCPC_WIDE_CTAS", "MCPC_TC_NOSPEC")
+_ENV_KNOBS = ("MCPC_FORCE_STREAMING", "MCPC_TC_ROWS", "MCPC_ROWS", "MCPC_WIDE_CTAS", "MCPC_TC_NOSPEC", "MCPC_WIDE_CG",
+              "MCPC_WIDE_SLOTS")
 
 
 def _env_key():
