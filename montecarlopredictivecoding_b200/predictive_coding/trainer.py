@@ -865,7 +865,6 @@ class PCTrainer(object):
                 (self._early_stop_condition.strip() != "False" and self._update_p_at_early_stop)
             save_g = save_f = None
             if need_grads:
-                flat, gW, gb = self._ensure_flat_grads(netp, zero=self._is_zero_grad_step(t))
                 g_w, f_w, s_dtype = self._save_layout(netp, top)
                 save_g = self._buffer("save_g", (1, B, g_w), s_dtype, device)
                 save_f = self._buffer("save_f", (1, B, f_w), s_dtype, device)
@@ -881,10 +880,8 @@ class PCTrainer(object):
                 precision=self._precision)
             eng.infer(call)
             n_launch += 1
-            if need_grads:
-                eng.weight_grad(netp, top, self._energy_coefficient, B, 1, save_g, save_f, inputs_dev, gW, gb,
-                                self._precision)
-                n_launch += 1
+            # early stop is decided from this step's readouts BEFORE the parameter gradients of the step are
+            # accumulated: it takes part in the zero_grad rule (pc_trainer.py:844-859)
             early_stop = False
             if self._early_stop_condition.strip() != "False" or is_dynamic_x_lr:
                 e_t, l_t = float(energy[t]), float(loss[t])
@@ -893,6 +890,13 @@ class PCTrainer(object):
                 early_stop = bool(eval(self._early_stop_condition, {}, {
                     "t": t, "overall": overall, "loss": l_t if loss_fn is not None else None, "energy": e_t,
                     "overalls": overalls, "self": self}))
+            if need_grads:
+                zero = self._is_zero_grad_step(t) or \
+                    (early_stop and self._update_p_at_early_stop and t not in self._acc_set)
+                flat, gW, gb = self._ensure_flat_grads(netp, zero=zero)
+                eng.weight_grad(netp, top, self._energy_coefficient, B, 1, save_g, save_f, inputs_dev, gW, gb,
+                                self._precision)
+                n_launch += 1
             if cb_bwd is not None:
                 cb_bwd(t, **cb_bwd_kwargs)
             if t in self._update_x_set:

@@ -111,7 +111,8 @@ def c4(prec, B=1024, T=250):
             "images_per_s": B / s}
 
 
-def c5(prec, B=2048, T=20, width=4096, L=4):
+def c5(prec, B=2048, T=None, width=4096, L=4):
+    T = T or int(os.environ.get("MCPC_C5_T", "20"))
     torch.manual_seed(0)
     mods, prev = [], width
     for _ in range(L):

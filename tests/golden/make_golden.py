@@ -124,7 +124,7 @@ def run_call(model, trainer, spec, call, inputs, target, out, prefix):
         if lin.bias is not None:
             out[f"{prefix}b{lin_i}_before"] = lin.bias.detach().numpy().copy()
     res = trainer.train_on_batch(**kwargs)
-    T = trainer.get_T()
+    T = len(res["energy"])          # < trainer.get_T() when early_stop_condition fired (pc_trainer.py:979-981)
     L = len(pclayers(model))
     out[f"{prefix}energy"] = np.array(res["energy"], dtype=np.float64)
     out[f"{prefix}loss"] = np.array(res["loss"], dtype=np.float64)
@@ -157,6 +157,8 @@ def make_trainer(model, tr):
         kw["accumulate_p_at"] = tr["accumulate_p_at"]
     if "energy_coefficient" in tr:
         kw["energy_coefficient"] = tr["energy_coefficient"]
+    if "early_stop_condition" in tr:
+        kw["early_stop_condition"] = tr["early_stop_condition"]
     return pc.PCTrainer(model, **kw)
 
 
@@ -294,6 +296,16 @@ CASES = {
             dict(trainer=dict(T=6, opt_x="adam", lr_x=0.1), sample_x=True),
             dict(trainer=dict(T=6, opt_x="adam", lr_x=0.1), trainer_of=0, sample_x=False, reset_opt_x=False),
             dict(trainer=dict(T=6, opt_x="adam", lr_x=0.1), trainer_of=0, sample_x=True, rows=5),
+        ]),
+    # early stop (pc_trainer.py:844-859, 904-914, 979-981): the p-step of the stopping step uses ONLY that step's gradient
+    # (zero_grad fires because the step is outside accumulate_p_at); the second call checks nothing is left over
+    "early_stop_p_update": dict(
+        dims=[4, 8], d_out=6, act="tanh", loss="gauss", var=1.0, B=5, sampler="normal", target="normal",
+        calls=[
+            dict(trainer=dict(T=6, opt_x="sgd", lr_x=0.05, update_p_at="last", opt_p="sgd", opt_p_kwargs={"lr": 0.05},
+                              early_stop_condition="t == 3"), sample_x=True),
+            dict(trainer=dict(T=6, opt_x="sgd", lr_x=0.05, update_p_at="last", opt_p="sgd", opt_p_kwargs={"lr": 0.05},
+                              early_stop_condition="t == 3"), trainer_of=0, sample_x=True),
         ]),
 }
 

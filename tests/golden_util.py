@@ -90,6 +90,10 @@ class GoldenCase:
         gb = [self.z.get(f"c{ci}_gb{i}") if f"c{ci}_gb{i}" in self.z else None for i in range(self.n_lin)]
         return gW, gb
 
+    def steps_run(self, ci):
+        """Steps the reference actually ran (< T when its early_stop_condition fired, pc_trainer.py:979-981)."""
+        return len(self.z[f"c{ci}_energy"])
+
     def step_lists(self, ci):
         tr = self.calls[ci]["trainer"]
         T = tr["T"]
@@ -104,8 +108,16 @@ class GoldenCase:
             if v == "never":
                 return []
             return list(v)
-        return (expand(tr.get("update_x_at", "all")), expand(tr.get("update_p_at", "never")),
-                expand(tr.get("accumulate_p_at", "never")))
+        upd_x, upd_p, acc = (expand(tr.get("update_x_at", "all")), expand(tr.get("update_p_at", "never")),
+                             expand(tr.get("accumulate_p_at", "never")))
+        n_run = self.steps_run(ci)
+        if n_run < T:
+            # the stopping step takes a p-update (update_p_at_early_stop=True, pc_trainer.py:853,904): for the oracle,
+            # which has no eval()'d condition, that is the schedule truncated at n_run with a p-step on its last step
+            upd_x = [t for t in upd_x if t < n_run]
+            upd_p = sorted(set([t for t in upd_p if t < n_run] + [n_run - 1]))
+            acc = [t for t in acc if t < n_run]
+        return upd_x, upd_p, acc
 
 
 def rel_err(a, b):

@@ -157,13 +157,13 @@ def test_c5_shape_vs_bf16_oracle(width, B, mixing, sampling, cg, monkeypatch):
 
 def test_c5_shape_bound_vs_fp32_oracle():
     """The stated bf16 bound of the streaming path against the plain fp32 oracle (no operand rounding) over the
-    benchmark's T=100 Langevin steps (C5: lr 0.01, var 2, dW over all steps) at 4 x 1024: latents 2e-2, per-step
-    energy / loss 5e-3, weight gradients 2e-2 (max-norm relative)."""
+    benchmark's T=100 Langevin steps (C5: lr 0.01, var 2, dW over all steps) at 4 x 1024: latents 5e-3, per-step
+    energy / loss 1e-4, weight gradients 5e-3 (max-norm relative; measured r02: 1.1e-3 / 1.1e-5 / 1.3e-3)."""
     errs = _run_case([1024] * 4, 1024, "tanh", "gauss", "sgd", B=256, mixing=0, sampling=100, lr=0.01, wide_init=True,
                      bf16_oracle=False, want_outputs=False)
     print("C5 bf16-vs-fp32 bound, T=100:", {k: f"{v:.2e}" for k, v in errs.items()})
     for k, v in errs.items():
-        tol = 5e-3 if k in ("energy", "loss") else 2e-2
+        tol = 1e-4 if k in ("energy", "loss") else 5e-3
         assert v < tol, (k, v)
 
 

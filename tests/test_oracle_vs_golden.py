@@ -48,13 +48,13 @@ def test_oracle_matches_reference(name):
         rows = gc.rows(ci)
         carry = None if call.get("reset_opt_x", True) or call.get("sample_x", True) else adam_prev.get(call.get("trainer_of", ci))
         res = orc.train_on_batch(
-            net, gc.x0(ci), gc.inputs[:rows], gc.target[:rows], tr["T"], update_p_at=upd_p, accumulate_p_at=acc,
+            net, gc.x0(ci), gc.inputs[:rows], gc.target[:rows], gc.steps_run(ci), update_p_at=upd_p, accumulate_p_at=acc,
             p_step=_p_stepper(net, call), grads_in=grads_prev, optimizer=tr["opt_x"], lr=tr["lr_x"],
             noise=gc.noise(ci), update_x_at=upd_x, energy_coefficient=tr.get("energy_coefficient", 1.0),
             adam_state_in=carry)
         adam_prev[call.get("trainer_of", ci)] = res.adam
         for l in range(gc.L):
-            got = np.stack([res.traj_xs[t][l] for t in range(tr["T"])])
+            got = np.stack([res.traj_xs[t][l] for t in range(gc.steps_run(ci))])
             assert rel_err(got, gc.traj(ci, l)) < TOL_X, (name, ci, l)
             assert rel_err(res.xs[l], gc.x_final(ci)[l]) < TOL_X, (name, ci, l, "final")
         assert rel_err(np.stack(res.traj_out), gc.z[f"c{ci}_outputs"]) < TOL_X

@@ -55,6 +55,8 @@ def make_trainer(model, tr):
         kw["accumulate_p_at"] = tr["accumulate_p_at"]
     if "energy_coefficient" in tr:
         kw["energy_coefficient"] = tr["energy_coefficient"]
+    if "early_stop_condition" in tr:
+        kw["early_stop_condition"] = tr["early_stop_condition"]
     return pc.PCTrainer(model, **kw)
 
 
@@ -77,7 +79,7 @@ def replay(name, device, engine_factory=None, precision="fp32", tol_x=1e-5, tol_
         if engine_factory is not None:
             trainer._engine = engine_factory()
         trainer.set_precision(precision)
-        T = tr["T"]
+        T = len(gc.z[f"c{ci}_energy"])        # < tr["T"] when the reference stopped early
         inputs, target = inputs_all[:gc.rows(ci)], target_all[:gc.rows(ci)]
         if teacher_force and ci > 0:
             # start every call from the reference's own state (latents and parameters) so that the bound
