@@ -167,6 +167,37 @@ int mcpc_marginal_ll_workspace_bytes(int32_t N, int32_t S, int32_t D, size_t* by
 int mcpc_marginal_ll_bernoulli(const float* logits, int32_t S, const float* data, int32_t N, int32_t D, float clamp_abs,
                                void* workspace, size_t workspace_bytes, double* ml_out, float* row_ll, void* stream);
 
+/* SURVEY 8(f) N2 -- running per-element mean / variance of a recorded trajectory, on the device.  Replaces the host-side
+ * reductions over per-step `.cpu()` copies of the reference (pc_trainer.py:772-774 feeding utils/model.py:143-149
+ * `temp.mean(0)` and figure_2.py:75-79).  traj: [n_rec, n_elems] fp32 ring as written through McpcIO.traj_x / traj_out;
+ * mean, m2: [n_elems] fp32 running accumulators (Welford: m2 = sum of squared deviations); count_before = samples
+ * already folded in (0: the accumulators are initialised here).  After the call they hold count_before + n_rec samples;
+ * the unbiased variance is m2 / (count - 1). */
+int mcpc_traj_stats_update(const float* traj, int32_t n_rec, uint64_t n_elems, uint64_t count_before, float* mean, float* m2,
+                           void* stream);
+
+/* SURVEY 8(f) N3 -- the parameter update of pc_trainer.py:904-914 in one launch over all W / b tensors:
+ *   grad *= inv_norm (= 1 / (len(accumulate_p_at) * batch), written back like the reference's `param.grad = param.grad / ...`),
+ *   then optim.SGD (momentum / dampening / nesterov / weight_decay) or optim.Adam (betas, eps, L2 weight_decay) exactly as
+ *   torch's single-tensor implementations compute them, IN PLACE on the optimizer's own state tensors:
+ *   state1 = momentum_buffer (SGD, NULL without momentum) or exp_avg (Adam); state2 = exp_avg_sq (Adam).
+ *   first_step: SGD momentum buffers are initialised with the gradient (torch clones it on the first step);
+ *   step: 1-based index of this Adam step (bias corrections). */
+#define MCPC_MAX_PTENSORS (2 * (MCPC_MAX_LAYERS + 1))
+typedef struct McpcPStep {
+  int32_t kind;                           /* MCPC_OPT_SGD | MCPC_OPT_ADAM */
+  int32_t n_tensors;
+  float* param[MCPC_MAX_PTENSORS];
+  float* grad[MCPC_MAX_PTENSORS];
+  float* state1[MCPC_MAX_PTENSORS];
+  float* state2[MCPC_MAX_PTENSORS];
+  uint64_t numel[MCPC_MAX_PTENSORS];
+  double inv_norm;
+  double lr, weight_decay, momentum, dampening, beta1, beta2, eps;
+  int32_t nesterov, first_step, step;
+} McpcPStep;
+int mcpc_p_step(const McpcPStep* step, void* stream);
+
 /* Validation only: known-answer test of the tcgen05/TMEM/bulk-copy primitives of the bf16 path.
  * Wt [128, Kin], Bx [N, Kin], G [N, 128] -> D1 [128, N] = Wt Bx^T,  D2 [128, N]: D2[m][n] = sum_j Wt[j][m] G[n][j]
  * (rows m >= Kin undefined).  ws: >= 128*Kin*2 bytes of device scratch. */

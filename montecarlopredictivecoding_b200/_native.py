@@ -88,6 +88,32 @@ class McpcGradIO(C.Structure):
     ]
 
 
+MAX_PTENSORS = 2 * (MAX_LAYERS + 1)
+
+
+class McpcPStep(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("n_tensors", C.c_int32),
+        ("param", _FP * MAX_PTENSORS),
+        ("grad", _FP * MAX_PTENSORS),
+        ("state1", _FP * MAX_PTENSORS),
+        ("state2", _FP * MAX_PTENSORS),
+        ("numel", C.c_uint64 * MAX_PTENSORS),
+        ("inv_norm", C.c_double),
+        ("lr", C.c_double),
+        ("weight_decay", C.c_double),
+        ("momentum", C.c_double),
+        ("dampening", C.c_double),
+        ("beta1", C.c_double),
+        ("beta2", C.c_double),
+        ("eps", C.c_double),
+        ("nesterov", C.c_int32),
+        ("first_step", C.c_int32),
+        ("step", C.c_int32),
+    ]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -96,11 +122,14 @@ _lib = None
 _lock = threading.Lock()
 LIB_NAME = "libmcpc_b200.so"
 EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer_mode", "mcpc_infer", "mcpc_weight_grad",
-           "mcpc_fill_noise", "mcpc_marginal_ll_workspace_bytes", "mcpc_marginal_ll_bernoulli", "mcpc_debug_umma",
-           "mcpc_debug_tma")
+           "mcpc_fill_noise", "mcpc_marginal_ll_workspace_bytes", "mcpc_marginal_ll_bernoulli", "mcpc_traj_stats_update",
+           "mcpc_p_step", "mcpc_debug_umma", "mcpc_debug_tma")
 
 
 def lib_path():
+    override = os.environ.get("MCPC_NATIVE_LIB")          # e.g. the -DMCPC_DEBUG_BUILD library (build.py --debug)
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
@@ -142,6 +171,11 @@ def load():
         lib.mcpc_marginal_ll_bernoulli.restype = C.c_int
         lib.mcpc_marginal_ll_bernoulli.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mcpc_traj_stats_update.restype = C.c_int
+        lib.mcpc_traj_stats_update.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                               C.c_void_p]
+        lib.mcpc_p_step.restype = C.c_int
+        lib.mcpc_p_step.argtypes = [C.POINTER(McpcPStep), C.c_void_p]
         lib.mcpc_debug_umma.restype = C.c_int
         lib.mcpc_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]

@@ -46,8 +46,17 @@ def nvcc_path():
     return "nvcc"
 
 
-def build(force=False, verbose=False):
-    """Compile when sources changed (sha256 stamp).  Returns the path of the library."""
+def build(force=False, verbose=False, debug=False):
+    """Compile when sources changed (sha256 stamp).  Returns the path of the library.
+    ``debug=True`` builds libmcpc_b200_debug.so with -DMCPC_DEBUG_BUILD (experiment knobs such as MCPC_WIDE_EPI_MODE;
+    select it at run time with MCPC_NATIVE_LIB=<path>); the product library never contains them."""
+    if debug:
+        lib = LIB.replace(".so", "_debug.so")
+        cmd = [nvcc_path()] + NVCC_FLAGS + ["-DMCPC_DEBUG_BUILD", "-o", lib] + sources()
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed building the debug library:\n" + proc.stderr[-4000:])
+        return lib
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
@@ -65,4 +74,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, debug="--debug" in sys.argv))

@@ -255,6 +255,37 @@ int mcpc_marginal_ll_bernoulli(const float* logits, int32_t S, const float* data
                             reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mcpc_traj_stats_update(const float* traj, int32_t n_rec, uint64_t n_elems, uint64_t count_before, float* mean, float* m2,
+                           void* stream) {
+  if (traj == nullptr || mean == nullptr || m2 == nullptr || n_rec < 1 || n_elems < 1) {
+    set_error("mcpc_traj_stats_update: bad arguments");
+    return MCPC_ERR_INVALID;
+  }
+  return launch_traj_stats(traj, n_rec, (size_t)n_elems, (double)count_before, mean, m2, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mcpc_p_step(const McpcPStep* s, void* stream) {
+  if (s == nullptr || s->n_tensors < 1 || s->n_tensors > MCPC_MAX_PTENSORS) {
+    set_error("mcpc_p_step: bad tensor count");
+    return MCPC_ERR_INVALID;
+  }
+  if (s->kind != MCPC_OPT_SGD && s->kind != MCPC_OPT_ADAM) {
+    set_error("mcpc_p_step: unknown optimizer %d", s->kind);
+    return MCPC_ERR_INVALID;
+  }
+  for (int i = 0; i < s->n_tensors; ++i) {
+    if (s->param[i] == nullptr || s->grad[i] == nullptr || (s->kind == MCPC_OPT_ADAM && (s->state1[i] == nullptr || s->state2[i] == nullptr))) {
+      set_error("mcpc_p_step: NULL param / grad / state for tensor %d", i);
+      return MCPC_ERR_INVALID;
+    }
+  }
+  if (s->kind == MCPC_OPT_ADAM && s->step < 1) {
+    set_error("mcpc_p_step: Adam step index must be >= 1");
+    return MCPC_ERR_INVALID;
+  }
+  return launch_p_step(s, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int mcpc_debug_umma(const float* Wt, const float* Bx, const float* G, int32_t Kin, int32_t N, float* D1, float* D2,
                     void* ws, void* stream) {
   if (Wt == nullptr || Bx == nullptr || G == nullptr || D1 == nullptr || D2 == nullptr || ws == nullptr) {

@@ -78,6 +78,7 @@ struct WideParams {
   float noise_scale;
   uint64_t seed, chain_offset;
   int mn3;                                // MN-major operands come in through 3-D tensor maps (all widths % 64 == 0)
+  int pf_x, pf_g, pf_t;                   // the fp32 prefetch maps exist (16-byte aligned bases and row strides)
   int skip_epilogue;                      // debug build only
 };
 
@@ -96,6 +97,9 @@ struct WideMaps {
   CUtensorMap act_k[kMaxL], act_mn[kMaxL];
   CUtensorMap gb_k[kMaxL + 1], gb_mn[kMaxL + 1];
   CUtensorMap w_k[kMaxL + 1], w_mn[kMaxL + 1];
+  // fp32 views used only for L2 prefetches of the epilogue inputs (box = 128 units x 256 chains): the latents, the
+  // own-layer term and the targets are first touched by latency-bound epilogue loads otherwise
+  CUtensorMap x32[kMaxL], g32, tgt;
 };
 
 struct Pipe {
@@ -103,6 +107,15 @@ struct Pipe {
 };
 
 enum { KIND_PREDICT = 0, KIND_UPDATE = 1, KIND_WGRAD = 2 };
+
+// Experiment hook of the DEBUG build (-DMCPC_DEBUG_BUILD, env MCPC_WIDE_EPI_MODE): 1 = epilogues skipped entirely (mainloop-only
+// rate), 2 = epilogues without their global stores, 3 = without their global loads.  Results are garbage in all three; the
+// release build compiles the constant 0.
+#ifdef MCPC_DEBUG_BUILD
+#define MCPC_EPI_MODE(p) ((p).skip_epilogue)
+#else
+#define MCPC_EPI_MODE(p) 0
+#endif
 
 __device__ __forceinline__ bool elect1() {
   uint32_t pred;
@@ -267,10 +280,93 @@ struct EpiPos {
   int q, h, lane, ew;     // TMEM lane quarter, column half, lane, epilogue warp index
 };
 
-// errors of the units a tile predicts: eps / energy / own-layer G (hidden Linears) or loss / dLoss (output)
-template <bool HAS_ACC>
+// errors of the units a tile predicts: eps / energy / own-layer G (hidden Linears) or loss / dLoss (output).
+// One chunk = 16 chains of one unit per lane; GUARD = false: every (lane, chain) of the chunk exists (steady state, no
+// predicates); GUARD = true: edge chunks.  All global offsets are 32-bit element indices from warp-uniform bases.
+struct PredCtx {
+  const float* in;             // hidden: p.x[lin]; output: p.target
+  float* g32;                  // p.G32 (hidden only)
+  __nv_bfloat16* gb;           // G ring slot of this step
+  float* traj;                 // output: trajectory record of this step or nullptr
+  uint32_t d_o, SD, g_pitch;
+  uint32_t io, go, bo;         // element offsets of (chain 0 of the tile half, this lane's unit) in in / g32 / gb
+  float bias, ce, gc, inv_var;
+  int mode;                    // output: 0 no target (TOP_NONE / ZERO), 1 Gaussian, 2 Bernoulli
+  bool on;                     // output: unit inside the loss mask
+  int dbg;                     // MCPC_EPI_MODE
+};
+
+template <bool GUARD>
+__device__ __forceinline__ void pred_load(const PredCtx& c, bool want, int cc, int n_ok, float (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool ok = want && (!GUARD || (cc + j < n_ok)) && c.dbg != 3;
+    v[j] = ok ? c.in[c.io + (uint32_t)(cc + j) * c.d_o] : 0.0f;
+  }
+}
+
+template <bool GUARD>
+__device__ __forceinline__ void pred_chunk_hidden(const PredCtx& c, int cc, int n_ok, uint32_t acc_addr, bool has_acc,
+                                                  const float (&xv)[16], float& e_part, float& gsum) {
+  float d[16];
+  if (has_acc) {
+    tmem_ld16(acc_addr, d);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool ok = !GUARD || (cc + j < n_ok);
+    const float eps = ok ? xv[j] - (d[j] + c.bias) : 0.0f;
+    e_part = fmaf(c.ce * eps, eps, e_part);
+    const float g = -c.gc * eps;
+    const __nv_bfloat16 gb16 = __float2bfloat16(g);
+    gsum += __bfloat162float(gb16);                                   // the bias gradient sums the operand the dW GEMM sees
+    if (ok && c.dbg != 2) {
+      c.g32[c.go + (uint32_t)(cc + j) * c.SD] = g;
+      c.gb[c.bo + (uint32_t)(cc + j) * c.g_pitch] = gb16;
+    }
+  }
+}
+
+template <bool GUARD>
+__device__ __forceinline__ void pred_chunk_out(const PredCtx& c, int cc, int n_ok, uint32_t acc_addr, bool has_acc,
+                                               const float (&yv)[16], float& l_part, float& gsum) {
+  float d[16];
+  if (has_acc) {
+    tmem_ld16(acc_addr, d);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool ok = !GUARD || (cc + j < n_ok);
+    const float o = d[j] + c.bias;
+    float lv = 0.0f, e = 0.0f;
+    if (c.mode == 2) {
+      const float z = __expf(-fabsf(o));
+      lv = fmaxf(o, 0.0f) - o * yv[j] + __logf(1.0f + z);
+      e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[j];
+    } else if (c.mode == 1) {
+      const float dd = o - yv[j];
+      lv = 0.5f * c.inv_var * dd * dd;
+      e = dd * c.inv_var;
+    }
+    const bool live = ok && c.on;
+    l_part += live ? lv : 0.0f;
+    const __nv_bfloat16 eb16 = __float2bfloat16(live ? e : 0.0f);
+    gsum += __bfloat162float(eb16);
+    if (ok && c.dbg != 2) {
+      c.gb[c.bo + (uint32_t)(cc + j) * c.g_pitch] = eb16;
+      if (c.traj != nullptr) c.traj[c.io + (uint32_t)(cc + j) * c.d_o] = o;
+    }
+  }
+}
+
 __device__ __forceinline__ void epilogue_predict(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc,
-                                                 const EpiPos& ep, int slot_id) {
+                                                 bool has_acc, const EpiPos& ep, int slot_id) {
   const NetDev& nd = p.net;
   const int lin = t.idx;
   const bool is_out = (lin == nd.L);
@@ -278,79 +374,47 @@ __device__ __forceinline__ void epilogue_predict(const WideParams& p, const Step
   const int u = t.m0 + ep.q * 32 + ep.lane;
   const bool u_ok = u < d_o;
   const int c_base = t.n0 + ep.h * (kTN / 2);
-  const float bias = (u_ok && p.b[lin] != nullptr) ? __ldg(p.b[lin] + u) : 0.0f;
-  const float ce = is_out ? 0.0f : 0.5f * nd.c[lin], gc = is_out ? 0.0f : nd.gc[lin];
+  PredCtx c;
+  c.d_o = (uint32_t)d_o; c.SD = (uint32_t)nd.SD; c.g_pitch = (uint32_t)p.g_pitch;
+  c.bias = (u_ok && p.b[lin] != nullptr) ? __ldg(p.b[lin] + u) : 0.0f;
+  c.ce = is_out ? 0.0f : 0.5f * nd.c[lin];
+  c.gc = is_out ? 0.0f : nd.gc[lin];
+  c.inv_var = nd.inv_var;
+  c.mode = nd.top == MCPC_TOP_BERNOULLI ? 2 : (nd.top == MCPC_TOP_GAUSS ? 1 : 0);
+  c.on = c.mode != 0 && u >= nd.mask_start;
+  c.dbg = MCPC_EPI_MODE(p);
+  c.in = is_out ? p.target : p.x[lin];
+  c.g32 = p.G32;
+  c.gb = p.Gb + ((size_t)st.slot * p.Bpad) * p.g_pitch;
+  c.traj = (is_out && st.do_traj && p.traj_out != nullptr) ? p.traj_out + (size_t)st.rec * p.B * d_o : nullptr;
+  c.io = (uint32_t)c_base * c.d_o + (uint32_t)u;
+  c.go = (uint32_t)c_base * c.SD + (uint32_t)(is_out ? 0 : nd.off[lin] + u);
+  c.bo = (uint32_t)c_base * c.g_pitch + (uint32_t)(p.poff[lin] + u);
+  const bool want_in = !is_out || c.mode != 0;                           // the output tile reads the target only under a loss
+  const int n_ok = u_ok ? (p.B - c_base) : 0;                            // chunk-relative chains cc < n_ok are this lane's
+  const int n_warp = min(kTN / 2, p.B - c_base);                         // chains of this tile half that exist (uniform)
+  const bool lanes_full = (t.m0 + ep.q * 32 + 32 <= d_o);                // uniform: every lane of the warp has a unit
   float e_part = 0.0f, l_part = 0.0f, gsum = 0.0f;
-  __nv_bfloat16* gbp = p.Gb + ((size_t)st.slot * p.Bpad) * p.g_pitch + p.poff[lin] + u;
-  if (!is_out) {
-    const float* xp = p.x[lin] + u;
-    float* g32 = p.G32 + nd.off[lin] + u;
+  if (n_warp > 0) {
+    float v[16];
+    if (lanes_full && n_warp >= 16) pred_load<false>(c, want_in, 0, n_ok, v);
+    else pred_load<true>(c, want_in, 0, n_ok, v);
 #pragma unroll 1
-    for (int ch = 0; ch < kTN / 32; ++ch) {
-      const int c0 = c_base + ch * 16;
-      if (c0 >= p.B) break;                                             // uniform over the warp
-      float xv[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) xv[j] = (u_ok && c0 + j < p.B) ? xp[(size_t)(c0 + j) * d_o] : 0.0f;
-      float d[16];
-      if (HAS_ACC) {
-        tmem_ld16(acc + ch * 16, d);
+    for (int cc = 0; cc < n_warp; cc += 16) {
+      float vn[16];                                                       // operands of the NEXT chunk: in flight meanwhile
+      const int cn = cc + 16;
+      if (lanes_full && cn + 16 <= n_warp) pred_load<false>(c, want_in, cn, n_ok, vn);
+      else pred_load<true>(c, want_in, cn, cn < n_warp ? n_ok : 0, vn);
+      const bool full = lanes_full && cc + 16 <= n_warp;
+      if (!is_out) {
+        if (full) pred_chunk_hidden<false>(c, cc, n_ok, acc + cc, has_acc, v, e_part, gsum);
+        else pred_chunk_hidden<true>(c, cc, n_ok, acc + cc, has_acc, v, e_part, gsum);
       } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+        if (full) pred_chunk_out<false>(c, cc, n_ok, acc + cc, has_acc, v, l_part, gsum);
+        else pred_chunk_out<true>(c, cc, n_ok, acc + cc, has_acc, v, l_part, gsum);
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (u_ok && c0 + j < p.B) {
-          const float eps = xv[j] - (d[j] + bias);
-          e_part = fmaf(ce * eps, eps, e_part);
-          const float g = -gc * eps;
-          g32[(size_t)(c0 + j) * nd.SD] = g;
-          const __nv_bfloat16 gb16 = __float2bfloat16(g);
-          gbp[(size_t)(c0 + j) * p.g_pitch] = gb16;
-          gsum += __bfloat162float(gb16);                               // the bias gradient sums the operand the dW GEMM sees
-        }
-    }
-  } else {
-    const bool use_y = nd.top >= MCPC_TOP_GAUSS;
-    const bool bern = nd.top == MCPC_TOP_BERNOULLI;
-    const bool on = use_y && (u >= nd.mask_start);
-    const float* yp = p.target + u;
-    float* to = (st.do_traj && p.traj_out != nullptr) ? p.traj_out + (size_t)st.rec * p.B * d_o + u : nullptr;
-#pragma unroll 1
-    for (int ch = 0; ch < kTN / 32; ++ch) {
-      const int c0 = c_base + ch * 16;
-      if (c0 >= p.B) break;
-      float yv[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) yv[j] = (use_y && u_ok && c0 + j < p.B) ? yp[(size_t)(c0 + j) * d_o] : 0.0f;
-      float d[16];
-      if (HAS_ACC) {
-        tmem_ld16(acc + ch * 16, d);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) d[j] = 0.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (u_ok && c0 + j < p.B) {
-          const float o = d[j] + bias;
-          float lv, e;
-          if (bern) {
-            const float z = __expf(-fabsf(o));
-            lv = fmaxf(o, 0.0f) - o * yv[j] + __logf(1.0f + z);
-            e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[j];
-          } else {
-            const float dd = o - yv[j];
-            lv = 0.5f * nd.inv_var * dd * dd;
-            e = dd * nd.inv_var;
-          }
-          l_part += on ? lv : 0.0f;
-          const __nv_bfloat16 eb16 = __float2bfloat16(on ? e : 0.0f);
-          gbp[(size_t)(c0 + j) * p.g_pitch] = eb16;
-          gsum += __bfloat162float(eb16);
-          if (to != nullptr) to[(size_t)(c0 + j) * d_o] = o;
-        }
+      for (int j = 0; j < 16; ++j) v[j] = vn[j];
     }
   }
   e_part = warp_sum_w(e_part);
@@ -395,13 +459,14 @@ struct UpdCtx {
   uint32_t xo, go, ao;         // element offsets of (chain 0 of the tile half, this lane's unit)
   uint32_t gu;                 // global unit index (Philox counter word 0)
   float nlr, nscale;
+  int dbg;                     // MCPC_EPI_MODE
 };
 
 template <bool GUARD>
 __device__ __forceinline__ void upd_load(const UpdCtx& c, int cc, int n_ok, float (&xv)[16], float (&gv)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const bool ok = !GUARD || (cc + j < n_ok);
+    const bool ok = (!GUARD || (cc + j < n_ok)) && c.dbg != 3;
     xv[j] = ok ? c.x[c.xo + (uint32_t)(cc + j) * c.dl] : 0.0f;
     gv[j] = ok ? c.g32[c.go + (uint32_t)(cc + j) * c.SD] : 0.0f;
   }
@@ -472,7 +537,7 @@ __device__ __forceinline__ void upd_chunk(const WideParams& p, const StepArgs& s
     }
     x = fmaf(c.nscale, nz[j], x);
     const __nv_bfloat16 a16 = __float2bfloat16(act_t<ACT>(kind, x));
-    if (ok) {
+    if (ok && c.dbg != 2) {
       c.x[xo] = x;
       c.act[c.ao + (uint32_t)(cc + j) * c.a_pitch] = a16;
     }
@@ -500,6 +565,7 @@ __device__ __forceinline__ void epilogue_update(const WideParams& p, const StepA
   c.gu = (uint32_t)(nd.off[l] + u);
   c.nlr = -p.lr;
   c.nscale = c.nlr * p.noise_scale;                                      // x <- x - lr * (noise_scale * xi)
+  c.dbg = MCPC_EPI_MODE(p);
   const int n_ok = u_ok ? (p.B - c_base) : 0;                            // chunk-relative chains cc < n_ok are this lane's
   const int n_warp = min(kTN / 2, p.B - c_base);                         // chains of this tile half that exist (uniform)
   const bool lanes_full = (t.m0 + ep.q * 32 + 32 <= dl);                 // uniform: every lane of the warp has a unit
@@ -593,6 +659,17 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
       for (int tile = first_tile; tile < n_tiles; tile += tile_stride) {
         const TileDesc t = decode_tile<KIND, CG>(p, st, mp, tile, rank);
         const int n_stage = (t.k_ext + kBK - 1) / kBK;
+        // what this tile's epilogue will read, into L2 now: the epilogue runs one mainloop later
+        if (KIND == KIND_PREDICT) {
+          if (t.idx < p.net.L) {
+            if (p.pf_x) tma_prefetch_l2_2d(&mp.x32[t.idx], t.m0, t.n0);
+          } else if (p.pf_t) {
+            tma_prefetch_l2_2d(&mp.tgt, t.m0, t.n0);
+          }
+        } else if (KIND == KIND_UPDATE) {
+          if (p.pf_x) tma_prefetch_l2_2d(&mp.x32[t.idx], t.m0, t.n0);
+          if (p.pf_g) tma_prefetch_l2_2d(&mp.g32, p.net.off[t.idx] + t.m0, t.n0);
+        }
         for (int s = 0; s < n_stage; ++s, ++issued) {
           const uint32_t slot = issued % NS;
           mbar_wait(&pipe.empty[slot], ((issued / NS) & 1u) ^ 1u);
@@ -677,14 +754,13 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
       }
       const uint32_t acc = tmem + ((uint32_t)(ep.q * 32) << 16) + ab * kTN + ep.h * (kTN / 2);
 #ifdef MCPC_DEBUG_BUILD
-      if (p.skip_epilogue) {
+      if (p.skip_epilogue == 1) {
         // debug (MCPC_WIDE_SKIP_EPI=1, results are garbage): mainloop-only rate of the three kernels
       } else
 #endif
       if (KIND == KIND_PREDICT) {
         const int slot_id = (tile * CG + rank) * kEpiWarps + ep.ew;
-        if (has_gemm) epilogue_predict<true>(p, st, t, acc, ep, slot_id);
-        else epilogue_predict<false>(p, st, t, acc, ep, slot_id);
+        epilogue_predict(p, st, t, acc, has_gemm, ep, slot_id);
       } else if (KIND == KIND_UPDATE) {
         if (SPEC == 1) {
           const int kind = p.net.act[t.idx];
@@ -745,7 +821,7 @@ struct WideLayout {
 };
 
 struct WideKnobs {
-  int cg, slots, ctas, nospec;
+  int cg, slots, ctas, nospec, epi_pf;
 #ifdef MCPC_DEBUG_BUILD
   int skip_epi;
 #endif
@@ -762,8 +838,11 @@ WideKnobs wide_knobs() {
   k.ctas = 0;
   if (const char* env = getenv("MCPC_WIDE_CTAS")) k.ctas = atoi(env);
   k.nospec = getenv("MCPC_TC_NOSPEC") != nullptr ? 1 : 0;
+  k.epi_pf = 0;      // measured on C5: 0.734 ms/step with the L2 prefetch of the epilogue inputs, 0.700 without
+  if (const char* env = getenv("MCPC_WIDE_EPIPF")) k.epi_pf = atoi(env) != 0 ? 1 : 0;
 #ifdef MCPC_DEBUG_BUILD
-  k.skip_epi = getenv("MCPC_WIDE_SKIP_EPI") != nullptr ? 1 : 0;
+  k.skip_epi = 0;
+  if (const char* env = getenv("MCPC_WIDE_EPI_MODE")) k.skip_epi = atoi(env);
 #endif
   return k;
 }
@@ -916,6 +995,19 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
                  : make_tmap_bf16(&mp.w_mn[l], Wb[l], d_i, d_o, wp, 64, 64);
     }
     if (rc != MCPC_OK) return rc;
+  }
+  // fp32 prefetch views (optional: skipped when a base or a row stride is not 16-byte aligned)
+  p.pf_x = p.pf_g = p.pf_t = 0;
+  if (kn.epi_pf) {
+    bool ok = true;
+    for (int l = 0; l < nd.L && ok; ++l)
+      ok = (nd.dims[l] % 4 == 0) && (reinterpret_cast<uintptr_t>(p.x[l]) % 16 == 0) &&
+           make_tmap_f32(&mp.x32[l], p.x[l], nd.dims[l], B, nd.dims[l], kTM, kTN) == MCPC_OK;
+    p.pf_x = ok ? 1 : 0;
+    p.pf_g = (nd.SD % 4 == 0 && make_tmap_f32(&mp.g32, p.G32, nd.SD, B, nd.SD, kTM, kTN) == MCPC_OK) ? 1 : 0;
+    p.pf_t = (p.target != nullptr && nd.top >= MCPC_TOP_GAUSS && nd.d_out % 4 == 0 &&
+              reinterpret_cast<uintptr_t>(p.target) % 16 == 0 &&
+              make_tmap_f32(&mp.tgt, p.target, nd.d_out, B, nd.d_out, kTM, kTN) == MCPC_OK) ? 1 : 0;
   }
   const size_t smem_g = (size_t)n_stages(CG) * stage_bytes(CG) + 1024;
   MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));

@@ -75,6 +75,9 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
 int marginal_ll_workspace(int N, int S, int D, size_t* bytes);
 int launch_marginal_ll(const float* logits, int S, const float* data, int N, int D, float clamp_abs, void* ws,
                        size_t ws_bytes, double* ml_out, float* row_ll, cudaStream_t stream);
+int launch_traj_stats(const float* traj, int n_rec, size_t n_elems, double count_before, float* mean, float* m2,
+                      cudaStream_t stream);
+int launch_p_step(const McpcPStep* s, cudaStream_t stream);
 int launch_tma_probe(const float* A, const float* B, int N, int a_mn, int b_mn, float* D, void* ws, cudaStream_t stream);
 int launch_umma_probe(const float* Wt, const float* Bx, const float* G, int Kin, int N, float* D1, float* D2, void* ws,
                       cudaStream_t stream);

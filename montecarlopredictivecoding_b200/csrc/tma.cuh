@@ -56,6 +56,21 @@ inline int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uin
   return MCPC_OK;
 }
 
+// Row-major fp32 matrix, no swizzle: only used for L2 prefetches (cp.async.bulk.prefetch.tensor), never as an operand.
+inline int make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
+                         uint32_t box_inner, uint32_t box_outer) {
+  TmapEncodeFn fn = tmap_encode_fn();
+  if (fn == nullptr) return MCPC_ERR_CUDA;
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstride[1] = {pitch * 4};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MCPC_OK : MCPC_ERR_CUDA;
+}
+
 // The same row-major matrix [k rows][n columns] viewed as 3-D (64 columns, k, column block): ONE box of
 // 64 x box_k x box_blocks lands as `box_blocks` consecutive MN-major operand blocks of 8 KB (n must be a
 // multiple of 64 so that no block straddles the end of the matrix).

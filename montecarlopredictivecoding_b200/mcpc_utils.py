@@ -6,6 +6,7 @@
   * utils/model.py:35-44   random_step   (the Langevin noise callback)
   * utils/model.py:47-69   get_model
   * utils/training_evaluation.py:16-70   get_pc_trainer, get_mcpc_trainer, get_mcpc_trainer_one_sample
+  * utils/model.py:71-163  get_representations   (trajectory consumer)
 
 so a user of the reference finds the same vocabulary.  The reference's own ``utils`` package also
 works unmodified on top of the drop-in ``predictive_coding`` (its ``random_step`` is recognised by
@@ -124,6 +125,78 @@ def get_mcpc_trainer_one_sample(gen_pc, config, training=True):
         gen_pc, T=config["K"], update_x_at="all", optimizer_x_fn=optim.SGD,
         optimizer_x_kwargs=config["optimizer_x_kwargs_mcpc"], update_p_at="last" if training else "never",
         plot_progress_at=[], **_mcpc_p_kwargs(config, training))
+
+
+# ---- trajectory consumers ---------------------------------------------------------------------
+def get_representations(gen_pc, config, trainers, loader, rep_type="MAP", use_cuda=False, n=None):
+    """utils/model.py:71-163 with the same arguments and return value (a TensorDataset of first-PCLayer
+    representations and labels), but the T-step trajectories never leave the GPU:
+
+      * "MAP"          the latent of the first PCLayer after MAP inference (as the reference);
+      * "expectation"  mean over ALL T steps of the Langevin chain (the reference's ``temp.mean(0)`` over per-step
+                       ``.cpu()`` copies, :143-149) -- here ``enable_trajectory_stats`` folds a bounded device ring into
+                       a running mean, nothing is returned per step;
+      * "full"         the samples at steps mixing, mixing+indent, ... (the reference records every step and slices
+                       ``temp[mixing::indent]``, :150-151) -- here only those steps are recorded
+                       (``set_trajectory_stride``) into one device ring."""
+    reps, labels = [], []
+    input_size = len(gen_pc[0].bias)
+    device = gen_pc[0].bias.device
+
+    def map_call(pc_trainer, data, log):
+        pseudo_input = torch.zeros(data.shape[0], input_size, device=device)
+        pc_trainer.train_on_batch(inputs=pseudo_input, loss_fn=config["loss_fn"],
+                                  loss_fn_kwargs={"_target": data, "_var": config["input_var"]}, is_log_progress=log,
+                                  is_return_results_every_t=False, is_checking_after_callback_after_t=False)
+        return pseudo_input
+
+    if rep_type == "MAP":
+        for data, label in loader:
+            data, label = data.to(device), label.to(device)
+            map_call(trainers[0], data, True)
+            reps.append(gen_pc[1].get_x().detach().clone())
+            labels.append(label)
+    elif len(trainers) == 2:
+        assert rep_type in ("full", "expectation")
+        pc_trainer, mcpc_trainer = trainers
+        indent = 1
+        if n is not None:
+            indent = int(config["sampling"] / n)
+        else:
+            n = config["sampling"]
+        saved = (mcpc_trainer._traj_stride, mcpc_trainer._traj_start, mcpc_trainer._traj_on_device,
+                 mcpc_trainer._traj_stats_cfg)
+        try:
+            for data, label in loader:
+                data, label = data.to(device), label.to(device)
+                pseudo_input = map_call(pc_trainer, data, False)
+                kw = dict(inputs=pseudo_input, loss_fn=config["loss_fn"],
+                          loss_fn_kwargs={"_target": data, "_var": config["input_var"]}, callback_after_t=random_step,
+                          callback_after_t_kwargs={"_pc_trainer": mcpc_trainer}, is_log_progress=False,
+                          is_return_results_every_t=True, is_checking_after_callback_after_t=False,
+                          is_sample_x_at_batch_start=False)
+                if rep_type == "expectation":
+                    mcpc_trainer.enable_trajectory_stats(start=0, stride=1, layers=[0])
+                    mcpc_trainer.train_on_batch(**kw)
+                    reps.append(mcpc_trainer.trajectory_stats()["mean"][0].clone())
+                    labels.append(label)
+                else:
+                    mcpc_trainer.disable_trajectory_stats()
+                    mcpc_trainer.set_trajectory_stride(indent, start=config["mixing"])
+                    mcpc_trainer.set_trajectories_on_device(True)
+                    mcpc_trainer.train_on_batch(is_return_representations=True, **kw)
+                    ring = mcpc_trainer.last_trajectories["x"][0]              # [n_rec, B, d] on the device
+                    reps.append(ring.reshape(-1, ring.shape[2]).clone())
+                    labels.append(label.repeat(ring.shape[0]))
+        finally:
+            (mcpc_trainer._traj_stride, mcpc_trainer._traj_start, mcpc_trainer._traj_on_device,
+             mcpc_trainer._traj_stats_cfg) = saved
+    else:
+        raise NotImplementedError
+    from torch.utils.data import TensorDataset
+    if not reps:
+        return TensorDataset(torch.tensor([]), torch.tensor([]).type(torch.int))
+    return TensorDataset(torch.cat(reps, dim=0), torch.cat(labels, dim=0))
 
 
 # ---- SURVEY §8(f) N1: prior sampling and the marginal-likelihood estimate of table_1 --------------------------

@@ -253,6 +253,40 @@ class NativeEngine:
             N.check(self._lib.mcpc_weight_grad(C.byref(net), C.byref(io), B, n_save, precision, C.c_void_p(stream)),
                     "mcpc_weight_grad")
 
+    def traj_stats(self, traj: torch.Tensor, n_rec: int, count_before: int, mean: torch.Tensor, m2: torch.Tensor) -> None:
+        """Fold ``traj[:n_rec]`` ([n_rec, ...] fp32 ring) into the running per-element (mean, m2) accumulators."""
+        dev = traj.device
+        n_elems = mean.numel()
+        if traj[0].numel() != n_elems or m2.numel() != n_elems:
+            raise RuntimeError("traj_stats: ring / accumulator shapes disagree")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with _OnDevice(dev):
+            N.check(self._lib.mcpc_traj_stats_update(_ptr(traj, "trajectory ring"), int(n_rec), n_elems, int(count_before),
+                                                     _ptr(mean, "mean"), _ptr(m2, "m2"), C.c_void_p(stream)),
+                    "mcpc_traj_stats_update")
+
+    def p_step(self, kind: int, params, grads, state1, state2, inv_norm: float, lr: float, weight_decay: float = 0.0,
+               momentum: float = 0.0, dampening: float = 0.0, nesterov: bool = False, first_step: int = 0,
+               beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, step: int = 0) -> None:
+        """One ``mcpc_p_step`` launch: normalise the gradients and apply optim.SGD / optim.Adam to every tensor."""
+        dev = params[0].device
+        a = N.McpcPStep()
+        a.kind = int(kind)
+        a.n_tensors = len(params)
+        for i, (q, g) in enumerate(zip(params, grads)):
+            a.param[i] = _ptr(q.data, "parameter")
+            a.grad[i] = _ptr(g, "parameter gradient")
+            a.state1[i] = _ptr(state1[i], "optimizer state") if state1[i] is not None else None
+            a.state2[i] = _ptr(state2[i], "optimizer state") if state2[i] is not None else None
+            a.numel[i] = q.numel()
+        a.inv_norm = float(inv_norm)
+        a.lr, a.weight_decay, a.momentum, a.dampening = float(lr), float(weight_decay), float(momentum), float(dampening)
+        a.beta1, a.beta2, a.eps = float(beta1), float(beta2), float(eps)
+        a.nesterov, a.first_step, a.step = int(bool(nesterov)), int(first_step), int(step)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with _OnDevice(dev):
+            N.check(self._lib.mcpc_p_step(C.byref(a), C.c_void_p(stream)), "mcpc_p_step")
+
     def fill_noise(self, seed: int, t_begin: int, n_steps: int, chain_offset: int, B: int, n_units: int,
                    noise_scale: float, device) -> torch.Tensor:
         out = torch.empty(n_steps, B, n_units, dtype=torch.float32, device=device)

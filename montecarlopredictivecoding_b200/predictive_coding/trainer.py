@@ -166,6 +166,14 @@ class PCTrainer(object):
         self._zero_inputs_cache = None
         self._save_budget_bytes = int(os.environ.get("MCPC_SAVE_BUDGET_BYTES", str(8 << 30)))
         self._supplied_noise = None            # validation hook: set_supplied_noise()
+        self._traj_stride = 1                  # set_trajectory_stride(): record every k-th step ...
+        self._traj_start = 0                   # ... from this step on
+        self._traj_on_device = False           # set_trajectories_on_device()
+        self._traj_stats_cfg = None            # enable_trajectory_stats()
+        self._traj_stats = None
+        self._traj_ring_bytes = int(os.environ.get("MCPC_TRAJ_RING_BYTES", str(256 << 20)))
+        self.last_trajectories = None          # device rings of the last call: {"x": [...], "out": ..., "steps": [...]}
+        self._fused_p_optimizer = os.environ.get("MCPC_FUSED_P_STEP", "1") != "0"
         self.last_call_info = {}
 
     # ======================================================================================
@@ -201,6 +209,41 @@ class PCTrainer(object):
             group = dist.group.WORLD
         self._dp_group = group
         self._dp_chain_offset = chain_offset
+
+    # ---- trajectories stay on the device ----------------------------------------------
+    def set_trajectory_stride(self, stride: int = 1, start: int = 0) -> None:
+        """Record ``outputs`` / ``representations`` / ``xs`` only at steps ``start, start+stride, ...`` (with
+        ``is_return_results_every_t=True``); the result lists then hold one entry per RECORDED step.  The reference
+        records every step and thins afterwards (``temp[mixing::indent]``, utils/model.py:151; ``xs[mixing::]``,
+        figure_5.py:108); ``stride=1, start=0`` (default) is exactly the reference's behaviour."""
+        assert isinstance(stride, int) and stride >= 1 and isinstance(start, int) and start >= 0
+        self._traj_stride, self._traj_start = stride, start
+
+    def set_trajectories_on_device(self, flag: bool = True) -> None:
+        """``representations`` / ``xs`` entries of the results dict stay CUDA tensors (views of one [n_rec, B, d] ring)
+        instead of being copied to the host step by step like pc_trainer.py:772-774 does."""
+        self._traj_on_device = bool(flag)
+
+    def enable_trajectory_stats(self, start: int = 0, stride: int = 1, layers="all") -> None:
+        """Fold the latents of the steps ``start, start+stride, ...`` of every following call into per-element running
+        mean / variance ON THE DEVICE (csrc/traj_stats.cu), without returning -- or even keeping -- the trajectory:
+        a bounded ring of recorded steps is reduced chunk by chunk.  Read them with :meth:`trajectory_stats`.
+        Replaces host-side reductions such as ``temp.mean(0)`` (utils/model.py:149) and the posterior mean / variance
+        of figure_2.py:75-79.  ``layers``: 'all' or a list of PCLayer indices (0 = ``get_model_representations()``)."""
+        assert isinstance(start, int) and start >= 0 and isinstance(stride, int) and stride >= 1
+        self._traj_stats_cfg = {"start": start, "stride": stride, "layers": layers}
+
+    def disable_trajectory_stats(self) -> None:
+        self._traj_stats_cfg = None
+
+    def trajectory_stats(self):
+        """{"count": n, "mean": [per-layer [B, d] tensor | None], "var": [...]} of the last call (unbiased variance)."""
+        st = self._traj_stats
+        if st is None:
+            return None
+        n = st["count"]
+        var = [None if m2 is None else (m2 / float(max(n - 1, 1))) for m2 in st["m2"]]
+        return {"count": n, "mean": list(st["mean"]), "var": var}
 
     def _get_engine(self):
         if self._engine is None:
@@ -692,8 +735,82 @@ class PCTrainer(object):
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._dp_group)
         Bg = self._global_batch(B)
         n_acc = len(self._accumulate_p_at)
-        flat.div_(float(n_acc * Bg if n_acc > 0 else Bg))
+        norm = float(n_acc * Bg if n_acc > 0 else Bg)
+        if self._fused_p_optimizer and self._fused_p_step(1.0 / norm):
+            return
+        flat.div_(norm)
         self._optimizer_p.step()
+
+    def _fused_p_step(self, inv_norm) -> bool:
+        """normalisation + ``optimizer_p.step()`` as ONE kernel per param group (``mcpc_p_step``), in
+        place on the torch optimizer's own state.  Returns False -- the caller then runs the plain torch path -- for
+        anything but a stock ``optim.SGD`` / ``optim.Adam`` over contiguous fp32 CUDA parameters."""
+        eng = self._get_engine()
+        opt = self._optimizer_p
+        if not hasattr(eng, "p_step") or type(opt) not in (optim.SGD, optim.Adam):
+            return False
+        plans = []
+        for group in opt.param_groups:
+            if group.get("maximize", False) or group.get("differentiable", False) or group.get("fused", False) or \
+                    group.get("capturable", False) or group.get("amsgrad", False) or group.get("decoupled_weight_decay", False):
+                return False
+            params = [q for q in group["params"] if q.grad is not None]
+            if not params:
+                continue
+            if len(params) > N.MAX_PTENSORS:
+                return False
+            for q in params:
+                if not (q.is_cuda and q.dtype == torch.float32 and q.is_contiguous() and q.grad.is_cuda and
+                        q.grad.dtype == torch.float32 and q.grad.is_contiguous()) or q.grad.is_sparse:
+                    return False
+            lr = float(group["lr"])
+            wd = float(group.get("weight_decay", 0.0))
+            if type(opt) is optim.SGD:
+                mom = float(group.get("momentum", 0.0))
+                bufs, first = [None] * len(params), 0
+                if mom != 0.0:
+                    have = ["momentum_buffer" in opt.state[q] and opt.state[q]["momentum_buffer"] is not None for q in params]
+                    if any(have) and not all(have):
+                        return False
+                    first = 0 if all(have) else 1
+                plans.append(dict(kind=N.OPT_SGD, params=params, lr=lr, wd=wd, momentum=mom, first=first,
+                                  dampening=float(group.get("dampening", 0.0)), nesterov=bool(group.get("nesterov", False))))
+            else:
+                b1, b2 = (float(v) for v in group["betas"])
+                for q in params:
+                    st = opt.state[q]
+                    if len(st) and (not torch.is_tensor(st.get("step")) or st["step"].is_cuda):
+                        return False
+                plans.append(dict(kind=N.OPT_ADAM, params=params, lr=lr, wd=wd, beta1=b1, beta2=b2, eps=float(group["eps"])))
+        for pl in plans:
+            params = pl["params"]
+            if pl["kind"] == N.OPT_SGD:
+                s1 = [None] * len(params)
+                if pl["momentum"] != 0.0:
+                    for i, q in enumerate(params):
+                        st = opt.state[q]
+                        if pl["first"]:
+                            st["momentum_buffer"] = torch.empty_like(q, memory_format=torch.preserve_format)
+                        s1[i] = st["momentum_buffer"]
+                eng.p_step(N.OPT_SGD, params, [q.grad for q in params], s1, [None] * len(params), inv_norm, lr=pl["lr"],
+                           weight_decay=pl["wd"], momentum=pl["momentum"], dampening=pl["dampening"],
+                           nesterov=pl["nesterov"], first_step=pl["first"])
+            else:
+                steps = set()
+                for q in params:
+                    st = opt.state[q]
+                    if len(st) == 0:           # torch/optim/adam.py::_init_group
+                        st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                        st["exp_avg"] = torch.zeros_like(q, memory_format=torch.preserve_format)
+                        st["exp_avg_sq"] = torch.zeros_like(q, memory_format=torch.preserve_format)
+                    st["step"] += 1
+                    steps.add(int(st["step"].item()))
+                for k in sorted(steps):       # parameters normally share one step count: one launch
+                    sel = [q for q in params if int(opt.state[q]["step"].item()) == k]
+                    eng.p_step(N.OPT_ADAM, sel, [q.grad for q in sel], [opt.state[q]["exp_avg"] for q in sel],
+                               [opt.state[q]["exp_avg_sq"] for q in sel], inv_norm, lr=pl["lr"], weight_decay=pl["wd"],
+                               beta1=pl["beta1"], beta2=pl["beta2"], eps=pl["eps"], step=k)
+        return True
 
     # --------------------------------------------------------------------------------------
     def _run_fused(self, ctx, x_opt, langevin):
@@ -710,10 +827,13 @@ class PCTrainer(object):
 
         want_traj = ctx["want_outputs"] or ctx["want_reps"] or ctx["want_xs"]
         every_t = ctx["every_t"]
-        n_rec = T if every_t else 1
+        # recorded steps: every step (reference), or start, start+stride, ... (set_trajectory_stride); last step only
+        # when is_return_results_every_t=False
+        k_rec, s_rec = (self._traj_stride, self._traj_start) if every_t else (1, 0)
+        n_rec = (max(0, -(-(T - s_rec) // k_rec)) if every_t else 1)
         traj_x = [None] * netp.L
         traj_out = None
-        if want_traj:
+        if want_traj and n_rec > 0:
             for l in range(netp.L):
                 need = ctx["want_xs"] or (ctx["want_reps"] and l == 0) or \
                     (ctx["want_outputs"] and netp.d_out == 0 and l == netp.L - 1)
@@ -721,6 +841,11 @@ class PCTrainer(object):
                     traj_x[l] = torch.empty(n_rec, B, netp.dims[l], dtype=torch.float32, device=device)
             if ctx["want_outputs"] and netp.d_out > 0:
                 traj_out = torch.empty(n_rec, B, netp.d_out, dtype=torch.float32, device=device)
+        # on-device statistics (enable_trajectory_stats): either over the rings above (same thinning), or -- when the
+        # trajectory itself is not wanted -- over a bounded ring that is folded into the accumulators chunk by chunk
+        stats = self._prepare_traj_stats(netp, B, T, device, traj_x, every_t, k_rec, s_rec)
+        if stats is not None and stats["own_ring"]:
+            k_rec, s_rec = stats["stride"], stats["start"]
 
         # Adam state of the fused x-optimizer persists while the torch optimizer object does
         adam_m = adam_v = None
@@ -777,7 +902,10 @@ class PCTrainer(object):
                 while s < t1:
                     cuts.append((s, min(t1, s + max_save)))
                     s += max_save
-            for (c0, c1) in cuts:
+            recording = (want_traj or stats is not None) and (every_t or stats is not None)
+            max_rec = stats["ring_len"] if (stats is not None and stats["own_ring"]) else None
+            cuts = self._split_cuts_for_recording(cuts, k_rec, s_rec, max_rec) if recording else [(c0, c1, None) for (c0, c1) in cuts]
+            for (c0, c1, r0) in cuts:
                 n = c1 - c0
                 sb = se = 0
                 save_g = save_f = None
@@ -786,7 +914,20 @@ class PCTrainer(object):
                     if not streaming:
                         save_g = self._buffer("save_g", (se - sb, B, g_w), s_dtype, device)
                         save_f = self._buffer("save_f", (se - sb, B, f_w), s_dtype, device)
-                rec_in_cut = want_traj and (every_t or c1 == T)
+                # trajectory slices of this cut: r0 = index of its first recorded step (None: nothing recorded here)
+                n_r = 0
+                tx_cut = [None] * netp.L
+                to_cut = None
+                if want_traj and not every_t:
+                    if c1 == T:                                        # last step only (split_last made it its own cut)
+                        tx_cut, to_cut = list(traj_x), traj_out
+                elif r0 is not None:
+                    n_r = -(-n // k_rec)
+                    if stats is not None and stats["own_ring"]:
+                        tx_cut = [None if ring is None else ring[:n_r] for ring in stats["rings"]]
+                    else:
+                        tx_cut = [None if tx is None else tx[r0:r0 + n_r] for tx in traj_x]
+                        to_cut = None if traj_out is None else traj_out[r0:r0 + n_r]
                 call = InferCall(
                     plan=netp, top=top, energy_coefficient=self._energy_coefficient, B=B, W=W, b=b, x=xs,
                     inputs=inputs_dev, target=target, energy=energy[c0:c1], loss=loss[c0:c1], n_steps=n, t_begin=c0,
@@ -795,14 +936,16 @@ class PCTrainer(object):
                     adam_step0=adam_step0, adam_m=adam_m, adam_v=adam_v,
                     noise_mode=noise_mode, noise=None if noise_all is None else noise_all[c0:c1],
                     noise_scale=noise_scale, seed=seed, chain_offset=self._chain_offset(B),
-                    traj_x=[None if (tx is None or not rec_in_cut) else (tx[c0:c1] if every_t else tx) for tx in traj_x],
-                    traj_out=None if (traj_out is None or not rec_in_cut) else (traj_out[c0:c1] if every_t else traj_out),
-                    traj_every=1, save_g=save_g, save_f=save_f, save_begin=sb, save_end=se,
+                    traj_x=tx_cut, traj_out=to_cut,
+                    traj_every=k_rec if every_t or stats is not None else 1,
+                    save_g=save_g, save_f=save_f, save_begin=sb, save_end=se,
                     precision=self._precision,
                     gW=gW if (streaming and need_grads and se > sb) else None,
                     gb=gb if (streaming and need_grads and se > sb) else None)
                 eng.infer(call)
                 n_launch += 1
+                if stats is not None and n_r > 0:
+                    self._fold_traj_stats(eng, stats, tx_cut, n_r)
                 if c1 == T:
                     # the per-step scalars are final here: start their read-back on a side stream now, so that the
                     # host gets them while the weight-gradient / optimizer_p kernels of this call are still running
@@ -821,8 +964,72 @@ class PCTrainer(object):
                 self._p_step(flat, B)
         self.last_call_info = {"mode": "fused", "launches": n_launch, "segments": len(segs),
                                "noise": noise_mode, "precision": self._precision}
+        if stats is not None:
+            self._traj_stats = {"count": stats["count"], "mean": stats["mean"], "m2": stats["m2"]}
+        steps = list(range(s_rec, T, k_rec)) if every_t else [T - 1]
+        self.last_trajectories = {"x": traj_x, "out": traj_out, "steps": steps} if want_traj else None
         return {"energy": energy, "loss": loss, "scalars": scalars, "host_scalars": host_scalars, "traj_x": traj_x,
                 "traj_out": traj_out, "n_rec": n_rec}
+
+    # --------------------------------------------------------------------------------------
+    #  SURVEY 8(f) N2 helpers: thinned recording and on-device statistics
+    # --------------------------------------------------------------------------------------
+    @staticmethod
+    def _split_cuts_for_recording(cuts, k, s0, max_rec):
+        """Split [c0, c1) launches so that every launch that records starts ON a recorded step (the kernels record
+        local steps 0, k, 2k, ...) and records at most ``max_rec`` steps.  Returns (c0, c1, r0) with r0 the global
+        record index of the launch's first recorded step, or None when the launch records nothing."""
+        out = []
+        for (c0, c1) in cuts:
+            first = s0 if c0 <= s0 else s0 + -(-(c0 - s0) // k) * k        # first recorded step >= c0
+            if first >= c1:
+                out.append((c0, c1, None))
+                continue
+            if first > c0:
+                out.append((c0, first, None))
+            t = first
+            while t < c1:
+                e = c1 if max_rec is None else min(c1, t + max_rec * k)
+                out.append((t, e, (t - s0) // k))
+                t = e
+        return out
+
+    def _prepare_traj_stats(self, netp, B, T, device, traj_x, every_t, k_rec, s_rec):
+        cfg = self._traj_stats_cfg
+        self._traj_stats = None
+        if cfg is None:
+            return None
+        if not every_t and any(t is not None for t in traj_x):
+            raise ValueError("trajectory statistics cannot be combined with last-step-only trajectories "
+                             "(is_return_results_every_t=False together with is_return_xs / representations)")
+        layers = list(range(netp.L)) if cfg["layers"] == "all" else [int(l) for l in cfg["layers"]]
+        shared = every_t and any(traj_x[l] is not None for l in layers)
+        if shared:
+            if (cfg["stride"], cfg["start"]) != (k_rec, s_rec) or any(traj_x[l] is None for l in layers):
+                raise ValueError("enable_trajectory_stats(start, stride) must equal set_trajectory_stride(stride, start) "
+                                 "when the same layers are also returned as trajectories (the kernels record once)")
+        st = {"own_ring": not shared, "start": cfg["start"], "stride": cfg["stride"], "layers": layers, "count": 0,
+              "mean": [None] * netp.L, "m2": [None] * netp.L, "rings": [None] * netp.L, "ring_len": 0}
+        n_total = max(0, -(-(T - cfg["start"]) // cfg["stride"]))
+        if n_total == 0:
+            return None
+        for l in layers:
+            st["mean"][l] = torch.zeros(B, netp.dims[l], dtype=torch.float32, device=device)
+            st["m2"][l] = torch.zeros(B, netp.dims[l], dtype=torch.float32, device=device)
+        if not shared:
+            widest = max(netp.dims[l] for l in layers)
+            st["ring_len"] = int(max(1, min(n_total, self._traj_ring_bytes // max(1, 4 * B * widest))))
+            for l in layers:
+                st["rings"][l] = self._buffer(f"traj_ring{l}", (st["ring_len"], B, netp.dims[l]), torch.float32, device)
+        return st
+
+    def _fold_traj_stats(self, eng, st, tx_cut, n_r):
+        for l in st["layers"]:
+            ring = tx_cut[l]
+            if ring is None:
+                continue
+            eng.traj_stats(ring, n_r, st["count"], st["mean"][l], st["m2"][l])
+        st["count"] += n_r
 
     # --------------------------------------------------------------------------------------
     def _run_stepwise(self, ctx, loss_fn, cb_bwd, cb_bwd_kwargs, cb_t, cb_t_kwargs, check_after_cb):
@@ -998,11 +1205,14 @@ class PCTrainer(object):
         n_rec = rec["n_rec"]
         if ctx["want_outputs"]:
             src = rec["traj_out"] if netp.d_out > 0 else rec["traj_x"][netp.L - 1]
-            results["outputs"] = list(src[:n_rec].unbind(0))
+            results["outputs"] = list(src[:n_rec].unbind(0)) if n_rec > 0 else []
+        # the reference returns host copies (pc_trainer.py:772-774); set_trajectories_on_device(True) keeps the rings on
+        # the GPU (ONE bulk copy per layer otherwise -- never one per step)
+        keep = (lambda t: t) if self._traj_on_device else (lambda t: t.cpu())
         if ctx["want_reps"]:
-            results["representations"] = list(rec["traj_x"][0][:n_rec].cpu().unbind(0))
+            results["representations"] = list(keep(rec["traj_x"][0][:n_rec]).unbind(0)) if n_rec > 0 else []
         if ctx["want_xs"]:
-            per_layer = [rec["traj_x"][l][:n_rec].cpu() for l in range(netp.L)]
+            per_layer = [keep(rec["traj_x"][l][:n_rec]) for l in range(netp.L)] if n_rec > 0 else []
             results["xs"] = [[per_layer[l][t] for l in range(netp.L)] for t in range(n_rec)]
         return results
 

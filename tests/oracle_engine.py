@@ -83,6 +83,18 @@ class OracleEngine:
                 c.adam_m[l].copy_(torch.from_numpy(adam_state.m[l]))
                 c.adam_v[l].copy_(torch.from_numpy(adam_state.v[l]))
 
+    def traj_stats(self, traj, n_rec, count_before, mean, m2):
+        """Same contract as NativeEngine.traj_stats (mcpc_traj_stats_update): merge a block of records (Chan et al.)."""
+        blk = traj[:n_rec].to(torch.float64).reshape(n_rec, -1)
+        nb, na = float(n_rec), float(count_before)
+        mb = blk.mean(0)
+        m2b = ((blk - mb) ** 2).sum(0)
+        mean64, m264 = mean.to(torch.float64).reshape(-1), m2.to(torch.float64).reshape(-1)
+        delta = mb - mean64
+        tot = na + nb
+        mean.copy_((mean64 + delta * nb / tot).to(torch.float32).view_as(mean))
+        m2.copy_((m264 + m2b + delta * delta * na * nb / tot).to(torch.float32).view_as(m2))
+
     def weight_grad(self, plan, top, energy_coefficient, B, n_save, save_g, save_f, inputs, gW, gb, precision):
         self.calls.append(("weight_grad", n_save))
         G = save_g.numpy().reshape(n_save * B, -1).astype(np.float64)
