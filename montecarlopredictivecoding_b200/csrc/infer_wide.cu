@@ -79,6 +79,7 @@ struct WideParams {
   uint64_t seed, chain_offset;
   int mn3;                                // MN-major operands come in through 3-D tensor maps (all widths % 64 == 0)
   int pf_x, pf_g, pf_t;                   // the fp32 prefetch maps exist (16-byte aligned bases and row strides)
+  int cs;                                 // streaming cache hints on the fp32 epilogue streams
   int skip_epilogue;                      // debug build only
 };
 
@@ -134,6 +135,14 @@ __device__ __forceinline__ float warp_sum_w(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Streaming (evict-first) accesses for the fp32 epilogue streams -- latents, own-layer term, targets: 134 MB each per C5
+// step, touched once per kernel -- so that they do not push the bf16 operand panels (reused by 8-16 tiles) out of L2.
+__device__ __forceinline__ float ld_stream(const float* p, bool cs) { return cs ? __ldcs(p) : *p; }
+__device__ __forceinline__ void st_stream(float* p, float v, bool cs) {
+  if (cs) __stcs(p, v);
+  else *p = v;
 }
 
 // ---- CTA-pair (cta_group::2) primitives ----------------------------------------------------------------------
@@ -294,6 +303,7 @@ struct PredCtx {
   int mode;                    // output: 0 no target (TOP_NONE / ZERO), 1 Gaussian, 2 Bernoulli
   bool on;                     // output: unit inside the loss mask
   int dbg;                     // MCPC_EPI_MODE
+  bool cs;
 };
 
 template <bool GUARD>
@@ -301,7 +311,7 @@ __device__ __forceinline__ void pred_load(const PredCtx& c, bool want, int cc, i
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const bool ok = want && (!GUARD || (cc + j < n_ok)) && c.dbg != 3;
-    v[j] = ok ? c.in[c.io + (uint32_t)(cc + j) * c.d_o] : 0.0f;
+    v[j] = ok ? ld_stream(c.in + (c.io + (uint32_t)(cc + j) * c.d_o), c.cs) : 0.0f;
   }
 }
 
@@ -324,7 +334,7 @@ __device__ __forceinline__ void pred_chunk_hidden(const PredCtx& c, int cc, int 
     const __nv_bfloat16 gb16 = __float2bfloat16(g);
     gsum += __bfloat162float(gb16);                                   // the bias gradient sums the operand the dW GEMM sees
     if (ok && c.dbg != 2) {
-      c.g32[c.go + (uint32_t)(cc + j) * c.SD] = g;
+      st_stream(c.g32 + (c.go + (uint32_t)(cc + j) * c.SD), g, c.cs);
       c.gb[c.bo + (uint32_t)(cc + j) * c.g_pitch] = gb16;
     }
   }
@@ -360,7 +370,7 @@ __device__ __forceinline__ void pred_chunk_out(const PredCtx& c, int cc, int n_o
     gsum += __bfloat162float(eb16);
     if (ok && c.dbg != 2) {
       c.gb[c.bo + (uint32_t)(cc + j) * c.g_pitch] = eb16;
-      if (c.traj != nullptr) c.traj[c.io + (uint32_t)(cc + j) * c.d_o] = o;
+      if (c.traj != nullptr) st_stream(c.traj + (c.io + (uint32_t)(cc + j) * c.d_o), o, c.cs);
     }
   }
 }
@@ -383,6 +393,7 @@ __device__ __forceinline__ void epilogue_predict(const WideParams& p, const Step
   c.mode = nd.top == MCPC_TOP_BERNOULLI ? 2 : (nd.top == MCPC_TOP_GAUSS ? 1 : 0);
   c.on = c.mode != 0 && u >= nd.mask_start;
   c.dbg = MCPC_EPI_MODE(p);
+  c.cs = p.cs != 0;
   c.in = is_out ? p.target : p.x[lin];
   c.g32 = p.G32;
   c.gb = p.Gb + ((size_t)st.slot * p.Bpad) * p.g_pitch;
@@ -460,6 +471,7 @@ struct UpdCtx {
   uint32_t gu;                 // global unit index (Philox counter word 0)
   float nlr, nscale;
   int dbg;                     // MCPC_EPI_MODE
+  bool cs;
 };
 
 template <bool GUARD>
@@ -467,8 +479,8 @@ __device__ __forceinline__ void upd_load(const UpdCtx& c, int cc, int n_ok, floa
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const bool ok = (!GUARD || (cc + j < n_ok)) && c.dbg != 3;
-    xv[j] = ok ? c.x[c.xo + (uint32_t)(cc + j) * c.dl] : 0.0f;
-    gv[j] = ok ? c.g32[c.go + (uint32_t)(cc + j) * c.SD] : 0.0f;
+    xv[j] = ok ? ld_stream(c.x + (c.xo + (uint32_t)(cc + j) * c.dl), c.cs) : 0.0f;
+    gv[j] = ok ? ld_stream(c.g32 + (c.go + (uint32_t)(cc + j) * c.SD), c.cs) : 0.0f;
   }
 }
 
@@ -538,7 +550,7 @@ __device__ __forceinline__ void upd_chunk(const WideParams& p, const StepArgs& s
     x = fmaf(c.nscale, nz[j], x);
     const __nv_bfloat16 a16 = __float2bfloat16(act_t<ACT>(kind, x));
     if (ok && c.dbg != 2) {
-      c.x[xo] = x;
+      st_stream(c.x + xo, x, c.cs);
       c.act[c.ao + (uint32_t)(cc + j) * c.a_pitch] = a16;
     }
   }
@@ -566,6 +578,7 @@ __device__ __forceinline__ void epilogue_update(const WideParams& p, const StepA
   c.nlr = -p.lr;
   c.nscale = c.nlr * p.noise_scale;                                      // x <- x - lr * (noise_scale * xi)
   c.dbg = MCPC_EPI_MODE(p);
+  c.cs = p.cs != 0;
   const int n_ok = u_ok ? (p.B - c_base) : 0;                            // chunk-relative chains cc < n_ok are this lane's
   const int n_warp = min(kTN / 2, p.B - c_base);                         // chains of this tile half that exist (uniform)
   const bool lanes_full = (t.m0 + ep.q * 32 + 32 <= dl);                 // uniform: every lane of the warp has a unit
@@ -821,7 +834,7 @@ struct WideLayout {
 };
 
 struct WideKnobs {
-  int cg, slots, ctas, nospec, epi_pf;
+  int cg, slots, ctas, nospec, epi_pf, cs;
 #ifdef MCPC_DEBUG_BUILD
   int skip_epi;
 #endif
@@ -838,6 +851,8 @@ WideKnobs wide_knobs() {
   k.ctas = 0;
   if (const char* env = getenv("MCPC_WIDE_CTAS")) k.ctas = atoi(env);
   k.nospec = getenv("MCPC_TC_NOSPEC") != nullptr ? 1 : 0;
+  k.cs = 1;
+  if (const char* env = getenv("MCPC_WIDE_CS")) k.cs = atoi(env) != 0 ? 1 : 0;
   k.epi_pf = 0;      // measured on C5: 0.734 ms/step with the L2 prefetch of the epilogue inputs, 0.700 without
   if (const char* env = getenv("MCPC_WIDE_EPIPF")) k.epi_pf = atoi(env) != 0 ? 1 : 0;
 #ifdef MCPC_DEBUG_BUILD
@@ -1174,6 +1189,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.noise_scale = (float)o->noise_scale;
   p.seed = o->seed;
   p.chain_offset = o->chain_offset;
+  p.cs = kn.cs;
 #ifdef MCPC_DEBUG_BUILD
   p.skip_epilogue = kn.skip_epi;
 #endif

@@ -239,6 +239,108 @@ class LangevinPlan:
     var: float
 
 
+_probe_cache = {}
+
+
+def _cached_probe(fn, kind, probe):
+    key = (kind, id(fn), id(getattr(fn, "__code__", None)))
+    hit = _probe_cache.get(key)
+    if hit is not None and hit[0] is fn:
+        return hit[1]
+    try:
+        ok = bool(probe(fn))
+    except Exception:  # noqa: BLE001 -- anything unexpected means "not the function we know"
+        ok = False
+    if len(_probe_cache) > 256:
+        _probe_cache.clear()
+    _probe_cache[key] = (fn, ok)
+    return ok
+
+
+def _behaves_like_random_step(cb) -> bool:
+    """Behavioural probe of utils/model.py:35-44: on a stand-in trainer the callback must (a) overwrite every
+    ``x.grad`` with torch's ``normal_(0, sqrt(var / optimizer.defaults['lr']))`` draws, layer by layer in order, (b) call
+    ``optimizer.step()`` exactly once, (c) touch nothing else -- for two (var, lr) pairs.  The generator state of the
+    caller is preserved."""
+    import numpy as np
+
+    class _Opt:
+        def __init__(self, lr):
+            self.defaults = {"lr": lr}
+            self.steps = 0
+            self.zeroed = 0
+
+        def step(self):
+            self.steps += 1
+
+        def zero_grad(self, *a, **k):
+            self.zeroed += 1
+
+    class _Trainer:
+        def __init__(self, xs, opt):
+            self._xs, self._opt = xs, opt
+
+        def get_model_xs(self):
+            return iter(self._xs)
+
+        def get_optimizer_x(self):
+            return self._opt
+
+    def probe(fn):
+        state = torch.random.get_rng_state()
+        try:
+            for var, lr in ((2.0, 0.03), (0.7, 0.25)):
+                xs = []
+                for shape in ((3, 5), (3, 2)):
+                    x = torch.full(shape, 1.25)
+                    x.grad = torch.full(shape, -7.0)
+                    xs.append(x)
+                opt = _Opt(lr)
+                torch.manual_seed(987654321)
+                fn(0, _pc_trainer=_Trainer(xs, opt), var=var)
+                torch.manual_seed(987654321)
+                std = float(np.sqrt(var / lr))
+                for x in xs:
+                    want = torch.empty_like(x).normal_(0.0, std)
+                    if not torch.equal(x.grad, want) or not torch.equal(x, torch.full_like(x, 1.25)):
+                        return False
+                if opt.steps != 1 or opt.zeroed != 0:
+                    return False
+            return True
+        finally:
+            torch.random.set_rng_state(state)
+    return _cached_probe(cb, "langevin", probe)
+
+
+def sampler_is_shape_only(fn) -> bool:
+    """True when a ``sample_x_fn`` provably ignores the VALUES of ``mu`` / ``x``: tagged (``__mcpc_shape_only__``) or, for
+    the functions named like the reference's utils/model.py:8-15 samplers, verified by a probe -- the same seed must give
+    the same draw for two different ``mu`` contents (one of them NaN).  Such samplers can be called without a model
+    forward; anything else gets the real t=0 forward of pc_trainer.py:717-733."""
+    if getattr(fn, "__mcpc_shape_only__", False):
+        return True
+    named = getattr(fn, "__name__", "") in ("sample_x_fn", "sample_x_fn_normal", "sample_x_fn_cte") and \
+        (getattr(fn, "__module__", "") or "").split(".")[-1] == "model"
+    if not named:
+        return False
+
+    def probe(f):
+        state = torch.random.get_rng_state()
+        try:
+            outs = []
+            for fill in (0.5, float("nan")):
+                torch.manual_seed(13579)
+                mu = torch.full((4, 3), fill)
+                out = f({"mu": mu, "x": None})
+                if not torch.is_tensor(out) or out.shape != mu.shape or not torch.isfinite(out).all():
+                    return False
+                outs.append(out)
+            return torch.equal(outs[0], outs[1])
+        finally:
+            torch.random.set_rng_state(state)
+    return _cached_probe(fn, "sampler", probe)
+
+
 _cb_default_var = {}
 
 
@@ -254,6 +356,10 @@ def classify_callback_after_t(cb, kwargs: dict, trainer) -> Optional[LangevinPla
     named = getattr(cb, "__name__", "") == "random_step" and \
         (getattr(cb, "__module__", "") or "").split(".")[-1] == "model"
     if not (tagged or named):
+        return None
+    # a name is not a contract: an untagged function is folded into the kernel only if it BEHAVES like the reference's
+    # random_step (a forked utils/model.py with another noise law keeps running as opaque Python, step by step)
+    if not tagged and not _behaves_like_random_step(cb):
         return None
     if kwargs.get("_pc_trainer", None) is not trainer:
         return None

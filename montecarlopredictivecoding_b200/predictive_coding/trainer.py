@@ -44,12 +44,9 @@ def _slow_down_warning(base, prop, solution):
 
 
 def _is_shape_only_sampler(fn) -> bool:
-    """True for the t=0 initialisers that use nothing but the shape of ``mu``: the ones of ``mcpc_utils`` (tagged) and
-    the reference's own ``utils/model.py`` functions (recognised by name and module, like ``random_step``)."""
-    if getattr(fn, "__mcpc_shape_only__", False):
-        return True
-    return getattr(fn, "__name__", "") in ("sample_x_fn", "sample_x_fn_normal", "sample_x_fn_cte") and \
-        (getattr(fn, "__module__", "") or "").split(".")[-1] == "model"
+    """t=0 initialisers that use nothing but the shape of ``mu`` (tagged, or the reference's own utils/model.py samplers
+    after a behavioural probe -- see plan.sampler_is_shape_only)."""
+    return P.sampler_is_shape_only(fn)
 
 
 class PCTrainer(object):

@@ -13,7 +13,7 @@ if ROOT not in sys.path:
 from oracle import mcpc_oracle as orc  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-ALL_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("mll_"))
+ALL_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("mll_", "stat_")))
 MLL_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("mll_"))
 
 ACT = {"identity": orc.ACT_IDENTITY, "relu": orc.ACT_RELU, "tanh": orc.ACT_TANH}

@@ -134,7 +134,8 @@ def test_fused_p_step_matches_torch_optimizers(name, cls, kw):
         trs[0]._p_step(flats[0], B)
         assert N.load().mcpc_launch_count() == launches0 + 1, "the fused path must be ONE mcpc_p_step launch"
         trs[1]._p_step(flats[1], B)
-        assert torch.allclose(flats[0], flats[1], rtol=1e-6, atol=1e-7), "normalised .grad"
+        if not kw.get("nesterov", False):     # torch's foreach SGD adds momentum*buf INTO .grad for nesterov (in place)
+            assert torch.allclose(flats[0], flats[1], rtol=1e-6, atol=1e-7), "normalised .grad"
         for pa, pb in zip(model_a.parameters(), model_b.parameters()):
             assert torch.allclose(pa, pb, rtol=2e-6, atol=2e-7), (name, it)
         sa, sb = trs[0].get_optimizer_p().state, trs[1].get_optimizer_p().state

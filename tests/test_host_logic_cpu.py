@@ -214,3 +214,44 @@ def test_compiled_plan_cache_rechecks_live_layer_flags():
     b = P.compile_net(model)
     assert b.dims == a.dims
     _ = torch
+
+
+def test_forked_reference_functions_are_not_folded_by_name_alone():
+    """a function that merely carries the reference's name/module must BEHAVE like it to be folded into the
+    kernel (random_step) or called without a forward (samplers)."""
+    import types
+    mod = types.ModuleType("model")
+
+    def random_step(t, _pc_trainer, var=2.0):           # same name, uniform instead of Gaussian noise
+        opt = _pc_trainer.get_optimizer_x()
+        for x in _pc_trainer.get_model_xs():
+            x.grad.uniform_(-1.0, 1.0)
+        opt.step()
+
+    def genuine(t, _pc_trainer, var=2.0):               # the reference's body under the reference's name
+        xs = _pc_trainer.get_model_xs()
+        optimizer = _pc_trainer.get_optimizer_x()
+        for x in xs:
+            x.grad.normal_(0., np.sqrt(var / optimizer.defaults['lr']))
+        optimizer.step()
+
+    def sample_x_fn(inputs):                            # same name, but uses the VALUES of mu
+        return inputs["mu"].detach().clone() + torch.randn_like(inputs["mu"])
+
+    def sample_x_fn_normal(inputs):
+        return torch.randn_like(inputs["mu"])
+
+    for f in (random_step, genuine, sample_x_fn, sample_x_fn_normal):
+        f.__module__ = "utils.model"
+    genuine.__name__ = "random_step"
+    trainer = object()
+    assert P.classify_callback_after_t(random_step, {"_pc_trainer": trainer}, trainer) is None
+    plan = P.classify_callback_after_t(genuine, {"_pc_trainer": trainer, "var": 1.5}, trainer)
+    assert plan is not None and plan.var == 1.5
+    assert P.classify_callback_after_t(mu.random_step, {"_pc_trainer": trainer}, trainer).var == 2.0    # tagged
+    assert not P.sampler_is_shape_only(sample_x_fn)
+    assert P.sampler_is_shape_only(sample_x_fn_normal)
+    assert P.sampler_is_shape_only(mu.sample_x_fn)
+    state = torch.random.get_rng_state()
+    P.sampler_is_shape_only(lambda inputs: torch.randn_like(inputs["mu"]))
+    assert torch.equal(state, torch.random.get_rng_state())
