@@ -47,7 +47,7 @@ FLOPS_DW_STEP = 2 * MAC
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="chains per GPU")
@@ -270,6 +270,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(precision, B):
+    """roofline.traffic: DRAM bytes per launch of the dominant kernel from ONE `ncu --set full` capture, read from the
+    committed summary profiles/ncu_traffic.json (written by scripts/ncu_traffic.py from the .ncu-rep; it names the
+    capture).  Nothing is hard-coded here: no matching capture => null."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            table = json.load(fh)
+        hit = table.get(f"C2_{precision}_B{B}")
+        if hit:
+            return {"traffic": hit["dram_bytes_per_launch"],
+                    "traffic_source": f"dram__bytes_read.sum + dram__bytes_write.sum, kernel {hit['kernel']}, capture {hit['capture']}"}
+    except (OSError, ValueError, KeyError):
+        pass
+    return {"traffic": None, "traffic_source": "no ncu --set full capture of this kernel/config in profiles/ncu_traffic.json"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -446,6 +463,24 @@ def run_ours(args):
     eng.infer = orig_infer
     infer_ms = float(np.median([a.elapsed_time(b) for a, b in k_ev]))
 
+    # ---- the other configs of BASELINE.json (every rank takes part: C3 shards its 65,536 chains, C5 all-reduces dW) ----
+    other = None
+    if not args.no_other_workloads:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_configs as bc
+            del model, map_trainer, mcpc_trainer
+            torch.cuda.empty_cache()
+            other = {
+                "C3_sampling_65536_chains": bc.c3(args.precision, B=65536, T=1000),
+                "C3_sampling_65536_chains_readout_every_100": bc.c3(args.precision, B=65536, T=1000, thin=100),
+                "C5_wide_4x4096_B2048_per_gpu_T100": bc.c5(args.precision, B=2048, T=100),
+            }
+            if world == 1:
+                other["C4_deterministic_pc_adam"] = bc.c4(args.precision)
+        except Exception as exc:  # noqa: BLE001
+            other = {"error": repr(exc)[:300]}
+
     if rank == 0:
         peak_tf, peak_hbm, peak_src = measured_peaks()
         step_s = total_s / K
@@ -471,28 +506,13 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "mcpc_infer (all T steps, one launch)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "traffic": (226595328 if (args.precision == "bf16" and B == 1024) else (499053568 if B == 1024 else None)),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                           "kernel (profiles/r01_*_ncu_summary.csv): the bf16 / fp32 saved dW operands",
+                         **ncu_traffic(args.precision, B),
                          "peak_source": peak_src, "kernel_ms": infer_ms,
                          "algorithmic_flops_per_launch": flops_infer_launch,
                          "note": "4*MAC flops per chain-step x B x T (SURVEY §8d); latents stay on chip, HBM traffic is the "
                                  "saved dW operands only"},
         }
-        if world == 1 and not args.no_other_workloads:
-            # the other configs of BASELINE.json, short runs (scripts/bench_configs.py has the full versions)
-            try:
-                sys.path.insert(0, os.path.join(ROOT, "scripts"))
-                import bench_configs as bc
-                del model, map_trainer, mcpc_trainer
-                torch.cuda.empty_cache()
-                line["other_workloads"] = {
-                    "C3_sampling_65536_chains": bc.c3(args.precision, B=65536, T=200),
-                    "C5_wide_4x4096_B2048": bc.c5(args.precision, B=2048, T=10),
-                    "C4_deterministic_pc_adam": bc.c4(args.precision),
-                }
-            except Exception as exc:  # noqa: BLE001
-                line["other_workloads"] = {"error": repr(exc)[:200]}
+        line["other_workloads"] = other
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_subprocess(B)
         print(json.dumps(line))

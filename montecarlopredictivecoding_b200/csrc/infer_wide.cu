@@ -1,9 +1,9 @@
 // mcpc_infer, MCPC_PREC_BF16, networks too wide to stay on chip (SURVEY config C5: 4 x 4096): the
-// "streaming" path.  Latents x (fp32), their activations (bf16) and the error signals live in HBM / L2;
+// "streaming" path.  Latents x (fp32), their activations (bf16) and the error signals (bf16) live in HBM / L2;
 // every Langevin step is two grouped tcgen05 GEMM kernels with fused epilogues, plus a third one every few steps:
 //
 //   PREDICT   for every Linear l:  mu = act(x_{l-1}) W_l^T + b  ->  eps = x_l - mu, energy, loss,
-//             G_l = d overall / d mu_l (bf16 operand copy + fp32 own-layer term), e_out, bias gradients
+//             G_l = d overall / d mu_l (bf16: GEMM operand AND own-layer gradient term of the update), e_out, bias gradients
 //   UPDATE    for every PCLayer l: bp = G_{l+1} W_{l+1};  grad = -G_l + act'(x_l) * bp;
 //             x <- SGD | Adam step; x <- x - lr * noise (Philox);  act(x) re-emitted as bf16
 //   WGRAD     gW_l += sum over the last s accumulate steps of G_l^T act(x_{l-1}): the bf16 operands of s steps stay
@@ -21,9 +21,18 @@
 // as the operand's storage order dictates -- no transposed copies of anything), mbarrier ring, two 256-column
 // accumulators in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.  CG = 2 runs the tile on a CTA
 // PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256): each CTA stages its 128 units of A and HALF of the chains of
-// B, so a stage is 32 KB per CTA instead of 48 KB (6 stages instead of 4) and every byte of B is fetched into shared
-// memory once per pair instead of once per CTA.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only),
-// warps 2-9 epilogue (TMEM lane quarter = warp % 4, chain half = (warp - 2) / 4).
+// B, so a stage is 32 KB per CTA instead of 48 KB and every byte of B is fetched into shared memory once per pair
+// instead of once per CTA.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warps 2-9 epilogue
+// (TMEM lane quarter = warp % 4, chain half = (warp - 2) / 4).
+//
+// Epilogue inputs (latents, own-layer term, targets) are staged through per-warp shared-memory rings by cp.async, several
+// 16-chain chunks ahead and across the tile boundary: with registers alone a warp keeps 32 requests in flight, and at
+// ~2 us of DRAM latency under load Little's law then makes a tile's epilogue as long as the mainloop it should hide
+// behind (measured: 27-34 k cycles per tile before, 10-17 k after, mainloop 33 k).
+//
+// Measured on C5 (profiles/r02_*): the mainloop issues at the full tensor rate (128 cycles per 256x256x16 MMA)
+// whenever operands are there; the step is bound by the 1 kW power cap (SM clock 1.05-1.3 GHz under this load, as
+// for cuBLAS in a long loop), so what remains is energy per step, not issue slots.
 // Reference semantics: predictive_coding/pc_trainer.py:733-918 + utils/model.py:35-44.
 #include <cstdlib>
 
@@ -43,7 +52,16 @@ constexpr int kTN = 256;                    // chains (PREDICT / UPDATE) or outp
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
-__host__ __device__ constexpr int n_stages(int cg) { return cg == 2 ? 6 : 4; }
+// operand ring depth: the UPDATE kernel trades one stage for deeper staging of its epilogue inputs (below)
+__host__ __device__ constexpr int n_stages(int cg, int kind) { return cg == 2 ? (kind == 1 ? 4 : 5) : 4; }
+// per epilogue warp: shared-memory staging of the epilogue's global INPUTS (latents, own-layer term, targets), filled by
+// cp.async several chunks ahead.  Registers could only keep one chunk (32 requests per warp) in flight, and with ~2 us
+// of DRAM latency under load Little's law then caps the eight epilogue warps of an SM at ~16 GB/s -- the tile
+// epilogues took as long as the mainloop they are supposed to hide behind.
+// UPDATE stages 3 KB per chunk (fp32 latents + the bf16 own-layer term), PREDICT 2 KB (latents or targets): 4 chunks deep
+// with CTA pairs, 1-2 chunks deep on single CTAs (whose operand stages are 48 KB).
+__host__ __device__ constexpr uint32_t kUpdSlot = 3072u, kPredSlot = 2048u;
+__host__ __device__ constexpr uint32_t stg_bytes(int cg, int kind) { return cg == 2 ? (kind == 1 ? 12288u : 8192u) : 4096u; }
 __host__ __device__ constexpr uint32_t a_bytes() { return kTM * kBK * 2; }
 __host__ __device__ constexpr uint32_t b_bytes(int cg) { return (kTN / cg) * kBK * 2; }
 __host__ __device__ constexpr uint32_t stage_bytes(int cg) { return a_bytes() + b_bytes(cg); }
@@ -57,16 +75,17 @@ struct WideParams {
   float* traj_x[kMaxL];
   float* traj_out;
   const float* b[kMaxL + 1];
-  __nv_bfloat16* act;                     // [S][Bpad][a_pitch]: act(x_l) at column poff[l]
-  __nv_bfloat16* Gb;                      // [S][Bpad][g_pitch]: G_l at column poff[l], e_out at poff[L]
-  float* G32;                             // [B][SD]: fp32 G_l (own-layer gradient term) at column off[l]
+  // One block per layer, each a dense row-major matrix of its own (pitch = width rounded up to 8): a tile's 256 chains
+  // x 4096 units are then ONE contiguous 2 MB (bf16) region -- one page -- instead of 256 row segments spread over a
+  // [chain][all layers] row of 32-40 KB.
+  __nv_bfloat16* act_l[kMaxL];            // [S][Bpad][apitch[l]]: act(x_l), S ring slots
+  __nv_bfloat16* gb_l[kMaxL + 1];         // [S][Bpad][gpitch[l]]: G_l (Linear l), e_out for l = L
+  int apitch[kMaxL], gpitch[kMaxL + 1];
   const float* target;
   const float* noise;
   float* gW[kMaxL + 1];
   float* gb[kMaxL + 1];
   float* partials;                        // [n_steps][n_part][2]
-  int poff[kMaxL + 1];
-  int a_pitch, g_pitch;
   int B, Bpad;                            // chains; rows of one ring slot (B rounded up to 64)
   int tP_first[kMaxL + 2];                // predict tiles: prefix over Linear 0..L (index lin)
   int tU_first[kMaxL + 1];                // update tiles: prefix over layers 0..L-1
@@ -78,9 +97,12 @@ struct WideParams {
   float noise_scale;
   uint64_t seed, chain_offset;
   int mn3;                                // MN-major operands come in through 3-D tensor maps (all widths % 64 == 0)
-  int pf_x, pf_g, pf_t;                   // the fp32 prefetch maps exist (16-byte aligned bases and row strides)
+  int pf_x, pf_t;                         // the fp32 prefetch maps exist (16-byte aligned bases and row strides)
   int cs;                                 // streaming cache hints on the fp32 epilogue streams
+  int pdl;                                // launched with programmatic stream serialization
+  int wpf;                                // stages ahead of the ring at which the WEIGHT operand is prefetched into L2 (0 = off)
   int skip_epilogue;                      // debug build only
+  long long* dbg_buf;                     // debug build only: per-tile timeline of CTA 0 (MCPC_WIDE_TIMING)
 };
 
 struct StepArgs {
@@ -100,7 +122,7 @@ struct WideMaps {
   CUtensorMap w_k[kMaxL + 1], w_mn[kMaxL + 1];
   // fp32 views used only for L2 prefetches of the epilogue inputs (box = 128 units x 256 chains): the latents, the
   // own-layer term and the targets are first touched by latency-bound epilogue loads otherwise
-  CUtensorMap x32[kMaxL], g32, tgt;
+  CUtensorMap x32[kMaxL], tgt;
 };
 
 struct Pipe {
@@ -139,10 +161,21 @@ __device__ __forceinline__ float warp_sum_w(float v) {
 
 // Streaming (evict-first) accesses for the fp32 epilogue streams -- latents, own-layer term, targets: 134 MB each per C5
 // step, touched once per kernel -- so that they do not push the bf16 operand panels (reused by 8-16 tiles) out of L2.
-__device__ __forceinline__ float ld_stream(const float* p, bool cs) { return cs ? __ldcs(p) : *p; }
 __device__ __forceinline__ void st_stream(float* p, float v, bool cs) {
   if (cs) __stcs(p, v);
   else *p = v;
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
 }
 
 // ---- CTA-pair (cta_group::2) primitives ----------------------------------------------------------------------
@@ -230,6 +263,7 @@ struct TileDesc {
   int m0;           // first unit (M) of THIS CTA's 128 rows of the tile
   int n0;           // first chain / output unit (N) of the tile (all 256 columns)
   int nb0;          // first N index this CTA stages into shared memory (its 256 / CG columns of B)
+  int ni, ntn;      // index of the tile along N inside its group and the number of N tiles (tiles sharing the A panel)
   int k_ext;        // contraction extent; 0: no GEMM for this tile
   int k_base;       // first row (chain axis) of the K-major B operand: ring slot * Bpad (PREDICT / UPDATE), 0 for WGRAD
   const CUtensorMap* mapA;
@@ -253,6 +287,7 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const StepA
     const int d_i = (lin == 0) ? 0 : nd.dims[lin - 1];            // Linear_0 sees zero inputs: mu_0 = b_0
     const int ntn = (p.B + kTN - 1) / kTN, local = tile - p.tP_first[lin];
     t.idx = lin; t.m0 = (local / ntn) * (kTM * CG) + rank * kTM; t.n0 = (local % ntn) * kTN; t.k_ext = d_i;
+    t.ni = local % ntn; t.ntn = ntn;
     t.k_base = st.slot * p.Bpad;
     if (d_i > 0) {
       t.mapA = &mp.w_k[lin];                                      // W_l [d_o x d_i], K-major
@@ -265,6 +300,7 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const StepA
     const bool has_above = (l + 1 < nd.L) || nd.top_has_grad;
     const int d_up = (l + 1 < nd.L) ? nd.dims[l + 1] : nd.d_out;
     t.idx = l; t.m0 = (local / ntn) * (kTM * CG) + rank * kTM; t.n0 = (local % ntn) * kTN; t.k_ext = has_above ? d_up : 0;
+    t.ni = local % ntn; t.ntn = ntn;
     t.k_base = st.slot * p.Bpad;
     if (has_above) {
       t.mapA = &mp.w_mn[l + 1];                                   // W_{l+1} [d_up x d_l] as A[m][k]: MN-major
@@ -276,6 +312,7 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const StepA
     const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
     const int ntn = (d_o + kTN - 1) / kTN, local = tile - p.tW_first[lin];
     t.idx = lin; t.m0 = (local / ntn) * (kTM * CG) + rank * kTM; t.n0 = (local % ntn) * kTN; t.k_ext = st.k_rows;
+    t.ni = local % ntn; t.ntn = ntn;
     t.k_base = 0;
     t.mapA = &mp.act_mn[lin - 1];                                 // act(x_{l-1}) as A[m = input unit][k = chain]: MN-major
     t.mapB = &mp.gb_mn[lin];                                      // G_l as B[n = output unit][k = chain]: MN-major
@@ -294,25 +331,35 @@ struct EpiPos {
 // predicates); GUARD = true: edge chunks.  All global offsets are 32-bit element indices from warp-uniform bases.
 struct PredCtx {
   const float* in;             // hidden: p.x[lin]; output: p.target
-  float* g32;                  // p.G32 (hidden only)
   __nv_bfloat16* gb;           // G ring slot of this step
   float* traj;                 // output: trajectory record of this step or nullptr
-  uint32_t d_o, SD, g_pitch;
-  uint32_t io, go, bo;         // element offsets of (chain 0 of the tile half, this lane's unit) in in / g32 / gb
+  uint32_t d_o, g_pitch;       // pitches of in and gb
+  uint32_t io, bo;             // element offsets of (chain 0 of the tile half, this lane's unit) in in / gb
   float bias, ce, gc, inv_var;
   int mode;                    // output: 0 no target (TOP_NONE / ZERO), 1 Gaussian, 2 Bernoulli
   bool on;                     // output: unit inside the loss mask
   int dbg;                     // MCPC_EPI_MODE
   bool cs;
+  // tile geometry of this warp
+  int lin, c_base, n_ok, n_warp, lane;
+  bool is_out, lanes_full, want_in, u_ok;
+  uint32_t stg;                // shared-memory address of the warp's staging buffer
 };
 
-template <bool GUARD>
-__device__ __forceinline__ void pred_load(const PredCtx& c, bool want, int cc, int n_ok, float (&v)[16]) {
+// stage chunk `cc` (16 chains of this lane's unit) of the predict input into ring slot `slot` of the warp's buffer
+__device__ __forceinline__ void pred_stage(const PredCtx& c, int cc, int slot) {
+  if (c.want_in && cc < c.n_warp) {
+    const uint32_t dst = c.stg + (uint32_t)slot * kPredSlot + (uint32_t)c.lane * 4u;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const bool ok = want && (!GUARD || (cc + j < n_ok)) && c.dbg != 3;
-    v[j] = ok ? ld_stream(c.in + (c.io + (uint32_t)(cc + j) * c.d_o), c.cs) : 0.0f;
+    for (int j = 0; j < 16; ++j)
+      if (cc + j < c.n_ok) cp_async4(dst + j * 128, c.in + (c.io + (uint32_t)(cc + j) * c.d_o));
   }
+  cp_async_commit();
+}
+__device__ __forceinline__ void pred_fetch(const PredCtx& c, int slot, float (&v)[16]) {
+  const uint32_t src = c.stg + (uint32_t)slot * kPredSlot + (uint32_t)c.lane * 4u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = c.want_in ? lds_f32(src + j * 128) : 0.0f;
 }
 
 template <bool GUARD>
@@ -328,13 +375,12 @@ __device__ __forceinline__ void pred_chunk_hidden(const PredCtx& c, int cc, int 
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const bool ok = !GUARD || (cc + j < n_ok);
-    const float eps = ok ? xv[j] - (d[j] + c.bias) : 0.0f;
+    const float eps = ok ? xv[j] - (d[j] + c.bias) : 0.0f;                // (unstaged slots hold stale bytes: never used)
     e_part = fmaf(c.ce * eps, eps, e_part);
     const float g = -c.gc * eps;
     const __nv_bfloat16 gb16 = __float2bfloat16(g);
     gsum += __bfloat162float(gb16);                                   // the bias gradient sums the operand the dW GEMM sees
     if (ok && c.dbg != 2) {
-      st_stream(c.g32 + (c.go + (uint32_t)(cc + j) * c.SD), g, c.cs);
       c.gb[c.bo + (uint32_t)(cc + j) * c.g_pitch] = gb16;
     }
   }
@@ -355,12 +401,13 @@ __device__ __forceinline__ void pred_chunk_out(const PredCtx& c, int cc, int n_o
     const bool ok = !GUARD || (cc + j < n_ok);
     const float o = d[j] + c.bias;
     float lv = 0.0f, e = 0.0f;
+    const float yj = (GUARD && !ok) ? 0.0f : yv[j];
     if (c.mode == 2) {
       const float z = __expf(-fabsf(o));
-      lv = fmaxf(o, 0.0f) - o * yv[j] + __logf(1.0f + z);
-      e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yv[j];
+      lv = fmaxf(o, 0.0f) - o * yj + __logf(1.0f + z);
+      e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - yj;
     } else if (c.mode == 1) {
-      const float dd = o - yv[j];
+      const float dd = o - yj;
       lv = 0.5f * c.inv_var * dd * dd;
       e = dd * c.inv_var;
     }
@@ -375,8 +422,9 @@ __device__ __forceinline__ void pred_chunk_out(const PredCtx& c, int cc, int n_o
   }
 }
 
-__device__ __forceinline__ void epilogue_predict(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc,
-                                                 bool has_acc, const EpiPos& ep, int slot_id) {
+// DEPTH = chunks the staging ring holds (stg_bytes / 2 KB)
+__device__ __forceinline__ void predict_ctx(const WideParams& p, const StepArgs& st, const TileDesc& t, const EpiPos& ep, uint32_t stg,
+                                            PredCtx& c) {
   const NetDev& nd = p.net;
   const int lin = t.idx;
   const bool is_out = (lin == nd.L);
@@ -384,8 +432,8 @@ __device__ __forceinline__ void epilogue_predict(const WideParams& p, const Step
   const int u = t.m0 + ep.q * 32 + ep.lane;
   const bool u_ok = u < d_o;
   const int c_base = t.n0 + ep.h * (kTN / 2);
-  PredCtx c;
-  c.d_o = (uint32_t)d_o; c.SD = (uint32_t)nd.SD; c.g_pitch = (uint32_t)p.g_pitch;
+  c.lin = lin; c.is_out = is_out; c.c_base = c_base; c.lane = ep.lane; c.u_ok = u_ok; c.stg = stg;
+  c.d_o = (uint32_t)d_o; c.g_pitch = (uint32_t)p.gpitch[lin];
   c.bias = (u_ok && p.b[lin] != nullptr) ? __ldg(p.b[lin] + u) : 0.0f;
   c.ce = is_out ? 0.0f : 0.5f * nd.c[lin];
   c.gc = is_out ? 0.0f : nd.gc[lin];
@@ -395,48 +443,55 @@ __device__ __forceinline__ void epilogue_predict(const WideParams& p, const Step
   c.dbg = MCPC_EPI_MODE(p);
   c.cs = p.cs != 0;
   c.in = is_out ? p.target : p.x[lin];
-  c.g32 = p.G32;
-  c.gb = p.Gb + ((size_t)st.slot * p.Bpad) * p.g_pitch;
+  c.gb = p.gb_l[lin] + ((size_t)st.slot * p.Bpad) * p.gpitch[lin];
   c.traj = (is_out && st.do_traj && p.traj_out != nullptr) ? p.traj_out + (size_t)st.rec * p.B * d_o : nullptr;
   c.io = (uint32_t)c_base * c.d_o + (uint32_t)u;
-  c.go = (uint32_t)c_base * c.SD + (uint32_t)(is_out ? 0 : nd.off[lin] + u);
-  c.bo = (uint32_t)c_base * c.g_pitch + (uint32_t)(p.poff[lin] + u);
-  const bool want_in = !is_out || c.mode != 0;                           // the output tile reads the target only under a loss
-  const int n_ok = u_ok ? (p.B - c_base) : 0;                            // chunk-relative chains cc < n_ok are this lane's
-  const int n_warp = min(kTN / 2, p.B - c_base);                         // chains of this tile half that exist (uniform)
-  const bool lanes_full = (t.m0 + ep.q * 32 + 32 <= d_o);                // uniform: every lane of the warp has a unit
-  float e_part = 0.0f, l_part = 0.0f, gsum = 0.0f;
-  if (n_warp > 0) {
-    float v[16];
-    if (lanes_full && n_warp >= 16) pred_load<false>(c, want_in, 0, n_ok, v);
-    else pred_load<true>(c, want_in, 0, n_ok, v);
-#pragma unroll 1
-    for (int cc = 0; cc < n_warp; cc += 16) {
-      float vn[16];                                                       // operands of the NEXT chunk: in flight meanwhile
-      const int cn = cc + 16;
-      if (lanes_full && cn + 16 <= n_warp) pred_load<false>(c, want_in, cn, n_ok, vn);
-      else pred_load<true>(c, want_in, cn, cn < n_warp ? n_ok : 0, vn);
-      const bool full = lanes_full && cc + 16 <= n_warp;
-      if (!is_out) {
-        if (full) pred_chunk_hidden<false>(c, cc, n_ok, acc + cc, has_acc, v, e_part, gsum);
-        else pred_chunk_hidden<true>(c, cc, n_ok, acc + cc, has_acc, v, e_part, gsum);
-      } else {
-        if (full) pred_chunk_out<false>(c, cc, n_ok, acc + cc, has_acc, v, l_part, gsum);
-        else pred_chunk_out<true>(c, cc, n_ok, acc + cc, has_acc, v, l_part, gsum);
-      }
+  c.bo = (uint32_t)c_base * c.g_pitch + (uint32_t)u;
+  c.want_in = (!is_out || c.mode != 0) && c.dbg != 3;                    // the output tile reads the target only under a loss
+  c.n_ok = u_ok ? (p.B - c_base) : 0;                                    // chunk-relative chains cc < n_ok are this lane's
+  c.n_warp = min(kTN / 2, p.B - c_base);                                 // chains of this tile half that exist (uniform)
+  c.lanes_full = (t.m0 + ep.q * 32 + 32 <= d_o);                         // uniform: every lane of the warp has a unit
+}
+
+template <int DEPTH>
+__device__ __forceinline__ void predict_prestage(const PredCtx& c) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = vn[j];
+  for (int k = 0; k < DEPTH; ++k) pred_stage(c, 16 * k, k);
+}
+
+template <int DEPTH>
+__device__ __forceinline__ void epilogue_predict(const WideParams& p, const StepArgs& st, const PredCtx& c, uint32_t acc, bool has_acc,
+                                                 int slot_id) {
+  const NetDev& nd = p.net;
+  float e_part = 0.0f, l_part = 0.0f, gsum = 0.0f;
+  int ci = 0;
+#pragma unroll 1
+  for (int cc = 0; cc < c.n_warp; cc += 16, ++ci) {
+    cp_async_wait<DEPTH - 1>();                                          // chunk ci has landed (its group is the oldest)
+    const int slot = ci % DEPTH;
+    float v[16];
+    pred_fetch(c, slot, v);
+    pred_stage(c, cc + 16 * DEPTH, slot);                                // refill the slot just read
+    const bool full = c.lanes_full && cc + 16 <= c.n_warp;
+    if (!c.is_out) {
+      if (full) pred_chunk_hidden<false>(c, cc, c.n_ok, acc + cc, has_acc, v, e_part, gsum);
+      else pred_chunk_hidden<true>(c, cc, c.n_ok, acc + cc, has_acc, v, e_part, gsum);
+    } else {
+      if (full) pred_chunk_out<false>(c, cc, c.n_ok, acc + cc, has_acc, v, l_part, gsum);
+      else pred_chunk_out<true>(c, cc, c.n_ok, acc + cc, has_acc, v, l_part, gsum);
     }
   }
+  cp_async_wait<0>();
   e_part = warp_sum_w(e_part);
   l_part = warp_sum_w(l_part);
-  if (ep.lane == 0) {
+  if (c.lane == 0) {
     float* dst = p.partials + ((size_t)st.ts * p.n_part + slot_id) * 2;
     dst[0] = e_part;
     dst[1] = l_part;
   }
   // gb_l += column sums of G over this warp's chains (lane = unit: the sum is already in a register)
-  if (st.acc && u_ok && p.gb[lin] != nullptr && ((lin < nd.L) || nd.top_has_grad)) atomicAdd(p.gb[lin] + u, gsum);
+  if (st.acc && c.u_ok && p.gb[c.lin] != nullptr && ((c.lin < nd.L) || nd.top_has_grad))
+    atomicAdd(p.gb[c.lin] + (c.io - (uint32_t)c.c_base * c.d_o), gsum);
 }
 
 // latent update of layer t.idx: x <- x - lr*grad (SGD | Adam), x <- x - lr*noise, act(x) re-emitted in bf16.
@@ -464,23 +519,48 @@ __device__ __forceinline__ float dact_t(int kind, float x, float a) {
 // All global offsets are 32-bit element indices from warp-uniform base pointers (wide_layout checks the ranges).
 struct UpdCtx {
   float* x;                    // p.x[l]
-  const float* g32;            // p.G32
+  const __nv_bfloat16* gown;   // G_l block of this step's ring slot: the own-layer gradient term (bf16 operand copy)
   __nv_bfloat16* act;          // act ring slot the update writes
-  uint32_t dl, SD, a_pitch;
-  uint32_t xo, go, ao;         // element offsets of (chain 0 of the tile half, this lane's unit)
+  uint32_t dl, a_pitch, g_pitch;
+  uint32_t xo, ao, bo;         // element offsets of (chain 0 of the tile half, this lane's unit) in x / act / gown
   uint32_t gu;                 // global unit index (Philox counter word 0)
   float nlr, nscale;
   int dbg;                     // MCPC_EPI_MODE
   bool cs;
+  // tile geometry of this warp
+  int l, kind, c_base, n_ok, n_warp, lane;
+  bool lanes_full;
+  uint32_t stg;                // shared-memory address of the warp's staging buffer
 };
 
-template <bool GUARD>
-__device__ __forceinline__ void upd_load(const UpdCtx& c, int cc, int n_ok, float (&xv)[16], float (&gv)[16]) {
+// stage chunk `cc` (latents and own-layer term of 16 chains of this lane's unit) into ring slot `slot`: fp32 x at bytes
+// [0, 2048), bf16 G_l at [2048, 3072).  cp.async moves at least 4 bytes, so the even lanes fetch their unit's and their
+// right neighbour's bf16 value (the block pitch is padded to 8 units: the pair always exists in memory).
+__device__ __forceinline__ void upd_stage(const UpdCtx& c, int cc, int slot) {
+  if (cc < c.n_warp && c.dbg != 3) {
+    const uint32_t dst = c.stg + (uint32_t)slot * kUpdSlot + (uint32_t)c.lane * 4u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (cc + j < c.n_ok) cp_async4(dst + j * 128, c.x + (c.xo + (uint32_t)(cc + j) * c.dl));
+    const int n_pair = max(c.n_ok, __shfl_down_sync(0xffffffffu, c.n_ok, 1));
+    if ((c.lane & 1) == 0) {
+      const uint32_t dstb = c.stg + (uint32_t)slot * kUpdSlot + 2048u + (uint32_t)c.lane * 2u;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (cc + j < n_pair) cp_async4(dstb + j * 64, c.gown + (c.bo + (uint32_t)(cc + j) * c.g_pitch));
+    }
+  }
+  cp_async_commit();
+}
+__device__ __forceinline__ void upd_fetch(const UpdCtx& c, int slot, float (&xv)[16], float (&gv)[16]) {
+  const uint32_t src = c.stg + (uint32_t)slot * kUpdSlot + (uint32_t)c.lane * 4u;
+  const uint32_t srcb = c.stg + (uint32_t)slot * kUpdSlot + 2048u + (uint32_t)c.lane * 2u;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const bool ok = (!GUARD || (cc + j < n_ok)) && c.dbg != 3;
-    xv[j] = ok ? ld_stream(c.x + (c.xo + (uint32_t)(cc + j) * c.dl), c.cs) : 0.0f;
-    gv[j] = ok ? ld_stream(c.g32 + (c.go + (uint32_t)(cc + j) * c.SD), c.cs) : 0.0f;
+    xv[j] = lds_f32(src + j * 128);
+    uint16_t h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(srcb + j * 64) : "memory");
+    gv[j] = __uint_as_float((uint32_t)h << 16);
   }
 }
 
@@ -512,7 +592,7 @@ __device__ __forceinline__ void upd_chunk(const WideParams& p, const StepArgs& s
   } else if (noise_kind == MCPC_NOISE_SUPPLIED) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      nz[j] = (!GUARD || cc + j < n_ok) ? __ldg(p.noise + ((size_t)st.ts * p.B + c_abs + j) * c.SD + c.gu) : 0.0f;
+      nz[j] = (!GUARD || cc + j < n_ok) ? __ldg(p.noise + ((size_t)st.ts * p.B + c_abs + j) * p.net.SD + c.gu) : 0.0f;
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) nz[j] = 0.0f;
@@ -528,10 +608,10 @@ __device__ __forceinline__ void upd_chunk(const WideParams& p, const StepArgs& s
   for (int j = 0; j < 16; ++j) {
     const bool ok = !GUARD || (cc + j < n_ok);
     const uint32_t xo = c.xo + (uint32_t)(cc + j) * c.dl;
-    float x = xv[j];
+    float x = (GUARD && !ok) ? 0.0f : xv[j];                              // (unstaged slots hold stale bytes)
     if (SPEC == 0 && do_traj && ok) p.traj_x[l][((size_t)st.rec * p.B + c_abs + j) * c.dl + (c.gu - (uint32_t)p.net.off[l])] = x;
     const float a = act_t<ACT>(kind, x);
-    const float grad = fmaf(dact_t<ACT>(kind, x, a), bp[j], -gv[j]);
+    const float grad = fmaf(dact_t<ACT>(kind, x, a), bp[j], -((GUARD && !ok) ? 0.0f : gv[j]));
     if (SPEC == 0 && want_xgrad && ok) p.xgrad[l][xo] = grad;
     if (SPEC == 1) {
       x = fmaf(c.nlr, grad, x);
@@ -556,53 +636,54 @@ __device__ __forceinline__ void upd_chunk(const WideParams& p, const StepArgs& s
   }
 }
 
-template <int SPEC, int ACT>
-__device__ __forceinline__ void epilogue_update(const WideParams& p, const StepArgs& st, const TileDesc& t, uint32_t acc,
-                                                bool has_acc, const EpiPos& ep) {
+__device__ __forceinline__ void update_ctx(const WideParams& p, const StepArgs& st, const TileDesc& t, const EpiPos& ep, uint32_t stg,
+                                           UpdCtx& c) {
   const NetDev& nd = p.net;
   const int l = t.idx;
   const int dl = nd.dims[l];
-  const int kind = nd.act[l];
   const int u = t.m0 + ep.q * 32 + ep.lane;
   const bool u_ok = u < dl;
   const int c_base = t.n0 + ep.h * (kTN / 2);
-  UpdCtx c;
+  c.l = l; c.kind = nd.act[l]; c.c_base = c_base; c.lane = ep.lane; c.stg = stg;
   c.x = p.x[l];
-  c.g32 = p.G32;
-  c.act = p.act + ((size_t)st.slot_next * p.Bpad) * p.a_pitch;
-  c.dl = (uint32_t)dl; c.SD = (uint32_t)nd.SD; c.a_pitch = (uint32_t)p.a_pitch;
+  c.gown = p.gb_l[l] + ((size_t)st.slot * p.Bpad) * p.gpitch[l];
+  c.act = p.act_l[l] + ((size_t)st.slot_next * p.Bpad) * p.apitch[l];
+  c.dl = (uint32_t)dl; c.a_pitch = (uint32_t)p.apitch[l]; c.g_pitch = (uint32_t)p.gpitch[l];
   c.xo = (uint32_t)c_base * c.dl + (uint32_t)u;
-  c.go = (uint32_t)c_base * c.SD + (uint32_t)(nd.off[l] + u);
-  c.ao = (uint32_t)c_base * c.a_pitch + (uint32_t)(p.poff[l] + u);
+  c.ao = (uint32_t)c_base * c.a_pitch + (uint32_t)u;
+  c.bo = (uint32_t)c_base * c.g_pitch + (uint32_t)u;
   c.gu = (uint32_t)(nd.off[l] + u);
   c.nlr = -p.lr;
   c.nscale = c.nlr * p.noise_scale;                                      // x <- x - lr * (noise_scale * xi)
   c.dbg = MCPC_EPI_MODE(p);
   c.cs = p.cs != 0;
-  const int n_ok = u_ok ? (p.B - c_base) : 0;                            // chunk-relative chains cc < n_ok are this lane's
-  const int n_warp = min(kTN / 2, p.B - c_base);                         // chains of this tile half that exist (uniform)
-  const bool lanes_full = (t.m0 + ep.q * 32 + 32 <= dl);                 // uniform: every lane of the warp has a unit
-  if (n_warp <= 0) return;
-  float xv[16], gv[16];
-  if (lanes_full && n_warp >= 16) upd_load<false>(c, 0, n_ok, xv, gv);
-  else upd_load<true>(c, 0, n_ok, xv, gv);
-#pragma unroll 1
-  for (int cc = 0; cc < n_warp; cc += 16) {
-    // operands of the NEXT chunk: in flight while this one is computed
-    float xn[16], gn[16];
-    const int cn = cc + 16;
-    if (lanes_full && cn + 16 <= n_warp) upd_load<false>(c, cn, n_ok, xn, gn);
-    else upd_load<true>(c, cn, cn < n_warp ? n_ok : 0, xn, gn);
-    if (lanes_full && cc + 16 <= n_warp)
-      upd_chunk<SPEC, ACT, false>(p, st, c, l, kind, c_base + cc, cc, n_ok, acc + cc, has_acc, xv, gv);
-    else
-      upd_chunk<SPEC, ACT, true>(p, st, c, l, kind, c_base + cc, cc, n_ok, acc + cc, has_acc, xv, gv);
+  c.n_ok = u_ok ? (p.B - c_base) : 0;                                    // chunk-relative chains cc < n_ok are this lane's
+  c.n_warp = min(kTN / 2, p.B - c_base);                                 // chains of this tile half that exist (uniform)
+  c.lanes_full = (t.m0 + ep.q * 32 + 32 <= dl);                          // uniform: every lane of the warp has a unit
+}
+
+template <int DEPTH>
+__device__ __forceinline__ void update_prestage(const UpdCtx& c) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      xv[j] = xn[j];
-      gv[j] = gn[j];
-    }
+  for (int k = 0; k < DEPTH; ++k) upd_stage(c, 16 * k, k);
+}
+
+template <int SPEC, int ACT, int DEPTH>
+__device__ __forceinline__ void epilogue_update(const WideParams& p, const StepArgs& st, const UpdCtx& c, uint32_t acc, bool has_acc) {
+  int ci = 0;
+#pragma unroll 1
+  for (int cc = 0; cc < c.n_warp; cc += 16, ++ci) {
+    cp_async_wait<DEPTH - 1>();                                          // chunk ci has landed (its group is the oldest)
+    const int slot = ci % DEPTH;
+    float xv[16], gv[16];
+    upd_fetch(c, slot, xv, gv);
+    upd_stage(c, cc + 16 * DEPTH, slot);                                 // refill the slot just read
+    if (c.lanes_full && cc + 16 <= c.n_warp)
+      upd_chunk<SPEC, ACT, false>(p, st, c, c.l, c.kind, c.c_base + cc, cc, c.n_ok, acc + cc, has_acc, xv, gv);
+    else
+      upd_chunk<SPEC, ACT, true>(p, st, c, c.l, c.kind, c.c_base + cc, cc, c.n_ok, acc + cc, has_acc, xv, gv);
   }
+  cp_async_wait<0>();
 }
 
 // gW tile += accumulator (exactly one CTA owns each tile: plain read-modify-write); lane = INPUT unit, so for a fixed
@@ -638,7 +719,7 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
   __shared__ Pipe pipe;
   __shared__ uint32_t tmem_s;
   constexpr bool A_MN = (KIND != KIND_PREDICT), B_MN = (KIND == KIND_WGRAD);
-  constexpr int NS = n_stages(CG);
+  constexpr int NS = n_stages(CG, KIND);
   constexpr uint32_t kA = a_bytes(), kB = b_bytes(CG), kStage = stage_bytes(CG);
   constexpr int kBRows = kTN / CG;                       // N indices of B this CTA stages
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -647,6 +728,13 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
   const int first_tile = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
+#ifdef MCPC_DEBUG_BUILD
+  if (p.dbg_buf != nullptr && blockIdx.x == 0 && tid == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.dbg_buf[KIND * 256 + 250] = (long long)ns;
+  }
+#endif
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&pipe.full[s], 1);
@@ -658,12 +746,17 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
     }
     fence_mbar_init();
   }
+  // Programmatic dependent launch: the next kernel of the step may become resident on this SM as soon as this CTA is gone
+  // (its barrier init / TMEM allocation then overlap the other SMs' last tiles instead of a full grid drain + launch);
+  // it touches no global memory before its own griddepcontrol.wait below.
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 1) tmem_alloc_cg<CG>(&tmem_s, 512);
   fence_before_sync();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_s;
   const uint32_t smem_base = smem_u32(smem);
+  if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");      // everything the previous kernels wrote is visible from here on
 
   if (warp == 0) {
     // ---------------- TMA producer: one elected lane, one mbarrier transaction per stage ----------------
@@ -681,9 +774,28 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
           }
         } else if (KIND == KIND_UPDATE) {
           if (p.pf_x) tma_prefetch_l2_2d(&mp.x32[t.idx], t.m0, t.n0);
-          if (p.pf_g) tma_prefetch_l2_2d(&mp.g32, p.net.off[t.idx] + t.m0, t.n0);
+        }
+        // The weight panel of a tile (A operand of PREDICT / UPDATE) is cold in L2: the tiles that share it -- the ntn chain
+        // tiles of one unit tile -- run in lock step on different SMs, so every one of them waits for the SAME DRAM fetch,
+        // whose latency under the epilogues' traffic exceeds what the shared-memory ring covers.  Each of the sharing tiles
+        // therefore prefetches every ntn-th stage of the panel into L2, p.wpf stages ahead (across the tile boundary too).
+        const bool do_wpf = (KIND != KIND_WGRAD) && p.wpf > 0;
+        TileDesc tn{};
+        int n_stage_next = 0;
+        if (do_wpf && tile + tile_stride < n_tiles) {
+          tn = decode_tile<KIND, CG>(p, st, mp, tile + tile_stride, rank);
+          n_stage_next = (tn.k_ext + kBK - 1) / kBK;
         }
         for (int s = 0; s < n_stage; ++s, ++issued) {
+          if (do_wpf) {
+            int sp = s + p.wpf;
+            const TileDesc* tp = &t;
+            if (sp >= n_stage) { sp -= n_stage; tp = (sp < n_stage_next) ? &tn : nullptr; }
+            if (tp != nullptr && (sp % tp->ntn) == tp->ni) {
+              if (!A_MN) tma_prefetch_l2_2d(tp->mapA, sp * kBK, tp->m0);
+              else if (p.mn3) tma_prefetch_l2_3d(tp->mapA, 0, sp * kBK, tp->m0 / 64);
+            }
+          }
           const uint32_t slot = issued % NS;
           mbar_wait(&pipe.empty[slot], ((issued / NS) & 1u) ^ 1u);
           uint8_t* sa = smem + slot * kStage;
@@ -728,8 +840,20 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
         const int n_stage = (t.k_ext + kBK - 1) / kBK;
         if (n_stage == 0) continue;
         const uint32_t ab = gi & 1u;
+#ifdef MCPC_DEBUG_BUILD
+        const bool tl = p.dbg_buf != nullptr && blockIdx.x == 0 && lane == 0 && gi < 16;
+        if (tl) {
+          p.dbg_buf[KIND * 256 + gi * 8 + 0] = clock64();
+          unsigned long long ns;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+          p.dbg_buf[KIND * 256 + gi * 8 + 7] = (long long)ns;
+        }
+#endif
         mbar_wait(&pipe.acc_empty[ab], ((gi >> 1) & 1u) ^ 1u);
         fence_after_sync();
+#ifdef MCPC_DEBUG_BUILD
+        if (tl) p.dbg_buf[KIND * 256 + gi * 8 + 1] = clock64();
+#endif
         for (int s = 0; s < n_stage; ++s, ++sc) {
           const uint32_t slot = sc % NS;
           mbar_wait(&pipe.full[slot], (sc / NS) & 1u);
@@ -745,6 +869,9 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
           }
           __syncwarp();
         }
+#ifdef MCPC_DEBUG_BUILD
+        if (tl) p.dbg_buf[KIND * 256 + gi * 8 + 2] = clock64();      // last MMA of the tile ISSUED
+#endif
         ++gi;
       }
     }
@@ -755,51 +882,86 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
     ep.ew = warp - 2;
     ep.h = ep.ew >> 2;
     ep.lane = lane;
+    constexpr int kDepthU = (int)(stg_bytes(CG, KIND_UPDATE) / kUpdSlot), kDepthP = (int)(stg_bytes(CG, KIND_PREDICT) / kPredSlot);
+    const uint32_t stg = smem_base + NS * kStage + (uint32_t)ep.ew * stg_bytes(CG, KIND);
     const uint32_t acc_empty_addr = (CG == 2) ? mapa_rank(smem_u32(&pipe.acc_empty[0]), 0) : smem_u32(&pipe.acc_empty[0]);
+    const bool run_epi = MCPC_EPI_MODE(p) != 1;            // debug mode 1: mainloop-only rate, results are garbage
     uint32_t gi = 0;
-    for (int tile = first_tile; tile < n_tiles; tile += tile_stride) {
-      const TileDesc t = decode_tile<KIND, CG>(p, st, mp, tile, rank);
+    int tile = first_tile;
+    TileDesc t{};
+    PredCtx pc;
+    UpdCtx uc;
+    // the inputs of a tile's first chunks are staged BEFORE the wait for its accumulator: they fly during the mainloop
+    auto begin_tile = [&]() {
+      t = decode_tile<KIND, CG>(p, st, mp, tile, rank);
+      if (!run_epi) return;
+      if (KIND == KIND_PREDICT) {
+        predict_ctx(p, st, t, ep, stg, pc);
+        predict_prestage<kDepthP>(pc);
+      } else if (KIND == KIND_UPDATE) {
+        update_ctx(p, st, t, ep, stg, uc);
+        update_prestage<kDepthU>(uc);
+      }
+    };
+    if (tile < n_tiles) begin_tile();
+    while (tile < n_tiles) {
       const bool has_gemm = t.k_ext > 0;
       const uint32_t ab = gi & 1u;
+#ifdef MCPC_DEBUG_BUILD
+      const bool tl = p.dbg_buf != nullptr && blockIdx.x == 0 && lane == 0 && ep.ew == 0 && gi < 16 && has_gemm;
+      if (tl) p.dbg_buf[KIND * 256 + gi * 8 + 3] = clock64();
+#endif
       if (has_gemm) {
         mbar_wait(&pipe.acc_full[ab], (gi >> 1) & 1u);
         fence_after_sync();
       }
-      const uint32_t acc = tmem + ((uint32_t)(ep.q * 32) << 16) + ab * kTN + ep.h * (kTN / 2);
 #ifdef MCPC_DEBUG_BUILD
-      if (p.skip_epilogue == 1) {
-        // debug (MCPC_WIDE_SKIP_EPI=1, results are garbage): mainloop-only rate of the three kernels
-      } else
+      if (tl) p.dbg_buf[KIND * 256 + gi * 8 + 4] = clock64();
 #endif
-      if (KIND == KIND_PREDICT) {
-        const int slot_id = (tile * CG + rank) * kEpiWarps + ep.ew;
-        epilogue_predict(p, st, t, acc, has_gemm, ep, slot_id);
+      const uint32_t acc = tmem + ((uint32_t)(ep.q * 32) << 16) + ab * kTN + ep.h * (kTN / 2);
+      if (!run_epi) {
+      } else if (KIND == KIND_PREDICT) {
+        epilogue_predict<kDepthP>(p, st, pc, acc, has_gemm, (tile * CG + rank) * kEpiWarps + ep.ew);
       } else if (KIND == KIND_UPDATE) {
         if (SPEC == 1) {
-          const int kind = p.net.act[t.idx];
-          if (kind == MCPC_ACT_TANH) epilogue_update<1, MCPC_ACT_TANH>(p, st, t, acc, has_gemm, ep);
-          else if (kind == MCPC_ACT_RELU) epilogue_update<1, MCPC_ACT_RELU>(p, st, t, acc, has_gemm, ep);
-          else epilogue_update<1, MCPC_ACT_IDENTITY>(p, st, t, acc, has_gemm, ep);
+          if (uc.kind == MCPC_ACT_TANH) epilogue_update<1, MCPC_ACT_TANH, kDepthU>(p, st, uc, acc, has_gemm);
+          else if (uc.kind == MCPC_ACT_RELU) epilogue_update<1, MCPC_ACT_RELU, kDepthU>(p, st, uc, acc, has_gemm);
+          else epilogue_update<1, MCPC_ACT_IDENTITY, kDepthU>(p, st, uc, acc, has_gemm);
         } else {
-          epilogue_update<0, -1>(p, st, t, acc, has_gemm, ep);
+          epilogue_update<0, -1, kDepthU>(p, st, uc, acc, has_gemm);
         }
       } else {
         epilogue_wgrad(p, t, acc, ep);
       }
       if (has_gemm) {
+#ifdef MCPC_DEBUG_BUILD
+        if (tl) p.dbg_buf[KIND * 256 + gi * 8 + 5] = clock64();
+#endif
         fence_before_sync();
         __syncwarp();
         if (lane == 0) {
           if (CG == 2) mbar_arrive_cluster(acc_empty_addr + ab * 8);
           else mbar_arrive(&pipe.acc_empty[ab]);
         }
+#ifdef MCPC_DEBUG_BUILD
+        if (tl) p.dbg_buf[KIND * 256 + gi * 8 + 6] = clock64();
+#endif
         ++gi;
       }
+      tile += tile_stride;
+      if (tile < n_tiles) begin_tile();
     }
   }
   fence_before_sync();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) tmem_dealloc_cg<CG>(tmem, 512);
+#ifdef MCPC_DEBUG_BUILD
+  if (p.dbg_buf != nullptr && blockIdx.x == 0 && tid == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.dbg_buf[KIND * 256 + 251] = (long long)ns;
+  }
+#endif
 }
 
 // fp32 [rows][cols] -> bf16 [rows][pitch] (pitch = cols rounded up to 8: TMA needs 16-byte row strides); pad columns zero
@@ -820,7 +982,7 @@ __global__ void init_act_kernel(WideParams p) {
     int l = 0;
     while (u >= nd.off[l + 1]) ++l;
     const int k = u - nd.off[l];
-    p.act[(size_t)row * p.a_pitch + p.poff[l] + k] = __float2bfloat16(act_w(nd.act[l], p.x[l][(size_t)row * nd.dims[l] + k]));
+    p.act_l[l][(size_t)row * p.apitch[l] + k] = __float2bfloat16(act_w(nd.act[l], p.x[l][(size_t)row * nd.dims[l] + k]));
   }
 }
 
@@ -828,13 +990,12 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline int pad8w(int v) { return (v + 7) & ~7; }
 
 struct WideLayout {
-  size_t wb_off[kMaxL + 1], act_off, gb_off, g32_off, part_off, total;
-  int poff[kMaxL + 1], a_pitch, g_pitch, n_part, Bpad, S, cg;
-  size_t act_slot, gb_slot;                  // bytes of one ring slot
+  size_t wb_off[kMaxL + 1], act_off[kMaxL], gb_off[kMaxL + 1], part_off, total;
+  int apitch[kMaxL], gpitch[kMaxL + 1], n_part, Bpad, S, cg;
 };
 
 struct WideKnobs {
-  int cg, slots, ctas, nospec, epi_pf, cs;
+  int cg, slots, ctas, nospec, epi_pf, cs, wpf, pdl;
 #ifdef MCPC_DEBUG_BUILD
   int skip_epi;
 #endif
@@ -851,8 +1012,12 @@ WideKnobs wide_knobs() {
   k.ctas = 0;
   if (const char* env = getenv("MCPC_WIDE_CTAS")) k.ctas = atoi(env);
   k.nospec = getenv("MCPC_TC_NOSPEC") != nullptr ? 1 : 0;
-  k.cs = 1;
+  k.cs = 0;          // measured on C5: no effect (0.724 / 0.710 ms per step without / with)
   if (const char* env = getenv("MCPC_WIDE_CS")) k.cs = atoi(env) != 0 ? 1 : 0;
+  k.pdl = 0;         // programmatic dependent launch: measured on C5 (T=100) 0.669 ms per step without, 0.687 with
+  if (const char* env = getenv("MCPC_WIDE_PDL")) k.pdl = atoi(env) != 0 ? 1 : 0;
+  k.wpf = 0;         // measured on C5: 0.719 ms per step without the weight-panel prefetch, 0.753-0.756 with 6 / 12 / 24 stages
+  if (const char* env = getenv("MCPC_WIDE_WPF")) k.wpf = atoi(env);
   k.epi_pf = 0;      // measured on C5: 0.734 ms/step with the L2 prefetch of the epilogue inputs, 0.700 without
   if (const char* env = getenv("MCPC_WIDE_EPIPF")) k.epi_pf = atoi(env) != 0 ? 1 : 0;
 #ifdef MCPC_DEBUG_BUILD
@@ -864,41 +1029,49 @@ WideKnobs wide_knobs() {
 
 int wide_layout(const NetDev& nd, int B, int n_steps, WideLayout* lay) {
   const WideKnobs kn = wide_knobs();
-  int f_off[kMaxL + 1];
-  save_layout_bf16(nd, lay->poff, &lay->g_pitch, f_off, &lay->a_pitch);
+  const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
   lay->cg = kn.cg;
   lay->Bpad = (B + 63) & ~63;
+  size_t slot_bytes = 0;                                 // one ring slot of all bf16 operand blocks
+  int widest = 8;
+  for (int l = 0; l < nd.L; ++l) {
+    lay->apitch[l] = pad8w(nd.dims[l]);
+    lay->gpitch[l] = pad8w(nd.dims[l]);
+    slot_bytes += (size_t)lay->Bpad * (lay->apitch[l] + lay->gpitch[l]) * 2;
+    if (lay->apitch[l] > widest) widest = lay->apitch[l];
+  }
+  lay->gpitch[nd.L] = pad8w(nd.d_out > 0 ? nd.d_out : 8);
+  if (nd.d_out > 0) slot_bytes += (size_t)lay->Bpad * lay->gpitch[nd.L] * 2;
+  if (lay->gpitch[nd.L] > widest) widest = lay->gpitch[nd.L];
   {
     // the epilogues index global memory with 32-bit element offsets
-    const size_t widest = (size_t)(lay->g_pitch > nd.SD ? lay->g_pitch : nd.SD);
-    if ((size_t)(lay->Bpad + kTN) * widest >= ((size_t)1 << 31)) {
-      set_error("bf16 streaming path: B * row width = %zu elements exceeds the 2^31 the kernels index; shard the batch",
-                (size_t)B * widest);
+    if ((size_t)(lay->Bpad + kTN) * (size_t)widest >= ((size_t)1 << 31)) {
+      set_error("bf16 streaming path: B * layer width = %zu elements exceeds the 2^31 the kernels index; shard the batch",
+                (size_t)B * (size_t)widest);
       return MCPC_ERR_UNSUPPORTED;
     }
   }
   size_t o = 0;
-  const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
   for (int l = 1; l < n_lin; ++l) {
     lay->wb_off[l] = o;
     o += align256((size_t)(l == nd.L ? nd.d_out : nd.dims[l]) * pad8w(nd.dims[l - 1]) * 2);
   }
   // ring of S slots of the bf16 operands: S steps of the accumulate window are contracted by ONE weight-gradient launch.
   // Default 4: with C5's 2048 chains both operands of a layer (134 MB) stay L2-resident during the launch.
-  lay->act_slot = (size_t)lay->Bpad * lay->a_pitch * 2;
-  lay->gb_slot = (size_t)lay->Bpad * lay->g_pitch * 2;
   int S = 4;
   const size_t budget = (size_t)4 << 30;
-  while (S > 1 && (size_t)S * (lay->act_slot + lay->gb_slot) > budget) --S;
+  while (S > 1 && (size_t)S * slot_bytes > budget) --S;
   if (kn.slots >= 1 && kn.slots <= 64) S = kn.slots;
   if (S > n_steps) S = n_steps;
   lay->S = S;
-  lay->act_off = o;
-  o += align256((size_t)S * lay->act_slot + 65536);
-  lay->gb_off = o;
-  o += align256((size_t)S * lay->gb_slot + 65536);
-  lay->g32_off = o;
-  o += align256((size_t)B * nd.SD * 4);
+  for (int l = 0; l < nd.L; ++l) {
+    lay->act_off[l] = o;
+    o += align256((size_t)S * lay->Bpad * lay->apitch[l] * 2 + 65536);
+  }
+  for (int l = 0; l < n_lin; ++l) {
+    lay->gb_off[l] = o;
+    o += align256((size_t)S * lay->Bpad * lay->gpitch[l] * 2 + 65536);
+  }
   const int ntn = (B + kTN - 1) / kTN;
   int n_part = 0;
   for (int l = 0; l < n_lin; ++l) {
@@ -924,13 +1097,15 @@ int launch_wide(const WideParams& p, const StepArgs& st, const WideMaps& mp, int
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = p.pdl ? 2 : 1;
   MCPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, wide_kernel<KIND, SPEC, CG>, p, st, mp));
   count_launch();
   return MCPC_OK;
@@ -990,18 +1165,18 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
   constexpr int kBRows = kTN / CG;
   int rc = MCPC_OK;
   for (int l = 0; l < nd.L; ++l) {
-    rc = make_tmap_bf16(&mp.act_k[l], p.act + p.poff[l], nd.dims[l], rows, p.a_pitch, 64, kBRows);             // predict B
+    rc = make_tmap_bf16(&mp.act_k[l], p.act_l[l], nd.dims[l], rows, p.apitch[l], 64, kBRows);                  // predict B
     if (rc == MCPC_OK)
-      rc = mn3 ? make_tmap_bf16_mn3(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], rows, p.a_pitch, 64, kTM / 64)  // wgrad A
-               : make_tmap_bf16(&mp.act_mn[l], p.act + p.poff[l], nd.dims[l], rows, p.a_pitch, 64, 64);
+      rc = mn3 ? make_tmap_bf16_mn3(&mp.act_mn[l], p.act_l[l], nd.dims[l], rows, p.apitch[l], 64, kTM / 64)       // wgrad A
+               : make_tmap_bf16(&mp.act_mn[l], p.act_l[l], nd.dims[l], rows, p.apitch[l], 64, 64);
     if (rc != MCPC_OK) return rc;
   }
   for (int l = 0; l < n_lin; ++l) {
     const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
-    rc = make_tmap_bf16(&mp.gb_k[l], p.Gb + p.poff[l], d_o, rows, p.g_pitch, 64, kBRows);                       // update B
+    rc = make_tmap_bf16(&mp.gb_k[l], p.gb_l[l], d_o, rows, p.gpitch[l], 64, kBRows);                            // update B
     if (rc == MCPC_OK)
-      rc = mn3 ? make_tmap_bf16_mn3(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, rows, p.g_pitch, 64, kBRows / 64)        // wgrad B
-               : make_tmap_bf16(&mp.gb_mn[l], p.Gb + p.poff[l], d_o, rows, p.g_pitch, 64, 64);
+      rc = mn3 ? make_tmap_bf16_mn3(&mp.gb_mn[l], p.gb_l[l], d_o, rows, p.gpitch[l], 64, kBRows / 64)             // wgrad B
+               : make_tmap_bf16(&mp.gb_mn[l], p.gb_l[l], d_o, rows, p.gpitch[l], 64, 64);
     if (rc == MCPC_OK && l >= 1) {
       const int d_i = nd.dims[l - 1], wp = pad8w(d_i);
       rc = make_tmap_bf16(&mp.w_k[l], Wb[l], d_i, d_o, wp, 64, kTM);                                             // predict A
@@ -1012,23 +1187,25 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
     if (rc != MCPC_OK) return rc;
   }
   // fp32 prefetch views (optional: skipped when a base or a row stride is not 16-byte aligned)
-  p.pf_x = p.pf_g = p.pf_t = 0;
+  p.pf_x = p.pf_t = 0;
   if (kn.epi_pf) {
     bool ok = true;
     for (int l = 0; l < nd.L && ok; ++l)
       ok = (nd.dims[l] % 4 == 0) && (reinterpret_cast<uintptr_t>(p.x[l]) % 16 == 0) &&
            make_tmap_f32(&mp.x32[l], p.x[l], nd.dims[l], B, nd.dims[l], kTM, kTN) == MCPC_OK;
     p.pf_x = ok ? 1 : 0;
-    p.pf_g = (nd.SD % 4 == 0 && make_tmap_f32(&mp.g32, p.G32, nd.SD, B, nd.SD, kTM, kTN) == MCPC_OK) ? 1 : 0;
     p.pf_t = (p.target != nullptr && nd.top >= MCPC_TOP_GAUSS && nd.d_out % 4 == 0 &&
               reinterpret_cast<uintptr_t>(p.target) % 16 == 0 &&
               make_tmap_f32(&mp.tgt, p.target, nd.d_out, B, nd.d_out, kTM, kTN) == MCPC_OK) ? 1 : 0;
   }
-  const size_t smem_g = (size_t)n_stages(CG) * stage_bytes(CG) + 1024;
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 1, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_WGRAD, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+  auto smem_of = [](int kind) {
+    return (size_t)n_stages(CG, kind) * stage_bytes(CG) + (size_t)kEpiWarps * stg_bytes(CG, kind) + 1024;
+  };
+  const size_t smem_p = smem_of(KIND_PREDICT), smem_u = smem_of(KIND_UPDATE), smem_w = smem_of(KIND_WGRAD);
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_PREDICT, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_UPDATE, 1, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
+  MCPC_CUDA_CHECK(cudaFuncSetAttribute(wide_kernel<KIND_WGRAD, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
   int n_sm = 148;
   {
     int dev = 0;
@@ -1040,7 +1217,7 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)(n_sm & ~1));
       cfg.blockDim = dim3(kThreads);
-      cfg.dynamicSmemBytes = smem_g;
+      cfg.dynamicSmemBytes = smem_u;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2;
@@ -1060,10 +1237,21 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
   // rows B..Bpad of every ring slot enter the weight-gradient contraction: they must be zero in both operands
   if (lay.Bpad > B) {
     for (int s = 0; s < lay.S; ++s) {
-      MCPC_CUDA_CHECK(cudaMemsetAsync(p.act + ((size_t)s * lay.Bpad + B) * p.a_pitch, 0, (size_t)(lay.Bpad - B) * p.a_pitch * 2, stream));
-      MCPC_CUDA_CHECK(cudaMemsetAsync(p.Gb + ((size_t)s * lay.Bpad + B) * p.g_pitch, 0, (size_t)(lay.Bpad - B) * p.g_pitch * 2, stream));
+      for (int l = 0; l < nd.L; ++l)
+        MCPC_CUDA_CHECK(cudaMemsetAsync(p.act_l[l] + ((size_t)s * lay.Bpad + B) * p.apitch[l], 0,
+                                        (size_t)(lay.Bpad - B) * p.apitch[l] * 2, stream));
+      for (int l = 0; l < n_lin; ++l)
+        MCPC_CUDA_CHECK(cudaMemsetAsync(p.gb_l[l] + ((size_t)s * lay.Bpad + B) * p.gpitch[l], 0,
+                                        (size_t)(lay.Bpad - B) * p.gpitch[l] * 2, stream));
     }
   }
+#ifdef MCPC_DEBUG_BUILD
+  const bool timing = getenv("MCPC_WIDE_TIMING") != nullptr;      // debug only: allocates + synchronises
+  if (timing) {
+    cudaMalloc(&p.dbg_buf, 3 * 256 * sizeof(long long));
+    cudaMemsetAsync(p.dbg_buf, 0, 3 * 256 * sizeof(long long), stream);
+  }
+#endif
   init_act_kernel<<<1184, 256, 0, stream>>>(p);
   count_launch();
   double b1p = pow(o->adam_beta1, (double)o->adam_step0), b2p = pow(o->adam_beta2, (double)o->adam_step0);
@@ -1088,7 +1276,7 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
     const bool acc = any_grad && ts >= o->save_begin && ts < o->save_end;
     st.acc = acc ? 1 : 0;                  // the predict epilogue adds the bias gradients (column sums of G) on these steps
     st.slot = used;
-    rc = launch_wide<KIND_PREDICT, 0, CG>(p, st, mp, n_predict, n_sm, smem_g, stream);
+    rc = launch_wide<KIND_PREDICT, 0, CG>(p, st, mp, n_predict, n_sm, smem_p, stream);
     if (rc != MCPC_OK) return rc;
     // the weight update reads G (this step's errors) and act(x) of the state BEFORE the update: it runs between the two,
     // once the ring is full or the window ends
@@ -1097,17 +1285,48 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
       const bool window_ends = (ts + 1 >= o->save_end) || (ts + 1 >= o->n_steps);
       if (used == lay.S || window_ends) {
         st.k_rows = used * lay.Bpad;
-        rc = launch_wide<KIND_WGRAD, 0, CG>(p, st, mp, n_wgrad, n_sm, smem_g, stream);
+        rc = launch_wide<KIND_WGRAD, 0, CG>(p, st, mp, n_wgrad, n_sm, smem_w, stream);
         if (rc != MCPC_OK) return rc;
         used = 0;
       }
     }
     st.slot_next = used;
-    if (spec_update) rc = launch_wide<KIND_UPDATE, 1, CG>(p, st, mp, n_update, n_sm, smem_g, stream);
-    else rc = launch_wide<KIND_UPDATE, 0, CG>(p, st, mp, n_update, n_sm, smem_g, stream);
+    if (spec_update) rc = launch_wide<KIND_UPDATE, 1, CG>(p, st, mp, n_update, n_sm, smem_u, stream);
+    else rc = launch_wide<KIND_UPDATE, 0, CG>(p, st, mp, n_update, n_sm, smem_u, stream);
     if (rc != MCPC_OK) return rc;
   }
   MCPC_CUDA_CHECK(cudaGetLastError());
+#ifdef MCPC_DEBUG_BUILD
+  if (timing) {
+    static long long h[3 * 256];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, p.dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg_buf);
+    const char* names[3] = {"predict", "update", "wgrad"};
+    fprintf(stderr, "[wide timeline] last step: predict exit -> %s entry %lld ns; predict entry -> update exit %lld ns\n",
+            h[2 * 256 + 250] > h[0 * 256 + 251] && h[2 * 256 + 250] < h[1 * 256 + 250] ? "wgrad" : "update",
+            (h[2 * 256 + 250] > h[0 * 256 + 251] && h[2 * 256 + 250] < h[1 * 256 + 250] ? h[2 * 256 + 250] : h[1 * 256 + 250]) - h[0 * 256 + 251],
+            h[1 * 256 + 251] - h[0 * 256 + 250]);
+    for (int k = 0; k < 3; ++k) {
+      const long long t0 = h[k * 256 + 0];
+      if (t0 == 0) continue;
+      fprintf(stderr, "[wide timeline] %s, CTA 0, last launch (cycles since the MMA warp's first wait)\n", names[k]);
+      for (int g = 0; g < 16 && h[k * 256 + g * 8 + 1] != 0; ++g) {
+        const long long* r = h + k * 256 + g * 8;
+        fprintf(stderr, "  tile %2d: mma wait-acc %7lld..%7lld issue-done %7lld | epi wait %7lld..%7lld done %7lld arrive %7lld\n", g,
+                r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);
+      }
+      fprintf(stderr, "  CTA 0 alive %lld ns (entry -> exit)\n", h[k * 256 + 251] - h[k * 256 + 250]);
+      int last = 0;
+      while (last + 1 < 16 && h[k * 256 + (last + 1) * 8 + 1] != 0) ++last;
+      if (last > 0) {
+        const double cyc = (double)(h[k * 256 + last * 8 + 0] - h[k * 256 + 0]);
+        const double ns = (double)(h[k * 256 + last * 8 + 7] - h[k * 256 + 7]);
+        fprintf(stderr, "  SM clock over tiles 0..%d: %.0f cycles / %.0f ns = %.3f GHz\n", last, cyc, ns, cyc / ns);
+      }
+    }
+  }
+#endif
   if (io->energy != nullptr || io->loss != nullptr) return launch_reduce_partials(p.partials, o->n_steps, p.n_part, io->energy, io->loss, stream);
   return MCPC_OK;
 }
@@ -1147,16 +1366,16 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.Bpad = lay.Bpad;
   const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
   for (int l = 0; l <= nd.L; ++l) {
-    p.poff[l] = lay.poff[l];
     p.b[l] = io->b[l];
     p.gW[l] = io->gW[l];
     p.gb[l] = io->gb[l];
+    p.gpitch[l] = lay.gpitch[l];
+    p.gb_l[l] = (l < nd.L || nd.d_out > 0) ? reinterpret_cast<__nv_bfloat16*>(wsb + lay.gb_off[l]) : nullptr;
   }
-  p.a_pitch = lay.a_pitch;
-  p.g_pitch = lay.g_pitch;
-  p.act = reinterpret_cast<__nv_bfloat16*>(wsb + lay.act_off);
-  p.Gb = reinterpret_cast<__nv_bfloat16*>(wsb + lay.gb_off);
-  p.G32 = reinterpret_cast<float*>(wsb + lay.g32_off);
+  for (int l = 0; l < nd.L; ++l) {
+    p.apitch[l] = lay.apitch[l];
+    p.act_l[l] = reinterpret_cast<__nv_bfloat16*>(wsb + lay.act_off[l]);
+  }
   p.partials = reinterpret_cast<float*>(wsb + lay.part_off);
   p.n_part = lay.n_part;
   const __nv_bfloat16* Wb[kMaxL + 1] = {};
@@ -1190,6 +1409,8 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.seed = o->seed;
   p.chain_offset = o->chain_offset;
   p.cs = kn.cs;
+  p.wpf = kn.wpf < 0 ? 0 : kn.wpf;
+  p.pdl = kn.pdl;
 #ifdef MCPC_DEBUG_BUILD
   p.skip_epilogue = kn.skip_epi;
 #endif

@@ -151,7 +151,13 @@ class PCTrainer(object):
 
         # ---- B200 execution state (not part of the reference API) ----
         self._engine = None                    # NativeEngine, created on first use
-        self._precision = N.PREC_FP32          # MCPC_PREC_*; see set_precision()
+        # MCPC_PREC_* of the next call.  Requested mode: env MCPC_PRECISION = auto (default) | bf16 | fp32, or
+        # set_precision().  'auto' takes the tcgen05 bf16 kernels whenever they implement the call (the stated bound:
+        # tests/test_gpu_bf16_bound.py) and the reference-exact fp32 kernels otherwise (non-zero `inputs`).
+        self._precision_req = os.environ.get("MCPC_PRECISION", "auto").strip().lower()
+        if self._precision_req not in ("auto", "bf16", "fp32"):
+            raise ValueError(f"MCPC_PRECISION={self._precision_req!r}: expected auto, bf16 or fp32")
+        self._precision = N.PREC_BF16 if self._precision_req == "bf16" else N.PREC_FP32
         self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self._noise_epoch = 0                  # advances every call so successive calls draw fresh noise
         self._keep_unused_param_grads = False  # see set_keep_unused_param_grads()
@@ -177,11 +183,21 @@ class PCTrainer(object):
     #  B200-specific knobs
     # ======================================================================================
     def set_precision(self, precision) -> None:
-        """'fp32' (reference-exact CUDA-core mode) or 'bf16' (tcgen05 tensor-core mode)."""
-        table = {"fp32": N.PREC_FP32, "bf16": N.PREC_BF16, N.PREC_FP32: N.PREC_FP32, N.PREC_BF16: N.PREC_BF16}
+        """'fp32' (reference-exact CUDA-core kernels, 1e-5 parity), 'bf16' (tcgen05 tensor-core kernels: bf16 operands,
+        fp32 latents and accumulation; stated bound in tests/test_gpu_bf16_bound.py) or 'auto' (bf16 whenever the bf16
+        kernels implement the call, else fp32).  Overrides the MCPC_PRECISION environment variable."""
+        table = {"fp32": "fp32", "bf16": "bf16", "auto": "auto", N.PREC_FP32: "fp32", N.PREC_BF16: "bf16"}
         if precision not in table:
             raise ValueError(f"unknown precision {precision!r}")
-        self._precision = table[precision]
+        self._precision_req = table[precision]
+        self._precision = N.PREC_BF16 if self._precision_req == "bf16" else N.PREC_FP32
+
+    def _resolve_precision(self, inputs) -> int:
+        """The MCPC_PREC_* this call runs in ('auto': bf16 unless the call has non-zero ``inputs``, which only the
+        fp32 kernels implement)."""
+        if self._precision_req != "auto":
+            return N.PREC_BF16 if self._precision_req == "bf16" else N.PREC_FP32
+        return N.PREC_BF16 if self._inputs_or_none(inputs) is None else N.PREC_FP32
 
     def set_noise_seed(self, seed: int) -> None:
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -513,6 +529,7 @@ class PCTrainer(object):
         self._start_of_batch(netp, inputs, is_sample_x_at_batch_start, is_reset_optimizer_x_at_batch_start,
                              is_reset_optimizer_p_at_batch_start)
 
+        self._precision = self._resolve_precision(inputs)
         langevin = P.classify_callback_after_t(callback_after_t, callback_after_t_kwargs, self)
         x_opt = self._classify_optimizer_x()
         fused = (
@@ -677,11 +694,15 @@ class PCTrainer(object):
             if lin.bias is not None:
                 params.append(lin.bias)
         total = sum(p.numel() for p in params)
+        # tail: room for the [2, T] per-step scalars as fp32 (hi, lo) pairs, so that a data-parallel learning call needs
+        # ONE all-reduce for the weight gradients and the results dict together (see _p_step)
+        tail = 4 * self._T
+        self._flat_total = total
         sig = tuple(id(p) for p in params)
         flat = self._flat_grad
-        fresh = flat is None or flat[0] != sig or flat[1].numel() != total or flat[1].device != params[0].device
+        fresh = flat is None or flat[0] != sig or flat[1].numel() != total + tail or flat[1].device != params[0].device
         if fresh:
-            buf = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+            buf = torch.zeros(total + tail, dtype=torch.float32, device=params[0].device)
             o = 0
             for p in params:
                 n = p.numel()
@@ -725,18 +746,32 @@ class PCTrainer(object):
         import torch.distributed as dist
         return dist.get_rank(self._dp_group) * B
 
-    def _p_step(self, flat, B):
-        """pc_trainer.py:904-914: normalise ``.grad`` in place, then the user's optimizer."""
+    def _p_step(self, flat, B, scalars=None):
+        """pc_trainer.py:904-914: normalise ``.grad`` in place, then the user's optimizer.  Data-parallel: ONE all-reduce
+        (sum) over the flat gradient buffer; when ``scalars`` (the [2, T] fp64 energy / loss sums of this rank) is given
+        they ride in the buffer's tail as fp32 (hi, lo) pairs and the reduced values are returned."""
+        total = self._flat_total
+        reduced = None
         if self._dp_group is not None:
             import torch.distributed as dist
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._dp_group)
+            n_tail = 0
+            if scalars is not None and 2 * scalars.numel() <= flat.numel() - total:
+                n_tail = 2 * scalars.numel()
+                hi = scalars.to(torch.float32)
+                lo = (scalars - hi.to(torch.float64)).to(torch.float32)
+                flat[total:total + n_tail].view(2, -1).copy_(torch.stack([hi.reshape(-1), lo.reshape(-1)]))
+            dist.all_reduce(flat[:total + n_tail], op=dist.ReduceOp.SUM, group=self._dp_group)
+            if n_tail:
+                pair = flat[total:total + n_tail].view(2, -1).to(torch.float64)
+                reduced = (pair[0] + pair[1]).view_as(scalars)
         Bg = self._global_batch(B)
         n_acc = len(self._accumulate_p_at)
         norm = float(n_acc * Bg if n_acc > 0 else Bg)
         if self._fused_p_optimizer and self._fused_p_step(1.0 / norm):
-            return
-        flat.div_(norm)
+            return reduced
+        flat[:total].div_(norm)
         self._optimizer_p.step()
+        return reduced
 
     def _fused_p_step(self, inv_norm) -> bool:
         """normalisation + ``optimizer_p.step()`` as ONE kernel per param group (``mcpc_p_step``), in
@@ -874,6 +909,7 @@ class PCTrainer(object):
         flat = None
         n_launch = 0
         host_scalars = None
+        scalars_reduced = False
         for si, (t0, t1) in enumerate(segs):
             ends_with_p = (t1 - 1) in self._update_p_set
             need_grads = self._keep_unused_param_grads or any(u >= t0 for u in later_p_updates)
@@ -943,9 +979,10 @@ class PCTrainer(object):
                 n_launch += 1
                 if stats is not None and n_r > 0:
                     self._fold_traj_stats(eng, stats, tx_cut, n_r)
-                if c1 == T:
+                if c1 == T and not (ends_with_p and self._dp_group is not None):
                     # the per-step scalars are final here: start their read-back on a side stream now, so that the
                     # host gets them while the weight-gradient / optimizer_p kernels of this call are still running
+                    # (data-parallel learning calls: they travel with the gradient all-reduce instead, see below)
                     host_scalars = self._start_scalar_readback(scalars)
                 if x_opt["kind"] == N.OPT_ADAM and (c0 in self._update_x_set):
                     adam_step0 += n
@@ -958,15 +995,20 @@ class PCTrainer(object):
                                     gW, gb, self._precision)
                     n_launch += 1
             if ends_with_p:
-                self._p_step(flat, B)
+                last = (t1 == T) and self._dp_group is not None
+                reduced = self._p_step(flat, B, scalars=scalars if last else None)
+                if last:
+                    if reduced is not None:
+                        scalars, scalars_reduced = reduced, True
+                    host_scalars = self._start_scalar_readback(scalars, reduced=scalars_reduced)
         self.last_call_info = {"mode": "fused", "launches": n_launch, "segments": len(segs),
                                "noise": noise_mode, "precision": self._precision}
         if stats is not None:
             self._traj_stats = {"count": stats["count"], "mean": stats["mean"], "m2": stats["m2"]}
         steps = list(range(s_rec, T, k_rec)) if every_t else [T - 1]
         self.last_trajectories = {"x": traj_x, "out": traj_out, "steps": steps} if want_traj else None
-        return {"energy": energy, "loss": loss, "scalars": scalars, "host_scalars": host_scalars, "traj_x": traj_x,
-                "traj_out": traj_out, "n_rec": n_rec}
+        return {"energy": energy, "loss": loss, "scalars": scalars, "scalars_reduced": scalars_reduced,
+                "host_scalars": host_scalars, "traj_x": traj_x, "traj_out": traj_out, "n_rec": n_rec}
 
     # --------------------------------------------------------------------------------------
     #  SURVEY 8(f) N2 helpers: thinned recording and on-device statistics
@@ -1147,12 +1189,12 @@ class PCTrainer(object):
             layer._energy = None
             layer._lazy_energy = recompute
 
-    def _start_scalar_readback(self, scalars):
+    def _start_scalar_readback(self, scalars, reduced=False):
         """Asynchronous device->host copy of the [2, T] energy / loss scalars on a side stream (CUDA tensors only).
         Returns (pinned host tensor, completion event) or None; ``_build_results`` waits for the event only."""
         if not scalars.is_cuda:
             return None
-        vec = self._reduce_scalars(scalars)                  # data-parallel: all-reduce on the main stream first
+        vec = scalars if reduced else self._reduce_scalars(scalars)   # data-parallel: all-reduce on the main stream first
         dev = vec.device
         side = getattr(self, "_copy_stream", None)
         if side is None or side.device != dev:
@@ -1186,7 +1228,9 @@ class PCTrainer(object):
             host = pending[0].numpy().copy()
         else:
             both = rec.get("scalars")
-            stacked = self._reduce_scalars(both if both is not None else torch.stack([rec["energy"], rec["loss"]]))
+            stacked = both if both is not None else torch.stack([rec["energy"], rec["loss"]])
+            if not rec.get("scalars_reduced", False):
+                stacked = self._reduce_scalars(stacked)
             host = stacked.to("cpu", torch.float64).numpy()   # the ONE device->host sync of the call
         e, l = host[0], host[1]
         sel = slice(None) if every_t else slice(len(e) - 1, len(e))

@@ -23,24 +23,34 @@ torch.cuda.set_device(LOCAL)
 DEV = torch.device("cuda", LOCAL)
 if WORLD > 1:
     import torch.distributed as dist
-    dist.init_process_group("nccl", device_id=DEV)
+    if not dist.is_initialized():          # bench.py imports this module after creating the group itself
+        dist.init_process_group("nccl", device_id=DEV)
 PEAK_TF = 1663.5
 if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")):
     PEAK_TF = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("bf16_tflops", PEAK_TF)
 
 
 def timed(fn, reps=3, warm=1):
+    """Best of `reps` device-timed calls (CUDA events on the launching stream); multi-GPU: barrier on both sides and the
+    MAX over ranks of every repetition."""
     for _ in range(warm):
         fn()
-    torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
+        if WORLD > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e-3)
+        dt = e0.elapsed_time(e1) * 1e-3
+        if WORLD > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=DEV)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        ts.append(dt)
     return min(ts)
 
 
@@ -72,10 +82,20 @@ def ml_model(act="relu", dims=(20, 128, 128)):
     return mu.get_model(cfg, use_cuda=False).to(DEV)
 
 
-def c3(prec, B=65536, T=1000):
+def c3(prec, B=65536, T=1000, thin=0):
+    """BASELINE.json configs[2]: 65,536 chains in total, sharded over the GPUs (B / WORLD chains each, no communication
+    at all: update_p_at='never'); `thin` > 0 additionally reads the sensory outputs out every thin-th step into a device
+    ring ("outputs read out every k-th step only")."""
+    B_total = B
+    B = B_total // WORLD
     model = ml_model()
     tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.1}, update_p_at="never", plot_progress_at=[])
     tr.set_precision(prec)
+    if WORLD > 1:
+        tr.set_data_parallel(chain_offset=int(os.environ.get("RANK", "0")) * B)      # global chain ids: one Philox stream
+    if thin:
+        tr.set_trajectory_stride(thin, 0)
+        tr.set_trajectories_on_device(True)
     z = torch.zeros(B, 20, device=DEV)
     pcs = [m for m in model if isinstance(m, pc.PCLayer)]
     x0 = [torch.randn(B, d, device=DEV) for d in (20, 128, 128)]
@@ -85,13 +105,17 @@ def c3(prec, B=65536, T=1000):
 
     def run():
         tr.train_on_batch(z, loss_fn=mu.zero_fn, callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": tr},
-                          is_sample_x_at_batch_start=first[0], is_log_progress=False, is_return_results_every_t=False)
+                          is_sample_x_at_batch_start=first[0], is_log_progress=False,
+                          is_return_results_every_t=bool(thin), is_return_outputs=bool(thin),
+                          is_checking_after_callback_after_t=False)
         first[0] = False
     s = timed(run, reps=2)
-    flops = B * T * 4 * (20 * 128 + 128 * 128)
-    return {"workload": f"C3 sampling, {B} chains, T={T}, zero_fn (sensory Linear is readout only)", "precision": prec,
-            "latent_updates_per_s": B * 3 * T / s, "ms": s * 1e3, "us_per_step": s / T * 1e6,
-            "algorithmic_tflops": flops / s / 1e12, "frac_of_bf16_peak": flops / s / 1e12 / PEAK_TF}
+    flops = B_total * T * 4 * (20 * 128 + 128 * 128)
+    return {"workload": f"C3 sampling, {B_total} chains over {WORLD} GPU(s), T={T}, zero_fn (sensory Linear is readout only)"
+                        + (f", outputs read out every {thin}th step into a device ring" if thin else ""),
+            "precision": prec, "n_gpus": WORLD, "chains_per_gpu": B, "scaling": "strong",
+            "latent_updates_per_s": B_total * 3 * T / s, "ms": s * 1e3, "us_per_step": s / T * 1e6,
+            "algorithmic_tflops": flops / s / 1e12, "frac_of_bf16_peak": flops / s / 1e12 / (PEAK_TF * WORLD)}
 
 
 def c4(prec, B=1024, T=250):
@@ -144,10 +168,19 @@ def c5(prec, B=2048, T=None, width=4096, L=4):
     s = timed(run, reps=2)
     mac = L * width * width          # Linear_0 sees zero inputs; 3 hidden + 1 output contraction of width^2 each ... L total
     flops = B * T * 6 * mac          # fwd + back-projection + dW every step
-    return {"workload": f"C5 wide {L}x{width}->{width} tanh Gaussian, B={B} per GPU, T={T}, dW every step", "precision": prec,
-            "n_gpus": WORLD, "ms_per_call": s * 1e3,
+    sustained = PEAK_TF
+    try:
+        sustained = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", PEAK_TF)
+    except Exception:  # noqa: BLE001
+        pass
+    return {"workload": f"C5 wide {L}x{width}->{width} tanh Gaussian, B={B} per GPU, T={T}, dW every step"
+                        + (f", one NCCL all-reduce of the {L * width * width * 4 / 1e6:.0f} MB dW per call" if WORLD > 1 else ""),
+            "precision": prec, "n_gpus": WORLD, "scaling": "weak", "ms_per_call": s * 1e3,
             "ms_per_step": s / T * 1e3, "latent_updates_per_s": WORLD * B * L * T / s, "images_per_s_T100": WORLD * B / (s / T * 100),
-            "algorithmic_tflops": flops / s / 1e12, "frac_of_bf16_peak": flops / s / 1e12 / PEAK_TF}
+            "algorithmic_tflops_per_gpu": flops / s / 1e12, "frac_of_bf16_peak": flops / s / 1e12 / PEAK_TF,
+            "frac_of_bf16_peak_sustained": flops / s / 1e12 / sustained,
+            "peak_note": "per-GPU algorithmic TFLOP/s (6 x MAC x B x T, whole call incl. weight conversion, reductions, "
+                         "all-reduce and p-step) over the measured cuBLAS bf16 burst / sustained peaks (MEASURED_PEAKS.json)"}
 
 
 def n1(prec, N=10000, S=5000, D=784):

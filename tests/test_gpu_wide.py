@@ -90,7 +90,8 @@ def _run_case(dims, d_out, act, top, opt, B, mixing, sampling, lr=0.02, wide_ini
         noise = [[nz[t][:, offs[l]:offs[l + 1]] for l in range(L)] for t in range(T)]
     net = orc.OracleNet(W=[l.weight.detach().cpu().numpy() for l in lins], b=[l.bias.detach().cpu().numpy() for l in lins],
                         n_layers=L, act=[orc.ACT_RELU if act == "relu" else orc.ACT_TANH] * L, energy_scale=[1.0] * L,
-                        top=orc.TOP_BERNOULLI if top == "bernoulli" else orc.TOP_GAUSS, bf16_operands=bf16_oracle)
+                        top=orc.TOP_BERNOULLI if top == "bernoulli" else orc.TOP_GAUSS, bf16_operands=bf16_oracle,
+                        bf16_own_term=bf16_oracle and os.environ.get("MCPC_WIDE_G32", "0") == "0")
     ref = orc.infer(net, [v.cpu().numpy() for v in x0], np.zeros((B, dims[0]), np.float32), y.cpu().numpy(), T,
                     optimizer=opt, lr=lr, noise=noise, acc_begin=mixing, acc_end=T, record_traj=want_outputs)
     errs = {f"x{l}": rel_err(pcs[l].get_x().detach().cpu().numpy(), ref.xs[l]) for l in range(L)}
