@@ -198,17 +198,6 @@ typedef struct McpcPStep {
 } McpcPStep;
 int mcpc_p_step(const McpcPStep* step, void* stream);
 
-/* Validation only: known-answer test of the tcgen05/TMEM/bulk-copy primitives of the bf16 path.
- * Wt [128, Kin], Bx [N, Kin], G [N, 128] -> D1 [128, N] = Wt Bx^T,  D2 [128, N]: D2[m][n] = sum_j Wt[j][m] G[n][j]
- * (rows m >= Kin undefined).  ws: >= 128*Kin*2 bytes of device scratch. */
-int mcpc_debug_umma(const float* Wt, const float* Bx, const float* G, int32_t Kin, int32_t N, float* D1, float* D2,
-                    void* ws, void* stream);
-
-/* Validation only: TMA (tensor-map) loads + SWIZZLE_128B operands, D [128, N] = A B^T with K = 64.
- * a_mn = 0: A is [128, 64], 1: A is stored transposed [64, 128]; b_mn likewise for B ([N, 64] / [64, N]);
- * N in {64,128,192,256}; ws: >= (128 + N) * 64 * 2 bytes of device scratch. */
-int mcpc_debug_tma(const float* A, const float* B, int32_t N, int32_t a_mn, int32_t b_mn, float* D, void* ws, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -123,7 +123,8 @@ _lock = threading.Lock()
 LIB_NAME = "libmcpc_b200.so"
 EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer_mode", "mcpc_infer", "mcpc_weight_grad",
            "mcpc_fill_noise", "mcpc_marginal_ll_workspace_bytes", "mcpc_marginal_ll_bernoulli", "mcpc_traj_stats_update",
-           "mcpc_p_step", "mcpc_debug_umma", "mcpc_debug_tma")
+           "mcpc_p_step")
+PROBE_EXPORTS = ("mcpc_probes_last_error", "mcpc_debug_umma", "mcpc_debug_tma")
 
 
 def lib_path():
@@ -142,9 +143,16 @@ def load():
         if _lib is not None:
             return _lib
         path = lib_path()
-        if not os.path.exists(path):
+        if not os.environ.get("MCPC_NATIVE_LIB"):
+            # never run kernels that do not match the sources in the tree: rebuild when the stamp disagrees (a no-op
+            # otherwise); without nvcc a stale library is an error, not a silent fallback
             from . import build as _build
-            _build.build()
+            if _build.is_stale():
+                import shutil
+                if shutil.which(_build.nvcc_path()) or os.path.exists(_build.nvcc_path()):
+                    _build.build()
+                elif os.path.exists(path):
+                    raise NativeError(f"{LIB_NAME} was built from different sources and nvcc is not available to rebuild it")
         lib = C.CDLL(path)
         lib.mcpc_version.restype = C.c_int
         lib.mcpc_last_error.restype = C.c_char_p
@@ -176,17 +184,37 @@ def load():
                                                C.c_void_p]
         lib.mcpc_p_step.restype = C.c_int
         lib.mcpc_p_step.argtypes = [C.POINTER(McpcPStep), C.c_void_p]
+        got = lib.mcpc_version()
+        if got != ABI_VERSION:
+            raise NativeError(f"{LIB_NAME} ABI version {got}, python binding expects {ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+_probes = None
+
+
+def load_probes():
+    """libmcpc_b200_probes.so (include/mcpc_b200_probes.h): validation-only known-answer tests of the tcgen05 / TMEM / TMA
+    primitives, kept out of the product library."""
+    global _probes
+    if _probes is None:
+        load()                              # builds both libraries when stale
+        lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmcpc_b200_probes.so"))
+        lib.mcpc_probes_last_error.restype = C.c_char_p
         lib.mcpc_debug_umma.restype = C.c_int
         lib.mcpc_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mcpc_debug_tma.restype = C.c_int
         lib.mcpc_debug_tma.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
-        got = lib.mcpc_version()
-        if got != ABI_VERSION:
-            raise NativeError(f"{LIB_NAME} ABI version {got}, python binding expects {ABI_VERSION}")
-        _lib = lib
-    return _lib
+        _probes = lib
+    return _probes
+
+
+def check_probe(rc, what):
+    if rc != 0:
+        raise NativeError(f"{what} failed (code {rc}): {load_probes().mcpc_probes_last_error().decode(errors='replace')}")
 
 
 def check(rc, what):

@@ -12,6 +12,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmcpc_b200.so")
 STAMP = LIB + ".stamp"
+PROBES_LIB = os.path.join(PKG, "libmcpc_b200_probes.so")      # validation-only known-answer tests (csrc/probes)
+PROBES_DIR = os.path.join(CSRC, "probes")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,16 +29,30 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def probe_sources():
+    return sorted(os.path.join(PROBES_DIR, f) for f in os.listdir(PROBES_DIR) if f.endswith(".cu"))
+
+
 def _digest():
     h = hashlib.sha256()
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    files += probe_sources()
     files.append(os.path.join(ROOT, "include", "mcpc_b200.h"))
+    files.append(os.path.join(ROOT, "include", "mcpc_b200_probes.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())      # relative: the same tree gives the same digest on every machine
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(a if not os.path.isabs(a) else os.path.relpath(a, ROOT) for a in NVCC_FLAGS).encode())
     return h.hexdigest()
+
+
+def is_stale():
+    """True when libmcpc_b200.so is missing or was built from other sources than the ones in the tree."""
+    if not (os.path.exists(LIB) and os.path.exists(PROBES_LIB) and os.path.exists(STAMP)):
+        return True
+    with open(STAMP) as fh:
+        return fh.read().strip() != _digest()
 
 
 def nvcc_path():
@@ -56,18 +72,23 @@ def build(force=False, verbose=False, debug=False):
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed building the debug library:\n" + proc.stderr[-4000:])
+        cmd = [nvcc_path()] + NVCC_FLAGS + ["-DMCPC_DEBUG_BUILD", "-o", PROBES_LIB.replace(".so", "_debug.so")] + probe_sources()
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed building the debug probes library:\n" + proc.stderr[-4000:])
         return lib
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+    if not force and os.path.exists(LIB) and os.path.exists(PROBES_LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == dig:
                 return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libmcpc_b200.so:\n" + proc.stderr[-4000:])
+    for lib, srcs in ((LIB, sources()), (PROBES_LIB, probe_sources())):
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + srcs
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed building {os.path.basename(lib)}:\n" + proc.stderr[-4000:])
     with open(STAMP, "w") as fh:
         fh.write(dig)
     return LIB

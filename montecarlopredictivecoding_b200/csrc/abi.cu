@@ -286,21 +286,4 @@ int mcpc_p_step(const McpcPStep* s, void* stream) {
   return launch_p_step(s, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int mcpc_debug_umma(const float* Wt, const float* Bx, const float* G, int32_t Kin, int32_t N, float* D1, float* D2,
-                    void* ws, void* stream) {
-  if (Wt == nullptr || Bx == nullptr || G == nullptr || D1 == nullptr || D2 == nullptr || ws == nullptr) {
-    set_error("mcpc_debug_umma: NULL argument");
-    return MCPC_ERR_INVALID;
-  }
-  return launch_umma_probe(Wt, Bx, G, Kin, N, D1, D2, ws, reinterpret_cast<cudaStream_t>(stream));
-}
-
-int mcpc_debug_tma(const float* A, const float* B, int32_t N, int32_t a_mn, int32_t b_mn, float* D, void* ws, void* stream) {
-  if (A == nullptr || B == nullptr || D == nullptr || ws == nullptr) {
-    set_error("mcpc_debug_tma: NULL argument");
-    return MCPC_ERR_INVALID;
-  }
-  return launch_tma_probe(A, B, N, a_mn, b_mn, D, ws, reinterpret_cast<cudaStream_t>(stream));
-}
-
 }  // extern "C"

@@ -208,7 +208,9 @@ int launch_umma_timing(cudaStream_t stream) {
 
 int launch_umma_probe(const float* Wt, const float* Bx, const float* G, int Kin, int N, float* D1, float* D2, void* ws,
                       cudaStream_t stream) {
-  if (getenv("MCPC_UMMA_TIMING") != nullptr) return launch_umma_timing(stream);
+#ifdef MCPC_DEBUG_BUILD
+  if (getenv("MCPC_UMMA_TIMING") != nullptr) return launch_umma_timing(stream);      // tcgen05.mma issue-cost table (experiment)
+#endif
   if (Kin % 16 != 0 || Kin < 16 || Kin > 256 || N % 16 != 0 || N < 16 || N > 32) {
     set_error("umma probe: Kin must be a multiple of 16 in [16,256], N in {16,32}");
     return MCPC_ERR_INVALID;

@@ -139,8 +139,9 @@ class NativeEngine:
         self._layout_cache = {}
         self._mode_cache = {}
 
-    def _workspace(self, net, B, n_steps, precision, device):
-        nkey = (C.addressof(net), B, n_steps, precision, _env_key())   # net structs are cached objects (net_struct)
+    def _workspace(self, net, B, n_steps, precision, device, net_key=None):
+        # keyed by the network DESCRIPTION (not the address of a cached struct, which can be reused after a cache flush)
+        nkey = (net_key if net_key is not None else bytes(net), B, n_steps, precision, _env_key())
         need_v = self._ws_need.get(nkey)
         if need_v is None:
             need = C.c_size_t(0)
@@ -230,7 +231,7 @@ class NativeEngine:
         o.save_begin = int(c.save_begin)
         o.save_end = int(c.save_end)
         o.precision = int(c.precision)
-        ws = self._workspace(net, c.B, c.n_steps, c.precision, dev)
+        ws = self._workspace(net, c.B, c.n_steps, c.precision, dev, _net_key(plan, c.top, c.energy_coefficient))
         stream = torch.cuda.current_stream(dev).cuda_stream
         with _OnDevice(dev):
             N.check(self._lib.mcpc_infer(C.byref(net), C.byref(io), C.byref(o), c.B, ws.data_ptr(), ws.numel(),

@@ -87,7 +87,10 @@ def classify_energy_fn(fn) -> float:
     return c
 
 
-_plan_cache = {}
+import collections
+
+_plan_cache = collections.OrderedDict()    # small LRU: a plan keeps its model (and the latents) alive
+_PLAN_CACHE_SIZE = 8
 
 
 def compile_net(model: nn.Module) -> NetPlan:
@@ -105,11 +108,12 @@ def compile_net(model: nn.Module) -> NetPlan:
         ok = ok and all(pcl._energy_fn is f for pcl, f in zip(plan.pc_layers, efns))
         ok = ok and all((lin.in_features, lin.out_features, lin.bias is None) == sh for lin, sh in zip(plan.linears, shapes))
         if ok:
+            _plan_cache.move_to_end(key)
             return plan
         del _plan_cache[key]
     plan = _compile_net(model, mods)
-    if len(_plan_cache) > 64:
-        _plan_cache.clear()
+    while len(_plan_cache) >= _PLAN_CACHE_SIZE:
+        _plan_cache.popitem(last=False)
     _plan_cache[key] = (plan, [pcl._energy_fn for pcl in plan.pc_layers],
                         [(lin.in_features, lin.out_features, lin.bias is None) for lin in plan.linears])
     return plan

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("b_mn", [0, 1])
 @pytest.mark.parametrize("Ncols", [64, 256])
 def test_tma_probe(a_mn, b_mn, Ncols):
-    lib = N.load()
+    lib = N.load_probes()
     dev = torch.device("cuda:0")
     torch.manual_seed(a_mn * 10 + b_mn + Ncols)
     A = torch.randn(128, 64, device=dev)
@@ -25,7 +25,7 @@ def test_tma_probe(a_mn, b_mn, Ncols):
     ws = torch.empty((128 + Ncols) * 64 * 2 + 1024, dtype=torch.uint8, device=dev)
     rc = lib.mcpc_debug_tma(A_st.data_ptr(), B_st.data_ptr(), Ncols, a_mn, b_mn, D.data_ptr(), ws.data_ptr(),
                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    N.check(rc, "mcpc_debug_tma")
+    N.check_probe(rc, "mcpc_debug_tma")
     torch.cuda.synchronize()
     ref = (A.bfloat16().double() @ B.bfloat16().double().t()).float()
     err = (D - ref).abs().max().item()

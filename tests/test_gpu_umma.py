@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("Kin,Nrows", [(128, 16), (32, 16), (256, 32), (128, 32), (16, 16)])
 def test_umma_probe(Kin, Nrows):
-    lib = N.load()
+    lib = N.load_probes()
     dev = torch.device("cuda:0")
     torch.manual_seed(Kin * 100 + Nrows)
     Wt = torch.randn(128, Kin, device=dev)
@@ -23,7 +23,7 @@ def test_umma_probe(Kin, Nrows):
     ws = torch.empty(128 * Kin * 2 + 1024, dtype=torch.uint8, device=dev)
     rc = lib.mcpc_debug_umma(Wt.data_ptr(), Bx.data_ptr(), G.data_ptr(), Kin, Nrows, D1.data_ptr(), D2.data_ptr(),
                              ws.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    N.check(rc, "mcpc_debug_umma")
+    N.check_probe(rc, "mcpc_debug_umma")
     torch.cuda.synchronize()
     Wb, Bb, Gb = Wt.bfloat16().double(), Bx.bfloat16().double(), G.bfloat16().double()
     ref1 = (Wb @ Bb.T).float()
