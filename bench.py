@@ -464,22 +464,22 @@ def run_ours(args):
     infer_ms = float(np.median([a.elapsed_time(b) for a, b in k_ev]))
 
     # ---- the other configs of BASELINE.json (every rank takes part: C3 shards its 65,536 chains, C5 all-reduces dW) ----
-    other = None
+    other_wl = None
     if not args.no_other_workloads:
         try:
             sys.path.insert(0, os.path.join(ROOT, "scripts"))
             import bench_configs as bc
             del model, map_trainer, mcpc_trainer
             torch.cuda.empty_cache()
-            other = {
+            other_wl = {
                 "C3_sampling_65536_chains": bc.c3(args.precision, B=65536, T=1000),
                 "C3_sampling_65536_chains_readout_every_100": bc.c3(args.precision, B=65536, T=1000, thin=100),
                 "C5_wide_4x4096_B2048_per_gpu_T100": bc.c5(args.precision, B=2048, T=100),
             }
             if world == 1:
-                other["C4_deterministic_pc_adam"] = bc.c4(args.precision)
+                other_wl["C4_deterministic_pc_adam"] = bc.c4(args.precision)
         except Exception as exc:  # noqa: BLE001
-            other = {"error": repr(exc)[:300]}
+            other_wl = {"error": repr(exc)[:300]}
 
     if rank == 0:
         peak_tf, peak_hbm, peak_src = measured_peaks()
@@ -512,7 +512,7 @@ def run_ours(args):
                          "note": "4*MAC flops per chain-step x B x T (SURVEY §8d); latents stay on chip, HBM traffic is the "
                                  "saved dW operands only"},
         }
-        line["other_workloads"] = other
+        line["other_workloads"] = other_wl
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_subprocess(B)
         print(json.dumps(line))

@@ -68,7 +68,10 @@ def build(force=False, verbose=False, debug=False):
     select it at run time with MCPC_NATIVE_LIB=<path>); the product library never contains them."""
     if debug:
         lib = LIB.replace(".so", "_debug.so")
-        cmd = [nvcc_path()] + NVCC_FLAGS + ["-DMCPC_DEBUG_BUILD", "-o", lib] + sources()
+        extra = os.environ.get("MCPC_EXTRA_NVCC_FLAGS", "").split()       # experiments: e.g. -DMCPC_UPD_NS=5 -DMCPC_UPD_STG=6144
+        if os.environ.get("MCPC_DEBUG_LIB_SUFFIX"):
+            lib = LIB.replace(".so", "_debug" + os.environ["MCPC_DEBUG_LIB_SUFFIX"] + ".so")
+        cmd = [nvcc_path()] + NVCC_FLAGS + ["-DMCPC_DEBUG_BUILD"] + extra + ["-o", lib] + sources()
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed building the debug library:\n" + proc.stderr[-4000:])

@@ -53,7 +53,13 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 // operand ring depth: the UPDATE kernel trades one stage for deeper staging of its epilogue inputs (below)
-__host__ __device__ constexpr int n_stages(int cg, int kind) { return cg == 2 ? (kind == 1 ? 4 : 5) : 4; }
+#ifndef MCPC_UPD_NS
+#define MCPC_UPD_NS 4
+#endif
+#ifndef MCPC_UPD_STG
+#define MCPC_UPD_STG 12288
+#endif
+__host__ __device__ constexpr int n_stages(int cg, int kind) { return cg == 2 ? (kind == 1 ? MCPC_UPD_NS : 5) : 4; }
 // per epilogue warp: shared-memory staging of the epilogue's global INPUTS (latents, own-layer term, targets), filled by
 // cp.async several chunks ahead.  Registers could only keep one chunk (32 requests per warp) in flight, and with ~2 us
 // of DRAM latency under load Little's law then caps the eight epilogue warps of an SM at ~16 GB/s -- the tile
@@ -61,7 +67,7 @@ __host__ __device__ constexpr int n_stages(int cg, int kind) { return cg == 2 ? 
 // UPDATE stages 3 KB per chunk (fp32 latents + the bf16 own-layer term), PREDICT 2 KB (latents or targets): 4 chunks deep
 // with CTA pairs, 1-2 chunks deep on single CTAs (whose operand stages are 48 KB).
 __host__ __device__ constexpr uint32_t kUpdSlot = 3072u, kPredSlot = 2048u;
-__host__ __device__ constexpr uint32_t stg_bytes(int cg, int kind) { return cg == 2 ? (kind == 1 ? 12288u : 8192u) : 4096u; }
+__host__ __device__ constexpr uint32_t stg_bytes(int cg, int kind) { return cg == 2 ? (kind == 1 ? (uint32_t)MCPC_UPD_STG : 8192u) : 4096u; }
 __host__ __device__ constexpr uint32_t a_bytes() { return kTM * kBK * 2; }
 __host__ __device__ constexpr uint32_t b_bytes(int cg) { return (kTN / cg) * kBK * 2; }
 __host__ __device__ constexpr uint32_t stage_bytes(int cg) { return a_bytes() + b_bytes(cg); }
@@ -119,7 +125,8 @@ struct StepArgs {
 struct WideMaps {
   CUtensorMap act_k[kMaxL], act_mn[kMaxL];
   CUtensorMap gb_k[kMaxL + 1], gb_mn[kMaxL + 1];
-  CUtensorMap w_k[kMaxL + 1], w_mn[kMaxL + 1];
+  CUtensorMap w_k[kMaxL + 1];              // W_l   [d_l x d_{l-1}] bf16, K-major A operand of PREDICT
+  CUtensorMap w_kt[kMaxL + 1];             // W_l^T [d_{l-1} x d_l] bf16 (transposed copy made per call), K-major A operand of UPDATE
   // fp32 views used only for L2 prefetches of the epilogue inputs (box = 128 units x 256 chains): the latents, the
   // own-layer term and the targets are first touched by latency-bound epilogue loads otherwise
   CUtensorMap x32[kMaxL], tgt;
@@ -303,7 +310,7 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const StepA
     t.ni = local % ntn; t.ntn = ntn;
     t.k_base = st.slot * p.Bpad;
     if (has_above) {
-      t.mapA = &mp.w_mn[l + 1];                                   // W_{l+1} [d_up x d_l] as A[m][k]: MN-major
+      t.mapA = &mp.w_kt[l + 1];                                   // W_{l+1}^T [d_l x d_up], K-major (like PREDICT's operands)
       t.mapB = &mp.gb_k[l + 1];                                   // G_{l+1} [chains x d_up], K-major
     }
   } else {
@@ -718,7 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1) wide_kernel(const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Pipe pipe;
   __shared__ uint32_t tmem_s;
-  constexpr bool A_MN = (KIND != KIND_PREDICT), B_MN = (KIND == KIND_WGRAD);
+  constexpr bool A_MN = (KIND == KIND_WGRAD), B_MN = (KIND == KIND_WGRAD);
   constexpr int NS = n_stages(CG, KIND);
   constexpr uint32_t kA = a_bytes(), kB = b_bytes(CG), kStage = stage_bytes(CG);
   constexpr int kBRows = kTN / CG;                       // N indices of B this CTA stages
@@ -973,6 +980,26 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __r
   }
 }
 
+// fp32 [rows][cols] -> bf16 TRANSPOSED [cols][pitch_t] (pitch_t = rows rounded up to 8), 32 x 32 tiles through shared memory
+__global__ void to_bf16_transposed_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols,
+                                          int pitch_t) {
+  __shared__ float tile[32][33];
+  const int tiles_c = (cols + 31) / 32, tiles_r = (pitch_t + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (c < cols && r < pitch_t) dst[(size_t)c * pitch_t + r] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+    __syncthreads();
+  }
+}
+
 // act(x) of the initial latents into ring slot 0
 __global__ void init_act_kernel(WideParams p) {
   const NetDev& nd = p.net;
@@ -990,7 +1017,7 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline int pad8w(int v) { return (v + 7) & ~7; }
 
 struct WideLayout {
-  size_t wb_off[kMaxL + 1], act_off[kMaxL], gb_off[kMaxL + 1], part_off, total;
+  size_t wb_off[kMaxL + 1], wbt_off[kMaxL + 1], act_off[kMaxL], gb_off[kMaxL + 1], part_off, total;
   int apitch[kMaxL], gpitch[kMaxL + 1], n_part, Bpad, S, cg;
 };
 
@@ -1053,8 +1080,11 @@ int wide_layout(const NetDev& nd, int B, int n_steps, WideLayout* lay) {
   }
   size_t o = 0;
   for (int l = 1; l < n_lin; ++l) {
+    const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
     lay->wb_off[l] = o;
-    o += align256((size_t)(l == nd.L ? nd.d_out : nd.dims[l]) * pad8w(nd.dims[l - 1]) * 2);
+    o += align256((size_t)d_o * pad8w(nd.dims[l - 1]) * 2);
+    lay->wbt_off[l] = o;                                  // transposed copy: the back-projection reads W^T K-major
+    o += align256((size_t)nd.dims[l - 1] * pad8w(d_o) * 2);
   }
   // ring of S slots of the bf16 operands: S steps of the accumulate window are contracted by ONE weight-gradient launch.
   // Default 4: with C5's 2048 chains both operands of a layer (134 MB) stay L2-resident during the launch.
@@ -1113,7 +1143,7 @@ int launch_wide(const WideParams& p, const StepArgs& st, const WideMaps& mp, int
 
 template <int CG>
 int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& p, const WideLayout& lay, const WideKnobs& kn,
-             const __nv_bfloat16* const* Wb, cudaStream_t stream) {
+             const __nv_bfloat16* const* Wb, const __nv_bfloat16* const* WbT, cudaStream_t stream) {
   const int B = p.B;
   const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
   // tile tables: (128 * CG) units x 256 chains per (pair) tile
@@ -1180,9 +1210,7 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
     if (rc == MCPC_OK && l >= 1) {
       const int d_i = nd.dims[l - 1], wp = pad8w(d_i);
       rc = make_tmap_bf16(&mp.w_k[l], Wb[l], d_i, d_o, wp, 64, kTM);                                             // predict A
-      if (rc == MCPC_OK)
-        rc = mn3 ? make_tmap_bf16_mn3(&mp.w_mn[l], Wb[l], d_i, d_o, wp, 64, kTM / 64)                            // update A
-                 : make_tmap_bf16(&mp.w_mn[l], Wb[l], d_i, d_o, wp, 64, 64);
+      if (rc == MCPC_OK) rc = make_tmap_bf16(&mp.w_kt[l], WbT[l], d_o, d_i, pad8w(d_o), 64, kTM);                // update A
     }
     if (rc != MCPC_OK) return rc;
   }
@@ -1379,13 +1407,18 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.partials = reinterpret_cast<float*>(wsb + lay.part_off);
   p.n_part = lay.n_part;
   const __nv_bfloat16* Wb[kMaxL + 1] = {};
+  const __nv_bfloat16* WbT[kMaxL + 1] = {};
   for (int l = 1; l < n_lin; ++l) {
     __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(wsb + lay.wb_off[l]);
+    __nv_bfloat16* wbt = reinterpret_cast<__nv_bfloat16*>(wsb + lay.wbt_off[l]);
     const int rows = (l == nd.L) ? nd.d_out : nd.dims[l], cols = nd.dims[l - 1];
     const size_t n = (size_t)rows * pad8w(cols);
     to_bf16_kernel<<<(int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184), 256, 0, stream>>>(io->W[l], wb, rows, cols, pad8w(cols));
-    count_launch();
+    const int n_t = ((cols + 31) / 32) * ((pad8w(rows) + 31) / 32);
+    to_bf16_transposed_kernel<<<n_t < 2368 ? n_t : 2368, dim3(32, 8), 0, stream>>>(io->W[l], wbt, rows, cols, pad8w(rows));
+    count_launch(2);
     Wb[l] = wb;
+    WbT[l] = wbt;
   }
   for (int l = 0; l < nd.L; ++l) {
     p.x[l] = io->x[l];
@@ -1414,7 +1447,7 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
 #ifdef MCPC_DEBUG_BUILD
   p.skip_epilogue = kn.skip_epi;
 #endif
-  return lay.cg == 2 ? run_wide<2>(nd, io, o, p, lay, kn, Wb, stream) : run_wide<1>(nd, io, o, p, lay, kn, Wb, stream);
+  return lay.cg == 2 ? run_wide<2>(nd, io, o, p, lay, kn, Wb, WbT, stream) : run_wide<1>(nd, io, o, p, lay, kn, Wb, WbT, stream);
 }
 
 }  // namespace mcpc

@@ -177,6 +177,11 @@ class PCTrainer(object):
         self._traj_ring_bytes = int(os.environ.get("MCPC_TRAJ_RING_BYTES", str(256 << 20)))
         self.last_trajectories = None          # device rings of the last call: {"x": [...], "out": ..., "steps": [...]}
         self._fused_p_optimizer = os.environ.get("MCPC_FUSED_P_STEP", "1") != "0"
+        # data-parallel learning calls: 0 (default) = the tiny [2, T] scalar all-reduce is issued right after the inference
+        # kernel, so the host gets the results while dW / gradient all-reduce / p-step still run; 1 = the scalars ride in
+        # the tail of the gradient buffer (ONE collective per call, but the host then waits for it: measured on 2 GPUs
+        # 1.55 ms per C2 call against 1.30 ms)
+        self._dp_single_collective = os.environ.get("MCPC_DP_SINGLE_COLLECTIVE", "0") == "1"
         self.last_call_info = {}
 
     # ======================================================================================
@@ -979,7 +984,7 @@ class PCTrainer(object):
                 n_launch += 1
                 if stats is not None and n_r > 0:
                     self._fold_traj_stats(eng, stats, tx_cut, n_r)
-                if c1 == T and not (ends_with_p and self._dp_group is not None):
+                if c1 == T and not (ends_with_p and self._dp_group is not None and self._dp_single_collective):
                     # the per-step scalars are final here: start their read-back on a side stream now, so that the
                     # host gets them while the weight-gradient / optimizer_p kernels of this call are still running
                     # (data-parallel learning calls: they travel with the gradient all-reduce instead, see below)
@@ -995,7 +1000,7 @@ class PCTrainer(object):
                                     gW, gb, self._precision)
                     n_launch += 1
             if ends_with_p:
-                last = (t1 == T) and self._dp_group is not None
+                last = (t1 == T) and self._dp_group is not None and self._dp_single_collective
                 reduced = self._p_step(flat, B, scalars=scalars if last else None)
                 if last:
                     if reduced is not None:

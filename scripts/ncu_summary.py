@@ -21,7 +21,7 @@ def main(path):
     print("unit," + ",".join(units[hdr.index(k)] if k in hdr else "" for k in KEYS))
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")].split("(")[0].split("::")[-1]
-        print(name + "," + ",".join(r[hdr.index(k)] if k in hdr else "" for k in KEYS))
+        print('"' + name + '",' + ",".join(r[hdr.index(k)] if k in hdr else "" for k in KEYS))
 
 
 if __name__ == "__main__":

@@ -71,9 +71,13 @@ def _worker(rank, world, port, B, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_run_equals_single_process_big_batch(tmp_path):
+@pytest.mark.parametrize("single_collective", ["0", "1"])
+def test_two_rank_run_equals_single_process_big_batch(tmp_path, single_collective, monkeypatch):
+    """single_collective = 1: the [2, T] scalars ride in the tail of the flat gradient buffer (ONE all-reduce per call);
+    0 (default): they are reduced right after the inference launch so that the host gets them early."""
     import warnings
     warnings.simplefilter("ignore")
+    monkeypatch.setenv("MCPC_DP_SINGLE_COLLECTIVE", single_collective)
     B, world = 16, 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
