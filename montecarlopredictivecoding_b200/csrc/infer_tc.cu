@@ -18,6 +18,7 @@
 //
 // Reference semantics: predictive_coding/pc_trainer.py:733-918 + utils/model.py:35-44 (see infer_rows.cu
 // for the fp32 restatement this kernel is validated against).
+#include <algorithm>
 #include <cstdlib>
 
 #include "mcpc_common.cuh"
@@ -109,8 +110,20 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 #define TC_STAMP(cond, ts, idx) do { if constexpr (TRACE) { if (blockIdx.x == 0 && (cond) && (unsigned)((ts) - p.dbg_t0) < 8u) p.dbg[((ts) - p.dbg_t0) * 64 + (idx)] = clock64(); } } while (0)
 
 // fp32 W [rows x cols] (nn.Linear layout) -> bf16 tiles of 128 output units in canonical K-major order
-__global__ void pack_weights_kernel(const float* __restrict__ W, int rows, int cols, int Kp, int n_tiles,
-                                    uint8_t* __restrict__ out) {
+// (every Linear of the network in ONE launch: blockIdx.y picks the Linear -- the call is latency-bound)
+struct PackJob {
+  const float* W;
+  uint8_t* out;
+  int rows, cols, Kp, n_tiles;
+};
+struct PackJobs {
+  PackJob job[kMaxL + 1];
+};
+__global__ void pack_weights_kernel(const PackJobs jobs) {
+  const PackJob& J = jobs.job[blockIdx.y];
+  const float* __restrict__ W = J.W;
+  uint8_t* __restrict__ out = J.out;
+  const int rows = J.rows, cols = J.cols, Kp = J.Kp, n_tiles = J.n_tiles;
   const uint32_t sbo = (uint32_t)(Kp / 8) * 128u;
   const int per_tile = 128 * Kp;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles * per_tile; i += gridDim.x * blockDim.x) {
@@ -1086,16 +1099,23 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     count_launch();
   }
   // pack the weights (fp32 nn.Linear layout -> bf16 canonical tiles); they change once per learning step
-  for (int t = 0; t < p.n_hid_tiles + p.n_out_tiles;) {
-    const Tile& T = p.tiles[t];
-    const int lin = T.lin;
-    const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
-    const int n_lin_tiles = (rows + 127) / 128;
-    const int n_elems = n_lin_tiles * 128 * T.Kp;                     // 2 elements per thread: the call is latency-bound
-    pack_weights_kernel<<<(n_elems + 511) / 512, 256, 0, stream>>>(
-        io->W[lin], rows, nd.dims[lin - 1], T.Kp, n_lin_tiles, wsb + T.gsrc);
-    count_launch();
-    t += n_lin_tiles;
+  {
+    PackJobs jobs{};
+    int n_jobs = 0, max_blocks = 1;
+    for (int t = 0; t < p.n_hid_tiles + p.n_out_tiles;) {
+      const Tile& T = p.tiles[t];
+      const int lin = T.lin;
+      const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
+      const int n_lin_tiles = (rows + 127) / 128;
+      const int n_elems = n_lin_tiles * 128 * T.Kp;                   // 2 elements per thread
+      jobs.job[n_jobs++] = PackJob{io->W[lin], wsb + T.gsrc, rows, nd.dims[lin - 1], T.Kp, n_lin_tiles};
+      max_blocks = std::max(max_blocks, (n_elems + 511) / 512);
+      t += n_lin_tiles;
+    }
+    if (n_jobs > 0) {
+      pack_weights_kernel<<<dim3(max_blocks, n_jobs), 256, 0, stream>>>(jobs);
+      count_launch();
+    }
   }
   for (int l = 0; l <= nd.L; ++l) p.b[l] = io->b[l];
   for (int l = 0; l < nd.L; ++l) {

@@ -60,9 +60,27 @@ _ENV_KNOBS = ("MCPC_FORCE_STREAMING", "MCPC_TC_ROWS", "MCPC_ROWS", "MCPC_WIDE_CT
               "MCPC_WIDE_SLOTS")
 
 
+_ENV_DATA = getattr(os.environ, "_data", None)       # CPython/posix: the dict behind os.environ (bytes keys)
+_ENV_KNOBS_B = tuple(k.encode() for k in _ENV_KNOBS)
+if not isinstance(_ENV_DATA, dict) or any(not isinstance(k, bytes) for k in list(_ENV_DATA)[:1]):
+    _ENV_DATA = None
+
+
 def _env_key():
-    """Debug / test knobs the library reads with getenv(): part of every cache key that depends on them."""
+    """Debug / test knobs the library reads with getenv(): part of every cache key that depends on them (read on
+    every call -- tests flip them between calls -- so through the raw dict: 7 lookups instead of 7 encode + lookups)."""
+    if _ENV_DATA is not None:
+        get = _ENV_DATA.get
+        return tuple(get(k) for k in _ENV_KNOBS_B)
     return tuple(os.environ.get(k) for k in _ENV_KNOBS)
+
+
+def _raw_stream(dev):
+    """cudaStream_t of torch's current stream on ``dev`` (the kernels are launched on it)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device())
+    except AttributeError:      # older / newer torch without the private accessor
+        return torch.cuda.current_stream(dev).cuda_stream
 
 
 
@@ -232,7 +250,7 @@ class NativeEngine:
         o.save_end = int(c.save_end)
         o.precision = int(c.precision)
         ws = self._workspace(net, c.B, c.n_steps, c.precision, dev, _net_key(plan, c.top, c.energy_coefficient))
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _raw_stream(dev)
         with _OnDevice(dev):
             N.check(self._lib.mcpc_infer(C.byref(net), C.byref(io), C.byref(o), c.B, ws.data_ptr(), ws.numel(),
                                          C.c_void_p(stream)), "mcpc_infer")
@@ -249,7 +267,7 @@ class NativeEngine:
         for i in range(len(gW)):
             io.gW[i] = _ptr(gW[i], "gW")
             io.gb[i] = _ptr(gb[i], "gb")
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _raw_stream(dev)
         with _OnDevice(dev):
             N.check(self._lib.mcpc_weight_grad(C.byref(net), C.byref(io), B, n_save, precision, C.c_void_p(stream)),
                     "mcpc_weight_grad")
@@ -260,7 +278,7 @@ class NativeEngine:
         n_elems = mean.numel()
         if traj[0].numel() != n_elems or m2.numel() != n_elems:
             raise RuntimeError("traj_stats: ring / accumulator shapes disagree")
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _raw_stream(dev)
         with _OnDevice(dev):
             N.check(self._lib.mcpc_traj_stats_update(_ptr(traj, "trajectory ring"), int(n_rec), n_elems, int(count_before),
                                                      _ptr(mean, "mean"), _ptr(m2, "m2"), C.c_void_p(stream)),
@@ -284,7 +302,7 @@ class NativeEngine:
         a.lr, a.weight_decay, a.momentum, a.dampening = float(lr), float(weight_decay), float(momentum), float(dampening)
         a.beta1, a.beta2, a.eps = float(beta1), float(beta2), float(eps)
         a.nesterov, a.first_step, a.step = int(bool(nesterov)), int(first_step), int(step)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _raw_stream(dev)
         with _OnDevice(dev):
             N.check(self._lib.mcpc_p_step(C.byref(a), C.c_void_p(stream)), "mcpc_p_step")
 

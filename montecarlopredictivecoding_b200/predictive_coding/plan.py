@@ -98,8 +98,13 @@ def compile_net(model: nn.Module) -> NetPlan:
 
     The result is cached per module list (identity of the children); what a user can flip on a live PCLayer
     (masks, per-datapoint energies, held errors, the energy function) and the Linear shapes are re-checked on a hit."""
-    mods = list(model.children()) if not isinstance(model, (nn.Linear, PCLayer)) else [model]
-    key = tuple(id(m) for m in mods)
+    if isinstance(model, (nn.Linear, PCLayer)):
+        mods = [model]
+    else:
+        mods = list(model._modules.values())              # == list(model.children()) unless a child is None / shared
+        if None in mods or len(set(map(id, mods))) != len(mods):
+            mods = list(model.children())
+    key = tuple(map(id, mods))
     hit = _plan_cache.get(key)
     if hit is not None:
         plan, efns, shapes = hit

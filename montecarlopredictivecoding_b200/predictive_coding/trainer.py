@@ -165,6 +165,8 @@ class PCTrainer(object):
         self._dp_chain_offset = None
         self._adam = None                      # persistent Adam state of the fused x-optimizer
         self._buffers = {}                     # cached device scratch keyed by role
+        self._buffer_views = {}                # role -> (shape, shaped view of the buffer)
+        self._param_cache = None               # detached Linear weights / biases of the last call
         self._flat_grad = None
         self._zero_inputs_cache = None
         self._save_budget_bytes = int(os.environ.get("MCPC_SAVE_BUDGET_BYTES", str(8 << 30)))
@@ -395,7 +397,7 @@ class PCTrainer(object):
         else:
             self._optimizer_x = self._manual_optimizer_x_fn()
 
-    def _reset_optimizer_x(self) -> None:
+    def _reset_optimizer_x(self, pc_layers=None) -> None:
         """``recreate_optimize_x`` without building a new torch object when nothing but its state has to go: the
         latents are the same Parameters as before (no re-sampling), so clearing the state and restoring the
         hyper-parameter defaults leaves the optimizer exactly as a freshly constructed one (pc_trainer.py:749-752)."""
@@ -403,7 +405,7 @@ class PCTrainer(object):
         if self._manual_optimizer_x_fn is not None or opt is None or len(opt.param_groups) != 1:
             return self.recreate_optimize_x()
         held = opt.param_groups[0]["params"]
-        xs = list(self.get_model_xs())
+        xs = list(self.get_model_xs()) if pc_layers is None else [layer._x for layer in pc_layers]
         if len(held) != len(xs) or any(a is not b for a, b in zip(held, xs)):
             return self.recreate_optimize_x()
         opt.state.clear()
@@ -458,12 +460,6 @@ class PCTrainer(object):
         """
         self.inputs = inputs
         # ---- sanitise exactly like the reference (pc_trainer.py:608-656) ----
-        assert (self.get_is_model_training() == True), (  # noqa: E712
-            "PCLayer behaves differently in train and eval modes, like Dropout or Batch Normalization. "
-            "Thus, call model.eval() before evaluation and model.train() before train. "
-            "Make sure your model is in train mode before calling <train_on_batch()>. "
-            "It can be done by calling <model.train()>. "
-            "Do remember switching your model back to eval mode before evaluating it by calling <model.eval()>. ")
         if loss_fn is not None:
             assert callable(loss_fn)
         assert isinstance(loss_fn_kwargs, dict)
@@ -522,6 +518,13 @@ class PCTrainer(object):
             raise NotImplementedError("inputs must be a [batch, features] tensor")
 
         netp = P.compile_net(self._model)
+        # the plan's PCLayers ARE the model's (flat module list): same check as get_is_model_training() without a walk
+        assert self._model.training and all(layer.training for layer in netp.pc_layers), (
+            "PCLayer behaves differently in train and eval modes, like Dropout or Batch Normalization. "
+            "Thus, call model.eval() before evaluation and model.train() before train. "
+            "Make sure your model is in train mode before calling <train_on_batch()>. "
+            "It can be done by calling <model.train()>. "
+            "Do remember switching your model back to eval mode before evaluating it by calling <model.eval()>. ")
         B = int(inputs.shape[0])
         if inputs.shape[1] != netp.d_in:
             raise RuntimeError(f"inputs has {inputs.shape[1]} features, the first Linear expects {netp.d_in}")
@@ -597,7 +600,7 @@ class PCTrainer(object):
             self.recreate_optimize_x()
             self._adam = None
         elif reset_x:
-            self._reset_optimizer_x()
+            self._reset_optimizer_x(netp.pc_layers)
             self._adam = None
         if reset_p:
             self.recreate_optimize_p()
@@ -621,6 +624,9 @@ class PCTrainer(object):
         return None
 
     def _buffer(self, role, shape, dtype, device):
+        hit = self._buffer_views.get(role)
+        if hit is not None and hit[0] == shape and hit[1].dtype == dtype and hit[1].device == device:
+            return hit[1]
         n = 1
         for s in shape:
             n *= int(s)
@@ -628,7 +634,11 @@ class PCTrainer(object):
         if buf is None or buf.dtype != dtype or buf.device != device or buf.numel() < n + 1024:
             buf = torch.zeros(n + 1024, dtype=dtype, device=device)     # 1024 elements of slack (mcpc_save_layout)
             self._buffers[role] = buf
-        return buf[:n].view(*shape)
+            self._buffer_views.pop(role, None)
+        hit = self._buffer_views.get(role)
+        if hit is None or hit[0] != shape:
+            hit = self._buffer_views[role] = (shape, buf[:n].view(*shape))
+        return hit[1]
 
     def _save_layout(self, netp, top):
         eng = self._get_engine()
@@ -647,8 +657,22 @@ class PCTrainer(object):
         return inputs.detach().to(torch.float32).contiguous()
 
     def _param_tensors(self, netp):
-        W = [lin.weight.detach() for lin in netp.linears]
-        b = [None if lin.bias is None else lin.bias.detach() for lin in netp.linears]
+        """Detached views of the Linear weights / biases; rebuilt only when a Parameter object (or its storage) changed."""
+        lins = netp.linears
+        hit = self._param_cache
+        if hit is not None and len(hit[0]) == len(lins):
+            ok = True
+            for lin, (pw, pb, wp, bp) in zip(lins, hit[0]):
+                w, bias = lin.weight, lin.bias
+                if w is not pw or bias is not pb or w.data_ptr() != wp or (bias is not None and bias.data_ptr() != bp):
+                    ok = False
+                    break
+            if ok:
+                return hit[1], hit[2]
+        W = [lin.weight.detach() for lin in lins]
+        b = [None if lin.bias is None else lin.bias.detach() for lin in lins]
+        self._param_cache = ([(lin.weight, lin.bias, lin.weight.data_ptr(), None if lin.bias is None else lin.bias.data_ptr())
+                              for lin in lins], W, b)
         return W, b
 
     # --------------------------------------------------------------------------------------
@@ -859,7 +883,8 @@ class PCTrainer(object):
         if target is not None:
             target = target.detach().to(torch.float32).contiguous()
         xs = [layer.get_x().data for layer in netp.pc_layers]
-        scalars = torch.zeros(2, T, dtype=torch.float64, device=device)     # one allocation, one D2H at the end
+        # one allocation, one D2H at the end; the launches below cover [0, T) and each OVERWRITES its slice (mcpc_b200.h)
+        scalars = torch.empty(2, T, dtype=torch.float64, device=device)
         energy, loss = scalars[0], scalars[1]
 
         want_traj = ctx["want_outputs"] or ctx["want_reps"] or ctx["want_xs"]
