@@ -123,6 +123,8 @@ typedef struct McpcGradIO {
   const float* inputs;                    /* [B, d_in] or NULL (zeros => gW_0 receives nothing) */
   float* gW[MCPC_MAX_LAYERS + 1];         /* accumulators, ADDED to (never zeroed here); NULL skips */
   float* gb[MCPC_MAX_LAYERS + 1];
+  void* scratch;                          /* device scratch, needed only for MCPC_PREC_BF16 with non-NULL inputs:      */
+  size_t scratch_bytes;                   /* B * dims[0] floats (sum over the saved steps of d overall / d mu_0)       */
 } McpcGradIO;
 
 int mcpc_version(void);

@@ -85,6 +85,8 @@ class McpcGradIO(C.Structure):
         ("inputs", _FP),
         ("gW", _FP * (MAX_LAYERS + 1)),
         ("gb", _FP * (MAX_LAYERS + 1)),
+        ("scratch", _FP),
+        ("scratch_bytes", C.c_size_t),
     ]
 
 

@@ -69,6 +69,7 @@ struct TcParams {
   float* xgrad[kMaxL];
   float* traj_x[kMaxL];
   float* traj_out;
+  const float* mu0;             // fp32 [B, dims[0]]: W_0 inputs + b_0 per chain (non-zero `inputs`), else nullptr
   __nv_bfloat16* save_g;        // bf16 [n_save, B, sg_pitch], layer blocks padded to 8 columns (wgrad_tc.cu)
   __nv_bfloat16* save_f;        // bf16 [n_save, B, sf_pitch]
   int sg_off[kMaxL + 1];
@@ -133,6 +134,43 @@ __global__ void pack_weights_kernel(const PackJobs jobs) {
     const float val = (row < rows && k < cols) ? W[(size_t)row * cols + k] : 0.0f;
     *reinterpret_cast<__nv_bfloat16*>(out + (size_t)t * per_tile * 2 + kmajor_off(r, k, 128u, sbo)) = __float2bfloat16(val);
   }
+}
+
+// mu_0 of non-zero `inputs` (they are fixed for the whole call, pc_trainer.py:733): mu0[c][u] = b0[u] + sum_k in[c][k] W0[u][k]
+// in fp32 -- Linear_0 has no weight tile in the resident kernel, its prediction is a per-chain constant of the launch.
+__global__ void __launch_bounds__(256) mu0_kernel(const float* __restrict__ in, const float* __restrict__ W0,
+                                                  const float* __restrict__ b0, int B, int d_in, int d0,
+                                                  float* __restrict__ mu0) {
+  __shared__ float As[16][64 + 1], Ws[16][64 + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int c0 = blockIdx.y * 64, u0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < d_in; k0 += 16) {
+    for (int i = tid; i < 64 * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      As[k][r] = (c0 + r < B && k0 + k < d_in) ? in[(size_t)(c0 + r) * d_in + k0 + k] : 0.0f;
+      Ws[k][r] = (u0 + r < d0 && k0 + k < d_in) ? W0[(size_t)(u0 + r) * d_in + k0 + k] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; w[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + ty * 4 + i, u = u0 + tx * 4 + j;
+      if (c < B && u < d0) mu0[(size_t)c * d0 + u] = acc[i][j] + (b0 != nullptr ? b0[u] : 0.0f);
+    }
 }
 
 // Adam bias corrections of steps step0+1 .. step0+n (torch.optim.Adam: step_size = lr / (1 - beta1^t), the second
@@ -441,6 +479,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
       for (int l = 0; l < L; ++l) mbar_arrive(&bars.acts_ready[l]);
 
       const bool adam = (opt_kind == MCPC_OPT_ADAM);
+      const float* mu0 = (SPEC == 0) ? p.mu0 : nullptr;      // the specialised instantiations are zero-input only
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const int t_abs = p.t_begin + ts;
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
@@ -488,7 +527,10 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
                 __nv_bfloat16* sg = sg_row + u;
 #pragma unroll
                 for (int i = 0; i < CH; ++i)
-                  if (c0 + i < nrow) sg[(size_t)(c0 + i) * p.sg_pitch] = __float2bfloat16(-nd.gc[0] * (xold[i] - b0));
+                  if (c0 + i < nrow) {
+                    const float m0 = (mu0 != nullptr) ? __ldg(mu0 + (size_t)(rb + c0 + i) * dl + u) : b0;
+                    sg[(size_t)(c0 + i) * p.sg_pitch] = __float2bfloat16(-nd.gc[0] * (xold[i] - m0));
+                  }
               }
             }
           };
@@ -582,11 +624,13 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
               if (l > 0) {
                 tmem_ld_tie(gown);
               } else {
-                // layer 0 is predicted by its bias alone (inputs are zero): eps_0 = x_0 - b_0
+                // layer 0 is predicted by its bias alone (zero inputs: eps_0 = x_0 - b_0) or by the per-chain constant
+                // mu0 = W_0 inputs + b_0 of mu0_kernel
                 const float ce = 0.5f * nd.c[0], gc = nd.gc[0];
 #pragma unroll
                 for (int i = 0; i < CH; ++i) {
-                  const float eps = xv[i] - b0;
+                  const float m0 = (mu0 != nullptr && uvalid && i < nrc) ? __ldg(mu0 + xoffc + (size_t)i * dl) : b0;
+                  const float eps = xv[i] - m0;
                   gown[i] = -gc * eps;
                   if (uvalid && i < nrc) e_part = fmaf(ce * eps, eps, e_part);
                 }
@@ -1058,16 +1102,12 @@ int infer_tc_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes) {
   if (rc != MCPC_OK) return rc;
   const int n_ctas = (B + rc_.rv - 1) / rc_.rv;
   *bytes = ((packed + 255) & ~(size_t)255) + (((size_t)n_steps * n_ctas * 4 * sizeof(float) + 255) & ~(size_t)255) +
-           (size_t)n_steps * 2 * sizeof(float) + 512;
+           (((size_t)n_steps * 2 * sizeof(float) + 255) & ~(size_t)255) + (size_t)B * nd.dims[0] * sizeof(float) + 512;
   return MCPC_OK;
 }
 
 int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B, void* ws, size_t ws_bytes,
                     cudaStream_t stream) {
-  if (io->inputs != nullptr) {
-    set_error("bf16 path: non-zero `inputs` are not implemented (Linear_0 is bias-only); use MCPC_PREC_FP32");
-    return MCPC_ERR_UNSUPPORTED;
-  }
   TcParams p{};
   size_t smem = 0, packed = 0;
   RowsChoice rows = choose_rows(B);
@@ -1093,6 +1133,15 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   float* adam_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.partials) +
                                              (((size_t)o->n_steps * p.n_ctas * 4 * sizeof(float) + 255) & ~(size_t)255));
   p.adam_tab = adam_tab;
+  if (io->inputs != nullptr) {
+    // non-zero inputs: Linear_0's prediction is a per-chain constant of this launch (fp32, exact operands)
+    float* mu0 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(adam_tab) +
+                                          (((size_t)o->n_steps * 2 * sizeof(float) + 255) & ~(size_t)255));
+    mu0_kernel<<<dim3((nd.dims[0] + 63) / 64, (B + 63) / 64), 256, 0, stream>>>(io->inputs, io->W[0], io->b[0], B, nd.d_in,
+                                                                               nd.dims[0], mu0);
+    count_launch();
+    p.mu0 = mu0;
+  }
   if (o->optimizer == MCPC_OPT_ADAM && o->update_x) {
     adam_table_kernel<<<(o->n_steps + 127) / 128, 128, 0, stream>>>(o->adam_beta1, o->adam_beta2, o->lr, o->adam_step0, o->n_steps,
                                                                      adam_tab);
@@ -1181,6 +1230,7 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   const bool sgd_philox = o->optimizer == MCPC_OPT_SGD && o->noise_mode == MCPC_NOISE_PHILOX;
   int spec = 0;
   if (getenv("MCPC_TC_NOSPEC") != nullptr) plain = false;      // testing hook: the generic instantiation
+  if (p.mu0 != nullptr) plain = false;                         // non-zero inputs: generic instantiation only
   if (plain && bern_grad && sgd_philox) spec = 1;
   else if (plain && bern_grad && o->optimizer == MCPC_OPT_ADAM && o->noise_mode == MCPC_NOISE_NONE) spec = 2;
   else if (plain && !nd.top_has_grad && sgd_philox) spec = 3;

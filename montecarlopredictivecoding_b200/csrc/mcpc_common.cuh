@@ -58,6 +58,8 @@ int infer_rows_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes);
 int launch_infer_rows(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B, void* ws, size_t ws_bytes,
                       cudaStream_t stream);
 int launch_weight_grad_fp32(const NetDev& nd, const McpcGradIO* io, int B, int n_save, cudaStream_t stream);
+int launch_wgrad_tn_fp32(const float* A, int lda, const float* Bm, int ldb, float* C, int M, int N, int rows,
+                         cudaStream_t stream);
 int launch_fill_noise(uint64_t seed, int t_begin, int n_steps, uint64_t chain_offset, int B, int n_units,
                       float noise_scale, float* out, cudaStream_t stream);
 

@@ -75,6 +75,21 @@ __global__ void __launch_bounds__(256) wgrad_tn_kernel(const float* __restrict__
 
 }  // namespace
 
+// C[M][N] += A^T Bm over `rows` fp32 rows (one launch; used by the bf16 path for Linear_0 with non-zero inputs)
+int launch_wgrad_tn_fp32(const float* A, int lda, const float* Bm, int ldb, float* C, int M, int N, int rows,
+                         cudaStream_t stream) {
+  const int gx = (N + kTN - 1) / kTN, gy = (M + kTM - 1) / kTM;
+  int slabs = (148 * 4 + gx * gy - 1) / (gx * gy);
+  int rows_per_slab = (rows + slabs - 1) / slabs;
+  rows_per_slab = ((rows_per_slab + kTK - 1) / kTK) * kTK;
+  if (rows_per_slab < 4 * kTK) rows_per_slab = 4 * kTK;
+  slabs = (rows + rows_per_slab - 1) / rows_per_slab;
+  wgrad_tn_kernel<<<dim3(gx, gy, slabs), 256, 0, stream>>>(A, lda, Bm, ldb, rows, C, nullptr, M, N, rows, rows_per_slab);
+  MCPC_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return MCPC_OK;
+}
+
 int launch_weight_grad_fp32(const NetDev& nd, const McpcGradIO* io, int B, int n_save, cudaStream_t stream) {
   const float* G = reinterpret_cast<const float*>(io->save_g);
   const float* F = reinterpret_cast<const float*>(io->save_f);

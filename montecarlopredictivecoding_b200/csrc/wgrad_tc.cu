@@ -167,6 +167,18 @@ __global__ void __launch_bounds__(160, 1) wgrad_tc_kernel(const __grid_constant_
   if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
+// GS[c][u] = sum over the saved steps of the bf16 G_0 operand (d overall / d mu_0) of chain c: with non-zero inputs
+// gW_0 = sum_steps G_0^T inputs = GS^T inputs, and the inputs do not change during the call.
+__global__ void sum_slots_kernel(const __nv_bfloat16* __restrict__ G, int n_save, int B, int gw, int d0,
+                                 float* __restrict__ GS) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * d0) return;
+  const int c = (int)(idx / d0), u = (int)(idx % d0);
+  float s = 0.0f;
+  for (int slot = 0; slot < n_save; ++slot) s += __bfloat162float(G[((size_t)slot * B + c) * gw + u]);
+  GS[idx] = s;
+}
+
 inline int pad8i(int v) { return (v + 7) & ~7; }
 inline int pad16i(int v) { return (v + 15) & ~15; }
 
@@ -186,9 +198,26 @@ void save_layout_bf16(const NetDev& nd, int* g_off, int* g_width, int* f_off, in
 }
 
 int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_save, cudaStream_t stream) {
-  if (io->inputs != nullptr) {
-    set_error("bf16 weight-grad: non-zero inputs are not implemented; use MCPC_PREC_FP32");
-    return MCPC_ERR_UNSUPPORTED;
+  if (io->inputs != nullptr && io->gW[0] != nullptr) {
+    // Linear_0 with non-zero inputs: the inputs are the same rows for every saved step, so its weight gradient is
+    // (sum over steps of G_0)^T inputs -- a [B]-row contraction with exact fp32 inputs (the bias gradient comes from
+    // the tensor-core kernel below like for zero inputs)
+    const size_t need = (size_t)B * nd.dims[0] * sizeof(float);
+    if (io->scratch == nullptr || io->scratch_bytes < need) {
+      set_error("bf16 weight-grad with non-zero inputs needs McpcGradIO.scratch of %zu bytes (%zu given)", need,
+                io->scratch == nullptr ? (size_t)0 : io->scratch_bytes);
+      return MCPC_ERR_WORKSPACE;
+    }
+    int g_off0[kMaxL + 1], f_off0[kMaxL + 1], gw0 = 0, fw0 = 0;
+    save_layout_bf16(nd, g_off0, &gw0, f_off0, &fw0);
+    float* GS = reinterpret_cast<float*>(io->scratch);
+    const size_t n = (size_t)B * nd.dims[0];
+    sum_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(io->save_g), n_save, B, gw0, nd.dims[0], GS);
+    MCPC_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    const int rc0 = launch_wgrad_tn_fp32(GS, nd.dims[0], io->inputs, nd.d_in, io->gW[0], nd.dims[0], nd.d_in, B, stream);
+    if (rc0 != MCPC_OK) return rc0;
   }
   WgradParams p{};
   int g_off[kMaxL + 1], f_off[kMaxL + 1], gw = 0, fw = 0;

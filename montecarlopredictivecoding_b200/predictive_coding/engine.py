@@ -156,6 +156,7 @@ class NativeEngine:
         self._ws_need = {}
         self._layout_cache = {}
         self._mode_cache = {}
+        self._grad_scratch = {}
 
     def _workspace(self, net, B, n_steps, precision, device, net_key=None):
         # keyed by the network DESCRIPTION (not the address of a cached struct, which can be reused after a cache flush)
@@ -267,6 +268,14 @@ class NativeEngine:
         for i in range(len(gW)):
             io.gW[i] = _ptr(gW[i], "gW")
             io.gb[i] = _ptr(gb[i], "gb")
+        if inputs is not None and precision == N.PREC_BF16:
+            # Linear_0 with non-zero inputs: scratch for the per-chain sum of its G operand over the saved steps
+            need = B * plan.dims[0]
+            buf = self._grad_scratch.get(dev.index)
+            if buf is None or buf.numel() < need:
+                buf = self._grad_scratch[dev.index] = torch.empty(need, dtype=torch.float32, device=dev)
+            io.scratch = buf.data_ptr()
+            io.scratch_bytes = buf.numel() * 4
         stream = _raw_stream(dev)
         with _OnDevice(dev):
             N.check(self._lib.mcpc_weight_grad(C.byref(net), C.byref(io), B, n_save, precision, C.c_void_p(stream)),

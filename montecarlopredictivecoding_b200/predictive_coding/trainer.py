@@ -199,12 +199,18 @@ class PCTrainer(object):
         self._precision_req = table[precision]
         self._precision = N.PREC_BF16 if self._precision_req == "bf16" else N.PREC_FP32
 
-    def _resolve_precision(self, inputs) -> int:
-        """The MCPC_PREC_* this call runs in ('auto': bf16 unless the call has non-zero ``inputs``, which only the
-        fp32 kernels implement)."""
+    def _resolve_precision(self, inputs, netp=None, top=None) -> int:
+        """The MCPC_PREC_* this call runs in.  'auto': bf16, except for non-zero ``inputs`` on a network that needs the
+        streaming kernels (only the resident bf16 kernel and the fp32 kernels implement them)."""
         if self._precision_req != "auto":
             return N.PREC_BF16 if self._precision_req == "bf16" else N.PREC_FP32
-        return N.PREC_BF16 if self._inputs_or_none(inputs) is None else N.PREC_FP32
+        if self._inputs_or_none(inputs) is None:
+            return N.PREC_BF16
+        eng = self._get_engine()
+        if netp is not None and hasattr(eng, "infer_mode") and \
+                eng.infer_mode(netp, top, int(inputs.shape[0]), N.PREC_BF16) == N.MODE_RESIDENT_BF16:
+            return N.PREC_BF16
+        return N.PREC_FP32
 
     def set_noise_seed(self, seed: int) -> None:
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -537,7 +543,7 @@ class PCTrainer(object):
         self._start_of_batch(netp, inputs, is_sample_x_at_batch_start, is_reset_optimizer_x_at_batch_start,
                              is_reset_optimizer_p_at_batch_start)
 
-        self._precision = self._resolve_precision(inputs)
+        self._precision = self._resolve_precision(inputs, netp, top)
         langevin = P.classify_callback_after_t(callback_after_t, callback_after_t_kwargs, self)
         x_opt = self._classify_optimizer_x()
         fused = (

@@ -46,7 +46,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(N.McpcNet) == 4 * (2 + 8 + 1 + 8 + 8 + 1 + 1 + 1 + 1)
     assert ctypes.sizeof(N.McpcIO) == 8 * (9 + 9 + 8 + 3 + 8 + 8 + 8 + 2 + 8 + 1 + 9 + 9 + 2)
     assert ctypes.sizeof(N.McpcOpts) == 8 * 7 + 4 * 10
-    assert ctypes.sizeof(N.McpcGradIO) == 8 * (3 + 9 + 9)
+    assert ctypes.sizeof(N.McpcGradIO) == 8 * (3 + 9 + 9 + 2)
     assert ctypes.sizeof(N.McpcPStep) == 4 * 2 + 8 * (4 * 18) + 8 * 18 + 8 * 8 + 4 * 3 + 4     # 4 bytes of tail padding
 
 
