@@ -87,6 +87,8 @@ struct WideParams {
   __nv_bfloat16* act_l[kMaxL];            // [S][Bpad][apitch[l]]: act(x_l), S ring slots
   __nv_bfloat16* gb_l[kMaxL + 1];         // [S][Bpad][gpitch[l]]: G_l (Linear l), e_out for l = L
   int apitch[kMaxL], gpitch[kMaxL + 1];
+  int d_in_eff;                           // width of non-zero `inputs` (they enter Linear_0 as a bf16 operand block replicated
+                                          // in every ring slot); 0: zero inputs, Linear_0 is bias-only
   const float* target;
   const float* noise;
   float* gW[kMaxL + 1];
@@ -124,6 +126,7 @@ struct StepArgs {
 //   *_mn: box 64 (inner = M/N index) x 64 rows (contraction)  -> MN-major operand stage, one 8 KB block per 64 units
 struct WideMaps {
   CUtensorMap act_k[kMaxL], act_mn[kMaxL];
+  CUtensorMap in_k, in_mn;                 // the inputs block (non-zero `inputs` only): B operand of PREDICT / A operand of WGRAD, Linear 0
   CUtensorMap gb_k[kMaxL + 1], gb_mn[kMaxL + 1];
   CUtensorMap w_k[kMaxL + 1];              // W_l   [d_l x d_{l-1}] bf16, K-major A operand of PREDICT
   CUtensorMap w_kt[kMaxL + 1];             // W_l^T [d_{l-1} x d_l] bf16 (transposed copy made per call), K-major A operand of UPDATE
@@ -291,14 +294,14 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const StepA
   if (KIND == KIND_PREDICT) {
     int lin = 0;
     while (tile >= p.tP_first[lin + 1]) ++lin;
-    const int d_i = (lin == 0) ? 0 : nd.dims[lin - 1];            // Linear_0 sees zero inputs: mu_0 = b_0
+    const int d_i = (lin == 0) ? p.d_in_eff : nd.dims[lin - 1];   // zero inputs: Linear_0 has no GEMM, mu_0 = b_0
     const int ntn = (p.B + kTN - 1) / kTN, local = tile - p.tP_first[lin];
     t.idx = lin; t.m0 = (local / ntn) * (kTM * CG) + rank * kTM; t.n0 = (local % ntn) * kTN; t.k_ext = d_i;
     t.ni = local % ntn; t.ntn = ntn;
     t.k_base = st.slot * p.Bpad;
     if (d_i > 0) {
       t.mapA = &mp.w_k[lin];                                      // W_l [d_o x d_i], K-major
-      t.mapB = &mp.act_k[lin - 1];                                // act(x_{l-1}) [chains x d_i], K-major
+      t.mapB = (lin == 0) ? &mp.in_k : &mp.act_k[lin - 1];        // act(x_{l-1}) (or the inputs) [chains x d_i], K-major
     }
   } else if (KIND == KIND_UPDATE) {
     int l = 0;
@@ -314,14 +317,14 @@ __device__ __forceinline__ TileDesc decode_tile(const WideParams& p, const StepA
       t.mapB = &mp.gb_k[l + 1];                                   // G_{l+1} [chains x d_up], K-major
     }
   } else {
-    int lin = 1;
+    int lin = 0;                                                  // Linear 0 owns tiles only with non-zero inputs
     while (tile >= p.tW_first[lin + 1]) ++lin;
     const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin];
     const int ntn = (d_o + kTN - 1) / kTN, local = tile - p.tW_first[lin];
     t.idx = lin; t.m0 = (local / ntn) * (kTM * CG) + rank * kTM; t.n0 = (local % ntn) * kTN; t.k_ext = st.k_rows;
     t.ni = local % ntn; t.ntn = ntn;
     t.k_base = 0;
-    t.mapA = &mp.act_mn[lin - 1];                                 // act(x_{l-1}) as A[m = input unit][k = chain]: MN-major
+    t.mapA = (lin == 0) ? &mp.in_mn : &mp.act_mn[lin - 1];        // act(x_{l-1}) (or the inputs) as A[m = input unit][k = chain]
     t.mapB = &mp.gb_mn[lin];                                      // G_l as B[n = output unit][k = chain]: MN-major
   }
   t.nb0 = t.n0 + rank * (kTN / CG);
@@ -698,7 +701,7 @@ __device__ __forceinline__ void epilogue_update(const WideParams& p, const StepA
 __device__ __forceinline__ void epilogue_wgrad(const WideParams& p, const TileDesc& t, uint32_t acc, const EpiPos& ep) {
   const NetDev& nd = p.net;
   const int lin = t.idx;
-  const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = nd.dims[lin - 1];
+  const int d_o = (lin == nd.L) ? nd.d_out : nd.dims[lin], d_i = (lin == 0) ? p.d_in_eff : nd.dims[lin - 1];
   const int mi = t.m0 + ep.q * 32 + ep.lane;
   const bool m_ok = mi < d_i && p.gW[lin] != nullptr;
   float* gW = p.gW[lin] + mi;
@@ -1017,8 +1020,8 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline int pad8w(int v) { return (v + 7) & ~7; }
 
 struct WideLayout {
-  size_t wb_off[kMaxL + 1], wbt_off[kMaxL + 1], act_off[kMaxL], gb_off[kMaxL + 1], part_off, total;
-  int apitch[kMaxL], gpitch[kMaxL + 1], n_part, Bpad, S, cg;
+  size_t wb_off[kMaxL + 1], wbt_off[kMaxL + 1], act_off[kMaxL], gb_off[kMaxL + 1], in_off, part_off, total;
+  int apitch[kMaxL], gpitch[kMaxL + 1], in_pitch, n_part, Bpad, S, cg;
 };
 
 struct WideKnobs {
@@ -1079,6 +1082,10 @@ int wide_layout(const NetDev& nd, int B, int n_steps, WideLayout* lay) {
     }
   }
   size_t o = 0;
+  lay->in_pitch = pad8w(nd.d_in > 0 ? nd.d_in : 8);
+  lay->wb_off[0] = o;                                     // W_0 (non-zero inputs only; no transposed copy: nothing flows into them)
+  o += align256((size_t)nd.dims[0] * lay->in_pitch * 2);
+  lay->wbt_off[0] = 0;
   for (int l = 1; l < n_lin; ++l) {
     const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
     lay->wb_off[l] = o;
@@ -1102,6 +1109,8 @@ int wide_layout(const NetDev& nd, int B, int n_steps, WideLayout* lay) {
     lay->gb_off[l] = o;
     o += align256((size_t)S * lay->Bpad * lay->gpitch[l] * 2 + 65536);
   }
+  lay->in_off = o;                                        // bf16 copy of the inputs in every ring slot (sized whether or not
+  o += align256((size_t)S * lay->Bpad * lay->in_pitch * 2 + 65536);   // the call has inputs: the workspace depends on the net only)
   const int ntn = (B + kTN - 1) / kTN;
   int n_part = 0;
   for (int l = 0; l < n_lin; ++l) {
@@ -1143,7 +1152,7 @@ int launch_wide(const WideParams& p, const StepArgs& st, const WideMaps& mp, int
 
 template <int CG>
 int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& p, const WideLayout& lay, const WideKnobs& kn,
-             const __nv_bfloat16* const* Wb, const __nv_bfloat16* const* WbT, cudaStream_t stream) {
+             const __nv_bfloat16* const* Wb, const __nv_bfloat16* const* WbT, __nv_bfloat16* in_l, cudaStream_t stream) {
   const int B = p.B;
   const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
   // tile tables: (128 * CG) units x 256 chains per (pair) tile
@@ -1164,14 +1173,14 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
   const int n_update = t;
   t = 0;
   bool any_grad = false;
-  p.tW_first[0] = p.tW_first[1] = 0;
-  for (int l = 1; l <= nd.L; ++l) {
+  for (int l = 0; l <= nd.L; ++l) {
     p.tW_first[l] = t;
     const bool is_out = (l == nd.L);
     if (is_out && (nd.d_out == 0 || !nd.top_has_grad)) continue;
     if (p.gW[l] == nullptr) continue;
-    const int d_o = is_out ? nd.d_out : nd.dims[l];
-    t += ((nd.dims[l - 1] + kTM * CG - 1) / (kTM * CG)) * ((d_o + kTN - 1) / kTN);     // M = input units, N = output units
+    const int d_o = is_out ? nd.d_out : nd.dims[l], d_i = (l == 0) ? p.d_in_eff : nd.dims[l - 1];
+    if (d_i == 0) continue;                                                             // zero inputs: gW_0 receives nothing
+    t += ((d_i + kTM * CG - 1) / (kTM * CG)) * ((d_o + kTN - 1) / kTN);                // M = input units, N = output units
   }
   p.tW_first[nd.L + 1] = t;
   const int n_wgrad = t;
@@ -1190,6 +1199,7 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
   WideMaps mp;
   bool mn3 = (nd.d_out % 64 == 0);
   for (int l = 0; l < nd.L; ++l) mn3 = mn3 && (nd.dims[l] % 64 == 0);
+  if (p.d_in_eff > 0) mn3 = mn3 && (p.d_in_eff % 64 == 0);
   p.mn3 = mn3 ? 1 : 0;
   const uint64_t rows = (uint64_t)lay.S * lay.Bpad;
   constexpr int kBRows = kTN / CG;
@@ -1199,6 +1209,14 @@ int run_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, WideParams& 
     if (rc == MCPC_OK)
       rc = mn3 ? make_tmap_bf16_mn3(&mp.act_mn[l], p.act_l[l], nd.dims[l], rows, p.apitch[l], 64, kTM / 64)       // wgrad A
                : make_tmap_bf16(&mp.act_mn[l], p.act_l[l], nd.dims[l], rows, p.apitch[l], 64, 64);
+    if (rc != MCPC_OK) return rc;
+  }
+  if (p.d_in_eff > 0) {
+    rc = make_tmap_bf16(&mp.in_k, in_l, p.d_in_eff, rows, lay.in_pitch, 64, kBRows);                            // predict B, Linear 0
+    if (rc == MCPC_OK)
+      rc = mn3 ? make_tmap_bf16_mn3(&mp.in_mn, in_l, p.d_in_eff, rows, lay.in_pitch, 64, kTM / 64)                // wgrad A, Linear 0
+               : make_tmap_bf16(&mp.in_mn, in_l, p.d_in_eff, rows, lay.in_pitch, 64, 64);
+    if (rc == MCPC_OK) rc = make_tmap_bf16(&mp.w_k[0], Wb[0], p.d_in_eff, nd.dims[0], lay.in_pitch, 64, kTM);    // predict A
     if (rc != MCPC_OK) return rc;
   }
   for (int l = 0; l < n_lin; ++l) {
@@ -1371,10 +1389,6 @@ int infer_wide_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes) {
 
 int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B, void* ws, size_t ws_bytes,
                       cudaStream_t stream) {
-  if (io->inputs != nullptr) {
-    set_error("bf16 streaming path: non-zero `inputs` are not implemented; use MCPC_PREC_FP32");
-    return MCPC_ERR_UNSUPPORTED;
-  }
   if (io->save_g != nullptr) {
     set_error("bf16 streaming path accumulates the weight update itself (McpcIO.gW/gb); save_g/save_f are not used");
     return MCPC_ERR_INVALID;
@@ -1408,6 +1422,28 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
   p.n_part = lay.n_part;
   const __nv_bfloat16* Wb[kMaxL + 1] = {};
   const __nv_bfloat16* WbT[kMaxL + 1] = {};
+  __nv_bfloat16* in_l = nullptr;
+  p.d_in_eff = 0;
+  if (io->inputs != nullptr && nd.d_in > 0) {
+    // non-zero inputs: Linear_0 becomes a GEMM like every other Linear -- its B operand is a bf16 copy of the inputs,
+    // replicated in every ring slot (the weight-gradient launch contracts over the slots), rows B..Bpad zero
+    p.d_in_eff = nd.d_in;
+    in_l = reinterpret_cast<__nv_bfloat16*>(wsb + lay.in_off);
+    __nv_bfloat16* wb0 = reinterpret_cast<__nv_bfloat16*>(wsb + lay.wb_off[0]);
+    const size_t n0 = (size_t)nd.dims[0] * lay.in_pitch;
+    to_bf16_kernel<<<(int)((n0 + 1023) / 1024 < 1184 ? (n0 + 1023) / 1024 : 1184), 256, 0, stream>>>(io->W[0], wb0, nd.dims[0], nd.d_in,
+                                                                                                  lay.in_pitch);
+    count_launch();
+    Wb[0] = wb0;
+    const size_t ni = (size_t)B * lay.in_pitch;
+    for (int s = 0; s < lay.S; ++s) {
+      __nv_bfloat16* dst = in_l + (size_t)s * lay.Bpad * lay.in_pitch;
+      to_bf16_kernel<<<(int)((ni + 1023) / 1024 < 1184 ? (ni + 1023) / 1024 : 1184), 256, 0, stream>>>(io->inputs, dst, B, nd.d_in, lay.in_pitch);
+      count_launch();
+      if (lay.Bpad > B)
+        MCPC_CUDA_CHECK(cudaMemsetAsync(dst + (size_t)B * lay.in_pitch, 0, (size_t)(lay.Bpad - B) * lay.in_pitch * 2, stream));
+    }
+  }
   for (int l = 1; l < n_lin; ++l) {
     __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(wsb + lay.wb_off[l]);
     __nv_bfloat16* wbt = reinterpret_cast<__nv_bfloat16*>(wsb + lay.wbt_off[l]);
@@ -1447,7 +1483,8 @@ int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int
 #ifdef MCPC_DEBUG_BUILD
   p.skip_epilogue = kn.skip_epi;
 #endif
-  return lay.cg == 2 ? run_wide<2>(nd, io, o, p, lay, kn, Wb, WbT, stream) : run_wide<1>(nd, io, o, p, lay, kn, Wb, WbT, stream);
+  return lay.cg == 2 ? run_wide<2>(nd, io, o, p, lay, kn, Wb, WbT, in_l, stream)
+                     : run_wide<1>(nd, io, o, p, lay, kn, Wb, WbT, in_l, stream);
 }
 
 }  // namespace mcpc

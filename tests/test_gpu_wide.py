@@ -36,10 +36,10 @@ def _clean_knobs():
             os.environ[k] = v
 
 
-def _model(dims, d_out, act, dev, seed=0, wide_init=False):
+def _model(dims, d_out, act, dev, seed=0, wide_init=False, d_in=None):
     torch.manual_seed(seed)
     A = {"relu": nn.ReLU, "tanh": nn.Tanh}[act]
-    mods, prev = [], dims[0]
+    mods, prev = [], (dims[0] if d_in is None else d_in)
     for d in dims:
         mods += [nn.Linear(prev, d), pc.PCLayer(), A()]
         prev = d
@@ -56,13 +56,13 @@ def _model(dims, d_out, act, dev, seed=0, wide_init=False):
 
 
 def _run_case(dims, d_out, act, top, opt, B, mixing, sampling, lr=0.02, wide_init=False, bf16_oracle=True,
-              want_outputs=True, seed=2024):
+              want_outputs=True, seed=2024, d_in=None):
     """One learning call on the GPU + the same call through the oracle with the kernel's own noise; returns the
     dict of max-norm relative errors."""
     dev = torch.device(DEV)
     L = len(dims)
     T = mixing + sampling
-    model = _model(dims, d_out, act, dev, wide_init=wide_init)
+    model = _model(dims, d_out, act, dev, wide_init=wide_init, d_in=d_in)
     opt_fn = optim.SGD if opt == "sgd" else optim.Adam
     tr = pc.PCTrainer(model, T=T, optimizer_x_fn=opt_fn, optimizer_x_kwargs={"lr": lr}, update_p_at="last",
                       accumulate_p_at=list(range(mixing, T)), optimizer_p_fn=optim.SGD, optimizer_p_kwargs={"lr": 0.0},
@@ -78,7 +78,9 @@ def _run_case(dims, d_out, act, top, opt, B, mixing, sampling, lr=0.02, wide_ini
         layer._sample_x_fn = (lambda inputs, v=v: v.clone())
     loss_fn = mu.bernoulli_fn if top == "bernoulli" else mu.fe_fn
     kw = dict(callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": tr}) if opt == "sgd" else {}
-    res = tr.train_on_batch(torch.zeros(B, dims[0], device=dev), loss_fn=loss_fn, loss_fn_kwargs={"_target": y, "_var": 1.0},
+    # d_in given: NON-ZERO inputs of that width (Linear_0 becomes a GEMM over a bf16 copy of them, and gets a weight gradient)
+    inputs = torch.zeros(B, dims[0], device=dev) if d_in is None else torch.randn(B, d_in, device=dev)
+    res = tr.train_on_batch(inputs, loss_fn=loss_fn, loss_fn_kwargs={"_target": y, "_var": 1.0},
                             is_log_progress=False, is_return_outputs=want_outputs, **kw)
     assert tr.last_call_info["mode"] == "fused"
     assert tr._get_engine().infer_mode(tr_plan(tr), tr_top(loss_fn, y, B, d_out), B, N.PREC_BF16) == N.MODE_STREAMING_BF16
@@ -91,8 +93,9 @@ def _run_case(dims, d_out, act, top, opt, B, mixing, sampling, lr=0.02, wide_ini
     net = orc.OracleNet(W=[l.weight.detach().cpu().numpy() for l in lins], b=[l.bias.detach().cpu().numpy() for l in lins],
                         n_layers=L, act=[orc.ACT_RELU if act == "relu" else orc.ACT_TANH] * L, energy_scale=[1.0] * L,
                         top=orc.TOP_BERNOULLI if top == "bernoulli" else orc.TOP_GAUSS, bf16_operands=bf16_oracle,
-                        bf16_own_term=bf16_oracle and os.environ.get("MCPC_WIDE_G32", "0") == "0")
-    ref = orc.infer(net, [v.cpu().numpy() for v in x0], np.zeros((B, dims[0]), np.float32), y.cpu().numpy(), T,
+                        bf16_own_term=bf16_oracle and os.environ.get("MCPC_WIDE_G32", "0") == "0",
+                        bf16_inputs=bf16_oracle)
+    ref = orc.infer(net, [v.cpu().numpy() for v in x0], inputs.cpu().numpy(), y.cpu().numpy(), T,
                     optimizer=opt, lr=lr, noise=noise, acc_begin=mixing, acc_end=T, record_traj=want_outputs)
     errs = {f"x{l}": rel_err(pcs[l].get_x().detach().cpu().numpy(), ref.xs[l]) for l in range(L)}
     errs["energy"] = rel_err(res["energy"], ref.energy)
@@ -104,7 +107,10 @@ def _run_case(dims, d_out, act, top, opt, B, mixing, sampling, lr=0.02, wide_ini
         errs[f"gW_{i}"] = rel_err(lins[i].weight.grad.cpu().numpy(), ref.gW[i] / div)
     for i in range(0, L + 1):
         errs[f"gb_{i}"] = rel_err(lins[i].bias.grad.cpu().numpy(), ref.gb[i] / div)
-    assert float(lins[0].weight.grad.abs().max()) == 0.0
+    if d_in is None:
+        assert float(lins[0].weight.grad.abs().max()) == 0.0
+    else:
+        errs["gW_0"] = rel_err(lins[0].weight.grad.cpu().numpy(), ref.gW[0] / div)
     return errs
 
 
@@ -141,6 +147,20 @@ def test_streaming_path_odd_widths(cg, monkeypatch):
     monkeypatch.setenv("MCPC_WIDE_CG", str(cg))
     errs = _run_case([20, 130, 77], 101, "tanh", "gauss", "sgd", B=150, mixing=1, sampling=3)
     _check(errs, 2e-3, f"odd widths cg={cg}")
+
+
+@pytest.mark.parametrize("cg", [pytest.param(1, id="cg1"), pytest.param(2, id="cg2")])
+@pytest.mark.parametrize("dims,d_out,d_in,B,slots", [([128, 256, 144], 272, 50, 200, 0), ([128, 320, 192], 576, 64, 300, 2),
+                                                     ([20, 130, 77], 101, 33, 150, 3), ([256, 256], 128, 300, 392, 1)])
+def test_streaming_path_nonzero_inputs(dims, d_out, d_in, B, slots, cg, monkeypatch):
+    """Non-zero ``inputs``: Linear_0 is a GEMM over the bf16 inputs block (PREDICT) and gets a weight gradient (WGRAD);
+    widths with and without the 3-D tensor maps (all % 64 == 0), d_in narrower and wider than a unit tile."""
+    monkeypatch.setenv("MCPC_FORCE_STREAMING", "1")
+    monkeypatch.setenv("MCPC_WIDE_CG", str(cg))
+    if slots:
+        monkeypatch.setenv("MCPC_WIDE_SLOTS", str(slots))
+    errs = _run_case(dims, d_out, "tanh", "gauss", "sgd", B, mixing=2, sampling=4, d_in=d_in)
+    _check(errs, 2e-3, f"inputs d_in={d_in} dims={dims} cg={cg}")
 
 
 @pytest.mark.parametrize("cg", [pytest.param(1, id="cg1"), pytest.param(2, id="cg2")])
