@@ -90,8 +90,11 @@ typedef struct McpcIO {
   double* loss;                           /* [n_steps] loss at the start of each step (0 when TOP_NONE) :777-780 */
   float* traj_x[MCPC_MAX_LAYERS];         /* optional [n_rec, B, d_l]: x_l at the start of step t_k = k*traj_every */
   float* traj_out;                        /* optional [n_rec, B, d_out]: outputs of the same steps (:769-770) */
-  float* gW[MCPC_MAX_LAYERS + 1];         /* MODE_STREAMING only: weight-gradient accumulators; the update of the steps */
-  float* gb[MCPC_MAX_LAYERS + 1];         /*   [save_begin, save_end) is ADDED here directly (no save_g/save_f)        */
+  float* gW[MCPC_MAX_LAYERS + 1];         /* optional weight-gradient accumulators: the update of the steps [save_begin,    */
+  float* gb[MCPC_MAX_LAYERS + 1];         /*   save_end) is ADDED here by mcpc_infer itself.  MODE_STREAMING: the only way     */
+                                          /*   (no save_g/save_f).  RESIDENT modes: save_g/save_f must be given too (scratch) */
+                                          /*   and no mcpc_weight_grad call is needed; RESIDENT_BF16 runs the update on the   */
+                                          /*   SMs the inference kernel leaves idle, WHILE it runs (pc_trainer.py:862)        */
   void* save_g;                           /* optional [n_save, B, g_width]: d overall / d mu_l and d loss / d out      */
   void* save_f;                           /* optional [n_save, B, f_width]: act_l(x_l); operands of mcpc_weight_grad;
                                              widths / element type from mcpc_save_layout                           */
@@ -146,6 +149,13 @@ int mcpc_infer_mode(const McpcNet* net, int32_t B, int32_t precision, int32_t* m
  * (pc_trainer.py:733-918 with utils/model.py:35-44 folded in). */
 int mcpc_infer(const McpcNet* net, const McpcIO* io, const McpcOpts* opts, int32_t B,
                void* workspace, size_t workspace_bytes, void* stream);
+
+/* *out = 1 when passing McpcIO.gW/gb to mcpc_infer is the faster way to get the weight update for this (net, B, precision):
+ * MODE_STREAMING (the only way there), or MODE_RESIDENT_BF16 with MCPC_TC_DW_OVERLAP=1 in the environment when the
+ * weight-gradient kernel fits the SMs the inference kernel leaves idle and runs NEXT to it (B <= ~1100 chains, zero
+ * inputs; opt-in: it pays only for callers that do not read results between calls).  0: mcpc_infer would
+ * run the update after the inference kernel -- a caller that wants the per-step scalars early calls mcpc_weight_grad itself. */
+int mcpc_infer_fuses_weight_grad(const McpcNet* net, int32_t B, int32_t precision, int32_t has_inputs, int32_t* out);
 
 /* Local weight update from the operands saved by mcpc_infer. */
 int mcpc_weight_grad(const McpcNet* net, const McpcGradIO* io, int32_t B, int32_t n_save,

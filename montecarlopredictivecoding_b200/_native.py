@@ -123,7 +123,7 @@ class NativeError(RuntimeError):
 _lib = None
 _lock = threading.Lock()
 LIB_NAME = "libmcpc_b200.so"
-EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer_mode", "mcpc_infer", "mcpc_weight_grad",
+EXPORTS = ("mcpc_version", "mcpc_last_error", "mcpc_launch_count", "mcpc_workspace_bytes", "mcpc_save_layout", "mcpc_infer_mode", "mcpc_infer_fuses_weight_grad", "mcpc_infer", "mcpc_weight_grad",
            "mcpc_fill_noise", "mcpc_marginal_ll_workspace_bytes", "mcpc_marginal_ll_bernoulli", "mcpc_traj_stats_update",
            "mcpc_p_step")
 PROBE_EXPORTS = ("mcpc_probes_last_error", "mcpc_debug_umma", "mcpc_debug_tma")
@@ -167,6 +167,8 @@ def load():
                                          C.POINTER(C.c_int32)]
         lib.mcpc_infer_mode.restype = C.c_int
         lib.mcpc_infer_mode.argtypes = [C.POINTER(McpcNet), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        lib.mcpc_infer_fuses_weight_grad.restype = C.c_int
+        lib.mcpc_infer_fuses_weight_grad.argtypes = [C.POINTER(McpcNet), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
         lib.mcpc_infer.restype = C.c_int
         lib.mcpc_infer.argtypes = [C.POINTER(McpcNet), C.POINTER(McpcIO), C.POINTER(McpcOpts), C.c_int32,
                                    C.c_void_p, C.c_size_t, C.c_void_p]

@@ -159,6 +159,20 @@ int mcpc_infer_mode(const McpcNet* net, int32_t B, int32_t precision, int32_t* m
   return MCPC_ERR_UNSUPPORTED;
 }
 
+int mcpc_infer_fuses_weight_grad(const McpcNet* net, int32_t B, int32_t precision, int32_t has_inputs, int32_t* out) {
+  NetDev nd;
+  int rc = check_net(net, &nd);
+  if (rc != MCPC_OK) return rc;
+  if (out == nullptr || B < 1) {
+    set_error("bad arguments");
+    return MCPC_ERR_INVALID;
+  }
+  *out = 0;
+  if (precision == MCPC_PREC_BF16)
+    *out = infer_tc_fits(nd, B) ? (infer_tc_overlaps_weight_grad(nd, B, has_inputs != 0) ? 1 : 0) : 1;
+  return MCPC_OK;
+}
+
 int mcpc_infer(const McpcNet* net, const McpcIO* io, const McpcOpts* o, int32_t B, void* workspace,
                size_t workspace_bytes, void* stream) {
   NetDev nd;
@@ -207,7 +221,25 @@ int mcpc_infer(const McpcNet* net, const McpcIO* io, const McpcOpts* o, int32_t 
     return MCPC_ERR_INVALID;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (o->precision == MCPC_PREC_FP32) return launch_infer_rows(nd, io, o, B, workspace, workspace_bytes, s);
+  if (o->precision == MCPC_PREC_FP32) {
+    rc = launch_infer_rows(nd, io, o, B, workspace, workspace_bytes, s);
+    if (rc != MCPC_OK) return rc;
+    // McpcIO.gW/gb given: the weight update of the saved steps is part of this call (same contract as the bf16 modes)
+    bool want_dw = false;
+    for (int l = 0; l <= nd.L; ++l) want_dw = want_dw || io->gW[l] != nullptr || io->gb[l] != nullptr;
+    if (want_dw && io->save_g != nullptr && o->save_end > o->save_begin) {
+      McpcGradIO gio{};
+      gio.save_g = io->save_g;
+      gio.save_f = io->save_f;
+      gio.inputs = io->inputs;
+      for (int l = 0; l <= nd.L; ++l) {
+        gio.gW[l] = io->gW[l];
+        gio.gb[l] = io->gb[l];
+      }
+      return launch_weight_grad_fp32(nd, &gio, B, o->save_end - o->save_begin, s);
+    }
+    return MCPC_OK;
+  }
   if (o->precision == MCPC_PREC_BF16)
     return infer_tc_fits(nd, B) ? launch_infer_tc(nd, io, o, B, workspace, workspace_bytes, s)
                                 : launch_infer_wide(nd, io, o, B, workspace, workspace_bytes, s);

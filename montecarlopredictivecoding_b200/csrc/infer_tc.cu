@@ -69,6 +69,8 @@ struct TcParams {
   float* xgrad[kMaxL];
   float* traj_x[kMaxL];
   float* traj_out;
+  unsigned* ready;              // [n_save] per saved step: += 1 per CTA once its rows of save_g / save_f are written (the
+                                // concurrent weight-gradient kernel consumes them while this kernel runs), or nullptr
   const float* mu0;             // fp32 [B, dims[0]]: W_0 inputs + b_0 per chain (non-zero `inputs`), else nullptr
   __nv_bfloat16* save_g;        // bf16 [n_save, B, sg_pitch], layer blocks padded to 8 columns (wgrad_tc.cu)
   __nv_bfloat16* save_f;        // bf16 [n_save, B, sf_pitch]
@@ -183,6 +185,17 @@ __global__ void adam_table_kernel(double beta1, double beta2, double lr, int ste
   out[2 * i + 1] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
 }
 
+// "the rows of saved step `slot` written by this warp group are in global memory": called by ONE thread after the group's
+// end-of-step bar.sync (CTA-scope order over the group's stores), so the gpu-scope release is cumulative over them
+__device__ __forceinline__ void signal_saved(unsigned* flag) {
+  asm volatile("fence.acq_rel.gpu;\n\tred.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+}
+
+// one epilogue group finished storing a saved step (called by one thread after the group's end-of-step bar.sync)
+__device__ __forceinline__ void saved_step(unsigned* cnt) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(umma::smem_u32(cnt)) : "memory");
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -222,7 +235,7 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
 // 3 = sampling without a sensory gradient (SGD + Philox, zero_fn / no loss: no output tile is ever visited),
 // 0 = everything read from the parameters.  SPEC != 0 also means: no trajectories, no x.grad read-out.
 template <int NR, int RV, bool TRACE, int SPEC>
-__global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int RPT = RV / 2;
   constexpr bool ALT = (RV <= 8);            // group T works on alternate tiles (see there)
   constexpr int kGrp = 256;                  // threads per epilogue group
@@ -231,11 +244,12 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
   constexpr int CH = RPT < 8 ? RPT : 8;      // chains a thread of group U processes at a time
   constexpr bool kNoiseEarly = (RV <= 8);    // draw the Langevin noise before waiting for the back-projection
                                              // (wider chain tiles have no registers to hold it across the wait)
-  constexpr int kMmaWarp = 16, kMmaWarpB = 17, kLoadWarp = 18;
+  constexpr int kMmaWarp = 16, kMmaWarpB = 17, kLoadWarp = 18, kSigWarp = 19;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Barriers bars;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_red[2][2][8][2];        // [group][step parity][warp][energy, loss]
+  __shared__ unsigned s_saved[2];            // saved steps whose rows group T / group U have finished storing (signal warp)
   __shared__ int2 s_tile[kMaxTiles];         // x = lin | out_tile << 8 | (h_out + 1) << 16, y = number of units of that Linear
 
   const NetDev& nd = p.net;
@@ -256,6 +270,8 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
     s_tile[tid] = make_int2(T.lin | (T.out_tile << 8) | ((T.h_out + 1) << 16), T.lin == nd.L ? nd.d_out : nd.dims[T.lin]);
   }
   if (tid == 0) {
+    s_saved[0] = 0;
+    s_saved[1] = 0;
     mbar_init(&bars.w_res, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.w_full[i], 1);
@@ -313,6 +329,27 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
           mbar_expect_tx(&bars.w_full[T.slot], (uint32_t)T.bytes);
           bulk_g2s(smem + T.smem_off, p.packed + T.gsrc, (uint32_t)T.bytes, &bars.w_full[T.slot]);
         }
+      }
+    }
+  } else if (warp == kSigWarp) {
+    // ---------------- signal warp (overlapped weight update only) ----------------
+    // Tells the concurrent weight-gradient kernel that this CTA's rows of saved step s are in global memory.  The
+    // gpu-scope release costs ~1 us (it waits for the write acknowledgements); issued by an epilogue thread it sat on the
+    // step's critical path (+2 us per step), so the groups only bump a shared-memory counter after their end-of-step
+    // barrier (release.cta) and this otherwise idle warp does the waiting.  Causality: group stores -> bar.sync ->
+    // red.release.cta -> ld.acquire.cta here -> fence.acq_rel.gpu + red.release.gpu -> the consumer's ld.acquire.gpu.
+    if (lane == 0 && p.ready != nullptr && p.save_g != nullptr) {
+      const int s_end = min(p.save_end, p.n_steps);
+      const uint32_t a0 = smem_u32(&s_saved[0]), a1 = smem_u32(&s_saved[1]);
+      for (int s = 0; s < s_end - p.save_begin; ++s) {
+        for (;;) {
+          unsigned v0, v1;
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v0) : "r"(a0) : "memory");
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v1) : "r"(a1) : "memory");
+          if (v0 > (unsigned)s && v1 > (unsigned)s) break;
+          __nanosleep(200);
+        }
+        signal_saved(p.ready + s);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -711,6 +748,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
           for (int w = 0; w < 8; ++w) s += red[w][gtid];
           p.partials[(((size_t)ts * p.n_ctas + blockIdx.x) * 2 + 1) * 2 + gtid] = s;
         }
+        if (gtid == 0 && do_save && p.ready != nullptr) saved_step(&s_saved[1]);
       }
       // ---------- write the latents back (group U owns x) ----------
       for (int h = 0; h < HT; ++h) {
@@ -945,6 +983,7 @@ __global__ void __launch_bounds__(608, 1) infer_tc_kernel(const __grid_constant_
           for (int w = 0; w < 8; ++w) s += red[w][gtid];
           p.partials[(((size_t)ts * p.n_ctas + blockIdx.x) * 2 + 0) * 2 + gtid] = s;
         }
+        if (gtid == 0 && do_save && p.ready != nullptr) saved_step(&s_saved[0]);
       }
     }
   }
@@ -1102,7 +1141,8 @@ int infer_tc_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes) {
   if (rc != MCPC_OK) return rc;
   const int n_ctas = (B + rc_.rv - 1) / rc_.rv;
   *bytes = ((packed + 255) & ~(size_t)255) + (((size_t)n_steps * n_ctas * 4 * sizeof(float) + 255) & ~(size_t)255) +
-           (((size_t)n_steps * 2 * sizeof(float) + 255) & ~(size_t)255) + (size_t)B * nd.dims[0] * sizeof(float) + 512;
+           (((size_t)n_steps * 2 * sizeof(float) + 255) & ~(size_t)255) +
+           (((size_t)B * nd.dims[0] * sizeof(float) + 255) & ~(size_t)255) + (size_t)n_steps * sizeof(unsigned) + 512;
   return MCPC_OK;
 }
 
@@ -1133,10 +1173,13 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   float* adam_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p.partials) +
                                              (((size_t)o->n_steps * p.n_ctas * 4 * sizeof(float) + 255) & ~(size_t)255));
   p.adam_tab = adam_tab;
+  float* mu0_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(adam_tab) +
+                                            (((size_t)o->n_steps * 2 * sizeof(float) + 255) & ~(size_t)255));
+  const size_t mu0_bytes = ((size_t)B * nd.dims[0] * sizeof(float) + 255) & ~(size_t)255;
+  unsigned* ready_buf = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(mu0_buf) + mu0_bytes);
   if (io->inputs != nullptr) {
     // non-zero inputs: Linear_0's prediction is a per-chain constant of this launch (fp32, exact operands)
-    float* mu0 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(adam_tab) +
-                                          (((size_t)o->n_steps * 2 * sizeof(float) + 255) & ~(size_t)255));
+    float* mu0 = mu0_buf;
     mu0_kernel<<<dim3((nd.dims[0] + 63) / 64, (B + 63) / 64), 256, 0, stream>>>(io->inputs, io->W[0], io->b[0], B, nd.d_in,
                                                                                nd.dims[0], mu0);
     count_launch();
@@ -1218,9 +1261,58 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     cudaMalloc(&p.dbg, 8 * 64 * sizeof(long long));
     cudaMemsetAsync(p.dbg, 0, 8 * 64 * sizeof(long long), stream);
   }
+  // ---- the weight update of the saved steps, when the caller passed accumulators (McpcIO.gW/gb) --------------------
+  // Overlapped: B <= 1184 chains occupy 8 chains x <= 148 CTAs of one SM each; when at least one CTA per output tile of the
+  // weight-gradient kernel fits the SMs left over, it is launched on a side stream NEXT to the inference kernel and
+  // consumes each saved step as soon as every inference CTA has signalled it (TcParams.ready) -- its operands come from L2
+  // and only the last step's tail is left when the inference kernel ends.  Otherwise it runs after the kernel.
+  bool want_dw = false;
+  for (int l = 0; l <= nd.L; ++l) want_dw = want_dw || io->gW[l] != nullptr || io->gb[l] != nullptr;
+  want_dw = want_dw && io->save_g != nullptr && o->save_end > o->save_begin;
+  McpcGradIO gio{};
+  bool overlap = false;
+  int free_sms = 0;
+  const int n_save = o->save_end - o->save_begin;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (want_dw) {
+    gio.save_g = io->save_g;
+    gio.save_f = io->save_f;
+    gio.inputs = io->inputs;
+    for (int l = 0; l <= nd.L; ++l) {
+      gio.gW[l] = io->gW[l];
+      gio.gb[l] = io->gb[l];
+    }
+    gio.scratch = mu0_buf;                                       // free again once the inference kernel has finished
+    gio.scratch_bytes = mu0_bytes;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    free_sms = n_sm - p.n_ctas;
+    const int nt = weight_grad_tc_tiles(nd, &gio);
+    const char* e = getenv("MCPC_TC_DW_OVERLAP");                // opt-in, see infer_tc_overlaps_weight_grad
+    overlap = io->inputs == nullptr && nt > 0 && free_sms >= nt && (e != nullptr && e[0] == '1') && !timing && dev < 16;
+    if (overlap) {
+      static cudaStream_t s_side[16] = {};
+      static cudaEvent_t s_fork[16] = {}, s_join[16] = {};
+      if (s_side[dev] == nullptr) {
+        MCPC_CUDA_CHECK(cudaStreamCreateWithFlags(&s_side[dev], cudaStreamNonBlocking));
+        MCPC_CUDA_CHECK(cudaEventCreateWithFlags(&s_fork[dev], cudaEventDisableTiming));
+        MCPC_CUDA_CHECK(cudaEventCreateWithFlags(&s_join[dev], cudaEventDisableTiming));
+      }
+      side = s_side[dev];
+      ev_fork = s_fork[dev];
+      ev_join = s_join[dev];
+      p.ready = ready_buf;
+      MCPC_CUDA_CHECK(cudaMemsetAsync(ready_buf, 0, (size_t)n_save * sizeof(unsigned), stream));
+      // everything the consumer depends on besides the flags (zeroed accumulators, the flags' reset) is in `stream` by now
+      MCPC_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+      MCPC_CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork, 0));
+    }
+  }
   auto launch = [&](auto kernel) -> int {
     MCPC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<p.n_ctas, 608, smem, stream>>>(p);
+    kernel<<<p.n_ctas, 640, smem, stream>>>(p);
     return MCPC_OK;
   };
   bool plain = (p.traj_every == 0) && o->update_x;           // what every specialisation assumes
@@ -1252,6 +1344,11 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   if (rc != MCPC_OK) return rc;
   MCPC_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  if (want_dw && overlap) {
+    rc = launch_weight_grad_tc_overlapped(nd, &gio, B, n_save, ready_buf, (unsigned)p.n_ctas, free_sms, side);
+    if (rc != MCPC_OK) return rc;
+    MCPC_CUDA_CHECK(cudaEventRecord(ev_join, side));
+  }
   if (timing) {
     long long h[8 * 64];
     cudaStreamSynchronize(stream);
@@ -1269,7 +1366,40 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     rc = launch_reduce_partials(p.partials, o->n_steps, 2 * p.n_ctas, io->energy, io->loss, stream);
     if (rc != MCPC_OK) return rc;
   }
+  if (want_dw) {
+    if (overlap) {
+      MCPC_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));      // the caller's stream continues after the weight update
+    } else {
+      rc = launch_weight_grad_tc(nd, &gio, B, n_save, stream);
+      if (rc != MCPC_OK) return rc;
+    }
+  }
   return MCPC_OK;
+}
+
+// Will mcpc_infer overlap the weight update with the inference kernel for this (net, B)?  (all accumulators given)
+bool infer_tc_overlaps_weight_grad(const NetDev& nd, int B, bool has_inputs) {
+  if (has_inputs) return false;
+  // Opt-in (MCPC_TC_DW_OVERLAP=1).  Measured on C2 (B = 1024, T = 150, r02): the weight update then ends 10 us after the
+  // inference kernel instead of 85 us, but a caller that reads the results of every call is bound by its own latency
+  // from "scalars ready" to "next kernel launched" (~115 us of Python), which the sequential order hides behind the
+  // weight-gradient and optimizer kernels: 1.23 ms per call overlapped vs 1.17 ms sequential.  It pays only for callers
+  // that enqueue calls without reading results in between.
+  const char* e = getenv("MCPC_TC_DW_OVERLAP");
+  if (e == nullptr || e[0] != '1') return false;
+  McpcGradIO gio{};
+  float* dummy = reinterpret_cast<float*>(0x100);
+  for (int l = 0; l <= nd.L; ++l) {
+    gio.gW[l] = dummy;
+    gio.gb[l] = dummy;
+  }
+  const int nt = weight_grad_tc_tiles(nd, &gio);
+  int dev = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return false;
+  const RowsChoice rows = choose_rows(B);
+  const int n_ctas = (B + rows.rv - 1) / rows.rv;
+  return nt > 0 && n_sm - n_ctas >= nt && dev < 16;
 }
 
 }  // namespace mcpc

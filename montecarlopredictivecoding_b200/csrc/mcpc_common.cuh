@@ -70,6 +70,10 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
                     cudaStream_t stream);
 void save_layout_bf16(const NetDev& nd, int* g_off, int* g_width, int* f_off, int* f_width);
 int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_save, cudaStream_t stream);
+int weight_grad_tc_tiles(const NetDev& nd, const McpcGradIO* io);
+bool infer_tc_overlaps_weight_grad(const NetDev& nd, int B, bool has_inputs);
+int launch_weight_grad_tc_overlapped(const NetDev& nd, const McpcGradIO* io, int B, int n_save, const unsigned* ready,
+                                     unsigned ready_target, int max_ctas, cudaStream_t stream);
 bool infer_tc_fits(const NetDev& nd, int B);
 int infer_wide_workspace(const NetDev& nd, int B, int n_steps, size_t* bytes);
 int launch_infer_wide(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B, void* ws, size_t ws_bytes,

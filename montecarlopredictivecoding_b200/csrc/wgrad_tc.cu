@@ -45,6 +45,11 @@ struct WgradParams {
   int d_out_units[kMaxL + 1];     // rows of gW_l
   int d_in_units[kMaxL + 1];      // cols of gW_l
   int rows, rows_per_slab;
+  // Overlapped mode (launched next to infer_tc_kernel on the SMs it leaves idle): CTA y takes the 64-row stages y, y + slabs,
+  // ... so that every CTA follows the producer, and waits until ready[step] == ready_target before it loads rows of a step
+  const unsigned* ready;
+  unsigned ready_target;
+  int rows_per_step;              // B
 };
 
 __device__ __forceinline__ bool elect_one_w() {
@@ -66,9 +71,18 @@ __global__ void __launch_bounds__(160, 1) wgrad_tc_kernel(const __grid_constant_
   const int n_tot = f_blocks * 64 + 16;                  // F blocks + the first 16 columns of the ones block
   const uint32_t a_bytes = 2 * kBlk, b_bytes = (uint32_t)f_blocks * kBlk;
   const uint32_t stage_bytes = a_bytes + 2 * kBlk + kBlk;          // fixed stride: A | up to 2 F blocks | ones block
-  const int r_begin = blockIdx.y * p.rows_per_slab;
-  const int r_end = min(p.rows, r_begin + p.rows_per_slab);
-  const int n_stage = (r_end > r_begin) ? (r_end - r_begin + kStageRows - 1) / kStageRows : 0;
+  int r_begin, r_stride, n_stage;
+  if (p.ready != nullptr) {
+    const int total = (p.rows + kStageRows - 1) / kStageRows;
+    r_begin = (int)blockIdx.y * kStageRows;
+    r_stride = (int)gridDim.y * kStageRows;
+    n_stage = ((int)blockIdx.y < total) ? (total - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
+  } else {
+    r_begin = blockIdx.y * p.rows_per_slab;
+    r_stride = kStageRows;
+    const int r_end = min(p.rows, r_begin + p.rows_per_slab);
+    n_stage = (r_end > r_begin) ? (r_end - r_begin + kStageRows - 1) / kStageRows : 0;
+  }
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -102,11 +116,30 @@ __global__ void __launch_bounds__(160, 1) wgrad_tc_kernel(const __grid_constant_
   if (warp == 0) {
     // ---------------- TMA producer: 64 rows x (128 + 64*nblk) units per stage, two instructions ----------------
     if (elect_one_w()) {
+      int steps_ready = 0;                                 // saved steps known to be complete (overlapped mode)
       for (int s = 0; s < n_stage; ++s) {
         const int slot = s % kStages;
         mbar_wait(&empty[slot], ((s / kStages) & 1) ^ 1);
         uint8_t* st = smem + slot * stage_bytes;
-        const int row = r_begin + s * kStageRows;          // rows past the end of the buffer are zero-filled by TMA
+        const int row = r_begin + s * r_stride;            // rows past the end of the buffer are zero-filled by TMA
+        if (p.ready != nullptr) {
+          const int step_hi = min(row + kStageRows - 1, p.rows - 1) / p.rows_per_step;
+          if (step_hi >= steps_ready) {
+            // every producer CTA finishes its steps in order, so the newest step's flag covers the older ones
+            unsigned v;
+            unsigned long long t0 = 0, t1;
+            for (;;) {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready + step_hi) : "memory");
+              if (v >= p.ready_target) break;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+              if (t0 == 0) t0 = t1;
+              if (t1 - t0 > 4000000000ull) __trap();      // 4 s without progress: the producer is gone -- fail, never hang
+              __nanosleep(200);
+            }
+            steps_ready = step_hi + 1;
+            asm volatile("fence.proxy.async;" ::: "memory");   // the TMA (async proxy) reads below come after the acquire
+          }
+        }
         mbar_expect_tx(&full[slot], a_bytes + b_bytes);
         tma_load_3d(st, &p.mapG[T.lin], 0, row, T.m0 / 64, &full[slot]);
         if (f_blocks > 0) tma_load_3d(st + a_bytes, &p.mapF[T.lin], 0, row, T.n0 / 64, &full[slot]);
@@ -198,6 +231,33 @@ void save_layout_bf16(const NetDev& nd, int* g_off, int* g_width, int* f_off, in
 }
 
 int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_save, cudaStream_t stream) {
+  return launch_weight_grad_tc_overlapped(nd, io, B, n_save, nullptr, 0, 0, stream);
+}
+
+// Number of output tiles (= CTAs per K slab) of the tensor-core weight-gradient kernel for this network
+int weight_grad_tc_tiles(const NetDev& nd, const McpcGradIO* io) {
+  int nt = 0;
+  const int n_lin = nd.L + (nd.d_out > 0 ? 1 : 0);
+  for (int l = 0; l < n_lin; ++l) {
+    if (l == nd.L && !nd.top_has_grad) continue;
+    const int d_o = (l == nd.L) ? nd.d_out : nd.dims[l];
+    const int d_i = (l == 0) ? 0 : nd.dims[l - 1];
+    const bool has_w = (l > 0) && io->gW[l] != nullptr;
+    if (!has_w && io->gb[l] == nullptr) continue;
+    nt += ((d_o + 127) / 128) * ((d_i == 0 || !has_w) ? 1 : (d_i + 127) / 128);
+  }
+  return nt;
+}
+
+// ready != nullptr: overlapped mode -- the kernel is launched while infer_tc_kernel is still writing save_g / save_f and
+// follows it step by step (ready[step] reaches ready_target when a step's rows are complete); at most max_ctas CTAs so
+// that it fits the SMs the inference kernel leaves idle.
+int launch_weight_grad_tc_overlapped(const NetDev& nd, const McpcGradIO* io, int B, int n_save, const unsigned* ready,
+                                     unsigned ready_target, int max_ctas, cudaStream_t stream) {
+  if (ready != nullptr && io->inputs != nullptr) {
+    set_error("internal: the overlapped weight-gradient launch does not take non-zero inputs");
+    return MCPC_ERR_INVALID;
+  }
   if (io->inputs != nullptr && io->gW[0] != nullptr) {
     // Linear_0 with non-zero inputs: the inputs are the same rows for every saved step, so its weight gradient is
     // (sum over steps of G_0)^T inputs -- a [B]-row contraction with exact fp32 inputs (the bias gradient comes from
@@ -270,8 +330,11 @@ int launch_weight_grad_tc(const NetDev& nd, const McpcGradIO* io, int B, int n_s
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  int slabs = n_sm / nt;
+  int slabs = (ready != nullptr ? max_ctas : n_sm) / nt;
   if (slabs < 1) slabs = 1;
+  p.ready = ready;
+  p.ready_target = ready_target;
+  p.rows_per_step = B;
   int rps = (p.rows + slabs - 1) / slabs;
   rps = ((rps + kStageRows - 1) / kStageRows) * kStageRows;
   slabs = (p.rows + rps - 1) / rps;

@@ -157,6 +157,7 @@ class NativeEngine:
         self._layout_cache = {}
         self._mode_cache = {}
         self._grad_scratch = {}
+        self._fuse_cache = {}
 
     def _workspace(self, net, B, n_steps, precision, device, net_key=None):
         # keyed by the network DESCRIPTION (not the address of a cached struct, which can be reused after a cache flush)
@@ -203,6 +204,20 @@ class NativeEngine:
         N.check(self._lib.mcpc_infer_mode(C.byref(net), B, precision, C.byref(mode)), "mcpc_infer_mode")
         self._mode_cache[key] = mode.value
         return mode.value
+
+    def infer_fuses_weight_grad(self, plan: NetPlan, top: TopPlan, B: int, precision: int, has_inputs: bool) -> bool:
+        """True when passing the ``.grad`` accumulators to ``infer`` (McpcIO.gW/gb) is the way to get the weight update:
+        streaming mode, or the resident bf16 kernel with idle SMs for the concurrent weight-gradient kernel."""
+        key = (_net_key(plan, top, 1.0), B, precision, bool(has_inputs), _env_key(), os.environ.get("MCPC_TC_DW_OVERLAP"))
+        hit = self._fuse_cache.get(key)
+        if hit is not None:
+            return hit
+        net = net_struct(plan, top, 1.0)
+        out = C.c_int32(0)
+        N.check(self._lib.mcpc_infer_fuses_weight_grad(C.byref(net), B, precision, 1 if has_inputs else 0, C.byref(out)),
+                "mcpc_infer_fuses_weight_grad")
+        self._fuse_cache[key] = bool(out.value)
+        return bool(out.value)
 
     def infer(self, c: InferCall) -> None:
         plan = c.plan

@@ -717,6 +717,34 @@ class PCTrainer(object):
 
     def _ensure_flat_grads(self, netp, zero):
         """All W/b ``.grad`` are views into ONE flat fp32 buffer (a single all-reduce covers them)."""
+        flat = self._flat_grad
+        if flat is not None and len(flat) == 5 and flat[2] is netp:
+            # hit path (it sits in front of the inference launch): same plan, every .grad still IS its view of the buffer
+            views = flat[3]
+            ok = flat[1].numel() == flat[4] + 4 * self._T
+            gW, gb = [], []
+            if ok:
+                i = 0
+                for lin in netp.linears:
+                    w, bias = lin.weight, lin.bias
+                    if i >= len(views) or w is not views[i][0] or w.grad is not views[i][1]:
+                        ok = False
+                        break
+                    gW.append(views[i][1])
+                    i += 1
+                    if bias is None:
+                        gb.append(None)
+                        continue
+                    if i >= len(views) or bias is not views[i][0] or bias.grad is not views[i][1]:
+                        ok = False
+                        break
+                    gb.append(views[i][1])
+                    i += 1
+                ok = ok and i == len(views)
+            if ok:
+                if zero:
+                    flat[1].zero_()
+                return flat[1], gW, gb
         params = []
         for lin in netp.linears:
             params.append(lin.weight)
@@ -740,7 +768,6 @@ class PCTrainer(object):
                     view.copy_(p.grad)
                 p.grad = view
                 o += n
-            self._flat_grad = (sig, buf)
         else:
             buf = flat[1]
             o = 0
@@ -757,6 +784,7 @@ class PCTrainer(object):
                 o += n
             if zero:
                 buf.zero_()
+        self._flat_grad = (sig, buf, netp, [(p_, p_.grad) for p_ in params], total)
         gW = [lin.weight.grad for lin in netp.linears]
         gb = [None if lin.bias is None else lin.bias.grad for lin in netp.linears]
         return buf, gW, gb
@@ -934,6 +962,10 @@ class PCTrainer(object):
         W, b = self._param_tensors(netp)
         streaming = hasattr(eng, "infer_mode") and \
             eng.infer_mode(netp, top, B, self._precision) == N.MODE_STREAMING_BF16
+        # the native library runs the weight update of the saved steps inside mcpc_infer when it gets the accumulators
+        # (resident bf16: on the SMs the inference kernel leaves idle, while it runs); the CPU test double does not
+        fused_dw = streaming or (hasattr(eng, "infer_fuses_weight_grad") and
+                                 eng.infer_fuses_weight_grad(netp, top, B, self._precision, inputs_dev is not None))
         later_p_updates = sorted(self._update_p_set)
         segs, seg_zero_steps = self._segments_cached(T, split_last=(want_traj and not every_t))
         flat = None
@@ -949,11 +981,11 @@ class PCTrainer(object):
             if need_grads:
                 zero_steps = seg_zero_steps[si]
                 win_begin = zero_steps[-1] if zero_steps else t0
-                if streaming:           # the streaming kernels accumulate dW themselves: buffers must exist up front
+                if fused_dw:            # mcpc_infer accumulates dW itself: the (zeroed) buffers must exist up front
                     flat, gW, gb = self._ensure_flat_grads(netp, zero=bool(zero_steps))
                     flat_ready = True
                 else:
-                    gW = gb = None      # resident modes: (re)zeroed after the inference launch, off the launch path
+                    gW = gb = None      # separate weight_grad call: (re)zeroed after the inference launch
             # the window may be cut further so the saved operands fit the scratch budget
             g_w, f_w, s_dtype = self._save_layout(netp, top)
             row_bytes = (4 if s_dtype == torch.float32 else 2) * B * (g_w + f_w)
@@ -1003,8 +1035,8 @@ class PCTrainer(object):
                     traj_every=k_rec if every_t or stats is not None else 1,
                     save_g=save_g, save_f=save_f, save_begin=sb, save_end=se,
                     precision=self._precision,
-                    gW=gW if (streaming and need_grads and se > sb) else None,
-                    gb=gb if (streaming and need_grads and se > sb) else None)
+                    gW=gW if (fused_dw and need_grads and se > sb) else None,
+                    gb=gb if (fused_dw and need_grads and se > sb) else None)
                 eng.infer(call)
                 n_launch += 1
                 if stats is not None and n_r > 0:
@@ -1020,7 +1052,7 @@ class PCTrainer(object):
                 if need_grads and not flat_ready:
                     flat, gW, gb = self._ensure_flat_grads(netp, zero=bool(zero_steps))
                     flat_ready = True
-                if save_g is not None:
+                if save_g is not None and not fused_dw:
                     eng.weight_grad(netp, top, self._energy_coefficient, B, se - sb, save_g, save_f, inputs_dev,
                                     gW, gb, self._precision)
                     n_launch += 1

@@ -46,13 +46,17 @@ if not os.environ.get("PLAIN"):
     def med(f): return float(np.median([f(r) for r in rows]))
     print("host stamps after entry (us):")
     for k in ("h_infer_in", "h_infer_out", "h_wg_out", "h_p_out", "h_br_in", "h_br_out"):
-        print(f"  {k:12s} {med(lambda r: (r[0][k] - r[3]) * 1e6):8.1f}")
+        if k in rows[0][0]:
+            print(f"  {k:12s} {med(lambda r: (r[0][k] - r[3]) * 1e6):8.1f}")
     print(f"  return       {med(lambda r: (r[4] - r[3]) * 1e6):8.1f}")
     print("device intervals (us):")
     print(f"  e0 -> infer start (GPU idle before the kernel) {med(lambda r: r[1].elapsed_time(r[0]['d_infer0']) * 1e3):8.1f}")
     print(f"  infer (packs + kernel)                         {med(lambda r: r[0]['d_infer0'].elapsed_time(r[0]['d_infer1']) * 1e3):8.1f}")
-    print(f"  infer end -> weight_grad end                   {med(lambda r: r[0]['d_infer1'].elapsed_time(r[0]['d_wg1']) * 1e3):8.1f}")
-    print(f"  weight_grad end -> p_step end                  {med(lambda r: r[0]['d_wg1'].elapsed_time(r[0]['d_p1']) * 1e3):8.1f}")
+    if "d_wg1" in rows[0][0]:
+        print(f"  infer end -> weight_grad end                   {med(lambda r: r[0]['d_infer1'].elapsed_time(r[0]['d_wg1']) * 1e3):8.1f}")
+        print(f"  weight_grad end -> p_step end                  {med(lambda r: r[0]['d_wg1'].elapsed_time(r[0]['d_p1']) * 1e3):8.1f}")
+    else:
+        print(f"  infer (+ overlapped dW) end -> p_step end      {med(lambda r: r[0]['d_infer1'].elapsed_time(r[0]['d_p1']) * 1e3):8.1f}")
     print(f"  p_step end -> e1                               {med(lambda r: r[0]['d_p1'].elapsed_time(r[2]) * 1e3):8.1f}")
 if os.environ.get("CPROF"):
     import cProfile, pstats

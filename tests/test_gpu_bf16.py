@@ -163,3 +163,55 @@ def test_specialised_instantiations_equal_the_generic_kernel(kind, B):
     assert len(a[2]) == len(b[2])
     for ga, gb in zip(a[2], b[2]):
         assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,T,mixing", [(1024, 150, 50), (1000, 40, 0), (333, 25, 5)])
+def test_overlapped_weight_update_equals_the_sequential_one(B, T, mixing, monkeypatch):
+    """Resident bf16 kernel, B <= ~1100: the weight-gradient kernel runs NEXT to the inference kernel on the idle SMs and
+    consumes each saved step behind per-step flags.  Same call with the overlap off (weight update after the kernel) must
+    give the same gradients; the saved-operand buffers are poisoned with NaN before the call, so a row that the consumer
+    read before the producer had written it would show up as NaN."""
+    dev = torch.device(DEV)
+
+    def run(overlap):
+        monkeypatch.setenv("MCPC_TC_DW_OVERLAP", "1" if overlap else "0")
+        torch.manual_seed(0)
+        cfg = {"input_size": 20, "hidden_size": 128, "hidden2_size": 128, "output_size": 784, "activation_fn": "relu"}
+        model = mu.get_model(cfg, use_cuda=False).to(dev)
+        tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.03}, update_p_at="last",
+                          accumulate_p_at=list(range(mixing, T)), optimizer_p_fn=optim.SGD, optimizer_p_kwargs={"lr": 0.0},
+                          plot_progress_at=[])
+        tr.set_precision("bf16")
+        tr.set_noise_seed(99)
+        y = (torch.rand(B, 784, device=dev) < 0.5).float()
+        x0 = [torch.randn(B, d, device=dev) for d in (20, 128, 128)]
+        pcs = [m for m in model if isinstance(m, pc.PCLayer)]
+        for layer, v in zip(pcs, x0):
+            layer._sample_x_fn = (lambda inputs, v=v: v.clone())
+        z = torch.zeros(B, 20, device=dev)
+        out = None
+        for rep in range(3):
+            tr._noise_epoch = 0
+            for role in ("save_g", "save_f"):
+                if role in tr._buffers:
+                    tr._buffers[role].fill_(float("nan"))
+            res = tr.train_on_batch(z, loss_fn=mu.bernoulli_fn, loss_fn_kwargs={"_target": y, "_var": 1.0},
+                                    callback_after_t=mu.random_step, callback_after_t_kwargs={"_pc_trainer": tr},
+                                    is_log_progress=False, is_checking_after_callback_after_t=False)
+            grads = [p.grad.detach().clone() for p in model.parameters() if p.grad is not None]
+            assert all(bool(torch.isfinite(g).all()) for g in grads), f"NaN in the weight gradients (overlap={overlap}, call {rep})"
+            out = (grads, torch.tensor(res["energy"]))
+        eng = tr._get_engine()
+        from montecarlopredictivecoding_b200.predictive_coding import plan as P
+        netp = P.compile_net(model)
+        top = P.classify_loss(mu.bernoulli_fn, {"_target": y, "_var": 1.0}, B, 784, dev)
+        assert eng.infer_fuses_weight_grad(netp, top, B, 1, False) == overlap
+        return out
+
+    g_seq, e_seq = run(False)
+    g_ovl, e_ovl = run(True)
+    assert torch.equal(e_seq, e_ovl)
+    for a, b in zip(g_seq, g_ovl):
+        scale = float(a.abs().max()) + 1e-12
+        # fp32 accumulation order differs (2 interleaved K slabs of 51,200 rows vs 15 contiguous ones)
+        assert float((a - b).abs().max()) / scale < 2e-4, float((a - b).abs().max()) / scale
