@@ -1086,20 +1086,44 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
     }
     const uint32_t ring_off = off;
     off += ring;
-    int next_slot = 0;
+    bool streamed[kMaxTiles] = {};
     for (int t = 0; t < nt; ++t) {
       Tile& T = p->tiles[t];
       if (off + (uint32_t)T.bytes + slack <= kSmemBudget) {
         T.smem_off = (int)off;
         off += (uint32_t)T.bytes;
       } else {
-        T.slot = next_slot;
-        T.smem_off = (int)(ring_off + next_slot * max_tile);
-        next_slot ^= 1;
+        streamed[t] = true;
       }
     }
-    // a streamed tile must find its slot free again before the same slot is needed twice in one step:
-    // with 2 slots used round-robin in tile order that holds by construction.
+    // Visiting order of the OUTPUT tiles (any order is valid: their back-projections sum into the same accumulator):
+    // streamed and resident tiles alternate, starting with a streamed one.  A streamed tile's bulk copy can only start
+    // when the previous user of its ring slot has finished its back-projection; with the streamed tiles at the end of the
+    // step (r01) the third one waited ~4,800 cycles for the first one's slot, on the step's critical path (cycle trace,
+    // profiles/r02_tc_trace.txt).  Interleaved, a slot is free 3 tile times before it is needed again.
+    if (p->n_out_tiles > 1) {
+      Tile res[kMaxTiles], str[kMaxTiles];
+      int n_res = 0, n_str = 0;
+      for (int t = p->n_hid_tiles; t < nt; ++t) {
+        if (streamed[t]) str[n_str++] = p->tiles[t];
+        else res[n_res++] = p->tiles[t];
+      }
+      int t = p->n_hid_tiles, i_r = 0, i_s = 0;
+      while (i_r < n_res || i_s < n_str) {
+        if (i_s < n_str) { p->tiles[t] = str[i_s++]; streamed[t++] = true; }
+        if (i_r < n_res) { p->tiles[t] = res[i_r++]; streamed[t++] = false; }
+      }
+    }
+    // 2 ring slots, used round-robin in visiting order: a streamed tile finds its slot free again before the same slot
+    // is needed twice in one step by construction
+    int next_slot = 0;
+    for (int t = 0; t < nt; ++t) {
+      if (!streamed[t]) continue;
+      Tile& T = p->tiles[t];
+      T.slot = next_slot;
+      T.smem_off = (int)(ring_off + next_slot * max_tile);
+      next_slot ^= 1;
+    }
   }
   *smem_bytes = off + slack;
   return MCPC_OK;
@@ -1200,7 +1224,9 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
       const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
       const int n_lin_tiles = (rows + 127) / 128;
       const int n_elems = n_lin_tiles * 128 * T.Kp;                   // 2 elements per thread
-      jobs.job[n_jobs++] = PackJob{io->W[lin], wsb + T.gsrc, rows, nd.dims[lin - 1], T.Kp, n_lin_tiles};
+      size_t gbase = T.gsrc;                                          // packed tiles of a Linear are contiguous in out_tile
+      for (int k = t; k < t + n_lin_tiles; ++k) gbase = std::min(gbase, p.tiles[k].gsrc);   // order; the table is in visiting order
+      jobs.job[n_jobs++] = PackJob{io->W[lin], wsb + gbase, rows, nd.dims[lin - 1], T.Kp, n_lin_tiles};
       max_blocks = std::max(max_blocks, (n_elems + 511) / 512);
       t += n_lin_tiles;
     }
