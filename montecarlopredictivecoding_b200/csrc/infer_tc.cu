@@ -100,6 +100,8 @@ struct Barriers {
   uint64_t acts_ready[kMaxL];   // act(x_l) / x_l of the coming step are in place (group U -> MMA warp, group T)
   uint64_t bp_ready[kMaxL];     // back-projection into layer l complete (MMA warp -> group U)
   uint64_t g_ready[kMaxL];      // own-layer error of layer l stored in TMEM (group T -> group U)
+  uint64_t out_read;            // read-out only output Linear (no loss gradient), on the steps that record outputs: every output
+                                // tile's prediction has READ act(x_{L-1}) (MMA warp -> group U, which overwrites it next)
 };
 
 __device__ __forceinline__ float warp_sum_tc(float v) {
@@ -233,7 +235,8 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
 // instruction fetch / issue, and every dead branch costs code footprint): 1 = MCPC learning / sampling (SGD + in-kernel
 // Philox noise, Bernoulli top, update_x), 2 = deterministic PC / MAP (Adam, no noise, Bernoulli top, update_x),
 // 3 = sampling without a sensory gradient (SGD + Philox, zero_fn / no loss: no output tile is ever visited),
-// 0 = everything read from the parameters.  SPEC != 0 also means: no trajectories, no x.grad read-out.
+// 4 = 3 + trajectory records (thinned read-outs: the output tiles are visited on the recorded steps only),
+// 0 = everything read from the parameters.  SPEC 1-3 also mean: no trajectories; SPEC != 0: no x.grad read-out.
 template <int NR, int RV, bool TRACE, int SPEC>
 __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int RPT = RV / 2;
@@ -255,13 +258,13 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
   const NetDev& nd = p.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = nd.L, HT = p.HT;
-  const int opt_kind = (SPEC == 1 || SPEC == 3) ? (int)MCPC_OPT_SGD : (SPEC == 2 ? (int)MCPC_OPT_ADAM : p.optimizer);
-  const int noise_kind = (SPEC == 1 || SPEC == 3) ? (int)MCPC_NOISE_PHILOX : (SPEC == 2 ? (int)MCPC_NOISE_NONE : p.noise_mode);
+  const int opt_kind = (SPEC == 1 || SPEC == 3 || SPEC == 4) ? (int)MCPC_OPT_SGD : (SPEC == 2 ? (int)MCPC_OPT_ADAM : p.optimizer);
+  const int noise_kind = (SPEC == 1 || SPEC == 3 || SPEC == 4) ? (int)MCPC_NOISE_PHILOX : (SPEC == 2 ? (int)MCPC_NOISE_NONE : p.noise_mode);
   const int top_kind = (SPEC == 1 || SPEC == 2) ? (int)MCPC_TOP_BERNOULLI : nd.top;
-  const bool top_has_grad = (SPEC == 1 || SPEC == 2) ? true : (SPEC == 3 ? false : (bool)nd.top_has_grad);
+  const bool top_has_grad = (SPEC == 1 || SPEC == 2) ? true : ((SPEC == 3 || SPEC == 4) ? false : (bool)nd.top_has_grad);
   const bool do_update_x = (SPEC != 0) ? true : (p.update_x != 0);
   // the specialisations also require (the host checks): targets and Adam state resident in TMEM, one unit tile per layer
-  const bool y_in_tmem = (SPEC == 1 || SPEC == 2) ? true : (SPEC == 3 ? false : (p.y_tmem != 0));   // 3: no output tile is visited
+  const bool y_in_tmem = (SPEC == 1 || SPEC == 2) ? true : ((SPEC == 3 || SPEC == 4) ? false : (p.y_tmem != 0));   // 3, 4: no targets
   const bool adam_in_tmem = (SPEC == 2) ? true : (SPEC != 0 ? false : (p.adam_tmem != 0));
   const int row0 = blockIdx.x * RV;
 
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
       mbar_init(&bars.dA_full[i], 1);
       mbar_init(&bars.dA_empty[i], kTileArr);
     }
+    mbar_init(&bars.out_read, 1);
     for (int l = 0; l < kMaxL; ++l) {
       mbar_init(&bars.acts_ready[l], kGrp);
       mbar_init(&bars.bp_ready[l], 1);
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
       }
       uint32_t empty_phase = 3;
       for (int ts = 0; ts < p.n_steps; ++ts) {
-        const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
         const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
         for (int t = 0; t < (need_out ? n_tiles_all : p.n_hid_tiles); ++t) {
           const Tile& T = p.tiles[t];
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
     uint32_t ph_wfull = 0, ph_dAe = (1u << kDA) - 1u;
     mbar_wait_parked(&bars.w_res, 0);
     for (int ts = 0; ts < p.n_steps; ++ts) {
-      const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
+      const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
       const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
       const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
       uint32_t acts_waited = 0;
@@ -407,6 +411,12 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
         __syncwarp();
         TC_STAMP(lane == 0, ts, 1 + k);
       }
+      if (need_out && !top_has_grad) {
+        // no back-projection follows these predictions, so nothing else tells group U that the top layer's activations
+        // have been read: without this its update of step ts could overwrite act(x_{L-1}) under the last output tiles
+        if (elect_one()) mma_commit(&bars.out_read);
+        __syncwarp();
+      }
       TC_STAMP(lane == 0, ts, 21);
     }
   } else if (warp == kMmaWarpB) {
@@ -416,7 +426,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
     uint32_t ph_gfull = 0;
     mbar_wait_parked(&bars.w_res, 0);
     for (int ts = 0; ts < p.n_steps; ++ts) {
-      const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
+      const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
       const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
       const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
       uint32_t bp_started = 0;
@@ -516,14 +526,16 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
       for (int l = 0; l < L; ++l) mbar_arrive(&bars.acts_ready[l]);
 
       const bool adam = (opt_kind == MCPC_OPT_ADAM);
+      uint32_t ph_out_read = 0;
       const float* mu0 = (SPEC == 0) ? p.mu0 : nullptr;      // the specialised instantiations are zero-input only
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const int t_abs = p.t_begin + ts;
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
         const int slot = ts - p.save_begin;
-        const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
         const int rec = do_traj ? ts / p.traj_every : 0;
         const bool last = (ts == p.n_steps - 1);
+        const bool wait_out_read = !top_has_grad && do_traj && p.traj_out != nullptr;   // see Barriers::out_read
         float e_part = 0.0f;
         __nv_bfloat16* sg_row = do_save ? p.save_g + ((size_t)slot * p.B + rb) * p.sg_pitch : nullptr;
         __nv_bfloat16* sf_row = do_save ? p.save_f + ((size_t)slot * p.B + rb) * p.sf_pitch : nullptr;
@@ -583,6 +595,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
               if (hi == 0) {
                 if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);
                 if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);
+                if (l == L - 1 && wait_out_read) mbar_wait_parked(&bars.out_read, ph_out_read);
               }
               continue;
             }
@@ -633,6 +646,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
               if (hi == 0 && c0 == 0) {
                 if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);      // all tiles of Linear l+1 back-projected
                 if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);           // group T stored the own-layer error of layer l
+                if (l == L - 1 && wait_out_read) mbar_wait_parked(&bars.out_read, ph_out_read);
                 fence_after_sync();
                 TC_STAMP(gtid == 0, ts, 40 + l);
               }
@@ -737,6 +751,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
           if (defer) global_stores(0);
         }
         TC_STAMP(gtid == 0, ts, 54);
+        if (wait_out_read) ph_out_read ^= 1u;
         // layer-0 energy of this step
         e_part = warp_sum_tc(e_part);
         float (*red)[2] = s_red[1][ts & 1];
@@ -815,7 +830,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
         const int slot = ts - p.save_begin;
-        const bool do_traj = (SPEC == 0) && (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
         const int rec = do_traj ? ts / p.traj_every : 0;
         const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
         const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
@@ -1352,8 +1367,17 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   if (plain && bern_grad && sgd_philox) spec = 1;
   else if (plain && bern_grad && o->optimizer == MCPC_OPT_ADAM && o->noise_mode == MCPC_NOISE_NONE) spec = 2;
   else if (plain && !nd.top_has_grad && sgd_philox) spec = 3;
+  else if (!nd.top_has_grad && sgd_philox && o->update_x && p.mu0 == nullptr && getenv("MCPC_TC_NOSPEC") == nullptr) {
+    // sampling with thinned read-outs (SURVEY 8f N2 / C3 "read out every k-th step"): instantiation 4 = 3 + trajectory
+    // records (it visits the output tiles on the recorded steps only); kept apart from 3, whose pure-sampling loop is 4 %
+    // faster without the recording code (C3: 181 vs 190 us per step)
+    bool ok4 = true;
+    for (int l = 0; l < nd.L; ++l) ok4 = ok4 && io->x_grad[l] == nullptr && p.ut[l] == 1;
+    if (ok4) spec = 4;
+  }
   if (rows.rv == 32) {
-    rc = spec == 3 ? launch(infer_tc_kernel<32, 32, false, 3>) : launch(infer_tc_kernel<32, 32, false, 0>);
+    rc = spec == 3 ? launch(infer_tc_kernel<32, 32, false, 3>)
+                   : (spec == 4 ? launch(infer_tc_kernel<32, 32, false, 4>) : launch(infer_tc_kernel<32, 32, false, 0>));
   } else if (rows.rv == 16) {
     rc = spec == 1 ? launch(infer_tc_kernel<16, 16, false, 1>) : launch(infer_tc_kernel<16, 16, false, 0>);
   } else if (timing) {
@@ -1364,6 +1388,8 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     rc = launch(infer_tc_kernel<16, 8, false, 2>);
   } else if (spec == 3) {
     rc = launch(infer_tc_kernel<16, 8, false, 3>);
+  } else if (spec == 4) {
+    rc = launch(infer_tc_kernel<16, 8, false, 4>);
   } else {
     rc = launch(infer_tc_kernel<16, 8, false, 0>);
   }

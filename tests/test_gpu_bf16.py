@@ -215,3 +215,39 @@ def test_overlapped_weight_update_equals_the_sequential_one(B, T, mixing, monkey
         scale = float(a.abs().max()) + 1e-12
         # fp32 accumulation order differs (2 interleaved K slabs of 51,200 rows vs 15 contiguous ones)
         assert float((a - b).abs().max()) / scale < 2e-4, float((a - b).abs().max()) / scale
+
+
+@pytest.mark.parametrize("B", [1024, 8192])
+def test_sampling_instantiation_records_the_same_trajectories_as_the_generic_kernel(B, monkeypatch):
+    """Instantiation 3 (SGD + Philox, no loss gradient) also serves sampling calls that record thinned read-outs
+    (set_trajectory_stride): outputs, latents of every recorded step and the energies must equal the generic kernel's."""
+    dev = torch.device(DEV)
+
+    def run(nospec):
+        if nospec:
+            monkeypatch.setenv("MCPC_TC_NOSPEC", "1")
+        else:
+            monkeypatch.delenv("MCPC_TC_NOSPEC", raising=False)
+        torch.manual_seed(0)
+        cfg = {"input_size": 20, "hidden_size": 128, "hidden2_size": 128, "output_size": 784, "activation_fn": "relu"}
+        model = mu.get_model(cfg, use_cuda=False, sample_x_fn=mu.sample_x_fn_normal).to(dev)
+        tr = pc.PCTrainer(model, T=40, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": 0.03}, update_p_at="never",
+                          plot_progress_at=[])
+        tr.set_precision("bf16")
+        tr.set_noise_seed(5)
+        tr.set_trajectory_stride(7, 3)
+        tr.set_trajectories_on_device(True)
+        torch.manual_seed(9)
+        res = tr.train_on_batch(torch.zeros(B, 20, device=dev), loss_fn=mu.zero_fn, callback_after_t=mu.random_step,
+                                callback_after_t_kwargs={"_pc_trainer": tr}, is_log_progress=False, is_return_outputs=True,
+                                is_return_xs=True, is_checking_after_callback_after_t=False)
+        return (torch.stack(res["outputs"]), [torch.stack([xs[l] for xs in res["xs"]]) for l in range(3)],
+                torch.tensor(res["energy"]))
+
+    out_g, xs_g, e_g = run(True)
+    out_s, xs_s, e_s = run(False)
+    assert out_s.shape[0] == len(range(3, 40, 7))
+    assert torch.equal(out_g, out_s)
+    for a, b in zip(xs_g, xs_s):
+        assert torch.equal(a, b)
+    assert torch.equal(e_g, e_s)
