@@ -661,6 +661,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
                 tmem_ld_nw<CH>(lac + col_v + h * NR, vv);
               }
               tmem_ld_wait();
+              TC_STAMP(gtid == 0 && l == 1, ts, 43);
               tmem_ld_tie(xv);
               if (adam_t) {
                 tmem_ld_tie(mv);
@@ -725,6 +726,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < CH; ++i) xv[i] = fmaf(-p.lr, nz[i], xv[i]);
               }
+              TC_STAMP(gtid == 0 && l == 1, ts, 44);
               // ---- 4. next step's operands: bf16 act(x) to shared memory, fp32 x back to TMEM ----
               uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbc >> 3) * asbo + (uint32_t)(cbc & 7) * 16u +
                               (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
@@ -742,13 +744,18 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
               if (!defer) global_stores(c0);
             }
           }
+          TC_STAMP(gtid == 0 && l == 1, ts, 45);
           tmem_st_wait();
+          TC_STAMP(gtid == 0 && l == 1, ts, 46);
           fence_async_smem();
+          TC_STAMP(gtid == 0 && l == 1, ts, 47);
           fence_before_sync();
           mbar_arrive(&bars.acts_ready[l]);                  // act(x_l) / x_l of step ts+1 are in place
+          TC_STAMP(gtid == 0 && l == 1, ts, 48);
           // the proxy fence above waits for every earlier memory operation of the thread: the global stores of a
           // single-tile layer are issued after the hand-over so that they do not delay it
           if (defer) global_stores(0);
+          TC_STAMP(gtid == 0 && l == 1, ts, 49);
         }
         TC_STAMP(gtid == 0, ts, 54);
         if (wait_out_read) ph_out_read ^= 1u;

@@ -1,3 +1,4 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out; rm -f gpurun_out/micro.txt
-timeout 900 python -m pytest tests/test_gpu_bf16.py tests/test_gpu_n2_n3.py tests/test_gpu_parity.py tests/test_gpu_bf16_bound.py tests/test_gpu_reference_callsites.py -x -q 2>&1 | grep -v "Warning\|warnings.warn" | tail -8 >> gpurun_out/micro.txt
-cat gpurun_out/micro.txt | cut -c1-300
+MIX=50 SAMP=100 MCPC_TC_TIMING=100 timeout 120 python scripts/tc_timing.py > gpurun_out/tc_trace.txt 2>&1
+MODE=map MCPC_TC_TIMING=100 timeout 120 python scripts/tc_timing.py > gpurun_out/tc_trace_map.txt 2>&1
+tail -2 gpurun_out/tc_trace.txt | cut -c1-800; tail -2 gpurun_out/tc_trace_map.txt | cut -c1-800
