@@ -69,6 +69,8 @@ struct TcParams {
   float* xgrad[kMaxL];
   float* traj_x[kMaxL];
   float* traj_out;
+  int nz_off;                   // pure sampling (instantiation 3): shared-memory offset of the two noise buffers that group T
+                                // fills one step ahead for group U ([2][HT][RV][128] fp32), or -1: group U draws its own noise
   unsigned* ready;              // [n_save] per saved step: += 1 per CTA once its rows of save_g / save_f are written (the
                                 // concurrent weight-gradient kernel consumes them while this kernel runs), or nullptr
   const float* mu0;             // fp32 [B, dims[0]]: W_0 inputs + b_0 per chain (non-zero `inputs`), else nullptr
@@ -100,6 +102,9 @@ struct Barriers {
   uint64_t acts_ready[kMaxL];   // act(x_l) / x_l of the coming step are in place (group U -> MMA warp, group T)
   uint64_t bp_ready[kMaxL];     // back-projection into layer l complete (MMA warp -> group U)
   uint64_t g_ready[kMaxL];      // own-layer error of layer l stored in TMEM (group T -> group U)
+  uint64_t nz_full[2][kMaxL];   // pure sampling: the noise of layer l for step s is in shared memory buffer s & 1 (group T -> U);
+                                // one barrier per buffer: group T is at most one step ahead, so a barrier never completes twice
+                                // before group U has waited on it (a single barrier per layer could, and U would wait forever)
   uint64_t out_read;            // read-out only output Linear (no loss gradient), on the steps that record outputs: every output
                                 // tile's prediction has READ act(x_{L-1}) (MMA warp -> group U, which overwrites it next)
 };
@@ -291,6 +296,8 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
       mbar_init(&bars.acts_ready[l], kGrp);
       mbar_init(&bars.bp_ready[l], 1);
       mbar_init(&bars.g_ready[l], kGrp);
+      mbar_init(&bars.nz_full[0][l], kGrp);
+      mbar_init(&bars.nz_full[1][l], kGrp);
     }
     fence_mbar_init();
   }
@@ -641,7 +648,17 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
                   }
                 }
               };
-              if (kNoiseEarly) draw_noise();                    // before the wait: off the critical hand-over chain
+              // pure sampling: group T (idle but for the hidden tiles) drew this step's noise into shared memory one step ahead
+              const bool nz_smem = (SPEC == 3) && (p.nz_off >= 0);
+              if (nz_smem) {
+                if (hi == 0 && c0 == 0) mbar_wait_parked(&bars.nz_full[ts & 1][l], (ts >> 1) & 1);
+                const float* nb = reinterpret_cast<const float*>(smem + p.nz_off) +
+                                  ((size_t)((ts & 1) * HT + h) * RV + (size_t)cbc) * 128 + ln;
+#pragma unroll
+                for (int i = 0; i < CH; ++i) nz[i] = nb[i * 128];
+              } else if (kNoiseEarly) {
+                draw_noise();                                   // before the wait: off the critical hand-over chain
+              }
               // ---- 2. wait for this layer's back-projection and own error, then ONE batch of TMEM loads ----
               if (hi == 0 && c0 == 0) {
                 if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);      // all tiles of Linear l+1 back-projected
@@ -687,7 +704,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
                   if (uvalid && i < nrc) e_part = fmaf(ce * eps, eps, e_part);
                 }
               }
-              if (!kNoiseEarly) draw_noise();
+              if (!kNoiseEarly && !nz_smem) draw_noise();
               // ---- 3. update (straight-line: CH independent chains interleave) ----
 #pragma unroll
               for (int i = 0; i < CH; ++i) {
@@ -834,6 +851,40 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
         }
       }
       tmem_st_wait();
+      // Pure sampling (instantiation 3): this group only has the hidden tiles to do, group U is the bottleneck and half
+      // of its time is the Philox + Box-Muller noise.  Group T draws the noise of step `step` for every latent into shared
+      // memory ([step & 1][unit tile][chain][unit], the element its twin thread of group U reads) one step ahead.  No
+      // "empty" barrier: the buffer of step s+1 was last read in step s-1, and this group has finished the tiles of step
+      // s, which needed every layer's update of step s-1 (hence its wait on and its reads of that buffer), before it writes.
+      auto produce_noise = [&](int step) {
+        float* nbuf = reinterpret_cast<float*>(smem + p.nz_off) + (size_t)((step & 1) * HT) * RV * 128;
+        const int cbN = ALT ? half * RPT : cbase;                // chains of this thread, like its twin in group U
+        for (int l = 0; l < L; ++l) {
+          const int dl = nd.dims[l];
+          for (int hi = 0; hi < p.ut[l]; ++hi) {
+            if (hi * 128 + q * 32 >= dl) continue;               // warp-uniform: all 32 units are padding
+            const int u = hi * 128 + ln;
+            if (u < dl) {
+              float* nb = nbuf + ((size_t)(p.h_off[l] + hi) * RV + cbN) * 128 + ln;
+              const uint32_t gu = (uint32_t)(nd.off[l] + u);
+              float nrm[4];
+              uint64_t cur_q = ~0ull;
+#pragma unroll 4
+              for (int i = 0; i < RPT; ++i) {
+                const uint64_t chain = p.chain_offset + (uint64_t)(row0 + cbN + i);
+                if ((chain >> 2) != cur_q) {
+                  cur_q = chain >> 2;
+                  langevin_normals4(p.seed, gu, (uint32_t)(p.t_begin + step), cur_q, nrm);
+                }
+                nb[i * 128] = p.noise_scale * sel4(nrm, (uint32_t)(chain & 3));
+              }
+            }
+          }
+          mbar_arrive(&bars.nz_full[step & 1][l]);               // (release: the stores above are visible to the waiter)
+        }
+      };
+      const bool nz_producer = (SPEC == 3) && (p.nz_off >= 0);
+      if (nz_producer) produce_noise(0);
       for (int ts = 0; ts < p.n_steps; ++ts) {
         const bool do_save = (p.save_g != nullptr) && ts >= p.save_begin && ts < p.save_end;
         const int slot = ts - p.save_begin;
@@ -1006,6 +1057,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
           p.partials[(((size_t)ts * p.n_ctas + blockIdx.x) * 2 + 0) * 2 + gtid] = s;
         }
         if (gtid == 0 && do_save && p.ready != nullptr) saved_step(&s_saved[0]);
+        if (nz_producer && ts + 1 < p.n_steps) produce_noise(ts + 1);
       }
     }
   }
@@ -1019,7 +1071,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
 inline int pad16(int v) { return (v + 15) & ~15; }
 
 // Fills the tile table + shared-memory plan.  Returns MCPC_OK or MCPC_ERR_UNSUPPORTED (message set).
-int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* packed_bytes) {
+int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* packed_bytes, bool with_out = true) {
   if (nd.L < 1) return MCPC_ERR_INVALID;
   int HT = 0;
   for (int l = 0; l < nd.L; ++l) {
@@ -1062,7 +1114,7 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
   uint32_t max_tile = 0;
   p->n_hid_tiles = 0;
   for (int lin = 1; lin <= nd.L; ++lin) {
-    if (lin == nd.L && nd.d_out == 0) continue;
+    if (lin == nd.L && (nd.d_out == 0 || !with_out)) continue;   // !with_out: the output Linear is never visited (pure sampling)
     const int rows = (lin == nd.L) ? nd.d_out : nd.dims[lin];
     const int Kp = pad16(nd.dims[lin - 1]);
     if (Kp > 1024) {
@@ -1381,6 +1433,26 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     bool ok4 = true;
     for (int l = 0; l < nd.L; ++l) ok4 = ok4 && io->x_grad[l] == nullptr && p.ut[l] == 1;
     if (ok4) spec = 4;
+  }
+  p.nz_off = -1;
+  if (spec == 3 && getenv("MCPC_TC_NOISE_BY_U") == nullptr) {
+    // pure sampling: no output tile is ever visited -- plan without them (everything resident) and give the shared memory
+    // to the two noise buffers group T fills one step ahead (see infer_tc_kernel); if they do not fit, group U keeps
+    // drawing its own noise
+    TcParams q = p;
+    size_t smem3 = 0, packed3 = 0;
+    if (plan_tc(nd, rows.nr, &q, &smem3, &packed3, false) == MCPC_OK) {
+      const size_t nz_bytes = (size_t)2 * q.HT * rows.rv * 128 * sizeof(float);
+      const size_t off = (smem3 + 127) & ~(size_t)127;
+      if (off + nz_bytes <= kSmemBudget) {
+        for (int t = 0; t < kMaxTiles; ++t) p.tiles[t] = q.tiles[t];
+        p.n_hid_tiles = q.n_hid_tiles;
+        p.n_out_tiles = q.n_out_tiles;
+        p.y_tmem = q.y_tmem;
+        p.nz_off = (int)off;
+        smem = off + nz_bytes;
+      }
+    }
   }
   if (rows.rv == 32) {
     rc = spec == 3 ? launch(infer_tc_kernel<32, 32, false, 3>)
