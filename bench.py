@@ -474,10 +474,10 @@ def run_ours(args):
             other_wl = {
                 "C3_sampling_65536_chains": bc.c3(args.precision, B=65536, T=1000),
                 "C3_sampling_65536_chains_readout_every_100": bc.c3(args.precision, B=65536, T=1000, thin=100),
-                "C5_wide_4x4096_B2048_per_gpu_T100": bc.c5(args.precision, B=2048, T=100),
             }
-            if world == 1:
+            if world == 1:      # before C5: its 1 kW load leaves the board in a lower power state for a while
                 other_wl["C4_deterministic_pc_adam"] = bc.c4(args.precision)
+            other_wl["C5_wide_4x4096_B2048_per_gpu_T100"] = bc.c5(args.precision, B=2048, T=100)
         except Exception as exc:  # noqa: BLE001
             other_wl = {"error": repr(exc)[:300]}
 
