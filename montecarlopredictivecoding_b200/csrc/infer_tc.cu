@@ -39,7 +39,8 @@ struct Tile {
   int out_tile;     // which block of 128 output units
   int Kp;           // in-features padded to 16 (phase-A K extent)
   int sbo;          // (Kp/8)*128: byte stride between 8-row groups
-  int bytes;        // 128*Kp*2
+  int bytes;        // shared-memory footprint = bytes copied: 128*Kp*2, or only the valid 16-row groups of the partial last
+                    // tile of the output Linear (plan_tc)
   int smem_off;     // byte offset of the tile (resident) or of its ring slot (streamed)
   int slot;         // -1 resident, else ring slot
   int h_out;        // hidden unit-tile index of the units this tile predicts (-1 for output tiles)
@@ -59,7 +60,7 @@ struct TcParams {
   int ut[kMaxL];                // unit tiles per layer
   int act_off[kMaxL];           // byte offset of layer l's bf16 activation operand [NR x Kp_act[l]]
   int act_kp[kMaxL];            // pad16(d_l)
-  int gbuf_off[2];              // byte offsets of the two bf16 G operand buffers [NR x 128]
+  int gbuf_off[4];              // byte offsets of the bf16 G operand buffers [NR x 128] (2, or 4 with four tile sub-groups)
   int n_resident_bytes;
   const uint8_t* packed;        // packed bf16 weight tiles
   const float* b[kMaxL + 1];
@@ -71,6 +72,9 @@ struct TcParams {
   float* traj_out;
   int nz_off;                   // pure sampling (instantiation 3): shared-memory offset of the two noise buffers that group T
                                 // fills one step ahead for group U ([2][HT][RV][128] fp32), or -1: group U draws its own noise
+  int tab_off;                  // byte offset of the MMA issuers' per-tile tables (kTabBytes at the end of the allocation)
+  int nz_tmem;                  // MCPC learning / sampling call on 8-chain CTAs (instantiation 1): four noise warps draw the Langevin
+                                // noise of every latent one step ahead into TMEM columns (lane = unit, column = chain)
   unsigned* ready;              // [n_save] per saved step: += 1 per CTA once its rows of save_g / save_f are written (the
                                 // concurrent weight-gradient kernel consumes them while this kernel runs), or nullptr
   const float* mu0;             // fp32 [B, dims[0]]: W_0 inputs + b_0 per chain (non-zero `inputs`), else nullptr
@@ -97,24 +101,64 @@ struct TcParams {
 struct Barriers {
   uint64_t w_res;            // resident tiles landed
   uint64_t w_full[2], w_empty[2];
-  uint64_t dA_full[4], dA_empty[4];   // prediction accumulators: 4 in flight with 16-column MMAs, 2 with 32
-  uint64_t g_full[2], g_empty[2];
+  uint64_t dA_full[8], dA_empty[8];   // prediction accumulators: 4 (8 with four tile sub-groups) in flight with 16-column MMAs, 2 with 32
+  uint64_t g_full[4], g_empty[4];
   uint64_t acts_ready[kMaxL];   // act(x_l) / x_l of the coming step are in place (group U -> MMA warp, group T)
   uint64_t bp_ready[kMaxL];     // back-projection into layer l complete (MMA warp -> group U)
   uint64_t g_ready[kMaxL];      // own-layer error of layer l stored in TMEM (group T -> group U)
   uint64_t nz_full[2][kMaxL];   // pure sampling: the noise of layer l for step s is in shared memory buffer s & 1 (group T -> U);
                                 // one barrier per buffer: group T is at most one step ahead, so a barrier never completes twice
                                 // before group U has waited on it (a single barrier per layer could, and U would wait forever)
+  uint64_t nz_empty[kMaxL];     // instantiation 1: group U has read the noise of layer l out of TMEM (-> noise warps)
   uint64_t out_read;            // read-out only output Linear (no loss gradient), on the steps that record outputs: every output
                                 // tile's prediction has READ act(x_{L-1}) (MMA warp -> group U, which overwrites it next)
 };
+
+// Per-tile constants of the two MMA issuers (shared memory, built once per launch)
+struct __align__(16) MmaA {
+  uint64_t ad0, bd0;      // descriptors of the weight tile (K-major) and of the activation operand of its input layer
+  int meta;               // in_layer [0,4) | slot + 1 [4,6) | has back-projection [6] | K steps of 16 [8,16)
+  int pad[3];
+};
+struct __align__(16) MmaB {
+  uint64_t ad0;           // descriptor of the MN-major view of the weight tile (first 128 input units)
+  uint32_t a_step;        // descriptor step per 16 output units
+  int meta;               // has back-projection [0] | last tile of its Linear [1] | slot + 1 [2,4) | in_layer [4,8) |
+                          // K steps (valid output units / 16) [8,12) | unit tiles of the input layer [12,16) | first [16,20)
+};
+
+// The chain-side operands (act(x_l) for the predictions, G for the back-projections: N = chains, K = units) are kept
+// MN-major: element (unit u, chain c) at (u/8)*(NR*16) + (c/8)*128 + (u%8)*16 + (c%8)*2, so the chains a thread holds for
+// its unit are 8 or 16 CONTIGUOUS bytes and go out as one vector store; a warp covers whole 128-byte rows.  (K-major they
+// were 2-byte stores 16 bytes apart: 9 shared-memory wavefronts per store instruction, a quarter of the shared-memory
+// data pipe that the tensor core's operand reads need -- ncu r02b.)  Descriptor: LBO = NR*16 (next 8 units), SBO = 128.
+template <int N>
+__device__ __forceinline__ void st_chains_bf16(uint8_t* dst, const float (&v)[N]) {
+  uint32_t w[N / 2];
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  if constexpr (N == 4) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N / 8; ++j) *reinterpret_cast<uint4*>(dst + j * 128) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  }
+}
+// byte offset of (unit u, chain c) inside such an operand
+__device__ __forceinline__ uint32_t chain_op_off(int NR, int u, int c) {
+  return (uint32_t)(u >> 3) * (uint32_t)(NR * 16) + (uint32_t)(c >> 3) * 128u + (uint32_t)(u & 7) * 16u + (uint32_t)(c & 7) * 2u;
+}
+
+constexpr uint32_t kTabBytes = kMaxTiles * (sizeof(MmaA) + sizeof(MmaB));
 
 __device__ __forceinline__ float warp_sum_tc(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 // compiled in only for the TRACE instantiation (MCPC_TC_TIMING): the stamps cost ~60 instructions per tile, and the
 // epilogue warps are bound by instruction fetch / issue
 #define TC_STAMP(cond, ts, idx) do { if constexpr (TRACE) { if (blockIdx.x == 0 && (cond) && (unsigned)((ts) - p.dbg_t0) < 8u) p.dbg[((ts) - p.dbg_t0) * 64 + (idx)] = clock64(); } } while (0)
@@ -242,13 +286,25 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
 // 3 = sampling without a sensory gradient (SGD + Philox, zero_fn / no loss: no output tile is ever visited),
 // 4 = 3 + trajectory records (thinned read-outs: the output tiles are visited on the recorded steps only),
 // 0 = everything read from the parameters.  SPEC 1-3 also mean: no trajectories; SPEC != 0: no x.grad read-out.
-template <int NR, int RV, bool TRACE, int SPEC>
-__global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
+// SUB = 4 (8-chain CTAs only): group T has four sub-groups of four warps (warps 20-27 are the third and fourth), each with
+// its own prediction accumulator pair and G operand buffer -- four tile epilogues in flight instead of two.
+// NZW = 1 (instantiation 1 on 8-chain CTAs): four more warps, one per TMEM lane quarter, draw the Langevin noise.
+template <int SUB, int NZW>
+constexpr int tc_threads() { return 640 + (SUB == 4 ? 256 : 0) + (NZW ? 128 : 0); }
+
+template <int NR, int RV, bool TRACE, int SPEC, int SUB = 2, int NZW = 0>
+__global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
+  static_assert(SUB == 2 || (SUB == 4 && RV == 8 && NR == 16), "four tile sub-groups: 8-chain CTAs");
+  static_assert(NZW == 0 || (SPEC == 1 && RV == 8), "noise warps: instantiation 1 on 8-chain CTAs");
   constexpr int RPT = RV / 2;
+  constexpr bool kNoiseWarps = (NZW != 0);
+  constexpr int kNoiseWarp0 = (SUB == 4) ? 28 : 20;
+  constexpr int kTThreads = SUB * 128;       // threads of group T
+  constexpr int kGB = (RV <= 8) ? SUB : 2;   // G operand buffers
   constexpr bool ALT = (RV <= 8);            // group T works on alternate tiles (see there)
   constexpr int kGrp = 256;                  // threads per epilogue group
   constexpr int kTileArr = ALT ? 128 : 256;  // group-T threads that hand one tile over
-  constexpr int kDA = (NR == 16) ? 4 : 2;    // prediction accumulators in flight (TMEM columns permitting)
+  constexpr int kDA = (NR == 16) ? 2 * SUB : 2;   // prediction accumulators in flight (TMEM columns permitting)
   constexpr int CH = RPT < 8 ? RPT : 8;      // chains a thread of group U processes at a time
   constexpr bool kNoiseEarly = (RV <= 8);    // draw the Langevin noise before waiting for the back-projection
                                              // (wider chain tiles have no registers to hold it across the wait)
@@ -256,7 +312,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Barriers bars;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_red[2][2][8][2];        // [group][step parity][warp][energy, loss]
+  __shared__ float s_red[2][2][16][2];       // [group][step parity][warp][energy, loss]
   __shared__ unsigned s_saved[2];            // saved steps whose rows group T / group U have finished storing (signal warp)
   __shared__ int2 s_tile[kMaxTiles];         // x = lin | out_tile << 8 | (h_out + 1) << 16, y = number of units of that Linear
 
@@ -272,10 +328,33 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
   const bool y_in_tmem = (SPEC == 1 || SPEC == 2) ? true : ((SPEC == 3 || SPEC == 4) ? false : (p.y_tmem != 0));   // 3, 4: no targets
   const bool adam_in_tmem = (SPEC == 2) ? true : (SPEC != 0 ? false : (p.adam_tmem != 0));
   const int row0 = blockIdx.x * RV;
+  // the issuers' tables live in the last kTabBytes of the dynamic allocation (inside the over-read slack of plan_tc:
+  // nothing is ever written there, and what an over-reading MMA makes of them lands in accumulator lanes nobody reads)
+  MmaA* const s_mA = reinterpret_cast<MmaA*>(smem + p.tab_off);
+  MmaB* const s_mB = reinterpret_cast<MmaB*>(smem + p.tab_off + kMaxTiles * sizeof(MmaA));
 
   if (tid < p.n_hid_tiles + p.n_out_tiles) {
     const Tile& T = p.tiles[tid];
     s_tile[tid] = make_int2(T.lin | (T.out_tile << 8) | ((T.h_out + 1) << 16), T.lin == nd.L ? nd.d_out : nd.dims[T.lin]);
+    const uint32_t sb = smem_u32(smem);
+    const int in_layer = T.lin - 1;
+    const bool has_b = (T.lin < L) || top_has_grad;
+    const bool last_of_lin = (tid + 1 == p.n_hid_tiles + p.n_out_tiles) || (p.tiles[tid + 1].lin != T.lin);   // (output tiles come last)
+    MmaA A;
+    A.ad0 = smem_desc(sb + T.smem_off, 128u, (uint32_t)T.sbo);
+    A.bd0 = smem_desc(sb + p.act_off[in_layer], (uint32_t)(NR * 16), 128u);          // MN-major (st_chains_bf16)
+    A.meta = in_layer | ((T.slot + 1) << 4) | ((has_b ? 1 : 0) << 6) | ((T.Kp / 16) << 8);
+    A.pad[0] = A.pad[1] = A.pad[2] = 0;
+    s_mA[tid] = A;
+    // K extent of the back-projection = the tile's valid output units in groups of 16 (rows of G beyond them are never written)
+    const int n_units = ((T.lin == L) ? nd.d_out : nd.dims[T.lin]) - T.out_tile * 128;
+    const int nkb = n_units >= 128 ? 8 : (n_units + 15) / 16;
+    MmaB Bm;
+    Bm.ad0 = smem_desc(sb + T.smem_off, (uint32_t)T.sbo, 128u);
+    Bm.a_step = (uint32_t)(2 * T.sbo) >> 4;
+    Bm.meta = (has_b ? 1 : 0) | ((last_of_lin ? 1 : 0) << 1) | ((T.slot + 1) << 2) | (in_layer << 4) | (nkb << 8) |
+              (p.ut[in_layer] << 12) | (p.h_off[in_layer] << 16);
+    s_mB[tid] = Bm;
   }
   if (tid == 0) {
     s_saved[0] = 0;
@@ -284,10 +363,12 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.w_full[i], 1);
       mbar_init(&bars.w_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars.g_full[i], kTileArr);
       mbar_init(&bars.g_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&bars.dA_full[i], 1);
       mbar_init(&bars.dA_empty[i], kTileArr);
     }
@@ -295,9 +376,10 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
     for (int l = 0; l < kMaxL; ++l) {
       mbar_init(&bars.acts_ready[l], kGrp);
       mbar_init(&bars.bp_ready[l], 1);
-      mbar_init(&bars.g_ready[l], kGrp);
-      mbar_init(&bars.nz_full[0][l], kGrp);
+      mbar_init(&bars.g_ready[l], kTThreads);
+      mbar_init(&bars.nz_full[0][l], kNoiseWarps ? 128 : kGrp);      // producers: the four noise warps (1) / group T (3)
       mbar_init(&bars.nz_full[1][l], kGrp);
+      mbar_init(&bars.nz_empty[l], kGrp);
     }
     fence_mbar_init();
   }
@@ -312,6 +394,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
   const uint32_t col_bias = (kDA + 3 * HT) * NR, col_y = col_bias + 32;
   // Adam on the latents (deterministic PC / MAP): m and v behind the targets, HT * NR columns each
   const uint32_t col_m = col_y + (y_in_tmem ? (uint32_t)p.n_out_tiles * NR : 0u), col_v = col_m + HT * NR;
+  const uint32_t col_nz = col_m;                              // instantiation 1 (SGD: no Adam state): the noise, HT * NR columns
   const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;      // table order: Linear 1 ... L-1, then the output tiles
 
   // =====================================================================================================
@@ -363,155 +446,182 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
         signal_saved(p.ready + s);
       }
     }
+  } else if (kNoiseWarps && warp >= kNoiseWarp0) {
+    // ---------------- noise warps (instantiation 1: MCPC learning / sampling calls of 8-chain CTAs) ----------------
+    // Group U closes the step's critical loop (output tiles -> back-projection -> update of the top hidden layer -> next
+    // step's output tiles) and ~40 % of its time per layer was the Philox + Box-Muller draw (cycle trace).  These four warps
+    // (one per TMEM lane quarter) draw the noise of every latent one step ahead into TMEM -- lane = unit, column = chain,
+    // the layout of x, so group U reads it in the same batch of tcgen05.ld as x and the back-projection.  Per layer: wait
+    // until group U has read the previous step's values (nz_empty), store, arrive on nz_full.  Same counters and keys as
+    // the in-thread draw: the values are bit-identical.
+    if (p.nz_tmem) {
+      static_assert(!kNoiseWarps || RV == 8, "noise warps: 8 chains = two (aligned) or three quads of Philox outputs");
+      const int qn = warp & 3;
+      const uint32_t lb = tmem + ((uint32_t)(qn * 32) << 16) + col_nz;
+      const uint64_t chain0 = p.chain_offset + (uint64_t)row0;
+      const uint64_t q0 = chain0 >> 2;
+      const int first = (int)(chain0 & 3);
+      for (int ts = 0; ts < p.n_steps; ++ts) {
+        const uint32_t t_abs = (uint32_t)(p.t_begin + ts);
+        for (int l = 0; l < L; ++l) {
+          if (ts > 0) {
+            mbar_wait_parked(&bars.nz_empty[l], (ts - 1) & 1);
+            fence_after_sync();
+          }
+          if (qn * 32 < nd.dims[l]) {                          // (one unit tile per layer; warp-uniform)
+            const uint32_t gu = (uint32_t)(nd.off[l] + qn * 32 + lane);
+            float all[12], nzv[8];
+            langevin_normals4(p.seed, gu, t_abs, q0, &all[0]);
+            langevin_normals4(p.seed, gu, t_abs, q0 + 1, &all[4]);
+            if (first != 0) {
+              langevin_normals4(p.seed, gu, t_abs, q0 + 2, &all[8]);
+            } else {
+#pragma unroll
+              for (int j = 8; j < 12; ++j) all[j] = 0.0f;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              nzv[c] = p.noise_scale * (first == 0 ? all[c] : (first == 1 ? all[c + 1] : (first == 2 ? all[c + 2] : all[c + 3])));
+            __syncwarp();
+            tmem_st<8>(lb + (uint32_t)(p.h_off[l] * NR), nzv);
+            tmem_st_wait();
+          }
+          fence_before_sync();
+          mbar_arrive(&bars.nz_full[0][l]);
+        }
+      }
+    }
   } else if (warp == kMmaWarp) {
-    // ---------------- MMA issuer A: predictions (converged warp; one elected lane issues) ----------------
+    // ---------------- MMA issuer A: predictions (ONE elected thread runs the whole loop) ----------------
     // Two issuer warps: this one runs ahead with the prediction GEMMs (phase A), warp kMmaWarpB issues the
     // back-projections (phase B) as soon as group T hands a G operand over.  Neither waits for the other's barriers,
     // so a late hand-over does not hold back the next tile's prediction.
-    const uint32_t id_a = idesc_bf16(128, NR, false, false);
-    const uint32_t smem_base = smem_u32(smem);
-    uint32_t ph_wfull = 0, ph_dAe = (1u << kDA) - 1u;
-    mbar_wait_parked(&bars.w_res, 0);
-    for (int ts = 0; ts < p.n_steps; ++ts) {
-      const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
-      const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
-      const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
-      uint32_t acts_waited = 0;
-      TC_STAMP(lane == 0, ts, 0);
-      for (int t = 0; t < t_end; ++t) {
-        const Tile& T = p.tiles[t];
-        const int k = t;
-        const int in_layer = T.lin - 1;
-        if (!((acts_waited >> in_layer) & 1u)) {                    // act(x_{lin-1}) of THIS step: written by group U
-          mbar_wait_parked(&bars.acts_ready[in_layer], ts & 1);
-          acts_waited |= 1u << in_layer;
-        }
-        if (T.slot >= 0) {
-          mbar_wait_parked(&bars.w_full[T.slot], (ph_wfull >> T.slot) & 1u);
-          ph_wfull ^= 1u << T.slot;
-        }
-        const int db = k & (kDA - 1);
-        mbar_wait_parked(&bars.dA_empty[db], (ph_dAe >> db) & 1u);
-        ph_dAe ^= 1u << db;
-        fence_after_sync();
-        const uint32_t act_sbo = (uint32_t)(p.act_kp[in_layer] / 8) * 128u;
-        const uint64_t ad0 = smem_desc(smem_base + T.smem_off, 128u, (uint32_t)T.sbo);
-        const uint64_t bd0 = smem_desc(smem_base + p.act_off[in_layer], 128u, act_sbo);
-        const uint32_t dcol = tmem + col_dA + db * NR;
-        const int nk = T.Kp / 16;
-        const bool has_b = (T.lin < L) || top_has_grad;
-        if (elect_one()) {
-          // groups of 8 K-steps fully unrolled: every MMA then reads its own pre-computed uniform registers and the
-          // instructions issue back to back (46 instead of 91 cycles each, scripts/umma_timing.py variants 6 / 1)
+    // The issuers pace the whole step (ncu r02b: T waits for accumulators half of its time, U a third; each issuer spent
+    // ~1,100 cycles and ~170 instructions per tile on descriptor arithmetic over indexed constant-bank loads, elect /
+    // reconvergence and re-derived flags).  Everything per tile that does not change from step to step is therefore
+    // precomputed into s_mA / s_mB, and one thread runs the loop: per tile two shared-memory loads, the waits, the MMAs.
+    if (elect_one()) {
+      const uint32_t id_a = idesc_bf16(128, NR, false, true);
+      constexpr int kBStep = NR * 2;                           // B descriptor step per 16 units (two rows of NR*16 bytes)
+      uint32_t ph_wfull = 0, ph_dAe = (1u << kDA) - 1u;
+      mbar_wait_parked(&bars.w_res, 0);
+      for (int ts = 0; ts < p.n_steps; ++ts) {
+        const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
+        const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
+        uint32_t acts_waited = 0;
+        TC_STAMP(true, ts, 0);
+        for (int t = 0; t < t_end; ++t) {
+          const MmaA M = s_mA[t];
+          const int in_layer = M.meta & 15, slot = ((M.meta >> 4) & 3) - 1, nk = (M.meta >> 8) & 0xff;
+          if (!((acts_waited >> in_layer) & 1u)) {                    // act(x_{lin-1}) of THIS step: written by group U
+            mbar_wait_parked(&bars.acts_ready[in_layer], ts & 1);
+            acts_waited |= 1u << in_layer;
+          }
+          if (slot >= 0) {
+            mbar_wait_parked(&bars.w_full[slot], (ph_wfull >> slot) & 1u);
+            ph_wfull ^= 1u << slot;
+          }
+          const int db = t & (kDA - 1);
+          mbar_wait_parked(&bars.dA_empty[db], (ph_dAe >> db) & 1u);
+          ph_dAe ^= 1u << db;
+          fence_after_sync();
+          const uint32_t dcol = tmem + col_dA + db * NR;
+          // groups of 8 K-steps fully unrolled: the instructions issue back to back (46 instead of 91 cycles each,
+          // scripts/umma_timing.py variants 6 / 1)
           int ks = 0;
           for (; ks + 8 <= nk; ks += 8) {
-            const uint64_t a8 = ad0 + (uint64_t)(ks * 16), b8 = bd0 + (uint64_t)(ks * 16);
+            const uint64_t a8 = M.ad0 + (uint64_t)(ks * 16), b8 = M.bd0 + (uint64_t)(ks * kBStep);
             mma_bf16_ss(dcol, a8, b8, id_a, ks > 0);
 #pragma unroll
-            for (int kk = 1; kk < 8; ++kk) mma_bf16_ss(dcol, a8 + (uint64_t)(kk * 16), b8 + (uint64_t)(kk * 16), id_a, true);
+            for (int kk = 1; kk < 8; ++kk) mma_bf16_ss(dcol, a8 + (uint64_t)(kk * 16), b8 + (uint64_t)(kk * kBStep), id_a, true);
           }
-          for (; ks < nk; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), id_a, ks > 0);
+          for (; ks < nk; ++ks) mma_bf16_ss(dcol, M.ad0 + (uint64_t)(ks * 16), M.bd0 + (uint64_t)(ks * kBStep), id_a, ks > 0);
           mma_commit(&bars.dA_full[db]);
           // a streamed tile without back-projection is free again once this prediction has read it
-          if (T.slot >= 0 && !has_b) mma_commit(&bars.w_empty[T.slot]);
+          if (slot >= 0 && !((M.meta >> 6) & 1)) mma_commit(&bars.w_empty[slot]);
+          TC_STAMP(true, ts, 1 + t);
         }
-        __syncwarp();
-        TC_STAMP(lane == 0, ts, 1 + k);
+        // no back-projection follows read-out only predictions, so nothing else tells group U that the top layer's
+        // activations have been read: without this its update of step ts could overwrite act(x_{L-1}) under the last tiles
+        if (need_out && !top_has_grad) mma_commit(&bars.out_read);
+        TC_STAMP(true, ts, 21);
       }
-      if (need_out && !top_has_grad) {
-        // no back-projection follows these predictions, so nothing else tells group U that the top layer's activations
-        // have been read: without this its update of step ts could overwrite act(x_{L-1}) under the last output tiles
-        if (elect_one()) mma_commit(&bars.out_read);
-        __syncwarp();
-      }
-      TC_STAMP(lane == 0, ts, 21);
     }
+    __syncwarp();
   } else if (warp == kMmaWarpB) {
     // ---------------- MMA issuer B: back-projections through the MN-major view of the same weight tiles ----------------
-    const uint32_t id_b = idesc_bf16(128, NR, true, false);
-    const uint32_t smem_base = smem_u32(smem);
-    uint32_t ph_gfull = 0;
-    mbar_wait_parked(&bars.w_res, 0);
-    for (int ts = 0; ts < p.n_steps; ++ts) {
-      const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
-      const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
-      const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
-      uint32_t bp_started = 0;
-      for (int t = 0; t < t_end; ++t) {
-        const Tile& T = p.tiles[t];
-        const int gb = t & 1;
-        const bool has_b = (T.lin < L) || top_has_grad;
-        if (!has_b) continue;                                         // read-out only: nothing flows back
-        const bool last_of_lin = (t + 1 == n_tiles_all) || (p.tiles[t + 1].lin != T.lin);   // (output tiles come last)
-        mbar_wait_parked(&bars.g_full[gb], (ph_gfull >> gb) & 1u);            // group T consumed the prediction of this tile,
-        ph_gfull ^= 1u << gb;                                         // so phase A has finished reading it as well
-        fence_after_sync();
-        const int in_layer = T.lin - 1;
-        const uint64_t bd0 = smem_desc(smem_base + p.gbuf_off[gb], 128u, 2048u);
-        const uint32_t a_step = (uint32_t)(2 * T.sbo) >> 4;
-        // K extent = the tile's valid output units in groups of 16 (rows of G beyond them are never written)
-        const int n_units = ((T.lin == L) ? nd.d_out : nd.dims[T.lin]) - T.out_tile * 128;
-        const int nkb = n_units >= 128 ? 8 : (n_units + 15) / 16;
-        for (int u = 0; u < p.ut[in_layer]; ++u) {
-          const int h = p.h_off[in_layer] + u;
-          const uint64_t ad0 = smem_desc(smem_base + T.smem_off + u * 2048, (uint32_t)T.sbo, 128u);
-          const uint32_t dcol = tmem + col_bp + h * NR;
-          const bool acc0 = (bp_started >> h) & 1u;
-          if (elect_one()) {
-            mma_bf16_ss(dcol, ad0, bd0, id_b, acc0);
+    if (elect_one()) {
+      const uint32_t id_b = idesc_bf16(128, NR, true, true);
+      constexpr int kBStep = NR * 2;
+      const uint64_t gd0 = smem_desc(smem_u32(smem) + p.gbuf_off[0], (uint32_t)(NR * 16), 128u);
+      const uint32_t gd_step = (uint32_t)(p.gbuf_off[1] - p.gbuf_off[0]) >> 4;
+      uint32_t ph_gfull = 0;
+      mbar_wait_parked(&bars.w_res, 0);
+      for (int ts = 0; ts < p.n_steps; ++ts) {
+        const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
+        const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
+        const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
+        uint32_t bp_started = 0;
+        for (int t = 0; t < t_end; ++t) {
+          const MmaB M = s_mB[t];
+          if (!(M.meta & 1)) continue;                                  // read-out only: nothing flows back
+          const int gb = t & (kGB - 1);
+          mbar_wait_parked(&bars.g_full[gb], (ph_gfull >> gb) & 1u);    // group T consumed the prediction of this tile,
+          ph_gfull ^= 1u << gb;                                         // so phase A has finished reading it as well
+          fence_after_sync();
+          const int in_layer = (M.meta >> 4) & 15, slot = ((M.meta >> 2) & 3) - 1;
+          const int nkb = (M.meta >> 8) & 15, n_ut = (M.meta >> 12) & 15, h0 = (M.meta >> 16) & 15;
+          const uint64_t bd0 = gd0 + (uint64_t)((uint32_t)gb * gd_step);
+          for (int u = 0; u < n_ut; ++u) {
+            const uint64_t ad0 = M.ad0 + (uint64_t)(u * (2048 >> 4));
+            const uint32_t dcol = tmem + col_bp + (h0 + u) * NR;
+            mma_bf16_ss(dcol, ad0, bd0, id_b, (bp_started >> (h0 + u)) & 1u);
             if (nkb == 8) {
 #pragma unroll
-              for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * 16), id_b, true);
+              for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * M.a_step), bd0 + (uint64_t)(ks * kBStep), id_b, true);
             } else {
-              for (int ks = 1; ks < nkb; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * 16), id_b, true);
+              for (int ks = 1; ks < nkb; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * M.a_step), bd0 + (uint64_t)(ks * kBStep), id_b, true);
             }
+            bp_started |= 1u << (h0 + u);
           }
-          __syncwarp();
-          bp_started |= 1u << h;
-        }
-        if (elect_one()) {
           mma_commit(&bars.g_empty[gb]);
-          if (last_of_lin) mma_commit(&bars.bp_ready[in_layer]);       // back-projection into layer lin-1 is complete
-          if (T.slot >= 0) mma_commit(&bars.w_empty[T.slot]);
+          if ((M.meta >> 1) & 1) mma_commit(&bars.bp_ready[in_layer]);   // back-projection into layer lin-1 is complete
+          if (slot >= 0) mma_commit(&bars.w_empty[slot]);
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     // ---------------- epilogue groups ----------------
     // The SM's warp arbiter favours higher warp ids: the latency-critical tile epilogues (group T) get warps
     // 8-15, the background layer updates (group U) warps 0-7, the MMA issuer the highest id of all.
     const int grp = (warp < 8) ? 1 : 0;                                // 0 = tiles (T), 1 = update (U)
-    const int gw = warp & 7;                                           // warp inside the group
-    const int gtid = tid & (kGrp - 1);
-    const int q = warp & 3, cg = (gw >> 2);
+    const int gw = (warp < 16) ? (warp & 7) : (warp - 12);             // warp inside the group (T: 8-15 -> 0-7, 20-27 -> 8-15)
+    const int gtid = gw * 32 + lane;
+    const int q = warp & 3, cg = (gw >> 2) & 1;
     const int ln = q * 32 + lane;                                      // unit index inside a 128-unit tile
     const int cbase = cg * RPT;
     const int rb = row0 + cbase;
     const int nrow = max(0, min(RPT, p.B - rb));
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t lane_addr = lane_base + (uint32_t)cbase;
-    const uint32_t g_thread_off = (uint32_t)(cbase >> 3) * 2048u + (uint32_t)(cbase & 7) * 16u + (uint32_t)(ln >> 3) * 128u +
-                                  (uint32_t)(ln & 7) * 2u;
 
     if (grp == 1) {
       // ======================= group U: initial state, then one layer update after the other =======================
       // activation AND G operand buffers: chains RV..NR-1 (if any) stay zero for the whole run
-      for (int i = gtid * 16; i < p.gbuf_off[1] + NR * 128 * 2 - p.act_off[0]; i += kGrp * 16)
+      for (int i = gtid * 16; i < p.gbuf_off[kGB - 1] + NR * 128 * 2 - p.act_off[0]; i += kGrp * 16)
         *reinterpret_cast<uint4*>(smem + p.act_off[0] + i) = make_uint4(0, 0, 0, 0);
       asm volatile("bar.sync 2, 256;" ::: "memory");
       for (int h = 0; h < HT; ++h) {
         const int l = p.h_layer[h], u = p.h_index[h] * 128 + ln, dl = nd.dims[l];
-        const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
-        uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbase >> 3) * asbo + (uint32_t)(cbase & 7) * 16u +
-                        (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
-        float xv[RPT];
+        float xv[RPT], av[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           xv[i] = (u < dl && i < nrow) ? p.x[l][(size_t)(rb + i) * dl + u] : 0.0f;
-          if (u < dl)
-            *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(nd.act[l], xv[i]));
+          av[i] = act_tc(nd.act[l], xv[i]);
         }
+        if (u < dl) st_chains_bf16<RPT>(smem + p.act_off[l] + chain_op_off(NR, u, cbase), av);
         __syncwarp();
         tmem_st<RPT>(lane_addr + col_x + h * NR, xv);
         if (adam_in_tmem) {
@@ -557,7 +667,6 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
           const bool has_above = (l + 1 < L) || top_has_grad;
           const int kind = nd.act[l];
           const int dl = nd.dims[l];
-          const uint32_t asbo = (uint32_t)(p.act_kp[l] / 8) * 128u;
           const int n_ut = p.ut[l];
           const bool defer = (RV <= 8) && (SPEC != 0 || n_ut == 1);   // one unit tile: global stores go out after the hand-over
                                                              // (wider chain tiles have no registers to spare for it)
@@ -603,6 +712,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
                 if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);
                 if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);
                 if (l == L - 1 && wait_out_read) mbar_wait_parked(&bars.out_read, ph_out_read);
+                if (kNoiseWarps && p.nz_tmem) mbar_arrive(&bars.nz_empty[l]);     // (nothing to read: hand the columns back)
               }
               continue;
             }
@@ -650,7 +760,10 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
               };
               // pure sampling: group T (idle but for the hidden tiles) drew this step's noise into shared memory one step ahead
               const bool nz_smem = (SPEC == 3) && (p.nz_off >= 0);
-              if (nz_smem) {
+              const bool nz_tm = kNoiseWarps && (p.nz_tmem != 0);  // instantiation 1: the noise warps drew it into TMEM
+              if (nz_tm) {
+                // read below, in the same batch of TMEM loads as x and the back-projection
+              } else if (nz_smem) {
                 if (hi == 0 && c0 == 0) mbar_wait_parked(&bars.nz_full[ts & 1][l], (ts >> 1) & 1);
                 const float* nb = reinterpret_cast<const float*>(smem + p.nz_off) +
                                   ((size_t)((ts & 1) * HT + h) * RV + (size_t)cbc) * 128 + ln;
@@ -664,11 +777,13 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
                 if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);      // all tiles of Linear l+1 back-projected
                 if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);           // group T stored the own-layer error of layer l
                 if (l == L - 1 && wait_out_read) mbar_wait_parked(&bars.out_read, ph_out_read);
+                if (nz_tm) mbar_wait_parked(&bars.nz_full[0][l], ts & 1);
                 fence_after_sync();
                 TC_STAMP(gtid == 0, ts, 40 + l);
               }
               __syncwarp();
               float xv[CH], bp[CH], gown[CH], gradv[CH];
+              if (nz_tm) tmem_ld_nw<CH>(lac + col_nz + h * NR, nz);
               tmem_ld_nw<CH>(lac + col_x + h * NR, xv);
               if (has_above) tmem_ld_nw<CH>(lac + col_bp + h * NR, bp);
               if (l > 0) tmem_ld_nw<CH>(lac + col_g + h * NR, gown);
@@ -679,6 +794,15 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
               }
               tmem_ld_wait();
               TC_STAMP(gtid == 0 && l == 1, ts, 43);
+              if (nz_tm) {
+                tmem_ld_tie(nz);
+                fence_before_sync();
+                mbar_arrive(&bars.nz_empty[l]);                  // (one unit tile, one chunk per layer: once per layer and step)
+                if (!uvalid) {
+#pragma unroll
+                  for (int i = 0; i < CH; ++i) nz[i] = 0.0f;
+                }
+              }
               tmem_ld_tie(xv);
               if (adam_t) {
                 tmem_ld_tie(mv);
@@ -704,7 +828,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
                   if (uvalid && i < nrc) e_part = fmaf(ce * eps, eps, e_part);
                 }
               }
-              if (!kNoiseEarly && !nz_smem) draw_noise();
+              if (!kNoiseEarly && !nz_smem && !nz_tm) draw_noise();
               // ---- 3. update (straight-line: CH independent chains interleave) ----
 #pragma unroll
               for (int i = 0; i < CH; ++i) {
@@ -745,13 +869,13 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
               }
               TC_STAMP(gtid == 0 && l == 1, ts, 44);
               // ---- 4. next step's operands: bf16 act(x) to shared memory, fp32 x back to TMEM ----
-              uint8_t* aptr = smem + p.act_off[l] + (uint32_t)(cbc >> 3) * asbo + (uint32_t)(cbc & 7) * 16u +
-                              (uint32_t)(u >> 3) * 128u + (uint32_t)(u & 7) * 2u;
+              float av[CH];
 #pragma unroll
               for (int i = 0; i < CH; ++i) {
                 if (i >= nrc || !uvalid) xv[i] = uvalid ? 0.0f : xold[i];   // chains past the batch keep their zeros
-                if (uvalid) *reinterpret_cast<__nv_bfloat16*>(aptr + (i >> 3) * asbo + (i & 7) * 16) = __float2bfloat16(act_tc(kind, xv[i]));
+                av[i] = act_tc(kind, xv[i]);
               }
+              if (uvalid) st_chains_bf16<CH>(smem + p.act_off[l] + chain_op_off(NR, u, cbc), av);
               __syncwarp();                                    // .sync.aligned store: every lane executes it
               tmem_st<CH>(lac + col_x + h * NR, xv);
               if (adam_t) {
@@ -816,15 +940,14 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
       // tiles in flight nearly double the tile rate.  Half h owns accumulator / G buffer h.  Otherwise the two warps of a
       // lane quarter split the chains of every tile.
       constexpr int RT = ALT ? RV : RPT;
-      const int half = gw >> 2;
+      const int half = gw >> 2;                                  // sub-group of this warp (0 .. SUB-1)
       const int cbT = ALT ? 0 : cbase;
       const int rbT = row0 + cbT;
       const int nrT = max(0, min(RT, p.B - rbT));
       const uint32_t laT = lane_base + (uint32_t)cbT;
-      const uint32_t gtoT = (uint32_t)(cbT >> 3) * 2048u + (uint32_t)(cbT & 7) * 16u + (uint32_t)(ln >> 3) * 128u +
-                            (uint32_t)(ln & 7) * 2u;
+      const uint32_t gtoT = chain_op_off(NR, ln, cbT);
       const bool stamp_thr = ALT ? ((gtid & 127) == 0) : (gtid == 0);
-      uint32_t ph_dAf = 0, ph_ge = 3;
+      uint32_t ph_dAf = 0, ph_ge = (1u << kGB) - 1u;
       const float qnan = __int_as_float(0x7fc00000);
       // Per-tile constants live in TMEM, not in global memory: one bias column per tile and, when they fit, the
       // targets of every output tile (NaN = "this element carries no loss": masked, past the batch, padding).
@@ -843,7 +966,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
         const float bv = (un < ti.y && p.b[lin] != nullptr) ? __ldg(p.b[lin] + un) : 0.0f;
         __syncwarp();
         tmem_st1(lane_base + col_bias + (uint32_t)t, bv);           // both warps of a lane quarter write the same value
-        if (y_in_tmem && lin == L && (!ALT || (t & 1) == half)) {
+        if (y_in_tmem && lin == L && (!ALT || (t & (SUB - 1)) == half)) {
           float yv[RT];
           target_of(t, yv);
           __syncwarp();
@@ -900,12 +1023,12 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
           const int2 ti = s_tile[t];
           const int lin = ti.x & 0xff, h = ((ti.x >> 16) & 0xff) - 1, dl = ti.y;
           const int k = t;
-          const int db = k & (kDA - 1), gb = k & 1;
+          const int db = k & (kDA - 1), gb = k & (kGB - 1);
           const bool is_out = (lin == L);
           const bool has_b = !is_out || top_has_grad;
           const int u = ((ti.x >> 8) & 0xff) * 128 + ln;
           const bool uvalid = u < dl;
-          if (ALT && (k & 1) != half) {                       // the other half's tile
+          if (ALT && (k & (SUB - 1)) != half) {               // another sub-group's tile
             if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) mbar_arrive(&bars.g_ready[lin]);
             continue;
           }
@@ -968,10 +1091,8 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
             }
             wait_g_buffer();
 #pragma unroll
-            for (int i = 0; i < RT; ++i) {
-              g16[i] = __float2bfloat16(gv[i]);
-              *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = g16[i];
-            }
+            for (int i = 0; i < RT; ++i) g16[i] = __float2bfloat16(gv[i]);
+            st_chains_bf16<RT>(gptr, gv);
             sg_ptr = sg;
             tmem_st<RT>(laT + col_g + h * NR, gv);
             tmem_st_wait();
@@ -1014,10 +1135,8 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
             }
             wait_g_buffer();
 #pragma unroll
-            for (int i = 0; i < RT; ++i) {
-              g16[i] = __float2bfloat16(ev[i]);
-              if (has_b) *reinterpret_cast<__nv_bfloat16*>(gptr + (i >> 3) * 2048 + (i & 7) * 16) = g16[i];
-            }
+            for (int i = 0; i < RT; ++i) g16[i] = __float2bfloat16(ev[i]);
+            if (has_b) st_chains_bf16<RT>(gptr, ev);
             sg_ptr = sg;
             if (to != nullptr) {
 #pragma unroll
@@ -1049,11 +1168,11 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
         l_part = warp_sum_tc(l_part);
         float (*red)[2] = s_red[0][ts & 1];
         if (lane == 0) { red[gw][0] = e_part; red[gw][1] = l_part; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kTThreads) : "memory");
         if (gtid < 2) {
           float s = 0.0f;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) s += red[w][gtid];
+          for (int w = 0; w < 4 * SUB; ++w) s += red[w][gtid];
           p.partials[(((size_t)ts * p.n_ctas + blockIdx.x) * 2 + 0) * 2 + gtid] = s;
         }
         if (gtid == 0 && do_save && p.ready != nullptr) saved_step(&s_saved[0]);
@@ -1071,7 +1190,8 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
 inline int pad16(int v) { return (v + 15) & ~15; }
 
 // Fills the tile table + shared-memory plan.  Returns MCPC_OK or MCPC_ERR_UNSUPPORTED (message set).
-int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* packed_bytes, bool with_out = true) {
+int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* packed_bytes, bool with_out = true,
+            bool shrink_partial = true, int n_sub = 2) {
   if (nd.L < 1) return MCPC_ERR_INVALID;
   int HT = 0;
   for (int l = 0; l < nd.L; ++l) {
@@ -1089,7 +1209,7 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
   }
   p->h_off[nd.L] = HT;
   p->HT = HT;
-  const int nda = (NR == 16) ? 4 : 2;
+  const int nda = (NR == 16) ? 2 * n_sub : 2;                  // prediction accumulators (kDA of the kernel)
   if ((nda + 3 * HT) * NR + 32 > 512) {
     set_error("bf16 path: %d hidden unit tiles x %d chains per CTA do not fit the 512 TMEM columns", HT, NR);
     return MCPC_ERR_UNSUPPORTED;
@@ -1101,7 +1221,7 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
     p->act_off[l] = (int)off;
     off += (uint32_t)NR * p->act_kp[l] * 2;
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < n_sub; ++i) {
     p->gbuf_off[i] = (int)off;
     off += (uint32_t)NR * 128 * 2;
   }
@@ -1132,10 +1252,15 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
       T.Kp = Kp;
       T.sbo = (Kp / 8) * 128;
       T.bytes = 128 * Kp * 2;
+      // Partial last tile of the OUTPUT Linear (784 = 6 x 128 + 16): in the canonical layout the 8-row groups are
+      // contiguous, so only the valid rows (in groups of 16, the back-projection's K step) are copied and kept; the
+      // prediction MMA (M = 128) reads whatever follows in shared memory into accumulator lanes nobody looks at (targets of
+      // padding units are NaN = "no loss", the stores are predicated).  mcpc_ml: 28 KB that keep one more tile resident.
+      if (shrink_partial && lin == nd.L && rows - i * 128 < 128) T.bytes = pad16(rows - i * 128) * Kp * 2;
       T.h_out = (lin < nd.L) ? p->h_off[lin] + i : -1;
       T.gsrc = gsrc;
       T.slot = -1;
-      gsrc += (size_t)T.bytes;
+      gsrc += (size_t)128 * Kp * 2;                                // the packed copy in global memory keeps whole tiles
       if ((uint32_t)T.bytes > max_tile) max_tile = (uint32_t)T.bytes;
     }
     if (lin < nd.L) p->n_hid_tiles = nt;
@@ -1147,11 +1272,18 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
   const uint32_t slack = 4096;             // MN-major reads of narrow tiles overrun their 128 x Kp footprint
   uint32_t total = 0;
   for (int t = 0; t < nt; ++t) total += (uint32_t)p->tiles[t].bytes;
+  // resident tiles: the shrunken partial tiles first, so that what the prediction MMA reads beyond them is weight data
+  auto place_resident = [&](const bool* streamed) {
+    for (int pass = 0; pass < 2; ++pass)
+      for (int t = 0; t < nt; ++t) {
+        Tile& T = p->tiles[t];
+        if ((streamed != nullptr && streamed[t]) || (T.bytes < 128 * T.Kp * 2) != (pass == 0)) continue;
+        T.smem_off = (int)off;
+        off += (uint32_t)T.bytes;
+      }
+  };
   if (off + total + slack <= kSmemBudget) {
-    for (int t = 0; t < nt; ++t) {
-      p->tiles[t].smem_off = (int)off;
-      off += (uint32_t)p->tiles[t].bytes;
-    }
+    place_resident(nullptr);
   } else {
     const uint32_t ring = 2 * max_tile;
     if (off + ring + slack > kSmemBudget) {
@@ -1161,15 +1293,13 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
     const uint32_t ring_off = off;
     off += ring;
     bool streamed[kMaxTiles] = {};
+    uint32_t res_bytes = 0;
     for (int t = 0; t < nt; ++t) {
-      Tile& T = p->tiles[t];
-      if (off + (uint32_t)T.bytes + slack <= kSmemBudget) {
-        T.smem_off = (int)off;
-        off += (uint32_t)T.bytes;
-      } else {
-        streamed[t] = true;
-      }
+      const Tile& T = p->tiles[t];
+      if (off + res_bytes + (uint32_t)T.bytes + slack <= kSmemBudget) res_bytes += (uint32_t)T.bytes;
+      else streamed[t] = true;
     }
+    place_resident(streamed);
     // Visiting order of the OUTPUT tiles (any order is valid: their back-projections sum into the same accumulator):
     // streamed and resident tiles alternate, starting with a streamed one.  A streamed tile's bulk copy can only start
     // when the previous user of its ring slot has finished its back-projection; with the streamed tiles at the end of the
@@ -1200,6 +1330,12 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
     }
   }
   *smem_bytes = off + slack;
+  // the M = 128 prediction MMA of a shrunken tile must stay inside the allocation; otherwise plan with whole tiles
+  for (int t = 0; t < nt; ++t)
+    if ((size_t)p->tiles[t].smem_off + (size_t)128 * p->tiles[t].Kp * 2 > *smem_bytes) {
+      if (!shrink_partial) return MCPC_ERR_INVALID;
+      return plan_tc(nd, NR, p, smem_bytes, packed_bytes, with_out, false, n_sub);
+    }
   return MCPC_OK;
 }
 
@@ -1256,6 +1392,7 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
     rc = plan_tc(nd, rows.nr, &p, &smem, &packed);
   }
   if (rc != MCPC_OK) return rc;
+  size_t plan_smem = smem;                                     // end of the shared-memory plan in use (incl. its slack)
   p.net = nd;
   p.B = B;
   p.n_ctas = (B + rows.rv - 1) / rows.rv;
@@ -1410,9 +1547,10 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
       MCPC_CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork, 0));
     }
   }
-  auto launch = [&](auto kernel) -> int {
+  auto launch = [&](auto kernel, int threads = 640) -> int {
+    p.tab_off = (int)((plan_smem - kTabBytes) & ~(size_t)15);    // inside the slack at the end of the PLAN (see s_mA)
     MCPC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<p.n_ctas, 640, smem, stream>>>(p);
+    kernel<<<p.n_ctas, threads, smem, stream>>>(p);
     return MCPC_OK;
   };
   bool plain = (p.traj_every == 0) && o->update_x;           // what every specialisation assumes
@@ -1450,9 +1588,31 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
         p.n_out_tiles = q.n_out_tiles;
         p.y_tmem = q.y_tmem;
         p.nz_off = (int)off;
+        plan_smem = smem3;
         smem = off + nz_bytes;
       }
     }
+  }
+  int n_sub = 2;
+  if (spec == 1 && rows.rv == 8 && !timing) {
+    // MCPC learning / sampling call on 8-chain CTAs: four tile sub-groups (8 accumulators, 4 G buffers) when TMEM and shared
+    // memory allow it, and the noise warps, which draw the Langevin noise into TMEM one step ahead (columns behind the
+    // targets, where instantiation 2 keeps Adam's state) -- see infer_tc_kernel
+    const char* es = getenv("MCPC_TC_SUB");
+    if (es != nullptr && atoi(es) == 4) {                        // experiment (measured slower)
+      TcParams q = p;
+      size_t smem4 = 0, packed4 = 0;
+      if (plan_tc(nd, rows.nr, &q, &smem4, &packed4, true, true, 4) == MCPC_OK && q.y_tmem && packed4 == packed) {
+        for (int t = 0; t < kMaxTiles; ++t) p.tiles[t] = q.tiles[t];
+        for (int i = 0; i < 4; ++i) p.gbuf_off[i] = q.gbuf_off[i];
+        for (int l = 0; l < nd.L; ++l) p.act_off[l] = q.act_off[l];
+        smem = smem4;
+        plan_smem = smem4;
+        n_sub = 4;
+      }
+    }
+    const int used = (2 * n_sub + 3 * p.HT) * rows.nr + 32 + p.n_out_tiles * rows.nr;
+    p.nz_tmem = (getenv("MCPC_TC_NOISE_WARPS") != nullptr && used + p.HT * rows.nr <= 512) ? 1 : 0;   // measured slower
   }
   if (rows.rv == 32) {
     rc = spec == 3 ? launch(infer_tc_kernel<32, 32, false, 3>)
@@ -1462,7 +1622,13 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   } else if (timing) {
     rc = launch(infer_tc_kernel<16, 8, true, 0>);    // the cycle trace exists for the generic 8-chain variant only
   } else if (spec == 1) {
-    rc = launch(infer_tc_kernel<16, 8, false, 1>);
+    if (n_sub == 4) {
+      rc = p.nz_tmem ? launch(infer_tc_kernel<16, 8, false, 1, 4, 1>, tc_threads<4, 1>())
+                     : launch(infer_tc_kernel<16, 8, false, 1, 4, 0>, tc_threads<4, 0>());
+    } else {
+      rc = p.nz_tmem ? launch(infer_tc_kernel<16, 8, false, 1, 2, 1>, tc_threads<2, 1>())
+                     : launch(infer_tc_kernel<16, 8, false, 1, 2, 0>, tc_threads<2, 0>());
+    }
   } else if (spec == 2) {
     rc = launch(infer_tc_kernel<16, 8, false, 2>);
   } else if (spec == 3) {
