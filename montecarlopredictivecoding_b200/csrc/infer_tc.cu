@@ -73,8 +73,6 @@ struct TcParams {
   int nz_off;                   // pure sampling (instantiation 3): shared-memory offset of the two noise buffers that group T
                                 // fills one step ahead for group U ([2][HT][RV][128] fp32), or -1: group U draws its own noise
   int tab_off;                  // byte offset of the MMA issuers' per-tile tables (kTabBytes at the end of the allocation)
-  int nz_tmem;                  // MCPC learning / sampling call on 8-chain CTAs (instantiation 1): four noise warps draw the Langevin
-                                // noise of every latent one step ahead into TMEM columns (lane = unit, column = chain)
   unsigned* ready;              // [n_save] per saved step: += 1 per CTA once its rows of save_g / save_f are written (the
                                 // concurrent weight-gradient kernel consumes them while this kernel runs), or nullptr
   const float* mu0;             // fp32 [B, dims[0]]: W_0 inputs + b_0 per chain (non-zero `inputs`), else nullptr
@@ -109,7 +107,6 @@ struct Barriers {
   uint64_t nz_full[2][kMaxL];   // pure sampling: the noise of layer l for step s is in shared memory buffer s & 1 (group T -> U);
                                 // one barrier per buffer: group T is at most one step ahead, so a barrier never completes twice
                                 // before group U has waited on it (a single barrier per layer could, and U would wait forever)
-  uint64_t nz_empty[kMaxL];     // instantiation 1: group U has read the noise of layer l out of TMEM (-> noise warps)
   uint64_t out_read;            // read-out only output Linear (no loss gradient), on the steps that record outputs: every output
                                 // tile's prediction has READ act(x_{L-1}) (MMA warp -> group U, which overwrites it next)
 };
@@ -153,6 +150,13 @@ __device__ __forceinline__ uint32_t chain_op_off(int NR, int u, int c) {
 }
 
 constexpr uint32_t kTabBytes = kMaxTiles * (sizeof(MmaA) + sizeof(MmaB));
+
+// One arrival per WARP on the epilogue groups' barriers: every lane has fenced its own writes, __syncwarp orders them
+// before lane 0's releasing arrive.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) umma::mbar_arrive(bar);
+}
 
 __device__ __forceinline__ float warp_sum_tc(float v) {
 #pragma unroll
@@ -286,19 +290,10 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
 // 3 = sampling without a sensory gradient (SGD + Philox, zero_fn / no loss: no output tile is ever visited),
 // 4 = 3 + trajectory records (thinned read-outs: the output tiles are visited on the recorded steps only),
 // 0 = everything read from the parameters.  SPEC 1-3 also mean: no trajectories; SPEC != 0: no x.grad read-out.
-// SUB = 4 (8-chain CTAs only): group T has four sub-groups of four warps (warps 20-27 are the third and fourth), each with
-// its own prediction accumulator pair and G operand buffer -- four tile epilogues in flight instead of two.
-// NZW = 1 (instantiation 1 on 8-chain CTAs): four more warps, one per TMEM lane quarter, draw the Langevin noise.
-template <int SUB, int NZW>
-constexpr int tc_threads() { return 640 + (SUB == 4 ? 256 : 0) + (NZW ? 128 : 0); }
-
-template <int NR, int RV, bool TRACE, int SPEC, int SUB = 2, int NZW = 0>
-__global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
-  static_assert(SUB == 2 || (SUB == 4 && RV == 8 && NR == 16), "four tile sub-groups: 8-chain CTAs");
-  static_assert(NZW == 0 || (SPEC == 1 && RV == 8), "noise warps: instantiation 1 on 8-chain CTAs");
+template <int NR, int RV, bool TRACE, int SPEC>
+__global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int RPT = RV / 2;
-  constexpr bool kNoiseWarps = (NZW != 0);
-  constexpr int kNoiseWarp0 = (SUB == 4) ? 28 : 20;
+  constexpr int SUB = 2;                     // sub-groups of group T on 8-chain CTAs (tiles in flight; 4 measured slower)
   constexpr int kTThreads = SUB * 128;       // threads of group T
   constexpr int kGB = (RV <= 8) ? SUB : 2;   // G operand buffers
   constexpr bool ALT = (RV <= 8);            // group T works on alternate tiles (see there)
@@ -365,21 +360,20 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
       mbar_init(&bars.w_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&bars.g_full[i], kTileArr);
+      mbar_init(&bars.g_full[i], kTileArr / 32);
       mbar_init(&bars.g_empty[i], 1);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&bars.dA_full[i], 1);
-      mbar_init(&bars.dA_empty[i], kTileArr);
+      mbar_init(&bars.dA_empty[i], kTileArr / 32);
     }
     mbar_init(&bars.out_read, 1);
     for (int l = 0; l < kMaxL; ++l) {
-      mbar_init(&bars.acts_ready[l], kGrp);
+      mbar_init(&bars.acts_ready[l], kGrp / 32);
       mbar_init(&bars.bp_ready[l], 1);
-      mbar_init(&bars.g_ready[l], kTThreads);
-      mbar_init(&bars.nz_full[0][l], kNoiseWarps ? 128 : kGrp);      // producers: the four noise warps (1) / group T (3)
-      mbar_init(&bars.nz_full[1][l], kGrp);
-      mbar_init(&bars.nz_empty[l], kGrp);
+      mbar_init(&bars.g_ready[l], kTThreads / 32);
+      mbar_init(&bars.nz_full[0][l], kGrp / 32);
+      mbar_init(&bars.nz_full[1][l], kGrp / 32);
     }
     fence_mbar_init();
   }
@@ -394,7 +388,6 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
   const uint32_t col_bias = (kDA + 3 * HT) * NR, col_y = col_bias + 32;
   // Adam on the latents (deterministic PC / MAP): m and v behind the targets, HT * NR columns each
   const uint32_t col_m = col_y + (y_in_tmem ? (uint32_t)p.n_out_tiles * NR : 0u), col_v = col_m + HT * NR;
-  const uint32_t col_nz = col_m;                              // instantiation 1 (SGD: no Adam state): the noise, HT * NR columns
   const int n_tiles_all = p.n_hid_tiles + p.n_out_tiles;      // table order: Linear 1 ... L-1, then the output tiles
 
   // =====================================================================================================
@@ -444,51 +437,6 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
           __nanosleep(200);
         }
         signal_saved(p.ready + s);
-      }
-    }
-  } else if (kNoiseWarps && warp >= kNoiseWarp0) {
-    // ---------------- noise warps (instantiation 1: MCPC learning / sampling calls of 8-chain CTAs) ----------------
-    // Group U closes the step's critical loop (output tiles -> back-projection -> update of the top hidden layer -> next
-    // step's output tiles) and ~40 % of its time per layer was the Philox + Box-Muller draw (cycle trace).  These four warps
-    // (one per TMEM lane quarter) draw the noise of every latent one step ahead into TMEM -- lane = unit, column = chain,
-    // the layout of x, so group U reads it in the same batch of tcgen05.ld as x and the back-projection.  Per layer: wait
-    // until group U has read the previous step's values (nz_empty), store, arrive on nz_full.  Same counters and keys as
-    // the in-thread draw: the values are bit-identical.
-    if (p.nz_tmem) {
-      static_assert(!kNoiseWarps || RV == 8, "noise warps: 8 chains = two (aligned) or three quads of Philox outputs");
-      const int qn = warp & 3;
-      const uint32_t lb = tmem + ((uint32_t)(qn * 32) << 16) + col_nz;
-      const uint64_t chain0 = p.chain_offset + (uint64_t)row0;
-      const uint64_t q0 = chain0 >> 2;
-      const int first = (int)(chain0 & 3);
-      for (int ts = 0; ts < p.n_steps; ++ts) {
-        const uint32_t t_abs = (uint32_t)(p.t_begin + ts);
-        for (int l = 0; l < L; ++l) {
-          if (ts > 0) {
-            mbar_wait_parked(&bars.nz_empty[l], (ts - 1) & 1);
-            fence_after_sync();
-          }
-          if (qn * 32 < nd.dims[l]) {                          // (one unit tile per layer; warp-uniform)
-            const uint32_t gu = (uint32_t)(nd.off[l] + qn * 32 + lane);
-            float all[12], nzv[8];
-            langevin_normals4(p.seed, gu, t_abs, q0, &all[0]);
-            langevin_normals4(p.seed, gu, t_abs, q0 + 1, &all[4]);
-            if (first != 0) {
-              langevin_normals4(p.seed, gu, t_abs, q0 + 2, &all[8]);
-            } else {
-#pragma unroll
-              for (int j = 8; j < 12; ++j) all[j] = 0.0f;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              nzv[c] = p.noise_scale * (first == 0 ? all[c] : (first == 1 ? all[c + 1] : (first == 2 ? all[c + 2] : all[c + 3])));
-            __syncwarp();
-            tmem_st<8>(lb + (uint32_t)(p.h_off[l] * NR), nzv);
-            tmem_st_wait();
-          }
-          fence_before_sync();
-          mbar_arrive(&bars.nz_full[0][l]);
-        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -597,7 +545,7 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
     // The SM's warp arbiter favours higher warp ids: the latency-critical tile epilogues (group T) get warps
     // 8-15, the background layer updates (group U) warps 0-7, the MMA issuer the highest id of all.
     const int grp = (warp < 8) ? 1 : 0;                                // 0 = tiles (T), 1 = update (U)
-    const int gw = (warp < 16) ? (warp & 7) : (warp - 12);             // warp inside the group (T: 8-15 -> 0-7, 20-27 -> 8-15)
+    const int gw = warp & 7;                                           // warp inside the group
     const int gtid = gw * 32 + lane;
     const int q = warp & 3, cg = (gw >> 2) & 1;
     const int ln = q * 32 + lane;                                      // unit index inside a 128-unit tile
@@ -640,7 +588,7 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
       tmem_st_wait();
       fence_async_smem();
       fence_before_sync();
-      for (int l = 0; l < L; ++l) mbar_arrive(&bars.acts_ready[l]);
+      for (int l = 0; l < L; ++l) warp_arrive(&bars.acts_ready[l], lane);
 
       const bool adam = (opt_kind == MCPC_OPT_ADAM);
       uint32_t ph_out_read = 0;
@@ -707,13 +655,13 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
             // a warp whose 32 units are all padding (e.g. 3 of 4 warps on a 20-unit layer) has nothing to update: its
             // TMEM lanes keep the zeros written at start-up; it only takes part in the waits and the hand-over
             const bool warp_idle = (hi * 128 + q * 32) >= dl;
+            auto wait_layer = [&]() {
+              if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);        // all tiles of Linear l+1 back-projected
+              if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);             // group T stored the own-layer error of layer l
+              if (l == L - 1 && wait_out_read) mbar_wait_parked(&bars.out_read, ph_out_read);
+            };
             if (warp_idle) {
-              if (hi == 0) {
-                if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);
-                if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);
-                if (l == L - 1 && wait_out_read) mbar_wait_parked(&bars.out_read, ph_out_read);
-                if (kNoiseWarps && p.nz_tmem) mbar_arrive(&bars.nz_empty[l]);     // (nothing to read: hand the columns back)
-              }
+              if (hi == 0) wait_layer();
               continue;
             }
             // the chains of the thread go through in chunks of CH <= 8: bounded register pressure and code size
@@ -760,10 +708,7 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
               };
               // pure sampling: group T (idle but for the hidden tiles) drew this step's noise into shared memory one step ahead
               const bool nz_smem = (SPEC == 3) && (p.nz_off >= 0);
-              const bool nz_tm = kNoiseWarps && (p.nz_tmem != 0);  // instantiation 1: the noise warps drew it into TMEM
-              if (nz_tm) {
-                // read below, in the same batch of TMEM loads as x and the back-projection
-              } else if (nz_smem) {
+              if (nz_smem) {
                 if (hi == 0 && c0 == 0) mbar_wait_parked(&bars.nz_full[ts & 1][l], (ts >> 1) & 1);
                 const float* nb = reinterpret_cast<const float*>(smem + p.nz_off) +
                                   ((size_t)((ts & 1) * HT + h) * RV + (size_t)cbc) * 128 + ln;
@@ -774,16 +719,12 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
               }
               // ---- 2. wait for this layer's back-projection and own error, then ONE batch of TMEM loads ----
               if (hi == 0 && c0 == 0) {
-                if (has_above) mbar_wait_parked(&bars.bp_ready[l], ts & 1);      // all tiles of Linear l+1 back-projected
-                if (l > 0) mbar_wait_parked(&bars.g_ready[l], ts & 1);           // group T stored the own-layer error of layer l
-                if (l == L - 1 && wait_out_read) mbar_wait_parked(&bars.out_read, ph_out_read);
-                if (nz_tm) mbar_wait_parked(&bars.nz_full[0][l], ts & 1);
+                wait_layer();
                 fence_after_sync();
                 TC_STAMP(gtid == 0, ts, 40 + l);
               }
               __syncwarp();
               float xv[CH], bp[CH], gown[CH], gradv[CH];
-              if (nz_tm) tmem_ld_nw<CH>(lac + col_nz + h * NR, nz);
               tmem_ld_nw<CH>(lac + col_x + h * NR, xv);
               if (has_above) tmem_ld_nw<CH>(lac + col_bp + h * NR, bp);
               if (l > 0) tmem_ld_nw<CH>(lac + col_g + h * NR, gown);
@@ -794,15 +735,6 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
               }
               tmem_ld_wait();
               TC_STAMP(gtid == 0 && l == 1, ts, 43);
-              if (nz_tm) {
-                tmem_ld_tie(nz);
-                fence_before_sync();
-                mbar_arrive(&bars.nz_empty[l]);                  // (one unit tile, one chunk per layer: once per layer and step)
-                if (!uvalid) {
-#pragma unroll
-                  for (int i = 0; i < CH; ++i) nz[i] = 0.0f;
-                }
-              }
               tmem_ld_tie(xv);
               if (adam_t) {
                 tmem_ld_tie(mv);
@@ -828,7 +760,7 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
                   if (uvalid && i < nrc) e_part = fmaf(ce * eps, eps, e_part);
                 }
               }
-              if (!kNoiseEarly && !nz_smem && !nz_tm) draw_noise();
+              if (!kNoiseEarly && !nz_smem) draw_noise();
               // ---- 3. update (straight-line: CH independent chains interleave) ----
 #pragma unroll
               for (int i = 0; i < CH; ++i) {
@@ -891,7 +823,7 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
           fence_async_smem();
           TC_STAMP(gtid == 0 && l == 1, ts, 47);
           fence_before_sync();
-          mbar_arrive(&bars.acts_ready[l]);                  // act(x_l) / x_l of step ts+1 are in place
+          warp_arrive(&bars.acts_ready[l], lane);            // act(x_l) / x_l of step ts+1 are in place
           TC_STAMP(gtid == 0 && l == 1, ts, 48);
           // the proxy fence above waits for every earlier memory operation of the thread: the global stores of a
           // single-tile layer are issued after the hand-over so that they do not delay it
@@ -1003,7 +935,7 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
               }
             }
           }
-          mbar_arrive(&bars.nz_full[step & 1][l]);               // (release: the stores above are visible to the waiter)
+          warp_arrive(&bars.nz_full[step & 1][l], lane);         // (release: the stores above are visible to the waiter)
         }
       };
       const bool nz_producer = (SPEC == 3) && (p.nz_off >= 0);
@@ -1029,7 +961,7 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
           const int u = ((ti.x >> 8) & 0xff) * 128 + ln;
           const bool uvalid = u < dl;
           if (ALT && (k & (SUB - 1)) != half) {               // another sub-group's tile
-            if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) mbar_arrive(&bars.g_ready[lin]);
+            if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) warp_arrive(&bars.g_ready[lin], lane);
             continue;
           }
           float yv[RT];
@@ -1052,9 +984,9 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
               ph_ge ^= 1u << gb;
             }
             fence_before_sync();
-            mbar_arrive(&bars.dA_empty[db]);
-            if (has_b) mbar_arrive(&bars.g_full[gb]);
-            if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) mbar_arrive(&bars.g_ready[lin]);
+            warp_arrive(&bars.dA_empty[db], lane);
+            if (has_b) warp_arrive(&bars.g_full[gb], lane);
+            if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) warp_arrive(&bars.g_ready[lin], lane);
             continue;
           }
           uint8_t* gptr = smem + p.gbuf_off[gb] + gtoT;
@@ -1146,11 +1078,11 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
           }
           TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 57);
           fence_before_sync();
-          mbar_arrive(&bars.dA_empty[db]);
+          warp_arrive(&bars.dA_empty[db], lane);
           TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 58);
           if (has_b) {
             fence_async_smem();
-            mbar_arrive(&bars.g_full[gb]);
+            warp_arrive(&bars.g_full[gb], lane);
           }
           // the saved dW operand goes out AFTER the hand-over: the proxy fence above waits for every earlier memory
           // operation of the thread, global stores included, so they must not sit in front of it
@@ -1161,7 +1093,7 @@ __global__ void __launch_bounds__((tc_threads<SUB, NZW>()), 1) infer_tc_kernel(c
           }
           TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 59);
           // own-layer errors of layer `lin` are complete after the last tile of Linear lin
-          if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) mbar_arrive(&bars.g_ready[lin]);
+          if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) warp_arrive(&bars.g_ready[lin], lane);
           TC_STAMP(stamp_thr, ts, 22 + k);
         }
         e_part = warp_sum_tc(e_part);
@@ -1191,7 +1123,8 @@ inline int pad16(int v) { return (v + 15) & ~15; }
 
 // Fills the tile table + shared-memory plan.  Returns MCPC_OK or MCPC_ERR_UNSUPPORTED (message set).
 int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* packed_bytes, bool with_out = true,
-            bool shrink_partial = true, int n_sub = 2) {
+            bool shrink_partial = true) {
+  const int n_sub = 2;                                         // G operand buffers / accumulator pairs (SUB of the kernel)
   if (nd.L < 1) return MCPC_ERR_INVALID;
   int HT = 0;
   for (int l = 0; l < nd.L; ++l) {
@@ -1334,7 +1267,7 @@ int plan_tc(const NetDev& nd, int NR, TcParams* p, size_t* smem_bytes, size_t* p
   for (int t = 0; t < nt; ++t)
     if ((size_t)p->tiles[t].smem_off + (size_t)128 * p->tiles[t].Kp * 2 > *smem_bytes) {
       if (!shrink_partial) return MCPC_ERR_INVALID;
-      return plan_tc(nd, NR, p, smem_bytes, packed_bytes, with_out, false, n_sub);
+      return plan_tc(nd, NR, p, smem_bytes, packed_bytes, with_out, false);
     }
   return MCPC_OK;
 }
@@ -1547,10 +1480,10 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
       MCPC_CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork, 0));
     }
   }
-  auto launch = [&](auto kernel, int threads = 640) -> int {
+  auto launch = [&](auto kernel) -> int {
     p.tab_off = (int)((plan_smem - kTabBytes) & ~(size_t)15);    // inside the slack at the end of the PLAN (see s_mA)
     MCPC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<p.n_ctas, threads, smem, stream>>>(p);
+    kernel<<<p.n_ctas, 640, smem, stream>>>(p);
     return MCPC_OK;
   };
   bool plain = (p.traj_every == 0) && o->update_x;           // what every specialisation assumes
@@ -1593,27 +1526,6 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
       }
     }
   }
-  int n_sub = 2;
-  if (spec == 1 && rows.rv == 8 && !timing) {
-    // MCPC learning / sampling call on 8-chain CTAs: four tile sub-groups (8 accumulators, 4 G buffers) when TMEM and shared
-    // memory allow it, and the noise warps, which draw the Langevin noise into TMEM one step ahead (columns behind the
-    // targets, where instantiation 2 keeps Adam's state) -- see infer_tc_kernel
-    const char* es = getenv("MCPC_TC_SUB");
-    if (es != nullptr && atoi(es) == 4) {                        // experiment (measured slower)
-      TcParams q = p;
-      size_t smem4 = 0, packed4 = 0;
-      if (plan_tc(nd, rows.nr, &q, &smem4, &packed4, true, true, 4) == MCPC_OK && q.y_tmem && packed4 == packed) {
-        for (int t = 0; t < kMaxTiles; ++t) p.tiles[t] = q.tiles[t];
-        for (int i = 0; i < 4; ++i) p.gbuf_off[i] = q.gbuf_off[i];
-        for (int l = 0; l < nd.L; ++l) p.act_off[l] = q.act_off[l];
-        smem = smem4;
-        plan_smem = smem4;
-        n_sub = 4;
-      }
-    }
-    const int used = (2 * n_sub + 3 * p.HT) * rows.nr + 32 + p.n_out_tiles * rows.nr;
-    p.nz_tmem = (getenv("MCPC_TC_NOISE_WARPS") != nullptr && used + p.HT * rows.nr <= 512) ? 1 : 0;   // measured slower
-  }
   if (rows.rv == 32) {
     rc = spec == 3 ? launch(infer_tc_kernel<32, 32, false, 3>)
                    : (spec == 4 ? launch(infer_tc_kernel<32, 32, false, 4>) : launch(infer_tc_kernel<32, 32, false, 0>));
@@ -1622,13 +1534,7 @@ int launch_infer_tc(const NetDev& nd, const McpcIO* io, const McpcOpts* o, int B
   } else if (timing) {
     rc = launch(infer_tc_kernel<16, 8, true, 0>);    // the cycle trace exists for the generic 8-chain variant only
   } else if (spec == 1) {
-    if (n_sub == 4) {
-      rc = p.nz_tmem ? launch(infer_tc_kernel<16, 8, false, 1, 4, 1>, tc_threads<4, 1>())
-                     : launch(infer_tc_kernel<16, 8, false, 1, 4, 0>, tc_threads<4, 0>());
-    } else {
-      rc = p.nz_tmem ? launch(infer_tc_kernel<16, 8, false, 1, 2, 1>, tc_threads<2, 1>())
-                     : launch(infer_tc_kernel<16, 8, false, 1, 2, 0>, tc_threads<2, 0>());
-    }
+    rc = launch(infer_tc_kernel<16, 8, false, 1>);
   } else if (spec == 2) {
     rc = launch(infer_tc_kernel<16, 8, false, 2>);
   } else if (spec == 3) {
