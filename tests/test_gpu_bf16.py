@@ -62,32 +62,47 @@ def test_auto_precision_takes_bf16_with_nonzero_inputs():
                                                    ("tanh", "bernoulli", 8192, False), ("tanh", "bernoulli", 1000, True),
                                                    ("tanh", "gauss", 2048, True), ("relu", "bernoulli", 6000, True)])
 def test_bf16_kernel_vs_bf16_oracle(act, top, B, with_inputs):
+    _bf16_kernel_vs_bf16_oracle(act, top, B, with_inputs, (20, 128, 128, 784))
+
+
+# Other tilings of the resident kernel: a single partial output tile (10 units: only its 16 valid rows are kept in shared
+# memory and the M = 128 prediction MMA reads the following tiles), partial tiles of 72 and 2 valid units behind full ones,
+# exactly 7 full output tiles, hidden layers of 2 and 3 unit tiles, a 12-unit input layer.
+@pytest.mark.parametrize("dims,act,top,B", [((12, 64, 200, 10), "tanh", "gauss", 300), ((20, 128, 128, 200), "relu", "bernoulli", 1024),
+                                            ((16, 300, 96, 130), "tanh", "bernoulli", 520), ((20, 128, 128, 896), "relu", "bernoulli", 1024),
+                                            ((20, 128, 128, 10), "relu", "zero", 2048)])
+def test_bf16_kernel_tilings_vs_bf16_oracle(dims, act, top, B):
+    _bf16_kernel_vs_bf16_oracle(act, top, B, False, dims)
+
+
+def _bf16_kernel_vs_bf16_oracle(act, top, B, with_inputs, dims):
     dev = torch.device(DEV)
     mixing, sampling, lr = 3, 5, 0.03
     T = mixing + sampling
     torch.manual_seed(1)
-    cfg = {"input_size": 20, "hidden_size": 128, "hidden2_size": 128, "output_size": 784, "activation_fn": act}
+    d0, d1, d2, d_out = dims
+    cfg = {"input_size": d0, "hidden_size": d1, "hidden2_size": d2, "output_size": d_out, "activation_fn": act}
     model = mu.get_model(cfg, use_cuda=False).to(dev)
     tr = pc.PCTrainer(model, T=T, optimizer_x_fn=optim.SGD, optimizer_x_kwargs={"lr": lr}, update_p_at="last",
                       accumulate_p_at=list(range(mixing, T)), optimizer_p_fn=optim.SGD, optimizer_p_kwargs={"lr": 0.0},
                       plot_progress_at=[])
     tr.set_precision("bf16")
     tr.set_noise_seed(31337)
-    y = (torch.rand(B, 784, device=dev) < 0.5).float() if top != "gauss" else torch.randn(B, 784, device=dev)
-    x0 = [torch.randn(B, d, device=dev) for d in (20, 128, 128)]
+    y = (torch.rand(B, d_out, device=dev) < 0.5).float() if top != "gauss" else torch.randn(B, d_out, device=dev)
+    x0 = [torch.randn(B, d, device=dev) for d in (d0, d1, d2)]
     pcs = [m for m in model if isinstance(m, pc.PCLayer)]
     lins = [m for m in model if isinstance(m, nn.Linear)]
     for layer, v in zip(pcs, x0):
         layer._sample_x_fn = (lambda inputs, v=v: v.clone())
     loss_fn = {"bernoulli": mu.bernoulli_fn, "gauss": mu.fe_fn, "zero": mu.zero_fn}[top]
     kw = {} if top == "zero" else {"loss_fn_kwargs": {"_target": y, "_var": 1.0}}
-    inputs = torch.randn(B, 20, device=dev) if with_inputs else torch.zeros(B, 20, device=dev)
+    inputs = torch.randn(B, d0, device=dev) if with_inputs else torch.zeros(B, d0, device=dev)
     res = tr.train_on_batch(inputs, loss_fn=loss_fn, callback_after_t=mu.random_step,
                             callback_after_t_kwargs={"_pc_trainer": tr}, is_log_progress=False,
                             is_return_results_every_t=True, is_return_outputs=True, **kw)
     assert tr.last_call_info["precision"] == 1
-    nz = tr._get_engine().fill_noise(31337, 0, T, 0, B, 276, float(np.sqrt(2.0 / lr)), dev).cpu().numpy()
-    offs = [0, 20, 148, 276]
+    nz = tr._get_engine().fill_noise(31337, 0, T, 0, B, d0 + d1 + d2, float(np.sqrt(2.0 / lr)), dev).cpu().numpy()
+    offs = [0, d0, d0 + d1, d0 + d1 + d2]
     noise = [[nz[t][:, offs[l]:offs[l + 1]] for l in range(3)] for t in range(T)]
     net = orc.OracleNet(W=[l.weight.detach().cpu().numpy() for l in lins], b=[l.bias.detach().cpu().numpy() for l in lins],
                         n_layers=3, act=[orc.ACT_RELU if act == "relu" else orc.ACT_TANH] * 3, energy_scale=[1.0] * 3,
@@ -107,7 +122,7 @@ def test_bf16_kernel_vs_bf16_oracle(act, top, B, with_inputs):
     errs["gb_0"] = rel_err(lins[0].bias.grad.cpu().numpy(), ref.gb[0] / div)
     if with_inputs:
         errs["gW_0"] = rel_err(lins[0].weight.grad.cpu().numpy(), ref.gW[0] / div)
-    print(act, top, B, {k: f"{v:.2e}" for k, v in errs.items()})
+    print(dims, act, top, B, {k: f"{v:.2e}" for k, v in errs.items()})
     for k, v in errs.items():
         assert v < 2e-3, (k, v)
 
