@@ -478,12 +478,14 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
           // groups of 8 K-steps fully unrolled: the instructions issue back to back (46 instead of 91 cycles each,
           // scripts/umma_timing.py variants 6 / 1)
           int ks = 0;
-          for (; ks + 8 <= nk; ks += 8) {
+#pragma unroll 1
+          for (; ks + 8 <= nk; ks += 8) {                      // (not unrolled further: the issuer's code must stay small)
             const uint64_t a8 = M.ad0 + (uint64_t)(ks * 16), b8 = M.bd0 + (uint64_t)(ks * kBStep);
             mma_bf16_ss(dcol, a8, b8, id_a, ks > 0);
 #pragma unroll
             for (int kk = 1; kk < 8; ++kk) mma_bf16_ss(dcol, a8 + (uint64_t)(kk * 16), b8 + (uint64_t)(kk * kBStep), id_a, true);
           }
+#pragma unroll 1
           for (; ks < nk; ++ks) mma_bf16_ss(dcol, M.ad0 + (uint64_t)(ks * 16), M.bd0 + (uint64_t)(ks * kBStep), id_a, ks > 0);
           mma_commit(&bars.dA_full[db]);
           // a streamed tile without back-projection is free again once this prediction has read it
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
 #pragma unroll
               for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * M.a_step), bd0 + (uint64_t)(ks * kBStep), id_b, true);
             } else {
+#pragma unroll 1
               for (int ks = 1; ks < nkb; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * M.a_step), bd0 + (uint64_t)(ks * kBStep), id_b, true);
             }
             bp_started |= 1u << (h0 + u);
