@@ -114,7 +114,8 @@ struct Barriers {
 // Per-tile constants of the two MMA issuers (shared memory, built once per launch)
 struct __align__(16) MmaA {
   uint64_t ad0, bd0;      // descriptors of the weight tile (K-major) and of the activation operand of its input layer
-  int meta;               // in_layer [0,4) | slot + 1 [4,6) | has back-projection [6] | K steps of 16 [8,16)
+  int meta;               // in_layer [0,4) | slot + 1 [4,6) | has back-projection [6] | first tile of the step that reads
+                          // this layer's activations [7] | K steps of 16 [8,16)
   int pad[3];
 };
 struct __align__(16) MmaB {
@@ -338,7 +339,9 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
     MmaA A;
     A.ad0 = smem_desc(sb + T.smem_off, 128u, (uint32_t)T.sbo);
     A.bd0 = smem_desc(sb + p.act_off[in_layer], (uint32_t)(NR * 16), 128u);          // MN-major (st_chains_bf16)
-    A.meta = in_layer | ((T.slot + 1) << 4) | ((has_b ? 1 : 0) << 6) | ((T.Kp / 16) << 8);
+    bool first_use = true;                                    // no earlier tile of the step reads this layer's activations
+    for (int k = 0; k < tid; ++k) first_use = first_use && (p.tiles[k].lin != T.lin);
+    A.meta = in_layer | ((T.slot + 1) << 4) | ((has_b ? 1 : 0) << 6) | ((first_use ? 1 : 0) << 7) | ((T.Kp / 16) << 8);
     A.pad[0] = A.pad[1] = A.pad[2] = 0;
     s_mA[tid] = A;
     // K extent of the back-projection = the tile's valid output units in groups of 16 (rows of G beyond them are never written)
@@ -457,15 +460,11 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
         const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
         const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
         const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
-        uint32_t acts_waited = 0;
         TC_STAMP(true, ts, 0);
         for (int t = 0; t < t_end; ++t) {
           const MmaA M = s_mA[t];
           const int in_layer = M.meta & 15, slot = ((M.meta >> 4) & 3) - 1, nk = (M.meta >> 8) & 0xff;
-          if (!((acts_waited >> in_layer) & 1u)) {                    // act(x_{lin-1}) of THIS step: written by group U
-            mbar_wait_parked(&bars.acts_ready[in_layer], ts & 1);
-            acts_waited |= 1u << in_layer;
-          }
+          if (M.meta & 128) mbar_wait_parked(&bars.acts_ready[in_layer], ts & 1);   // act(x_{lin-1}) of THIS step (group U)
           if (slot >= 0) {
             mbar_wait_parked(&bars.w_full[slot], (ph_wfull >> slot) & 1u);
             ph_wfull ^= 1u << slot;
@@ -941,6 +940,10 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
           warp_arrive(&bars.nz_full[step & 1][l], lane);         // (release: the stores above are visible to the waiter)
         }
       };
+      // bit t: tile t is the last tile of a hidden Linear (the own-layer errors of that layer are complete after it)
+      uint32_t last_hid = 0;
+      for (int t = 0; t < p.n_hid_tiles; ++t)
+        if (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != (s_tile[t].x & 0xff)) last_hid |= 1u << t;
       const bool nz_producer = (SPEC == 3) && (p.nz_off >= 0);
       if (nz_producer) produce_noise(0);
       for (int ts = 0; ts < p.n_steps; ++ts) {
@@ -955,18 +958,18 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
         uint32_t x_waited = 0;
         TC_STAMP(gtid == 0, ts, 32);
         for (int t = 0; t < t_end; ++t) {
+          const int k = t;
+          if (ALT && (k & (SUB - 1)) != half) {               // another sub-group's tile: a handful of instructions
+            if ((last_hid >> t) & 1u) warp_arrive(&bars.g_ready[s_tile[t].x & 0xff], lane);
+            continue;
+          }
           const int2 ti = s_tile[t];
           const int lin = ti.x & 0xff, h = ((ti.x >> 16) & 0xff) - 1, dl = ti.y;
-          const int k = t;
           const int db = k & (kDA - 1), gb = k & (kGB - 1);
           const bool is_out = (lin == L);
           const bool has_b = !is_out || top_has_grad;
           const int u = ((ti.x >> 8) & 0xff) * 128 + ln;
           const bool uvalid = u < dl;
-          if (ALT && (k & (SUB - 1)) != half) {               // another sub-group's tile
-            if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) warp_arrive(&bars.g_ready[lin], lane);
-            continue;
-          }
           float yv[RT];
           if (!y_in_tmem && is_out) target_of(t, yv);          // targets do not fit TMEM: plain loads
           TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 60);
@@ -989,7 +992,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
             fence_before_sync();
             warp_arrive(&bars.dA_empty[db], lane);
             if (has_b) warp_arrive(&bars.g_full[gb], lane);
-            if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) warp_arrive(&bars.g_ready[lin], lane);
+            if ((last_hid >> t) & 1u) warp_arrive(&bars.g_ready[lin], lane);
             continue;
           }
           uint8_t* gptr = smem + p.gbuf_off[gb] + gtoT;
@@ -1096,7 +1099,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
           }
           TC_STAMP(stamp_thr && (k == 2 || k == 3), ts, 59);
           // own-layer errors of layer `lin` are complete after the last tile of Linear lin
-          if (!is_out && (t + 1 == n_tiles_all || (s_tile[t + 1].x & 0xff) != lin)) warp_arrive(&bars.g_ready[lin], lane);
+          if ((last_hid >> t) & 1u) warp_arrive(&bars.g_ready[lin], lane);
           TC_STAMP(stamp_thr, ts, 22 + k);
         }
         e_part = warp_sum_tc(e_part);
