@@ -252,6 +252,11 @@ __device__ __forceinline__ void saved_step(unsigned* cnt) {
   asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(umma::smem_u32(cnt)) : "memory");
 }
 
+__device__ __forceinline__ float exp2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -1052,7 +1057,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
                 const float o = d[i] + bias;
                 const float y = yv[i];
                 const bool on = (y == y);                      // NaN marks "no loss on this element"
-                const float z = __expf(-fabsf(o));
+                const float z = exp2_ftz(-1.4426950408889634f * fabsf(o));   // exp(-|o|): MUFU ex2 without the denormal wrapper
                 const float lv = fmaxf(o, 0.0f) - o * y + __logf(1.0f + z);
                 const float e = __fdividef(o >= 0.0f ? 1.0f : z, 1.0f + z) - y;
                 l_part += on ? lv : 0.0f;

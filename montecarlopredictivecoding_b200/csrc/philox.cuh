@@ -34,6 +34,13 @@ __device__ __forceinline__ float u01_24(uint32_t bits) {
   return (static_cast<float>(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
 
+// MUFU lg2 without the denormal-input wrapper of __log2f (the arguments are >= 2^-25): same value, three instructions less
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -46,8 +53,8 @@ __device__ __forceinline__ void langevin_normals4(uint64_t seed, uint32_t unit, 
                                   static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   // -2 ln u = (-2 ln 2) log2 u; MUFU lg2 / sqrt (approx, ~1 ulp): the radius of a N(0,1) draw needs no IEEE rounding,
   // and sqrtf's correctly rounded slow path was a function call per draw
-  const float ra = sqrt_approx(-1.38629436111989062f * __log2f(u01_24(r.v[0])));
-  const float rb = sqrt_approx(-1.38629436111989062f * __log2f(u01_24(r.v[2])));
+  const float ra = sqrt_approx(-1.38629436111989062f * lg2_approx(u01_24(r.v[0])));
+  const float rb = sqrt_approx(-1.38629436111989062f * lg2_approx(u01_24(r.v[2])));
   // MUFU sin/cos on an argument in (-pi, pi): absolute error ~2^-21, far below the noise it shapes
   float sa, ca, sb, cb;
   __sincosf(6.28318530717958648f * (u01_24(r.v[1]) - 0.5f), &sa, &ca);
