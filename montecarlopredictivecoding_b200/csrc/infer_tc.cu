@@ -122,7 +122,8 @@ struct __align__(16) MmaB {
   uint64_t ad0;           // descriptor of the MN-major view of the weight tile (first 128 input units)
   uint32_t a_step;        // descriptor step per 16 output units
   int meta;               // has back-projection [0] | last tile of its Linear [1] | slot + 1 [2,4) | in_layer [4,8) |
-                          // K steps (valid output units / 16) [8,12) | unit tiles of the input layer [12,16) | first [16,20)
+                          // K steps (valid output units / 16) [8,12) | unit tiles of the input layer [12,16) | first [16,20) |
+                          // first tile of its Linear [20]
 };
 
 // The chain-side operands (act(x_l) for the predictions, G for the back-projections: N = chains, K = units) are kept
@@ -355,8 +356,9 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
     MmaB Bm;
     Bm.ad0 = smem_desc(sb + T.smem_off, (uint32_t)T.sbo, 128u);
     Bm.a_step = (uint32_t)(2 * T.sbo) >> 4;
+    const bool first_of_lin = (tid == 0) || (p.tiles[tid - 1].lin != T.lin);   // overwrites the back-projection accumulators
     Bm.meta = (has_b ? 1 : 0) | ((last_of_lin ? 1 : 0) << 1) | ((T.slot + 1) << 2) | (in_layer << 4) | (nkb << 8) |
-              (p.ut[in_layer] << 12) | (p.h_off[in_layer] << 16);
+              (p.ut[in_layer] << 12) | (p.h_off[in_layer] << 16) | ((first_of_lin ? 1 : 0) << 20);
     s_mB[tid] = Bm;
   }
   if (tid == 0) {
@@ -516,7 +518,6 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
         const bool do_traj = (SPEC == 0 || SPEC == 4) && (p.traj_every > 0) && (ts % p.traj_every == 0);
         const bool need_out = top_has_grad || (do_traj && p.traj_out != nullptr);
         const int t_end = need_out ? n_tiles_all : p.n_hid_tiles;
-        uint32_t bp_started = 0;
         for (int t = 0; t < t_end; ++t) {
           const MmaB M = s_mB[t];
           if (!(M.meta & 1)) continue;                                  // read-out only: nothing flows back
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
           for (int u = 0; u < n_ut; ++u) {
             const uint64_t ad0 = M.ad0 + (uint64_t)(u * (2048 >> 4));
             const uint32_t dcol = tmem + col_bp + (h0 + u) * NR;
-            mma_bf16_ss(dcol, ad0, bd0, id_b, (bp_started >> (h0 + u)) & 1u);
+            mma_bf16_ss(dcol, ad0, bd0, id_b, !((M.meta >> 20) & 1));
             if (nkb == 8) {
 #pragma unroll
               for (int ks = 1; ks < 8; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * M.a_step), bd0 + (uint64_t)(ks * kBStep), id_b, true);
@@ -538,7 +539,6 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
 #pragma unroll 1
               for (int ks = 1; ks < nkb; ++ks) mma_bf16_ss(dcol, ad0 + (uint64_t)(ks * M.a_step), bd0 + (uint64_t)(ks * kBStep), id_b, true);
             }
-            bp_started |= 1u << (h0 + u);
           }
           mma_commit(&bars.g_empty[gb]);
           if ((M.meta >> 1) & 1) mma_commit(&bars.bp_ready[in_layer]);   // back-projection into layer lin-1 is complete
