@@ -5,13 +5,14 @@
 // batch tile still fills the MMA:
 //     phase A   mu_l^T  [128 units x NR] = W_l tile [128 x K]   . act(x_{l-1})^T      (A K-major)
 //     phase B   bp_l^T  [128 units x NR] += (W_{l+1} tile)^T    . G_{l+1}^T           (A MN-major view of the SAME tile)
+// (the chain-side B operands of both phases are MN-major, see st_chains_bf16)
 // Weight tiles (bf16, canonical no-swizzle layout, packed once per launch by pack_weights_kernel) are
 // resident in shared memory as far as they fit; the rest streams through a 2-slot ring with bulk async
 // copies (UBLKCP) every step.  The latents never leave the SM: the fp32 master copy of x, the fp32
 // own-layer error and all accumulators live in TMEM (lane = unit, column = chain), the bf16 operand
 // copies in shared memory.
 //
-// Warp roles are listed at the kernel (8 tile-epilogue warps, 8 update warps, 2 MMA issuers, 1 loader).  Per step and
+// Warp roles are listed at the kernel (8 tile-epilogue warps, 8 update warps, 2 MMA issuers, 1 loader, 1 signal).  Per step and
 // per weight tile t:  MMA_A(t) -> tile epilogue(t): eps, energy / loss, G (bf16 -> smem)  -> MMA_B(t); then the update
 // epilogue applies  x <- x - lr*grad (SGD | Adam)  and  x <- x - lr*noise (Philox)  and re-emits act(x).
 // All hand-offs are mbarriers; the tensor pipe never waits on a __syncthreads.
@@ -279,18 +280,20 @@ __device__ __forceinline__ float sel4(const float (&n)[4], uint32_t k) {
   return k == 0 ? n[0] : (k == 1 ? n[1] : (k == 2 ? n[2] : n[3]));
 }
 
-// NR chains per CTA.  Warp roles (19 warps):
+// NR chains per CTA.  Warp roles (20 warps):
 //   warps 8-15  group T: per-tile epilogue (errors of the units a weight tile predicts, G operand for phase B)
 //   warps 0-7   group U: latent update of one layer as soon as its back-projection is complete
-//   warp 16/17  MMA issuers (converged warps, one elected lane issues tcgen05.mma / commit): predictions / back-projections
+//   warp 16/17  MMA issuers (one elected thread each runs the whole loop over per-tile tables): predictions / back-projections
 //   warp 18     weight-tile loader (bulk async copies for tiles that are not resident)
+//   warp 19     signal warp of the opt-in overlapped weight update (idle otherwise)
 // Every epilogue thread owns one unit (TMEM lane) and RPT = RV/2 of the chains (two warps per 32-lane quarter).
 // RV <= NR is the number of chains the CTA really holds: the epilogues are issue-bound (not the tensor pipe), so a
 // batch that would leave SMs idle at RV = NR = 16 runs with RV = 8 on twice as many SMs; the MMA stays N = 16 (the
 // minimum at M = 128) and simply carries 8 zero columns.
-// Tiles are visited top-down (output tiles first, then Linear L-1 ... 1): the update of layer l only needs the
-// tiles of Linear l+1 (back-projection) and Linear l (own error), so group U works on layer l while the tensor
-// pipe and group T are already busy with the NEXT step's output tiles -- the step is pipelined across layers.
+// Tiles are visited bottom-up (Linear 1 ... L-1, then the output tiles, plan_tc): the update of layer l only needs the
+// tiles of Linear l+1 (back-projection) and Linear l (own error), so group U works on the lower layers while the tensor
+// pipe and group T are busy with the output tiles, and the lower Linears of the NEXT step overlap with the update of the
+// top hidden layer -- the step is pipelined across layers.
 // SPEC folds the modes of the two calls that matter most into compile-time constants (the epilogue warps are bound by
 // instruction fetch / issue, and every dead branch costs code footprint): 1 = MCPC learning / sampling (SGD + in-kernel
 // Philox noise, Bernoulli top, update_x), 2 = deterministic PC / MAP (Adam, no noise, Bernoulli top, update_x),
