@@ -704,6 +704,16 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
                   for (int i = 0; i < CH; ++i) nz[i] = (i < nrc) ? __ldg(np_ + (size_t)i * nd.SD) : 0.0f;
                 } else if (noise_kind == MCPC_NOISE_PHILOX) {
                   float nrm[4];
+                  const uint64_t chain0 = p.chain_offset + (uint64_t)rbc;
+                  if ((chain0 & 3) == 0) {                       // the usual case: the chunk is whole groups of four chains
+#pragma unroll
+                    for (int g = 0; g < CH / 4; ++g) {
+                      langevin_normals4(p.seed, (uint32_t)gu, (uint32_t)t_abs, (chain0 >> 2) + g, nrm);
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) nz[4 * g + j] = p.noise_scale * nrm[j];
+                    }
+                    return;
+                  }
                   uint64_t cur_q = ~0ull;
 #pragma unroll
                   for (int i = 0; i < CH; ++i) {
