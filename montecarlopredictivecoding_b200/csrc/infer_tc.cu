@@ -943,6 +943,16 @@ __global__ void __launch_bounds__(640, 1) infer_tc_kernel(const __grid_constant_
               float* nb = nbuf + ((size_t)(p.h_off[l] + hi) * RV + cbN) * 128 + ln;
               const uint32_t gu = (uint32_t)(nd.off[l] + u);
               float nrm[4];
+              const uint64_t chain0 = p.chain_offset + (uint64_t)(row0 + cbN);
+              if ((chain0 & 3) == 0) {                           // whole groups of four chains (the usual case)
+#pragma unroll 2
+                for (int g = 0; g < RPT / 4; ++g) {
+                  langevin_normals4(p.seed, gu, (uint32_t)(p.t_begin + step), (chain0 >> 2) + g, nrm);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) nb[(4 * g + j) * 128] = p.noise_scale * nrm[j];
+                }
+                continue;
+              }
               uint64_t cur_q = ~0ull;
 #pragma unroll 4
               for (int i = 0; i < RPT; ++i) {
