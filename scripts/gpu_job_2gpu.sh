@@ -3,8 +3,8 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/n2.txt
-timeout 900 python -m pytest tests/test_gpu_dp_nccl.py -q -s --timeout 800 2>&1 | grep -v "Warning\|warnings.warn" | tail -40 >> gpurun_out/n2.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 30 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+timeout 900 python -m pytest tests/test_gpu_dp_nccl.py -q --timeout 800 2>&1 | grep -E "passed|failed|Error" >> gpurun_out/n2.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps ${N2_STEPS:-100} --warmup 3 --no-cpu-baseline > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
 tail -3 gpurun_out/bench_n2.err >> gpurun_out/n2.txt
 cat gpurun_out/n2.txt | cut -c1-300
 python - <<'PY'
